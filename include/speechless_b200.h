@@ -1,0 +1,150 @@
+/*
+ * speechless_b200.h — C-ABI of libspeechless_b200.so
+ *
+ * Drop-in boundary for the wav2letter hot path of juliuskunze/speechless
+ * (speechless/net.py::Wav2Letter).  The reference has no FFI layer of its own:
+ * below the Python class surface it hands numpy batches to Keras/TensorFlow.
+ * Each entry point below replaces one Keras/TF call site; the citation names
+ * the reference line whose arithmetic the entry point reproduces.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller unless the name ends
+ *    in `_host`; the library allocates nothing on the hot path;
+ *  - `stream` is a cudaStream_t passed as void*; calls are stream ordered and
+ *    re-entrant;
+ *  - return value 0 = ok, non-zero = error (message via sl_last_error);
+ *    nothing throws or aborts across the ABI;
+ *  - activations are channels-last (B, T, C) like Keras' Conv1D
+ *    (net.py:304-305).  The tensor-core kernels read/write the *packed* form:
+ *    bf16, channels zero-padded to a multiple of 64, optionally followed by a
+ *    second "lo" plane (x - bf16(x)) in the same row for the split-bf16
+ *    (fp32-parity) mode: row = [hi(C_pad) | lo(C_pad)].
+ */
+#ifndef SPEECHLESS_B200_H
+#define SPEECHLESS_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SL_OK 0
+#define SL_ERR_INVALID 1   /* bad shape / argument (host-detected)        */
+#define SL_ERR_CUDA 2      /* CUDA runtime / driver error                 */
+#define SL_ERR_INFEASIBLE 3 /* CTC label not alignable in the given frames */
+
+/* precision of the packed bf16 tensors */
+#define SL_PREC_BF16 1    /* one bf16 plane, fp32 accumulate                 */
+#define SL_PREC_BF16X2 2  /* hi+lo bf16 planes, 3-term product (~fp32 parity) */
+
+/* epilogue / activation selector of sl_conv1d_fwd (net.py:298,304-305,328-330) */
+#define SL_ACT_NONE 0
+#define SL_ACT_RELU 1
+#define SL_ACT_SOFTMAX 2 /* output_conv: bias + softmax, fp32 outputs */
+
+int sl_version(void);
+/* copies the calling thread's last error message (NUL terminated) into buf */
+int sl_last_error(char* buf, size_t n);
+/* device sync + sticky async error check (surfaces device-side traps) */
+int sl_sync_check(void);
+
+/* ---- packing between the Keras-facing fp32 tensors and the packed bf16 form ---- */
+
+/* net.py:583-585 `_input_batch_and_prediction_lengths` feeds a zero padded
+ * (B,T,F) float batch; this casts it to packed bf16 rows of `c_pad` channels
+ * (T_alloc >= T rows per utterance, rows T..T_alloc zero).  */
+int sl_pack_activation(const float* x, void* x_packed, int B, int T, int C,
+                       int T_alloc, int c_pad, int prec, void* stream);
+/* inverse (debug / tests): packed -> fp32 (B,T,C) (hi + lo) */
+int sl_unpack_activation(const void* x_packed, float* x, int B, int T, int C,
+                         int T_alloc, int c_pad, int prec, void* stream);
+
+/* Keras kernel layout (k, Cin, Cout) fp32 (net.py:251-255,264-265) ->
+ *   w_fwd  (k, cout_pad, [hi cin_pad | lo cin_pad]) bf16   B operand of fwd
+ *   w_dgrad(k, cin_pad,  [hi cout_pad| lo cout_pad]) bf16  B operand of dgrad (may be NULL) */
+int sl_pack_weights(const float* w_keras, void* w_fwd, void* w_dgrad, int k,
+                    int Cin, int Cout, int cin_pad, int cout_pad, int prec,
+                    void* stream);
+
+/* ---- Conv1D tower (replaces keras.layers.Conv1D(padding="same"), net.py:304-305) ---- */
+
+/* y = act(bias + conv1d_same(x, w)).  x_packed (B,T_in_alloc,..), w_fwd from
+ * sl_pack_weights, bias fp32 (Cout).  T_out = ceil(T_in/stride); pad_l per TF
+ * SAME rule is computed inside.
+ *  act NONE/RELU : y_packed (B,T_out,[hi cout_pad|lo]) bf16
+ *  act SOFTMAX   : probs (B,T_out,Cout) fp32  [net.py:328-330]; optional
+ *                  logits (B,T_out,Cout) fp32 (pre-softmax, for parity tests) and
+ *                  logp (B,T_out,64) fp32 = log_softmax(log(p+1e-8)), the
+ *                  quantity tf.nn.ctc_loss consumes after K.ctc_batch_cost. */
+int sl_conv1d_fwd(const void* x_packed, const void* w_fwd, const float* bias,
+                  void* y_packed, float* probs, float* logits, float* logp,
+                  int B, int T_in, int T_in_alloc, int Cin, int Cout, int k,
+                  int stride, int act, int prec, void* stream);
+
+/* dX = conv1d_same_backward_input(dY, w) masked by the ReLU of the layer below
+ * (TF autodiff of net.py:304-305; stride 1 only — the strided first layer needs
+ * no dX).  x_saved = packed output of the layer below (post-ReLU), or NULL. */
+int sl_conv1d_dgrad(const void* dy_packed, const void* w_dgrad,
+                    const void* x_saved, void* dx_packed, int B, int T,
+                    int Cin, int Cout, int k, int prec, void* stream);
+
+/* dW (k,cout_pad,cin_pad) fp32 += sum_{b,t} x[b,t*s+j-pad_l,ci]*dy[b,t,co];
+ * db (Cout) fp32 = sum_{b,t} dy.  dW/db are overwritten (accumulate=0) or
+ * accumulated into (accumulate=1). */
+int sl_conv1d_wgrad(const void* x_packed, const void* dy_packed, float* dw,
+                    float* db, int B, int T_in, int T_in_alloc, int Cin,
+                    int Cout, int k, int stride, int prec, int accumulate,
+                    void* stream);
+
+/* master-weight layout helpers: Keras (k,Cin,Cout) fp32 <-> internal (k,cout_pad,cin_pad) fp32 */
+int sl_weights_keras_to_internal(const float* w_keras, float* w_int, int k,
+                                 int Cin, int Cout, int cin_pad, int cout_pad,
+                                 void* stream);
+int sl_weights_internal_to_keras(const float* w_int, float* w_keras, int k,
+                                 int Cin, int Cout, int cin_pad, int cout_pad,
+                                 void* stream);
+/* internal fp32 master (k,cout_pad,cin_pad) -> packed bf16 w_fwd / w_dgrad */
+int sl_pack_weights_internal(const float* w_int, void* w_fwd, void* w_dgrad,
+                             int k, int cin_pad, int cout_pad, int prec,
+                             void* stream);
+
+/* ---- CTC (replaces K.ctc_batch_cost -> tf.nn.ctc_loss, net.py:402-406) ---- */
+
+size_t sl_ctc_workspace_bytes(int B, int T, int L_max);
+/* logp (B,T,64) fp32 natural-log probabilities (from sl_conv1d_fwd);
+ * labels (B,L_max) int32 padded with -1 (grapheme_enconding.py:25-32);
+ * input_len[b] = prediction length P_b (net.py:582), label_len[b];
+ * loss (B) fp32 = -log p(label|x).
+ * If dlogits_packed != NULL also writes the gradient of
+ *   grad_scale * sum_b loss_b  w.r.t. the pre-softmax logits, chained through
+ *   log(p+1e-8) and the softmax (probs required), as packed bf16 rows of 64
+ *   channels ([hi 64 | lo 64] in SL_PREC_BF16X2), zero for t >= P_b;
+ *   optional fp32 copy dlogits_f32 (B,T,V) for tests. */
+int sl_ctc_loss(const float* logp, const float* probs, const int32_t* labels,
+                const int32_t* input_len, const int32_t* label_len,
+                float* loss, void* dlogits_packed, float* dlogits_f32,
+                float grad_scale, int B, int T, int V, int L_max, int blank,
+                int prec, void* workspace, size_t workspace_bytes,
+                void* stream);
+
+/* ---- greedy decode (replaces tf.nn.ctc_greedy_decoder, net.py:453-454) ---- */
+/* argmax over V (lowest index wins), drop repeats (merge_repeated) and blanks;
+ * out (B,T) int32 padded with -1 (tf.sparse_to_dense default, net.py:436),
+ * out_len (B). */
+int sl_ctc_greedy_decode(const float* probs, const int32_t* input_len,
+                         int32_t* out, int32_t* out_len, int B, int T, int V,
+                         int blank, int merge_repeated, void* stream);
+
+/* ---- optimizer (replaces keras.optimizers.Adam, net.py:132,389) ---- */
+/* Keras-2 Adam on a flat fp32 buffer: t = step (1-based);
+ * lr_t = lr*sqrt(1-b2^t)/(1-b1^t); p -= lr_t*m/(sqrt(v)+eps). */
+int sl_adam_step(float* p, const float* g, float* m, float* v, size_t n,
+                 float lr, float beta1, float beta2, float eps, int t,
+                 void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPEECHLESS_B200_H */

@@ -1,0 +1,354 @@
+// api.cu — the extern "C" surface declared in include/speechless_b200.h
+#include "../../include/speechless_b200.h"
+
+#include <cmath>
+#include <cstring>
+
+#include "conv_umma.h"
+#include "tmap.h"
+
+namespace sl {
+
+static thread_local std::string g_last_error;
+
+void set_error(const std::string& msg) { g_last_error = msg; }
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+  g_last_error = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what + " at " + file +
+                 ":" + std::to_string(line);
+  return SL_ERR_CUDA;
+}
+
+// launchers implemented in the other translation units
+int pack_activation_launch(const float*, void*, int, int, int, int, int, int, cudaStream_t);
+int unpack_activation_launch(const void*, float*, int, int, int, int, int, int, cudaStream_t);
+int keras_to_internal_launch(const float*, float*, int, int, int, int, int, cudaStream_t);
+int internal_to_keras_launch(const float*, float*, int, int, int, int, int, cudaStream_t);
+int pack_weights_internal_launch(const float*, void*, void*, int, int, int, int, cudaStream_t);
+int bias_grad_launch(const void*, float*, size_t, int, int, int, cudaStream_t);
+int adam_launch(float*, const float*, float*, float*, size_t, float, float, float, float, int,
+                cudaStream_t);
+size_t ctc_workspace_bytes(int B, int T, int L_max);
+int ctc_loss_launch(const float*, const float*, const int32_t*, const int32_t*, const int32_t*,
+                    float*, void*, float*, float, int, int, int, int, int, int, void*, size_t,
+                    cudaStream_t);
+int ctc_greedy_launch(const float*, const int32_t*, int32_t*, int32_t*, int, int, int, int, int,
+                      cudaStream_t);
+
+static int round64(int c) { return (c + 63) & ~63; }
+static int planes_of(int prec) { return prec == SL_PREC_BF16X2 ? 2 : 1; }
+
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+// TF "SAME" padding
+static void same_padding(int T, int k, int stride, int* T_out, int* pad_l) {
+  *T_out = (T + stride - 1) / stride;
+  int total = (*T_out - 1) * stride + k - T;
+  if (total < 0) total = 0;
+  *pad_l = total / 2;
+}
+
+// rank-4 view {C_total, stride, T_alloc/stride, B} of a packed activation
+static int make_act_load_map(CUtensorMap* m, const void* base, int c_total, int stride, int T_alloc,
+                             int B, int box_rows) {
+  const uint64_t row_bytes = static_cast<uint64_t>(c_total) * 2;
+  const uint64_t dims[4] = {static_cast<uint64_t>(c_total), static_cast<uint64_t>(stride),
+                            static_cast<uint64_t>(T_alloc / stride), static_cast<uint64_t>(B)};
+  const uint64_t strides[3] = {row_bytes, row_bytes * stride, row_bytes * T_alloc};
+  const uint32_t box[4] = {64, 1, static_cast<uint32_t>(box_rows), 1};
+  return make_tmap(m, TMAP_BF16, 4, base, dims, strides, box, true);
+}
+// rank-3 view {C_total, T, B}
+static int make_act_map3(CUtensorMap* m, const void* base, int c_total, int T, int B, int box_rows) {
+  const uint64_t row_bytes = static_cast<uint64_t>(c_total) * 2;
+  const uint64_t dims[3] = {static_cast<uint64_t>(c_total), static_cast<uint64_t>(T),
+                            static_cast<uint64_t>(B)};
+  const uint64_t strides[2] = {row_bytes, row_bytes * T};
+  const uint32_t box[3] = {64, static_cast<uint32_t>(box_rows), 1};
+  return make_tmap(m, TMAP_BF16, 3, base, dims, strides, box, true);
+}
+// weights {K_total, rows, taps}
+static int make_weight_map(CUtensorMap* m, const void* base, int k_total, int rows, int taps,
+                           int box_rows) {
+  const uint64_t row_bytes = static_cast<uint64_t>(k_total) * 2;
+  const uint64_t dims[3] = {static_cast<uint64_t>(k_total), static_cast<uint64_t>(rows),
+                            static_cast<uint64_t>(taps)};
+  const uint64_t strides[2] = {row_bytes, row_bytes * rows};
+  const uint32_t box[3] = {64, static_cast<uint32_t>(box_rows), 1};
+  return make_tmap(m, TMAP_BF16, 3, base, dims, strides, box, true);
+}
+
+}  // namespace sl
+
+using namespace sl;
+
+extern "C" {
+
+int sl_version(void) { return 100; }
+
+int sl_last_error(char* buf, size_t n) {
+  if (buf == nullptr || n == 0) return SL_ERR_INVALID;
+  std::strncpy(buf, g_last_error.c_str(), n - 1);
+  buf[n - 1] = '\0';
+  return SL_OK;
+}
+
+int sl_sync_check(void) {
+  SL_CUDA(cudaDeviceSynchronize());
+  SL_CUDA(cudaGetLastError());
+  return SL_OK;
+}
+
+int sl_pack_activation(const float* x, void* x_packed, int B, int T, int C, int T_alloc, int c_pad,
+                       int prec, void* stream) {
+  SL_REQUIRE(x && x_packed, "null pointer");
+  SL_REQUIRE(B > 0 && T > 0 && C > 0 && T_alloc >= T, "bad shape");
+  SL_REQUIRE(c_pad % 64 == 0 && c_pad >= C, "c_pad must be a multiple of 64 and >= C");
+  return pack_activation_launch(x, x_packed, B, T, C, T_alloc, c_pad, planes_of(prec),
+                                static_cast<cudaStream_t>(stream));
+}
+
+int sl_unpack_activation(const void* x_packed, float* x, int B, int T, int C, int T_alloc, int c_pad,
+                         int prec, void* stream) {
+  SL_REQUIRE(x && x_packed, "null pointer");
+  SL_REQUIRE(B > 0 && T > 0 && C > 0 && T_alloc >= T && c_pad >= C, "bad shape");
+  return unpack_activation_launch(x_packed, x, B, T, C, T_alloc, c_pad, planes_of(prec),
+                                  static_cast<cudaStream_t>(stream));
+}
+
+int sl_weights_keras_to_internal(const float* w_keras, float* w_int, int k, int Cin, int Cout,
+                                 int cin_pad, int cout_pad, void* stream) {
+  SL_REQUIRE(w_keras && w_int, "null pointer");
+  SL_REQUIRE(cin_pad >= Cin && cout_pad >= Cout && k > 0, "bad shape");
+  return keras_to_internal_launch(w_keras, w_int, k, Cin, Cout, cin_pad, cout_pad,
+                                  static_cast<cudaStream_t>(stream));
+}
+int sl_weights_internal_to_keras(const float* w_int, float* w_keras, int k, int Cin, int Cout,
+                                 int cin_pad, int cout_pad, void* stream) {
+  SL_REQUIRE(w_keras && w_int, "null pointer");
+  SL_REQUIRE(cin_pad >= Cin && cout_pad >= Cout && k > 0, "bad shape");
+  return internal_to_keras_launch(w_int, w_keras, k, Cin, Cout, cin_pad, cout_pad,
+                                  static_cast<cudaStream_t>(stream));
+}
+int sl_pack_weights_internal(const float* w_int, void* w_fwd, void* w_dgrad, int k, int cin_pad,
+                             int cout_pad, int prec, void* stream) {
+  SL_REQUIRE(w_int, "null pointer");
+  SL_REQUIRE(cin_pad % 64 == 0 && cout_pad % 64 == 0 && k > 0, "bad shape");
+  return pack_weights_internal_launch(w_int, w_fwd, w_dgrad, k, cin_pad, cout_pad, planes_of(prec),
+                                      static_cast<cudaStream_t>(stream));
+}
+
+int sl_pack_weights(const float* w_keras, void* w_fwd, void* w_dgrad, int k, int Cin, int Cout,
+                    int cin_pad, int cout_pad, int prec, void* stream) {
+  // convenience path (tests, weight loading): via a temporary internal master copy
+  SL_REQUIRE(w_keras, "null pointer");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  float* tmp = nullptr;
+  const size_t bytes = static_cast<size_t>(k) * cin_pad * cout_pad * sizeof(float);
+  SL_CUDA(cudaMallocAsync(&tmp, bytes, s));
+  int rc = keras_to_internal_launch(w_keras, tmp, k, Cin, Cout, cin_pad, cout_pad, s);
+  if (rc == 0) rc = pack_weights_internal_launch(tmp, w_fwd, w_dgrad, k, cin_pad, cout_pad, planes_of(prec), s);
+  cudaFreeAsync(tmp, s);
+  return rc;
+}
+
+int sl_conv1d_fwd(const void* x_packed, const void* w_fwd, const float* bias, void* y_packed,
+                  float* probs, float* logits, float* logp, int B, int T_in, int T_in_alloc, int Cin,
+                  int Cout, int k, int stride, int act, int prec, void* stream) {
+  SL_REQUIRE(x_packed && w_fwd, "null pointer");
+  SL_REQUIRE(B > 0 && T_in > 0 && Cin > 0 && Cout > 0 && k > 0, "bad shape");
+  SL_REQUIRE(stride == 1 || stride == 2, "stride must be 1 or 2");
+  SL_REQUIRE(T_in_alloc >= T_in && T_in_alloc % stride == 0, "T_in_alloc must cover T_in and divide by stride");
+  SL_REQUIRE(prec == SL_PREC_BF16 || prec == SL_PREC_BF16X2, "bad precision");
+  const int planes = planes_of(prec);
+  const int cin_pad = round64(Cin), cout_pad = round64(Cout);
+  int T_out, pad_l;
+  same_padding(T_in, k, stride, &T_out, &pad_l);
+
+  ConvGemmParams p;
+  std::memset(&p, 0, sizeof(p));
+  int bn = cout_pad >= 256 ? 256 : cout_pad;
+  SL_REQUIRE(cout_pad % bn == 0 && (bn == 64 || bn == 128 || bn == 256), "unsupported filter count");
+  int rc = make_act_load_map(&p.tmA, x_packed, planes * cin_pad, stride, T_in_alloc, B, 128);
+  if (rc) return rc;
+  rc = make_weight_map(&p.tmB, w_fwd, planes * cin_pad, cout_pad, k, bn);
+  if (rc) return rc;
+  p.B = B;
+  p.T_out = T_out;
+  p.m_tiles_per_utt = (T_out + 127) / 128;
+  p.n_tiles = cout_pad / bn;
+  p.taps = k;
+  p.chunks = cin_pad / 64;
+  p.terms = planes == 2 ? 3 : 1;
+  p.a_lo_off = cin_pad;
+  p.b_lo_off = cin_pad;
+  p.stride = stride;
+  p.pad_l = pad_l;
+  p.tap_reverse = 0;
+  p.bias = bias;
+  p.n_valid = Cout;
+  int epi = EPI_PACKED;
+  if (act == SL_ACT_SOFTMAX) {
+    SL_REQUIRE(probs != nullptr, "softmax epilogue needs the probs output");
+    SL_REQUIRE(cout_pad == 64, "softmax epilogue supports up to 64 symbols");
+    epi = EPI_SOFTMAX;
+    p.probs = probs;
+    p.logits = logits;
+    p.logp = logp;
+    p.V = Cout;
+  } else {
+    SL_REQUIRE(act == SL_ACT_NONE || act == SL_ACT_RELU, "bad activation");
+    SL_REQUIRE(y_packed != nullptr, "null output");
+    p.relu = act == SL_ACT_RELU;
+    p.y_planes = planes;
+    p.y_lo_off = cout_pad;
+    rc = make_act_map3(&p.tmY, y_packed, planes * cout_pad, T_out, B, 128);
+    if (rc) return rc;
+  }
+  return conv_gemm_launch(p, bn, epi, num_sms(), static_cast<cudaStream_t>(stream));
+}
+
+int sl_conv1d_dgrad(const void* dy_packed, const void* w_dgrad, const void* x_saved, void* dx_packed,
+                    int B, int T, int Cin, int Cout, int k, int prec, void* stream) {
+  SL_REQUIRE(dy_packed && w_dgrad && dx_packed, "null pointer");
+  SL_REQUIRE(B > 0 && T > 0 && Cin > 0 && Cout > 0 && k > 0, "bad shape");
+  SL_REQUIRE(prec == SL_PREC_BF16 || prec == SL_PREC_BF16X2, "bad precision");
+  const int planes = planes_of(prec);
+  const int cin_pad = round64(Cin), cout_pad = round64(Cout);
+  int T_out, pad_l;
+  same_padding(T, k, 1, &T_out, &pad_l);
+
+  ConvGemmParams p;
+  std::memset(&p, 0, sizeof(p));
+  const int bn = cin_pad >= 256 ? 256 : cin_pad;
+  SL_REQUIRE(cin_pad % bn == 0 && (bn == 64 || bn == 128 || bn == 256), "unsupported channel count");
+  int rc = make_act_load_map(&p.tmA, dy_packed, planes * cout_pad, 1, T, B, 128);
+  if (rc) return rc;
+  rc = make_weight_map(&p.tmB, w_dgrad, planes * cout_pad, cin_pad, k, bn);
+  if (rc) return rc;
+  rc = make_act_map3(&p.tmY, dx_packed, planes * cin_pad, T, B, 128);
+  if (rc) return rc;
+  p.B = B;
+  p.T_out = T;
+  p.m_tiles_per_utt = (T + 127) / 128;
+  p.n_tiles = cin_pad / bn;
+  p.taps = k;
+  p.chunks = cout_pad / 64;
+  p.terms = planes == 2 ? 3 : 1;
+  p.a_lo_off = cout_pad;
+  p.b_lo_off = cout_pad;
+  p.stride = 1;
+  p.pad_l = k - 1 - pad_l;  // dX[u] = sum_j dY[u + pad_l - j] W[j]  
+  p.tap_reverse = 1;
+  p.bias = nullptr;
+  p.n_valid = Cin;
+  p.relu = 0;
+  p.y_planes = planes;
+  p.y_lo_off = cin_pad;
+  p.mask = reinterpret_cast<const __nv_bfloat16*>(x_saved);
+  p.mask_row_stride = static_cast<long long>(planes) * cin_pad;
+  p.mask_utt_stride = p.mask_row_stride * T;
+  return conv_gemm_launch(p, bn, EPI_PACKED, num_sms(), static_cast<cudaStream_t>(stream));
+}
+
+int sl_conv1d_wgrad(const void* x_packed, const void* dy_packed, float* dw, float* db, int B, int T_in,
+                    int T_in_alloc, int Cin, int Cout, int k, int stride, int prec, int accumulate,
+                    void* stream) {
+  SL_REQUIRE(x_packed && dy_packed && dw, "null pointer");
+  SL_REQUIRE(B > 0 && T_in > 0 && Cin > 0 && Cout > 0 && k > 0, "bad shape");
+  SL_REQUIRE(stride == 1 || stride == 2, "stride must be 1 or 2");
+  SL_REQUIRE(T_in_alloc >= T_in && T_in_alloc % stride == 0, "T_in_alloc must cover T_in and divide by stride");
+  SL_REQUIRE(prec == SL_PREC_BF16 || prec == SL_PREC_BF16X2, "bad precision");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int planes = planes_of(prec);
+  const int cin_pad = round64(Cin), cout_pad = round64(Cout);
+  int T_out, pad_l;
+  same_padding(T_in, k, stride, &T_out, &pad_l);
+
+  WgradParams p;
+  std::memset(&p, 0, sizeof(p));
+  const int bn = cin_pad >= 256 ? 256 : cin_pad;
+  SL_REQUIRE(cin_pad % bn == 0 && (bn == 64 || bn == 128 || bn == 256), "unsupported channel count");
+  int rc = make_act_map3(&p.tmDY, dy_packed, planes * cout_pad, T_out, B, 64);
+  if (rc) return rc;
+  rc = make_act_load_map(&p.tmX, x_packed, planes * cin_pad, stride, T_in_alloc, B, 64);
+  if (rc) return rc;
+  p.dw = dw;
+  p.B = B;
+  p.T_out = T_out;
+  p.taps = k;
+  p.m_tiles = (cout_pad + 127) / 128;
+  p.n_tiles = cin_pad / bn;
+  p.tchunks = (T_out + 63) / 64;
+  p.terms = planes == 2 ? 3 : 1;
+  p.dy_lo_off = cout_pad;
+  p.x_lo_off = cin_pad;
+  p.stride = stride;
+  p.pad_l = pad_l;
+  p.cout_pad = cout_pad;
+  p.cin_pad = cin_pad;
+  p.dy_c_total = planes * cout_pad;
+  // K split: aim for >= 4 waves of work units, each with at least 8 pipeline steps
+  const int base_units = k * p.m_tiles * p.n_tiles;
+  const int k_total = B * p.tchunks;
+  int ksplit = (4 * num_sms() + base_units - 1) / base_units;
+  if (ksplit > k_total / 8) ksplit = k_total / 8;
+  if (ksplit < 1) ksplit = 1;
+  // no empty splits: ceil(k_total / ksplit) * (ksplit - 1) < k_total
+  while (ksplit > 1 && ((k_total + ksplit - 1) / ksplit) * (ksplit - 1) >= k_total) --ksplit;
+  p.ksplit = ksplit;
+  p.use_atomics = (ksplit > 1 || accumulate) ? 1 : 0;
+  const size_t dw_bytes = static_cast<size_t>(k) * cout_pad * cin_pad * sizeof(float);
+  if (p.use_atomics && !accumulate) SL_CUDA(cudaMemsetAsync(dw, 0, dw_bytes, s));
+  rc = wgrad_launch(p, bn, num_sms(), s);
+  if (rc) return rc;
+  if (db != nullptr) {
+    if (!accumulate) SL_CUDA(cudaMemsetAsync(db, 0, static_cast<size_t>(Cout) * sizeof(float), s));
+    rc = bias_grad_launch(dy_packed, db, static_cast<size_t>(B) * T_out, cout_pad, planes, Cout, s);
+  }
+  return rc;
+}
+
+size_t sl_ctc_workspace_bytes(int B, int T, int L_max) {
+  return ctc_workspace_bytes(B, T, L_max < 1 ? 1 : L_max);
+}
+
+int sl_ctc_loss(const float* logp, const float* probs, const int32_t* labels, const int32_t* input_len,
+                const int32_t* label_len, float* loss, void* dlogits_packed, float* dlogits_f32,
+                float grad_scale, int B, int T, int V, int L_max, int blank, int prec, void* workspace,
+                size_t workspace_bytes, void* stream) {
+  SL_REQUIRE(logp && labels && input_len && label_len && loss && workspace, "null pointer");
+  SL_REQUIRE(B > 0 && T > 0, "bad shape");
+  return ctc_loss_launch(logp, probs, labels, input_len, label_len, loss, dlogits_packed, dlogits_f32,
+                         grad_scale, B, T, V, L_max, blank, planes_of(prec), workspace, workspace_bytes,
+                         static_cast<cudaStream_t>(stream));
+}
+
+int sl_ctc_greedy_decode(const float* probs, const int32_t* input_len, int32_t* out, int32_t* out_len,
+                         int B, int T, int V, int blank, int merge_repeated, void* stream) {
+  SL_REQUIRE(probs && input_len && out && out_len, "null pointer");
+  SL_REQUIRE(B > 0 && T > 0 && V > 0, "bad shape");
+  return ctc_greedy_launch(probs, input_len, out, out_len, B, T, V, blank, merge_repeated,
+                           static_cast<cudaStream_t>(stream));
+}
+
+int sl_adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1,
+                 float beta2, float eps, int t, void* stream) {
+  SL_REQUIRE(p && g && m && v, "null pointer");
+  SL_REQUIRE(t >= 1, "Adam step counter is 1-based");
+  SL_REQUIRE((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) |
+              reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) % 16 == 0,
+             "Adam buffers must be 16-byte aligned");
+  if (n == 0) return SL_OK;
+  return adam_launch(p, g, m, v, n, lr, beta1, beta2, eps, t, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,380 @@
+// conv_umma.cu — Conv1D forward and input-gradient as an sm_100a implicit GEMM.
+//
+// Replaces keras.layers.Conv1D(padding="same") forward (reference net.py:304-305) and
+// the TF autodiff input gradient of the same layer.  Nothing is materialised as im2col:
+// with channels-last activations (B, T, C) the A operand of tap j is the *same* tile of
+// 128 time frames shifted by j rows, so one TMA box load per (tap, 64-channel chunk)
+// with signed coordinates fetches it, and TMA's out-of-bounds zero fill implements the
+// TF "SAME" padding (asymmetric pads included) for free.
+//
+//   D[128 frames x BN filters] (TMEM, fp32) += A[128 x 64] (smem, K-major, SW128)
+//                                              * B[BN x 64]^T (smem, K-major, SW128)
+//
+// Warp roles (256 threads, 1 CTA / SM, persistent over output tiles):
+//   warp 0   TMA producer (kStages-deep smem ring, mbarrier full/empty)
+//   warp 1   tcgen05.mma issuer (one elected lane), commits to empty / tmem_full
+//   warp 2   TMEM allocator (2 accumulator stages -> epilogue overlaps next tile's MMA)
+//   warps 4-7 epilogue: tcgen05.ld -> bias/ReLU/mask or softmax -> bf16 -> swizzled smem
+//             -> TMA store (clips the ragged last tile of every utterance)
+//
+// Split-bf16 ("bf16x2") mode: activations and weights carry a second bf16 plane holding
+// x - bf16(x); the K loop then issues hi*hi + hi*lo + lo*hi (3 MMAs per chunk), which
+// restores ~16 mantissa bits and lets the tensor-core path meet the fp32 parity
+// tolerance (logits <= 1e-3 rel) that plain bf16 cannot.
+#include "conv_umma.h"
+
+namespace sl {
+
+using namespace ptx;
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // bf16 elements per smem row = 128 B = one swizzle span
+constexpr int UMMA_K = 16;
+constexpr int kThreads = 256;
+constexpr int kEpiThreads = 128;
+constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+constexpr int STAGING_BYTES = BLOCK_M * 128;  // 128 rows x 128 B
+
+template <int BN>
+struct Cfg {
+  static constexpr int B_BYTES = BN * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int kStages = BN >= 256 ? 4 : 6;
+  static constexpr int TMEM_COLS = (2 * BN) < 32 ? 32 : 2 * BN;
+  // stages | 2 staging buffers | bias | barriers
+  static constexpr int SMEM_BYTES =
+      kStages * STAGE_BYTES + 2 * STAGING_BYTES + BN * 4 + 256 + 1024 /*align slack*/;
+};
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* staging = smem + C::kStages * C::STAGE_BYTES;
+  float* bias_s = reinterpret_cast<float*>(staging + 2 * STAGING_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + BN);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + C::kStages;
+  uint64_t* tmem_full = bars + 2 * C::kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.tmA);
+    prefetch_tmap(&p.tmB);
+    if (EPI == EPI_PACKED) prefetch_tmap(&p.tmY);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr_s, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  const int tiles_per_n = p.B * p.m_tiles_per_utt;
+  const int num_tiles = tiles_per_n * p.n_tiles;
+  const int ksteps = p.taps * p.chunks * p.terms;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n_tile = tile / tiles_per_n;
+        const int rem = tile - n_tile * tiles_per_n;
+        const int b = rem / p.m_tiles_per_utt;
+        const int t0 = (rem - b * p.m_tiles_per_utt) * BLOCK_M;
+        const int n0 = n_tile * BN;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int jp = tap - p.pad_l;  // signed frame offset of this tap
+          int q, par;
+          if (p.stride == 1) {
+            q = jp;
+            par = 0;
+          } else {  // floor division / non-negative modulo by the stride
+            q = jp >= 0 ? jp / p.stride : -((-jp + p.stride - 1) / p.stride);
+            par = jp - q * p.stride;
+          }
+          const int wtap = p.tap_reverse ? (p.taps - 1 - tap) : tap;
+          for (int chunk = 0; chunk < p.chunks; ++chunk) {
+            for (int term = 0; term < p.terms; ++term) {
+              const int a_c = chunk * BLOCK_K + (term == 2 ? p.a_lo_off : 0);
+              const int b_c = chunk * BLOCK_K + (term == 1 ? p.b_lo_off : 0);
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              uint8_t* a_s = smem + stage * C::STAGE_BYTES;
+              uint8_t* b_s = a_s + A_BYTES;
+              mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+              tma_load_4d(&p.tmA, &full_bar[stage], a_s, a_c, par, t0 + q, b);
+              tma_load_3d(&p.tmB, &full_bar[stage], b_s, b_c, n0, wtap);
+              if (++stage == C::kStages) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BN, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tmem_empty[as], aphase ^ 1);
+      tcgen05_fence_after();
+      const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * BN);
+      for (int ks = 0; ks < ksteps; ++ks) {
+        mbar_wait(&full_bar[stage], phase);
+        tcgen05_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t da = make_smem_desc_sw128(a_addr + k * UMMA_K * 2, 16, 1024);
+            const uint64_t db = make_smem_desc_sw128(b_addr + k * UMMA_K * 2, 16, 1024);
+            umma_bf16(tmem_d, da, db, idesc, (ks | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (ks == ksteps - 1) umma_commit(&tmem_full[as]);
+        }
+        __syncwarp();
+        if (++stage == C::kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int ew = warp - 4;  // == warp % 4 : TMEM lane quadrant this warp may read
+    const int row = ew * 32 + lane;
+    const int et = threadIdx.x - 128;
+    int it = 0;
+    uint32_t store_count = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int n_tile = tile / tiles_per_n;
+      const int rem = tile - n_tile * tiles_per_n;
+      const int b = rem / p.m_tiles_per_utt;
+      const int t0 = (rem - b * p.m_tiles_per_utt) * BLOCK_M;
+      const int n0 = n_tile * BN;
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const int t = t0 + row;
+      const bool row_valid = t < p.T_out;
+
+      // stage the bias slice of this tile (previous tile's readers are past the
+      // barrier below because every chunk iteration ends behind a named barrier)
+      named_bar_sync(2, kEpiThreads);
+      for (int i = et; i < BN; i += kEpiThreads)
+        bias_s[i] = (p.bias != nullptr && (n0 + i) < p.n_valid) ? p.bias[n0 + i] : 0.f;
+      named_bar_sync(2, kEpiThreads);
+
+      mbar_wait(&tmem_full[as], aphase);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) +
+                             static_cast<uint32_t>(as * BN);
+
+      if (EPI == EPI_PACKED) {
+#pragma unroll 1
+        for (int c = 0; c < BN / 64; ++c) {
+          uint32_t r0[32], r1[32];
+          tmem_ld_32x32(taddr + c * 64, r0);
+          tmem_ld_32x32(taddr + c * 64 + 32, r1);
+          tmem_ld_wait();
+          if (c == BN / 64 - 1) {
+            // accumulator fully drained: hand the TMEM stage back to the MMA warp
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[as]);
+          }
+          float v[64];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            v[i] = __uint_as_float(r0[i]) + bias_s[c * 64 + i];
+            v[32 + i] = __uint_as_float(r1[i]) + bias_s[c * 64 + 32 + i];
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 64; ++i) v[i] = fmaxf(v[i], 0.f);
+          }
+          if (p.mask != nullptr && row_valid) {
+            // ReLU backward: zero where the saved (post-ReLU) activation is not > 0
+            const uint4* mp = reinterpret_cast<const uint4*>(
+                p.mask + static_cast<size_t>(b) * p.mask_utt_stride +
+                static_cast<size_t>(t) * p.mask_row_stride + n0 + c * 64);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint4 m = __ldg(mp + j);
+              const uint32_t w[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                // bf16 > 0  <=>  sign bit clear and magnitude non-zero
+                const uint32_t lo16 = w[e] & 0xFFFFu, hi16 = w[e] >> 16;
+                if (!(lo16 != 0 && (lo16 & 0x8000u) == 0)) v[j * 8 + e * 2] = 0.f;
+                if (!(hi16 != 0 && (hi16 & 0x8000u) == 0)) v[j * 8 + e * 2 + 1] = 0.f;
+              }
+            }
+          }
+          for (int plane = 0; plane < p.y_planes; ++plane) {
+            uint32_t packed[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              if (plane == 0) {
+                packed[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+              } else {
+                packed[i] = pack_bf16x2(v[2 * i] - bf16_round(v[2 * i]),
+                                        v[2 * i + 1] - bf16_round(v[2 * i + 1]));
+              }
+            }
+            uint8_t* sbuf = staging + (store_count & 1) * STAGING_BYTES;
+            if (et == 0) tma_wait_group_read<1>();  // the store that last read sbuf is done
+            named_bar_sync(1, kEpiThreads);
+            uint8_t* rowp = sbuf + row * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int phys = j ^ (row & 7);  // SWIZZLE_128B: 16-byte chunk index ^= row % 8
+              *reinterpret_cast<uint4*>(rowp + phys * 16) =
+                  make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(1, kEpiThreads);
+            if (et == 0) {
+              tma_store_3d(&p.tmY, sbuf, n0 + c * 64 + (plane ? p.y_lo_off : 0), t0, b);
+              tma_commit_group();
+            }
+            ++store_count;
+          }
+        }
+      } else {
+        // EPI_SOFTMAX: BN == 64, one row of V logits per thread (net.py:328-330)
+        uint32_t r0[32], r1[32];
+        tmem_ld_32x32(taddr, r0);
+        tmem_ld_32x32(taddr + 32, r1);
+        tmem_ld_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[as]);
+        if (row_valid) {
+          float z[64];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            z[i] = __uint_as_float(r0[i]) + bias_s[i];
+            z[32 + i] = __uint_as_float(r1[i]) + bias_s[32 + i];
+          }
+          const int V = p.V;
+          float m = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 64; ++i)
+            if (i < V) m = fmaxf(m, z[i]);
+          float e[64];
+          float sum = 0.f;
+#pragma unroll
+          for (int i = 0; i < 64; ++i) {
+            e[i] = i < V ? expf(z[i] - m) : 0.f;
+            sum += e[i];
+          }
+          const float inv = 1.f / sum;
+          float sum_eps = 0.f;
+#pragma unroll
+          for (int i = 0; i < 64; ++i) {
+            e[i] *= inv;
+            if (i < V) sum_eps += e[i] + 1e-8f;
+          }
+          const size_t ro = static_cast<size_t>(b) * p.T_out + t;
+          float* pr = p.probs + ro * V;
+#pragma unroll
+          for (int i = 0; i < 64; ++i)
+            if (i < V) pr[i] = e[i];
+          if (p.logits != nullptr) {
+            float* lg = p.logits + ro * V;
+#pragma unroll
+            for (int i = 0; i < 64; ++i)
+              if (i < V) lg[i] = z[i];
+          }
+          if (p.logp != nullptr) {
+            // K.ctc_batch_cost feeds log(p + 1e-8) to tf.nn.ctc_loss, which applies its own
+            // log-softmax: logp = log(p+eps) - log(sum_v (p_v+eps))      
+            const float lse = logf(sum_eps);
+            float* lp = p.logp + ro * 64;
+#pragma unroll
+            for (int i = 0; i < 64; ++i) lp[i] = i < V ? logf(e[i] + 1e-8f) - lse : -INFINITY;
+          }
+        }
+      }
+    }
+    if (EPI == EPI_PACKED && et == 0) tma_wait_group<0>();
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+template <int BN, int EPI>
+int launch(const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
+  using C = Cfg<BN>;
+  static bool configured = false;  // benign race: attribute set is idempotent
+  if (!configured) {
+    SL_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, EPI>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    configured = true;
+  }
+  const int num_tiles = p.B * p.m_tiles_per_utt * p.n_tiles;
+  const int grid = num_tiles < num_sms ? num_tiles : num_sms;
+  conv_gemm_kernel<BN, EPI><<<grid, kThreads, C::SMEM_BYTES, stream>>>(p);
+  SL_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+int conv_gemm_launch(const ConvGemmParams& p, int block_n, int epi, int num_sms,
+                     cudaStream_t stream) {
+  if (epi == EPI_SOFTMAX) {
+    SL_REQUIRE(block_n == 64, "softmax epilogue needs a 64-wide tile");
+    return launch<64, EPI_SOFTMAX>(p, num_sms, stream);
+  }
+  switch (block_n) {
+    case 64:
+      return launch<64, EPI_PACKED>(p, num_sms, stream);
+    case 128:
+      return launch<128, EPI_PACKED>(p, num_sms, stream);
+    case 256:
+      return launch<256, EPI_PACKED>(p, num_sms, stream);
+    default:
+      set_error("conv_gemm: unsupported block_n");
+      return 1;
+  }
+}
+
+}  // namespace sl

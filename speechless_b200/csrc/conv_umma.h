@@ -1,0 +1,68 @@
+// conv_umma.h — parameter blocks of the tcgen05 implicit-GEMM kernels
+#pragma once
+#include "common.cuh"
+
+namespace sl {
+
+enum { EPI_PACKED = 0, EPI_SOFTMAX = 1 };
+
+// Forward / input-gradient implicit GEMM (conv_umma.cu)
+struct ConvGemmParams {
+  CUtensorMap tmA;  // activations, rank 4 {C_total, stride, T_alloc/stride, B}, box {64,1,128,1}
+  CUtensorMap tmB;  // weights, rank 3 {K_total (contiguous), N rows, taps}, box {64, BN, 1}
+  CUtensorMap tmY;  // packed bf16 output, rank 3 {C_total, T_out, B}, box {64,128,1}
+  int B;
+  int T_out;
+  int m_tiles_per_utt;
+  int n_tiles;
+  int taps;
+  int chunks;  // 64-channel chunks of the contraction dimension
+  int terms;   // 1 = bf16, 3 = split bf16 (hi*hi + hi*lo + lo*hi)
+  int a_lo_off;
+  int b_lo_off;
+  int stride;
+  int pad_l;
+  int tap_reverse;  // dgrad walks the filter taps backwards
+  const float* bias;
+  int n_valid;  // number of real (unpadded) output channels: bias bound
+  int relu;
+  int y_planes;  // 1 or 2 (hi | lo)
+  int y_lo_off;
+  const __nv_bfloat16* mask;  // saved post-ReLU activation of the layer below (dgrad) or null
+  long long mask_row_stride;
+  long long mask_utt_stride;
+  float* probs;   // EPI_SOFTMAX outputs
+  float* logits;
+  float* logp;
+  int V;
+};
+
+int conv_gemm_launch(const ConvGemmParams& p, int block_n, int epi, int num_sms,
+                     cudaStream_t stream);
+
+// Weight-gradient GEMM (wgrad_umma.cu): both operands MN-major, contraction over time
+struct WgradParams {
+  CUtensorMap tmDY;  // rank 3 {Cout_total, T_out, B}, box {64, 64, 1}
+  CUtensorMap tmX;   // rank 4 {Cin_total, stride, T_alloc/stride, B}, box {64, 1, 64, 1}
+  float* dw;         // (taps, cout_pad, cin_pad) fp32
+  int B;
+  int T_out;
+  int taps;
+  int m_tiles;  // ceil(cout_pad / 128)
+  int n_tiles;  // cin_pad / BN
+  int ksplit;
+  int tchunks;  // ceil(T_out / 64)
+  int terms;
+  int dy_lo_off;
+  int x_lo_off;
+  int stride;
+  int pad_l;
+  int cout_pad;
+  int cin_pad;
+  int dy_c_total;  // channel extent of the dY tensor map (an OOB coordinate for zero tiles)
+  int use_atomics;  // 1: red.add into dw, 0: plain stores
+};
+
+int wgrad_launch(const WgradParams& p, int block_n, int num_sms, cudaStream_t stream);
+
+}  // namespace sl

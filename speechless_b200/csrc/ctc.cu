@@ -1,0 +1,363 @@
+// ctc.cu — CTC loss, gradient and greedy decode.
+//
+// Replaces K.ctc_batch_cost -> tf.nn.ctc_loss (reference net.py:402-406; blank = V-1,
+// grapheme_enconding.py:125-126) and tf.nn.ctc_greedy_decoder (net.py:453-454).
+// Semantics restated in SURVEY.md Appendix A.2 / A.3.
+//
+// Three phases per batch:
+//   1. ctc_alpha_beta_kernel — the sequential part.  One CTA per (utterance, direction):
+//      the alpha CTA walks t = 0..P-1, the beta CTA walks t = P-1..0 concurrently on
+//      another SM (2B CTAs).  States live one-or-more per thread, the previous column in
+//      a double-buffered smem row, log-prob rows are prefetched 32 frames at a time with
+//      cp.async, and every column is streamed to HBM (fire-and-forget stores).
+//   2. ctc_grad_kernel — the bandwidth part, parallel over every (utterance, frame):
+//      one warp per frame folds alpha+beta over the states of each symbol and chains the
+//      gradient through log(p+1e-8) and the softmax to the pre-softmax logits, writing
+//      the packed bf16 tile the output_conv wgrad/dgrad kernels consume.
+//   3. (host) nothing: the loss per utterance is written by the alpha CTA.
+#include "common.cuh"
+
+namespace sl {
+
+namespace {
+
+constexpr int CHUNK = 32;  // frames of log-probs staged per cp.async group
+constexpr int VP = 64;     // padded symbol row of the logp tensor (V <= 64)
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(ptx::smem_u32(smem_dst)),
+               "l"(gmem_src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+__device__ __forceinline__ float lse3(float a, float b, float c) {
+  const float m = fmaxf(a, fmaxf(b, c));
+  if (m == -INFINITY) return -INFINITY;
+  return m + __logf(__expf(a - m) + __expf(b - m) + __expf(c - m));
+}
+__device__ __forceinline__ float lse2_accurate(float a, float b) {
+  const float m = fmaxf(a, b);
+  if (m == -INFINITY) return -INFINITY;
+  return m + logf(expf(a - m) + expf(b - m));
+}
+
+// dir 0: alpha (forward in time); dir 1: beta, computed as the same recurrence on the
+// time- and state-reversed problem (the skip condition is symmetric).
+template <int SPT>
+__global__ void ctc_alpha_beta_kernel(const float* __restrict__ logp,
+                                      const int32_t* __restrict__ labels,
+                                      const int32_t* __restrict__ input_len,
+                                      const int32_t* __restrict__ label_len,
+                                      float* __restrict__ loss, float* __restrict__ beta_loss,
+                                      float* __restrict__ alpha, float* __restrict__ beta, int T,
+                                      int L_max, int blank, int S_stride) {
+  extern __shared__ uint8_t smem_raw[];
+  const int dir = blockIdx.x & 1;
+  const int b = blockIdx.x >> 1;
+  const int tid = threadIdx.x;
+  const int L = label_len[b];
+  const int P = min(input_len[b], T);
+  const int S = 2 * L + 1;
+
+  // smem carve-up
+  float* lp_s = reinterpret_cast<float*>(smem_raw);              // [2][CHUNK][VP]
+  float* col = lp_s + 2 * CHUNK * VP;                            // [2][S_stride + 2]
+  int* ext = reinterpret_cast<int*>(col + 2 * (S_stride + 2));   // [S_stride]
+
+  const int col_stride = S_stride + 2;
+  // extended label sequence in walking order (reversed for beta)
+  for (int s = tid; s < S_stride; s += blockDim.x) {
+    int e = blank;
+    if (s < S) {
+      const int so = dir ? (S - 1 - s) : s;
+      if (so & 1) e = labels[static_cast<size_t>(b) * L_max + (so >> 1)];
+    }
+    ext[s] = e;
+  }
+  for (int i = tid; i < 2 * col_stride; i += blockDim.x) col[i] = -INFINITY;
+
+  const float* lp_b = logp + static_cast<size_t>(b) * T * VP;
+  auto issue_chunk = [&](int c) {
+    // rows tt = c*CHUNK .. +CHUNK-1 in walking order -> buffer c & 1
+    float* dst = lp_s + (c & 1) * CHUNK * VP;
+    for (int i = tid; i < CHUNK * (VP / 4); i += blockDim.x) {
+      const int r = i / (VP / 4), piece = i % (VP / 4);
+      const int tt = c * CHUNK + r;
+      if (tt < P) {
+        const int t = dir ? (P - 1 - tt) : tt;
+        cp_async16(dst + r * VP + piece * 4, lp_b + static_cast<size_t>(t) * VP + piece * 4);
+      }
+    }
+    cp_async_commit();
+  };
+  issue_chunk(0);
+  issue_chunk(1);
+  __syncthreads();
+
+  // per-thread state bookkeeping
+  int my_e[SPT];
+  bool my_skip[SPT];
+#pragma unroll
+  for (int i = 0; i < SPT; ++i) {
+    const int s = tid * SPT + i;
+    my_e[i] = s < S_stride ? ext[s] : blank;
+    my_skip[i] = (s >= 2 && s < S) ? (ext[s] != blank && ext[s] != ext[s - 2]) : false;
+  }
+
+  float* out = (dir ? beta : alpha) + static_cast<size_t>(b) * T * S_stride;
+
+  for (int tt = 0; tt < P; ++tt) {
+    if ((tt & (CHUNK - 1)) == 0) {
+      cp_async_wait<1>();
+      __syncthreads();
+    }
+    const float* lp_row = lp_s + ((tt / CHUNK) & 1) * CHUNK * VP + (tt & (CHUNK - 1)) * VP;
+    const float* prev = col + ((tt & 1) ^ 1) * col_stride + 2;
+    float* cur = col + (tt & 1) * col_stride + 2;
+    const int t = dir ? (P - 1 - tt) : tt;
+    float* out_row = out + static_cast<size_t>(t) * S_stride;
+#pragma unroll
+    for (int i = 0; i < SPT; ++i) {
+      const int s = tid * SPT + i;
+      if (s < S) {
+        float val;
+        const float em = lp_row[my_e[i]];
+        if (tt == 0) {
+          val = (s <= 1) ? em : -INFINITY;
+        } else {
+          const float a0 = prev[s];
+          const float a1 = prev[s - 1];
+          const float a2 = my_skip[i] ? prev[s - 2] : -INFINITY;
+          val = lse3(a0, a1, a2) + em;
+        }
+        cur[s] = val;
+        out_row[dir ? (S - 1 - s) : s] = val;
+      }
+    }
+    __syncthreads();
+    if ((tt & (CHUNK - 1)) == CHUNK - 1) issue_chunk(tt / CHUNK + 2);
+  }
+  cp_async_wait<0>();
+
+  if (tid == 0) {
+    float l = INFINITY;
+    if (P > 0) {
+      const float* last = col + ((P - 1) & 1) * col_stride + 2;
+      const float a = last[S - 1];
+      const float c = S >= 2 ? last[S - 2] : -INFINITY;
+      l = -lse2_accurate(a, c);
+    }
+    if (dir == 0)
+      loss[b] = l;
+    else
+      beta_loss[b] = l;
+  }
+}
+
+// One warp per (utterance, frame).  grad wrt logits z of  grad_scale * sum_b loss_b:
+//   u = log(p+eps), lp = log_softmax(u);  g_u(v) = exp(lp_v) - occ(v)
+//   occ(v) = sum_{s: e[s]=v} exp(alpha_t(s) + beta_t(s) - lp_t(v) + loss_b)
+//   dL/dp_v = g_u(v)/(p_v+eps);  dL/dz_v = p_v (dL/dp_v - sum_w p_w dL/dp_w)
+__global__ void ctc_grad_kernel(const float* __restrict__ logp, const float* __restrict__ probs,
+                                const int32_t* __restrict__ labels,
+                                const int32_t* __restrict__ input_len,
+                                const int32_t* __restrict__ label_len,
+                                const float* __restrict__ loss, const float* __restrict__ alpha,
+                                const float* __restrict__ beta, __nv_bfloat16* __restrict__ dz_packed,
+                                float* __restrict__ dz_f32, float grad_scale, int T, int V,
+                                int L_max, int blank, int S_stride, int planes, int frames_per_block) {
+  extern __shared__ uint8_t smem_raw[];
+  int* lab_s = reinterpret_cast<int*>(smem_raw);                    // [L_max]
+  float* bins = reinterpret_cast<float*>(lab_s + ((L_max + 31) & ~31));  // [warps][VP]
+  const int b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int L = label_len[b];
+  const int P = min(input_len[b], T);
+  const int S = 2 * L + 1;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) lab_s[i] = labels[static_cast<size_t>(b) * L_max + i];
+  __syncthreads();
+  const float loss_b = loss[b];
+  float* my_bins = bins + warp * VP;
+  const int t_begin = blockIdx.x * frames_per_block;
+  const int t_end = min(t_begin + frames_per_block, T);
+  const int row_elems = planes * 64;
+
+  for (int t = t_begin + warp; t < t_end; t += nwarps) {
+    const size_t ro = static_cast<size_t>(b) * T + t;
+    float dz[2] = {0.f, 0.f};  // symbols lane and lane + 32
+    if (t < P && isfinite(loss_b)) {
+      my_bins[lane] = 0.f;
+      my_bins[lane + 32] = 0.f;
+      __syncwarp();
+      const float* a_row = alpha + ro * S_stride;
+      const float* b_row = beta + ro * S_stride;
+      const float* lp_row = logp + ro * VP;
+      const float lp_blank = lp_row[blank];
+      float blank_acc = 0.f;
+      for (int s = lane; s < S; s += 32) {
+        const float ab = a_row[s] + b_row[s];
+        if (s & 1) {
+          const int v = lab_s[s >> 1];
+          const float x = expf(ab - lp_row[v] + loss_b);
+          if (x != 0.f) atomicAdd(&my_bins[v], x);
+        } else {
+          blank_acc += expf(ab - lp_blank + loss_b);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) blank_acc += __shfl_xor_sync(0xffffffffu, blank_acc, o);
+      __syncwarp();
+      float pv[2] = {0.f, 0.f}, dLdp[2] = {0.f, 0.f};
+      float dot = 0.f;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int v = lane + 32 * h;
+        if (v < V) {
+          const float occ = (v == blank) ? blank_acc : my_bins[v];
+          pv[h] = probs[ro * V + v];
+          const float g = expf(lp_row[v]) - occ;
+          dLdp[h] = g / (pv[h] + 1e-8f);
+          dot += pv[h] * dLdp[h];
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) dz[h] = pv[h] * (dLdp[h] - dot) * grad_scale;
+      __syncwarp();
+    }
+    if (dz_f32 != nullptr) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+        if (lane + 32 * h < V) dz_f32[ro * V + lane + 32 * h] = dz[h];
+    }
+    if (dz_packed != nullptr) {
+      __nv_bfloat16* row = dz_packed + ro * row_elems;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const __nv_bfloat16 hi = __float2bfloat16_rn(dz[h]);
+        row[lane + 32 * h] = hi;
+        if (planes == 2) row[64 + lane + 32 * h] = __float2bfloat16_rn(dz[h] - __bfloat162float(hi));
+      }
+    }
+  }
+}
+
+// Greedy decode: one warp per utterance, 32 frames per iteration.  argmax (lowest index
+// wins ties), emit iff not blank and (merge_repeated ? differs from previous frame's
+// argmax : true); positions by ballot/popc prefix.
+__global__ void ctc_greedy_kernel(const float* __restrict__ probs,
+                                  const int32_t* __restrict__ input_len, int32_t* __restrict__ out,
+                                  int32_t* __restrict__ out_len, int B, int T, int V, int blank,
+                                  int merge_repeated) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const int P = min(input_len[b], T);
+  const float* pb = probs + static_cast<size_t>(b) * T * V;
+  int32_t* ob = out + static_cast<size_t>(b) * T;
+  int count = 0;
+  int carry = -1;  // argmax of the frame before this 32-frame group
+  for (int t0 = 0; t0 < P; t0 += 32) {
+    const int t = t0 + lane;
+    int c = -1;
+    if (t < P) {
+      const float* row = pb + static_cast<size_t>(t) * V;
+      float best = row[0];
+      c = 0;
+      for (int v = 1; v < V; ++v) {
+        const float x = row[v];
+        if (x > best) {
+          best = x;
+          c = v;
+        }
+      }
+    }
+    int prev = __shfl_up_sync(0xffffffffu, c, 1);
+    if (lane == 0) prev = carry;
+    const bool emit = (t < P) && (c != blank) && !(merge_repeated && c == prev);
+    const unsigned m = __ballot_sync(0xffffffffu, emit);
+    if (emit) ob[count + __popc(m & ((1u << lane) - 1))] = c;
+    count += __popc(m);
+    carry = __shfl_sync(0xffffffffu, c, 31);
+  }
+  for (int i = count + lane; i < T; i += 32) ob[i] = -1;
+  if (lane == 0) out_len[b] = count;
+}
+
+}  // namespace
+
+int ctc_s_stride(int L_max) { return ((2 * L_max + 1) + 31) & ~31; }
+
+size_t ctc_workspace_bytes(int B, int T, int L_max) {
+  const size_t lat = static_cast<size_t>(B) * T * ctc_s_stride(L_max) * sizeof(float);
+  return 2 * lat + 256 + static_cast<size_t>(B) * sizeof(float);
+}
+
+int ctc_loss_launch(const float* logp, const float* probs, const int32_t* labels,
+                    const int32_t* input_len, const int32_t* label_len, float* loss,
+                    void* dlogits_packed, float* dlogits_f32, float grad_scale, int B, int T, int V,
+                    int L_max, int blank, int planes, void* workspace, size_t workspace_bytes,
+                    cudaStream_t stream) {
+  SL_REQUIRE(V <= VP && V >= 2, "CTC kernels support 2..64 symbols (incl. blank)");
+  SL_REQUIRE(blank >= 0 && blank < V, "blank out of range");
+  SL_REQUIRE(L_max >= 1, "L_max must be >= 1 (pad empty label batches to width 1)");
+  SL_REQUIRE(workspace_bytes >= ctc_workspace_bytes(B, T, L_max), "CTC workspace too small");
+  const int S_stride = ctc_s_stride(L_max);
+  const size_t lat = static_cast<size_t>(B) * T * S_stride;
+  float* alpha = reinterpret_cast<float*>(workspace);
+  float* beta = alpha + lat;
+  float* beta_loss = beta + lat;
+
+  // threads: one per state up to 1024, then 2 or 4 states per thread
+  const int S_max = 2 * L_max + 1;
+  int spt = 1;
+  if (S_max > 1024) spt = 2;
+  if (S_max > 2048) spt = 4;
+  SL_REQUIRE(S_max <= 4096, "label too long (max 2047 characters)");
+  int threads = ((S_max + spt - 1) / spt + 31) & ~31;
+  if (threads < 64) threads = 64;
+  const size_t smem = (2 * CHUNK * VP + 2 * (S_stride + 2)) * sizeof(float) + S_stride * sizeof(int);
+#define SL_LAUNCH_AB(SPT)                                                                        \
+  ctc_alpha_beta_kernel<SPT><<<2 * B, threads, smem, stream>>>(logp, labels, input_len, label_len, \
+                                                               loss, beta_loss, alpha, beta, T,  \
+                                                               L_max, blank, S_stride)
+  if (spt == 1)
+    SL_LAUNCH_AB(1);
+  else if (spt == 2)
+    SL_LAUNCH_AB(2);
+  else
+    SL_LAUNCH_AB(4);
+#undef SL_LAUNCH_AB
+  SL_CUDA(cudaGetLastError());
+
+  if (dlogits_packed != nullptr || dlogits_f32 != nullptr) {
+    SL_REQUIRE(probs != nullptr, "gradient needs the softmax probabilities");
+    const int frames_per_block = 64;
+    const int warps = 8;
+    dim3 grid((T + frames_per_block - 1) / frames_per_block, B);
+    const size_t gsmem = ((L_max + 31) & ~31) * sizeof(int) + warps * VP * sizeof(float);
+    ctc_grad_kernel<<<grid, warps * 32, gsmem, stream>>>(
+        logp, probs, labels, input_len, label_len, loss, alpha, beta,
+        reinterpret_cast<__nv_bfloat16*>(dlogits_packed), dlogits_f32, grad_scale, T, V, L_max,
+        blank, S_stride, planes, frames_per_block);
+    SL_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+int ctc_greedy_launch(const float* probs, const int32_t* input_len, int32_t* out, int32_t* out_len,
+                      int B, int T, int V, int blank, int merge_repeated, cudaStream_t stream) {
+  const int warps = 4;
+  ctc_greedy_kernel<<<(B + warps - 1) / warps, warps * 32, 0, stream>>>(
+      probs, input_len, out, out_len, B, T, V, blank, merge_repeated);
+  SL_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace sl

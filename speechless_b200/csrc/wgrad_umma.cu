@@ -1,0 +1,271 @@
+// wgrad_umma.cu — Conv1D weight gradient on tcgen05 (TF autodiff of net.py:304-305):
+//
+//   dW[j, co, ci] = sum_{b,t} dY[b, t, co] * X[b, t*s + j - pad_l, ci]
+//
+// The contraction runs over time, which is the *slow* axis of both channels-last
+// tensors, so both UMMA operands are MN-major: a TMA box of 64 frames x 64 channels
+// lands as 64 rows of 128 B (SWIZZLE_128B) and is consumed directly with the
+// transposing smem descriptors (a_major = b_major = MN).  As in the forward kernel the
+// tap shift j and the SAME padding are signed TMA coordinates + OOB zero fill.
+//
+//   D[128 co x BN ci] (TMEM fp32) += dY_tile^T[128 co x 64 t] * X_tile[64 t x BN ci]
+//
+// Work unit = (tap, 128-filter tile, BN-channel tile, K split); the K range of a unit
+// is a contiguous run of (utterance, 64-frame chunk) pairs.  Partial sums of different
+// K splits meet in HBM through fp32 red.add (dW is zeroed by the caller).
+#include "conv_umma.h"
+
+namespace sl {
+
+using namespace ptx;
+
+namespace {
+
+constexpr int BLOCK_M = 128;  // filters (co) per tile
+constexpr int KT = 64;        // frames per pipeline stage
+constexpr int UMMA_K = 16;
+constexpr int kThreads = 256;
+constexpr int BOX_BYTES = KT * 128;          // one 64-frame x 64-channel box
+constexpr int A_BYTES = 2 * BOX_BYTES;       // 128 filters
+constexpr int LBO = BOX_BYTES;               // byte stride between 64-channel groups
+constexpr int SBO = 1024;                    // byte stride between 8-frame groups
+
+template <int BN>
+struct WCfg {
+  static constexpr int B_BYTES = (BN / 64) * BOX_BYTES;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int kStages = BN >= 256 ? 4 : 6;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int SMEM_BYTES = kStages * STAGE_BYTES + 256 + 1024;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_kernel(const __grid_constant__ WgradParams p) {
+  using C = WCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + C::kStages;
+  uint64_t* tmem_full = bars + 2 * C::kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.tmDY);
+    prefetch_tmap(&p.tmX);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr_s, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  // unit -> (split, n_tile, m_tile, tap): split fastest so that the CTAs that share a
+  // weight tile's red.add target run at different times only by accident, while CTAs
+  // running together read the same dY / X slabs from L2.
+  const int num_units = p.taps * p.m_tiles * p.n_tiles * p.ksplit;
+  const int k_total = p.B * p.tchunks;  // (utterance, frame chunk) pairs
+  const int k_per = (k_total + p.ksplit - 1) / p.ksplit;
+
+  auto decode = [&](int unit, int& tap, int& mt, int& nt, int& k_begin, int& k_end) {
+    int u = unit;
+    tap = u % p.taps;
+    u /= p.taps;
+    mt = u % p.m_tiles;
+    u /= p.m_tiles;
+    nt = u % p.n_tiles;
+    u /= p.n_tiles;
+    const int sp = u;
+    k_begin = sp * k_per;
+    k_end = k_begin + k_per < k_total ? k_begin + k_per : k_total;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+        int tap, mt, nt, k_begin, k_end;
+        decode(unit, tap, mt, nt, k_begin, k_end);
+        const int jp = tap - p.pad_l;
+        int q, par;
+        if (p.stride == 1) {
+          q = jp;
+          par = 0;
+        } else {
+          q = jp >= 0 ? jp / p.stride : -((-jp + p.stride - 1) / p.stride);
+          par = jp - q * p.stride;
+        }
+        const int co0 = mt * BLOCK_M;
+        const int ci0 = nt * BN;
+        for (int kk = k_begin; kk < k_end; ++kk) {
+          const int b = kk / p.tchunks;
+          const int tr = (kk - b * p.tchunks) * KT;
+          for (int term = 0; term < p.terms; ++term) {
+            const int dy_off = term == 2 ? p.dy_lo_off : 0;
+            const int x_off = term == 1 ? p.x_lo_off : 0;
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* a_s = smem + stage * C::STAGE_BYTES;
+            uint8_t* b_s = a_s + A_BYTES;
+            mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              // filter groups beyond cout_pad (output_conv: 64 < 128) read as zeros via an
+              // out-of-range channel coordinate
+              const int c = (co0 + 64 * i < p.cout_pad) ? (co0 + 64 * i + dy_off) : p.dy_c_total;
+              tma_load_3d(&p.tmDY, &full_bar[stage], a_s + i * BOX_BYTES, c, tr, b);
+            }
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i)
+              tma_load_4d(&p.tmX, &full_bar[stage], b_s + i * BOX_BYTES, ci0 + 64 * i + x_off, par,
+                          tr + q, b);
+            if (++stage == C::kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BN, 1, 1);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
+      int tap, mt, nt, k_begin, k_end;
+      decode(unit, tap, mt, nt, k_begin, k_end);
+      const int ksteps = (k_end - k_begin) * p.terms;
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tmem_empty[as], aphase ^ 1);
+      tcgen05_fence_after();
+      const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * BN);
+      for (int ks = 0; ks < ksteps; ++ks) {
+        mbar_wait(&full_bar[stage], phase);
+        tcgen05_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < KT / UMMA_K; ++k) {
+            // 16 frames = two 8-row swizzle atoms = 2048 B further along K
+            const uint64_t da = make_smem_desc_sw128(a_addr + k * 2048, LBO, SBO);
+            const uint64_t db = make_smem_desc_sw128(b_addr + k * 2048, LBO, SBO);
+            umma_bf16(tmem_d, da, db, idesc, (ks | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (ks == ksteps - 1) umma_commit(&tmem_full[as]);
+        }
+        __syncwarp();
+        if (++stage == C::kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if (ksteps == 0 && lane == 0) mbar_arrive(&tmem_full[as]);  // empty K range: nothing to add
+    }
+  } else if (warp >= 4) {
+    const int ew = warp - 4;
+    const int row = ew * 32 + lane;
+    int it = 0;
+    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
+      int tap, mt, nt, k_begin, k_end;
+      decode(unit, tap, mt, nt, k_begin, k_end);
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tmem_full[as], aphase);
+      tcgen05_fence_after();
+      const bool has_data = k_end > k_begin;
+      const int co = mt * BLOCK_M + row;
+      const bool row_valid = co < p.cout_pad && has_data;
+      float* dst = p.dw + (static_cast<size_t>(tap) * p.cout_pad + co) * p.cin_pad + nt * BN;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) +
+                             static_cast<uint32_t>(as * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        if (has_data) {
+          tmem_ld_32x32(taddr + c * 32, r);
+          tmem_ld_wait();
+        }
+        if (row_valid) {
+          if (p.use_atomics) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) atomicAdd(dst + c * 32 + i, __uint_as_float(r[i]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              *reinterpret_cast<float4*>(dst + c * 32 + i * 4) =
+                  make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                              __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+template <int BN>
+int launch(const WgradParams& p, int num_sms, cudaStream_t stream) {
+  using C = WCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    SL_CUDA(cudaFuncSetAttribute(wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 C::SMEM_BYTES));
+    configured = true;
+  }
+  const int num_units = p.taps * p.m_tiles * p.n_tiles * p.ksplit;
+  const int grid = num_units < num_sms ? num_units : num_sms;
+  wgrad_kernel<BN><<<grid, kThreads, C::SMEM_BYTES, stream>>>(p);
+  SL_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+int wgrad_launch(const WgradParams& p, int block_n, int num_sms, cudaStream_t stream) {
+  switch (block_n) {
+    case 64:
+      return launch<64>(p, num_sms, stream);
+    case 128:
+      return launch<128>(p, num_sms, stream);
+    case 256:
+      return launch<256>(p, num_sms, stream);
+    default:
+      set_error("wgrad: unsupported block_n");
+      return 1;
+  }
+}
+
+}  // namespace sl
