@@ -169,6 +169,16 @@ def _logsumexp(*args):
         return np.where(np.isfinite(m), safe + np.log(sum(np.exp(a - safe) for a in args)), -np.inf)
 
 
+def _shift(a: np.ndarray, n: int) -> np.ndarray:
+    """out[s] = a[s - n] (n > 0) or a[s + |n|] (n < 0), -inf where out of range."""
+    out = np.full_like(a, -np.inf)
+    if n > 0:
+        out[n:] = a[:len(a) - n] if len(a) > n else []
+    else:
+        out[:len(a) + n if len(a) + n > 0 else 0] = a[-n:]
+    return out
+
+
 def ctc_log_probs(probs: np.ndarray) -> np.ndarray:
     """What tf.nn.ctc_loss works on after K.ctc_batch_cost: log_softmax(log(p + eps))."""
     u = np.log(probs + EPSILON)
@@ -191,8 +201,8 @@ def ctc_alpha_beta(lp: np.ndarray, label: Sequence[int], blank: int):
         alpha[0, 1] = lp[0, ext[1]]
     for t in range(1, P):
         a0 = alpha[t - 1]
-        a1 = np.concatenate(([neg], a0[:-1]))
-        a2 = np.where(skip, np.concatenate(([neg, neg], a0[:-2])), neg)
+        a1 = _shift(a0, 1)
+        a2 = np.where(skip, _shift(a0, 2), neg)
         alpha[t] = _logsumexp(a0, a1, a2) + lp[t, ext]
     beta = np.full((P, S), neg)
     beta[P - 1, S - 1] = lp[P - 1, blank]
@@ -202,8 +212,8 @@ def ctc_alpha_beta(lp: np.ndarray, label: Sequence[int], blank: int):
     skip_b[:-2] = skip[2:]
     for t in range(P - 2, -1, -1):
         b0 = beta[t + 1]
-        b1 = np.concatenate((b0[1:], [neg]))
-        b2 = np.where(skip_b, np.concatenate((b0[2:], [neg, neg])), neg)
+        b1 = _shift(b0, -1)
+        b2 = np.where(skip_b, _shift(b0, -2), neg)
         beta[t] = _logsumexp(b0, b1, b2) + lp[t, ext]
     ll = alpha[P - 1, S - 1] if S == 1 else _logsumexp(alpha[P - 1, S - 1], alpha[P - 1, S - 2])
     return alpha, beta, float(ll), ext

@@ -1,0 +1,426 @@
+"""Device-side engine of the wav2letter hot path: owns the HBM layout and drives the C-ABI.
+
+This is what replaces the Keras `Sequential` of reference net.py:291-341 and the TF graph
+behind `loss_net.fit_generator` / `backend.function` (net.py:350-390,456-459,550).  PyTorch
+is used for storage (`torch.empty`), streams and `torch.distributed` only; every arithmetic
+operation on the path is a kernel of libspeechless_b200.so.
+
+HBM layout
+  params / grads / adam_m / adam_v : one flat fp32 buffer each; per layer the kernel in the
+        *internal master layout* (k, cout_pad, cin_pad) followed by the bias (cout_pad).
+        Channel pads are zero and stay zero (their gradients are exactly zero).
+  w_fwd[l]  (k, cout_pad, planes*cin_pad)  bf16   B operand of the forward implicit GEMM
+  w_dgrad[l](k, cin_pad,  planes*cout_pad) bf16   B operand of the input-gradient GEMM
+  act[l]    (B, T', planes*cout_pad)       bf16   post-ReLU output of layer l (kept for backward)
+  probs (B,T',V) fp32, logp (B,T',64) fp32, CTC lattices alpha/beta (B,T',S_pad) fp32.
+"""
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from speechless_b200 import _lib
+from speechless_b200._lib import ACT_NONE, ACT_RELU, ACT_SOFTMAX, PREC_BF16, PREC_BF16X2, check, ptr
+
+
+def round_up(value: int, multiple: int) -> int:
+    return (value + multiple - 1) // multiple * multiple
+
+
+@dataclass
+class LayerSpec:
+    name: str
+    cin: int
+    cout: int
+    kernel: int
+    stride: int
+    activation: str  # "relu" | "linear" | "softmax"
+    w_offset: int = 0  # offsets into the flat parameter buffer (floats)
+    b_offset: int = 0
+
+    @property
+    def cin_pad(self) -> int:
+        return round_up(self.cin, 64)
+
+    @property
+    def cout_pad(self) -> int:
+        return round_up(self.cout, 64)
+
+    @property
+    def w_size(self) -> int:
+        return self.kernel * self.cout_pad * self.cin_pad
+
+
+def wav2letter_layers(input_size_per_time_step: int, grapheme_set_size: int, activation: str = "relu",
+                      output_activation: str = "softmax", main_filter_count: int = 250,
+                      out_filter_count: int = 2000) -> List[LayerSpec]:
+    """The 11 Conv1D layers of `Wav2Letter.create_predictive_net` (reference net.py:307-331):
+    striding_conv k48 s2, inner_conv_1..7 k7, big_conv_1 k32, big_conv_2 k1, output_conv k1."""
+    m, o = main_filter_count, out_filter_count
+    layers = [LayerSpec("striding_conv", input_size_per_time_step, m, 48, 2, activation)]
+    layers += [LayerSpec("inner_conv_{}".format(i), m, m, 7, 1, activation) for i in range(1, 8)]
+    layers += [LayerSpec("big_conv_1", m, o, 32, 1, activation),
+               LayerSpec("big_conv_2", o, o, 1, 1, activation),
+               LayerSpec("output_conv", o, grapheme_set_size, 1, 1, output_activation)]
+    offset = 0
+    for layer in layers:
+        layer.w_offset = offset
+        offset += layer.w_size
+        layer.b_offset = offset
+        offset += layer.cout_pad
+    return layers
+
+
+def same_padding(T: int, k: int, stride: int) -> Tuple[int, int]:
+    """TF SAME rule -> (T_out, pad_left)."""
+    t_out = -(-T // stride)
+    total = max((t_out - 1) * stride + k - T, 0)
+    return t_out, total // 2
+
+
+def ctc_required_frames(label: Sequence[int]) -> int:
+    """tf.nn.ctc_loss needs len(label) + #adjacent repeats frames."""
+    return len(label) + sum(1 for a, b in zip(label[:-1], label[1:]) if a == b)
+
+
+class _Workspace:
+    """Device buffers for one (B, T) batch shape; reused across steps."""
+
+    def __init__(self, tower: "ConvTower", B: int, T: int):
+        dev, planes = tower.device, tower.planes
+        first = tower.layers[0]
+        self.B, self.T = B, T
+        self.T_alloc = round_up(T, first.stride)
+        self.x_f32 = torch.empty((B, T, first.cin), dtype=torch.float32, device=dev)
+        self.x_host = torch.empty((B, T, first.cin), dtype=torch.float32, pin_memory=True)
+        self.x_packed = torch.zeros((B, self.T_alloc, planes * first.cin_pad), dtype=torch.bfloat16, device=dev)
+        self.t_out: List[int] = []
+        self.acts: List[torch.Tensor] = []
+        t = T
+        for layer in tower.layers:
+            t, _ = same_padding(t, layer.kernel, layer.stride)
+            self.t_out.append(t)
+        self.Tp = self.t_out[-1]
+        for layer, t_out in zip(tower.layers[:-1], self.t_out[:-1]):
+            self.acts.append(torch.empty((B, t_out, planes * layer.cout_pad), dtype=torch.bfloat16, device=dev))
+        V = tower.layers[-1].cout
+        self.probs = torch.empty((B, self.Tp, V), dtype=torch.float32, device=dev)
+        self.logits = torch.empty((B, self.Tp, V), dtype=torch.float32, device=dev)
+        self.logp = torch.empty((B, self.Tp, 64), dtype=torch.float32, device=dev)
+        self.loss = torch.empty((B,), dtype=torch.float32, device=dev)
+        self.input_len = torch.empty((B,), dtype=torch.int32, device=dev)
+        self.label_len = torch.empty((B,), dtype=torch.int32, device=dev)
+        self.decoded = torch.empty((B, self.Tp), dtype=torch.int32, device=dev)
+        self.decoded_len = torch.empty((B,), dtype=torch.int32, device=dev)
+        self.labels: Optional[torch.Tensor] = None
+        self.ctc_ws: Optional[torch.Tensor] = None
+        self.dz_packed: Optional[torch.Tensor] = None
+        self.dz_f32: Optional[torch.Tensor] = None
+        self.dact: List[Optional[torch.Tensor]] = [None, None]
+
+    def ensure_backward(self, tower: "ConvTower"):
+        if self.dz_packed is None:
+            dev, planes = tower.device, tower.planes
+            self.dz_packed = torch.empty((self.B, self.Tp, planes * 64), dtype=torch.bfloat16, device=dev)
+            widest = max(layer.cout_pad for layer in tower.layers[:-1])
+            rows = max(self.t_out)
+            for i in range(2):
+                self.dact[i] = torch.empty((self.B, rows, planes * widest), dtype=torch.bfloat16, device=dev)
+
+
+class ConvTower:
+    """Weights + kernels of the 11-layer tower, CTC objective and Keras-2 Adam on one GPU."""
+
+    def __init__(self, layers: List[LayerSpec], device: torch.device, precision: int = PREC_BF16X2,
+                 frozen_layer_count: int = 0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("speechless_b200 needs a CUDA device (B200); there is no CPU fallback.")
+        self.lib = _lib.load()
+        self.layers = layers
+        self.device = device
+        self.precision = precision
+        self.planes = 2 if precision == PREC_BF16X2 else 1
+        self.frozen_layer_count = frozen_layer_count
+        for layer in layers:
+            if layer.activation not in ("relu", "linear", "softmax"):
+                raise NotImplementedError("activation '{}' has no sm_100a epilogue".format(layer.activation))
+            if layer.stride not in (1, 2):
+                raise NotImplementedError("stride {} is not supported (raw-wave input is out of scope)".format(
+                    layer.stride))
+        if layers[-1].activation != "softmax":
+            raise NotImplementedError("the output layer must be a softmax (CTC objective)")
+        self.param_count = layers[-1].b_offset + layers[-1].cout_pad
+        with torch.cuda.device(device):
+            self.params = torch.zeros(self.param_count, dtype=torch.float32, device=device)
+            self.grads: Optional[torch.Tensor] = None
+            self.adam_m: Optional[torch.Tensor] = None
+            self.adam_v: Optional[torch.Tensor] = None
+            self.w_fwd = [torch.zeros((l.kernel, l.cout_pad, self.planes * l.cin_pad), dtype=torch.bfloat16,
+                                      device=device) for l in layers]
+            self.w_dgrad: List[Optional[torch.Tensor]] = [None] * len(layers)
+        self._workspaces: Dict[Tuple[int, int], _Workspace] = {}
+        self._current: Optional[_Workspace] = None
+        self.launches = 0  # kernels launched through the C-ABI (bench.py reports it)
+        # optional per-kernel timing: list of (kind, layer name, start event, stop event) on the
+        # launching stream; bench.py turns it on to measure roofline fractions live
+        self.profile: Optional[list] = None
+
+    # ------------------------------------------------------------------ helpers
+    @property
+    def stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _timed(self, kind: str, name: str, rc_fn) -> None:
+        """Run one C-ABI launch (rc_fn returns its code), bracketed by CUDA events when profiling."""
+        if self.profile is None:
+            check(rc_fn())
+            return
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        stream = torch.cuda.current_stream(self.device)
+        start.record(stream)
+        check(rc_fn())
+        stop.record(stream)
+        self.profile.append((kind, name, start, stop))
+
+    def _w(self, buf: torch.Tensor, layer: LayerSpec) -> torch.Tensor:
+        return buf[layer.w_offset:layer.w_offset + layer.w_size]
+
+    def _b(self, buf: torch.Tensor, layer: LayerSpec) -> torch.Tensor:
+        return buf[layer.b_offset:layer.b_offset + layer.cout_pad]
+
+    def first_trainable(self) -> int:
+        return min(self.frozen_layer_count, len(self.layers))
+
+    # ------------------------------------------------------------------ weights
+    def init_glorot(self, seed: Optional[int] = None) -> None:
+        """Keras defaults: glorot_uniform kernels, zero biases."""
+        rng = np.random.default_rng(seed)
+        for index, layer in enumerate(self.layers):
+            limit = np.sqrt(6.0 / (layer.kernel * layer.cin + layer.kernel * layer.cout))
+            kernel = rng.uniform(-limit, limit, size=(layer.kernel, layer.cin, layer.cout)).astype(np.float32)
+            self.set_layer_weights(index, kernel, np.zeros(layer.cout, dtype=np.float32), repack=False)
+        self.repack()
+
+    def set_layer_weights(self, index: int, kernel: np.ndarray, bias: np.ndarray, repack: bool = True) -> None:
+        """kernel in the Keras layout (k, Cin, Cout), bias (Cout,)."""
+        layer = self.layers[index]
+        kernel = np.ascontiguousarray(kernel, dtype=np.float32)
+        bias = np.ascontiguousarray(bias, dtype=np.float32)
+        if kernel.shape != (layer.kernel, layer.cin, layer.cout) or bias.shape != (layer.cout,):
+            raise ValueError("layer {} expects kernel {} and bias {}, got {} and {}".format(
+                layer.name, (layer.kernel, layer.cin, layer.cout), (layer.cout,), kernel.shape, bias.shape))
+        with torch.cuda.device(self.device):
+            w_keras = torch.from_numpy(kernel).to(self.device)
+            check(self.lib.sl_weights_keras_to_internal(ptr(w_keras), ptr(self._w(self.params, layer)), layer.kernel,
+                                                        layer.cin, layer.cout, layer.cin_pad, layer.cout_pad,
+                                                        self.stream))
+            b = self._b(self.params, layer)
+            b.zero_()
+            b[:layer.cout].copy_(torch.from_numpy(bias).to(self.device))
+            if repack:
+                self.repack([index])
+            torch.cuda.current_stream(self.device).synchronize()  # w_keras must outlive the kernel
+
+    def get_layer_weights(self, index: int) -> List[np.ndarray]:
+        layer = self.layers[index]
+        with torch.cuda.device(self.device):
+            w_keras = torch.empty((layer.kernel, layer.cin, layer.cout), dtype=torch.float32, device=self.device)
+            check(self.lib.sl_weights_internal_to_keras(ptr(self._w(self.params, layer)), ptr(w_keras), layer.kernel,
+                                                        layer.cin, layer.cout, layer.cin_pad, layer.cout_pad,
+                                                        self.stream))
+            return [w_keras.cpu().numpy(), self._b(self.params, layer)[:layer.cout].cpu().numpy()]
+
+    def repack(self, indices: Optional[Sequence[int]] = None, with_dgrad: Optional[bool] = None) -> None:
+        """fp32 master -> bf16 tensor-core operands (after a weight load or an optimizer step)."""
+        with torch.cuda.device(self.device):
+            for index in (range(len(self.layers)) if indices is None else indices):
+                layer = self.layers[index]
+                need_dgrad = self.w_dgrad[index] is not None if with_dgrad is None else with_dgrad
+                need_dgrad = need_dgrad and index > 0
+                if need_dgrad and self.w_dgrad[index] is None:
+                    self.w_dgrad[index] = torch.zeros((layer.kernel, layer.cin_pad, self.planes * layer.cout_pad),
+                                                      dtype=torch.bfloat16, device=self.device)
+                check(self.lib.sl_pack_weights_internal(ptr(self._w(self.params, layer)), ptr(self.w_fwd[index]),
+                                                        ptr(self.w_dgrad[index]) if need_dgrad else None,
+                                                        layer.kernel, layer.cin_pad, layer.cout_pad, self.precision,
+                                                        self.stream))
+                self.launches += 2 if need_dgrad else 1
+
+    # ------------------------------------------------------------------ forward
+    def workspace(self, B: int, T: int) -> _Workspace:
+        key = (B, T)
+        ws = self._workspaces.get(key)
+        if ws is None:
+            if len(self._workspaces) >= 4:  # bound HBM held by stale batch shapes
+                self._workspaces.pop(next(iter(self._workspaces)))
+            with torch.cuda.device(self.device):
+                ws = _Workspace(self, B, T)
+            self._workspaces[key] = ws
+        return ws
+
+    def upload(self, input_batch) -> _Workspace:
+        """Host (B,T,F) float array (any float dtype, net.py:583) or a device fp32 tensor -> packed bf16."""
+        with torch.cuda.device(self.device):
+            if isinstance(input_batch, torch.Tensor) and input_batch.is_cuda:
+                B, T, F = input_batch.shape
+                ws = self.workspace(B, T)
+                x = input_batch.to(torch.float32).contiguous()
+            elif isinstance(input_batch, torch.Tensor) and input_batch.is_pinned() \
+                    and input_batch.dtype == torch.float32 and input_batch.is_contiguous():
+                B, T, F = input_batch.shape  # already in pinned host memory: one async H2D copy
+                ws = self.workspace(B, T)
+                ws.x_f32.copy_(input_batch, non_blocking=True)
+                x = ws.x_f32
+            else:
+                array = np.asarray(input_batch)
+                B, T, F = array.shape
+                if F != self.layers[0].cin:
+                    raise ValueError("expected {} features per time step, got {}".format(self.layers[0].cin, F))
+                ws = self.workspace(B, T)
+                ws.x_host.copy_(torch.from_numpy(np.ascontiguousarray(array, dtype=np.float32)))
+                ws.x_f32.copy_(ws.x_host, non_blocking=True)
+                x = ws.x_f32
+            first = self.layers[0]
+            if F != first.cin:
+                raise ValueError("expected {} features per time step, got {}".format(first.cin, F))
+            check(self.lib.sl_pack_activation(ptr(x), ptr(ws.x_packed), B, T, F, ws.T_alloc, first.cin_pad,
+                                              self.precision, self.stream))
+            self.launches += 1
+            self._current = ws
+            return ws
+
+    def forward(self, ws: Optional[_Workspace] = None, want_logits: bool = False) -> _Workspace:
+        ws = ws or self._current
+        with torch.cuda.device(self.device):
+            x, t_in, t_alloc = ws.x_packed, ws.T, ws.T_alloc
+            for index, layer in enumerate(self.layers):
+                bias = self._b(self.params, layer)
+                if layer.activation == "softmax":
+                    self._timed("fwd", layer.name, lambda: self.lib.sl_conv1d_fwd(
+                        ptr(x), ptr(self.w_fwd[index]), ptr(bias), None, ptr(ws.probs),
+                        ptr(ws.logits) if want_logits else None, ptr(ws.logp), ws.B, t_in, t_alloc, layer.cin,
+                        layer.cout, layer.kernel, layer.stride, ACT_SOFTMAX, self.precision, self.stream))
+                else:
+                    y = ws.acts[index]
+                    act = ACT_RELU if layer.activation == "relu" else ACT_NONE
+                    self._timed("fwd", layer.name, lambda: self.lib.sl_conv1d_fwd(
+                        ptr(x), ptr(self.w_fwd[index]), ptr(bias), ptr(y), None, None, None, ws.B, t_in, t_alloc,
+                        layer.cin, layer.cout, layer.kernel, layer.stride, act, self.precision, self.stream))
+                    x, t_in, t_alloc = y, ws.t_out[index], ws.t_out[index]
+                self.launches += 1
+        return ws
+
+    # ------------------------------------------------------------------ CTC
+    def set_labels(self, ws: _Workspace, label_batch: np.ndarray, prediction_lengths: Sequence[int],
+                   label_lengths: Sequence[int]) -> None:
+        """label_batch (B, L_max) int32 padded with -1 (grapheme_enconding.py:25-32)."""
+        label_batch = np.ascontiguousarray(label_batch, dtype=np.int32)
+        if label_batch.ndim != 2 or label_batch.shape[0] != ws.B:
+            raise ValueError("label batch must have shape (batch, max label length)")
+        if label_batch.shape[1] == 0:
+            label_batch = -np.ones((ws.B, 1), dtype=np.int32)
+        V = self.layers[-1].cout
+        pl = np.asarray(prediction_lengths, dtype=np.int64).reshape(-1)
+        ll = np.asarray(label_lengths, dtype=np.int64).reshape(-1)
+        for b in range(ws.B):
+            label = label_batch[b, :ll[b]]
+            if pl[b] > ws.Tp or pl[b] < 1:
+                raise ValueError("prediction length {} outside [1, {}]".format(pl[b], ws.Tp))
+            if label.size and (label.min() < 0 or label.max() >= V - 1):
+                raise ValueError("label of example {} contains a grapheme outside [0, {})".format(b, V - 1))
+            need = ctc_required_frames(label.tolist())
+            if pl[b] < need:
+                raise ValueError("Not enough time for target transition sequence "
+                                 "(required: {}, available: {}) in example {}".format(need, pl[b], b))
+        with torch.cuda.device(self.device):
+            ws.labels = torch.from_numpy(label_batch).to(self.device)
+            ws.input_len.copy_(torch.from_numpy(pl.astype(np.int32)))
+            ws.label_len.copy_(torch.from_numpy(ll.astype(np.int32)))
+            need_bytes = self.lib.sl_ctc_workspace_bytes(ws.B, ws.Tp, ws.labels.shape[1])
+            if ws.ctc_ws is None or ws.ctc_ws.numel() < need_bytes:
+                ws.ctc_ws = torch.empty(need_bytes, dtype=torch.uint8, device=self.device)
+
+    def set_prediction_lengths(self, ws: _Workspace, prediction_lengths: Sequence[int]) -> None:
+        pl = np.asarray(prediction_lengths, dtype=np.int32).reshape(-1)
+        with torch.cuda.device(self.device):
+            ws.input_len.copy_(torch.from_numpy(pl))
+
+    def ctc(self, ws: _Workspace, want_grad: bool, grad_scale: float = 1.0, want_f32_grad: bool = False) -> torch.Tensor:
+        """Per-utterance loss (device, (B,)); optionally d(grad_scale*sum loss)/d logits as packed bf16."""
+        V = self.layers[-1].cout
+        with torch.cuda.device(self.device):
+            if want_grad:
+                ws.ensure_backward(self)
+                if want_f32_grad and ws.dz_f32 is None:
+                    ws.dz_f32 = torch.empty((ws.B, ws.Tp, V), dtype=torch.float32, device=self.device)
+            self._timed("ctc", "ctc_loss", lambda: self.lib.sl_ctc_loss(
+                ptr(ws.logp), ptr(ws.probs), ptr(ws.labels), ptr(ws.input_len), ptr(ws.label_len), ptr(ws.loss),
+                ptr(ws.dz_packed) if want_grad else None,
+                ptr(ws.dz_f32) if (want_grad and want_f32_grad) else None, float(grad_scale), ws.B, ws.Tp, V,
+                ws.labels.shape[1], V - 1, self.precision, ptr(ws.ctc_ws), ws.ctc_ws.numel(), self.stream))
+            self.launches += 2 if want_grad else 1
+        return ws.loss
+
+    def greedy_decode(self, ws: _Workspace, merge_repeated: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+        V = self.layers[-1].cout
+        with torch.cuda.device(self.device):
+            check(self.lib.sl_ctc_greedy_decode(ptr(ws.probs), ptr(ws.input_len), ptr(ws.decoded), ptr(ws.decoded_len),
+                                                ws.B, ws.Tp, V, V - 1, 1 if merge_repeated else 0, self.stream))
+            self.launches += 1
+        return ws.decoded, ws.decoded_len
+
+    # ------------------------------------------------------------------ backward + update
+    def ensure_training_state(self) -> None:
+        with torch.cuda.device(self.device):
+            if self.grads is None:
+                self.grads = torch.zeros_like(self.params)
+                self.adam_m = torch.zeros_like(self.params)
+                self.adam_v = torch.zeros_like(self.params)
+            missing = [i for i in range(max(1, self.first_trainable() + 1), len(self.layers))
+                       if self.w_dgrad[i] is None]
+            if missing:
+                self.repack(missing, with_dgrad=True)
+
+    def backward(self, ws: Optional[_Workspace] = None) -> None:
+        """Fill self.grads from ws.dz_packed (set by ctc(want_grad=True))."""
+        ws = ws or self._current
+        self.ensure_training_state()
+        first = self.first_trainable()
+        with torch.cuda.device(self.device):
+            self.grads.zero_()
+            dy = ws.dz_packed
+            flip = 0
+            for index in range(len(self.layers) - 1, first - 1, -1):
+                layer = self.layers[index]
+                x = ws.x_packed if index == 0 else ws.acts[index - 1]
+                t_in = ws.T if index == 0 else ws.t_out[index - 1]
+                t_alloc = ws.T_alloc if index == 0 else t_in
+                self._timed("wgrad", layer.name, lambda: self.lib.sl_conv1d_wgrad(
+                    ptr(x), ptr(dy), ptr(self._w(self.grads, layer)), ptr(self._b(self.grads, layer)), ws.B, t_in,
+                    t_alloc, layer.cin, layer.cout, layer.kernel, layer.stride, self.precision, 1, self.stream))
+                self.launches += 2
+                if index > first:
+                    below = self.layers[index - 1]
+                    dx = ws.dact[flip].view(-1)[:ws.B * t_in * self.planes * below.cout_pad].view(
+                        ws.B, t_in, self.planes * below.cout_pad)
+                    mask = ws.acts[index - 1] if below.activation == "relu" else None
+                    self._timed("dgrad", layer.name, lambda: self.lib.sl_conv1d_dgrad(
+                        ptr(dy), ptr(self.w_dgrad[index]), ptr(mask), ptr(dx), ws.B, t_in, layer.cin, layer.cout,
+                        layer.kernel, self.precision, self.stream))
+                    self.launches += 1
+                    dy = dx
+                    flip ^= 1
+
+    def adam_step(self, lr: float, beta_1: float, beta_2: float, epsilon: float, iteration: int) -> None:
+        """Keras-2 Adam over the whole flat buffer (frozen layers have zero gradients and zero
+        moments, so they do not move), then refresh the bf16 operands."""
+        with torch.cuda.device(self.device):
+            self._timed("adam", "adam", lambda: self.lib.sl_adam_step(
+                ptr(self.params), ptr(self.grads), ptr(self.adam_m), ptr(self.adam_v), self.param_count, lr, beta_1,
+                beta_2, epsilon, iteration, self.stream))
+            self.launches += 1
+            self.repack(range(self.first_trainable(), len(self.layers)))
+
+    def sync(self) -> None:
+        torch.cuda.current_stream(self.device).synchronize()

@@ -1,0 +1,565 @@
+"""`Wav2Letter` — the reference's model/loss/decode/train surface on hand-written sm_100a kernels.
+
+Host-side mirror of `speechless/net.py::Wav2Letter` (reference net.py:117-607): same class,
+method and argument names, return types, log lines and error behaviour, so
+`Configuration.train` (configuration.py:96-101), `test_model` (:124-125), `load_model`
+(:168-178), `main.py:144,202-206` and the README snippets call it unchanged.  Below the
+surface nothing is Keras/TensorFlow: `ConvTower` (engine.py) drives libspeechless_b200.so.
+
+Differences that are deliberate and documented in DESIGN.md:
+* `optimizer` defaults to a fresh `Adam(1e-4)` per instance (the reference shares one
+  default-argument instance between all models, net.py:132);
+* batches of size 1 work (the reference needs the duplication workaround of net.py:492-495,
+  which is kept so results are identical either way);
+* weights are saved as `.npz` keyed by the Keras layer names when `h5py` is unavailable;
+* `dropout`, `use_raw_wave_input` and `kenlm_directory` raise `NotImplementedError`
+  (SURVEY.md §8f "next" rows); `use_asg=True` raises at loss time exactly like the reference.
+"""
+import itertools
+import json
+import queue
+import threading
+import time
+from collections import OrderedDict
+from functools import reduce
+from pathlib import Path
+from typing import Callable, Dict, Iterable, List, Optional, Tuple
+
+import numpy
+from numpy import ndarray, zeros, array, reshape, concatenate
+
+from speechless_b200._lib import PREC_BF16, PREC_BF16X2
+from speechless_b200.grapheme_enconding import CtcGraphemeEncoding, AsgGraphemeEncoding
+from speechless_b200.labeled_example import LabeledSpectrogram
+from speechless_b200.results import (ExpectationVsPrediction, ExpectationsVsPredictions,
+                                     ExpectationsVsPredictionsInBatches, ExpectationsVsPredictionsInGroupedBatches)
+from speechless_b200.tools import log, mkdir, read_text, single, single_or_none
+
+__all__ = ["Adam", "Wav2Letter", "ExpectationVsPrediction", "ExpectationsVsPredictions",
+           "ExpectationsVsPredictionsInBatches", "ExpectationsVsPredictionsInGroupedBatches"]
+
+
+class Adam:
+    """Stands in for `keras.optimizers.Adam` (reference net.py:12,132): Keras-2 update rule,
+    hyper-parameter names as in Keras.  The state (moments) lives on the device in `ConvTower`."""
+
+    def __init__(self, lr: float = 0.001, beta_1: float = 0.9, beta_2: float = 0.999, epsilon: float = 1e-8):
+        self.lr = lr
+        self.beta_1 = beta_1
+        self.beta_2 = beta_2
+        self.epsilon = epsilon
+        self.iterations = 0
+
+
+class _ConvLayerView:
+    """What callers of `predictive_net.layers[i]` use: name, strides, trainable, get/set_weights."""
+
+    def __init__(self, tower, index: int):
+        self._tower = tower
+        self._index = index
+        spec = tower.layers[index]
+        self.name = spec.name
+        self.filters = spec.cout
+        self.kernel_size = (spec.kernel,)
+        self.strides = (spec.stride,)
+        self.trainable = index >= tower.frozen_layer_count
+
+    def get_weights(self) -> List[ndarray]:
+        """[kernel (k, C_in, C_out), bias (C_out,)] — the Keras layout (reference net.py:238,251-255)."""
+        return self._tower.get_layer_weights(self._index)
+
+    def set_weights(self, weights: List[ndarray]) -> None:
+        kernel, bias = weights
+        self._tower.set_layer_weights(self._index, kernel, bias)
+
+
+class PredictiveNet:
+    """Shim for the Keras `Sequential` the reference exposes as `Wav2Letter.predictive_net`
+    (net.py:168, used by main.py:121 and load_weights :212,237-269)."""
+
+    def __init__(self, tower, input_size_per_time_step: int):
+        self._tower = tower
+        self.layers = [_ConvLayerView(tower, index) for index in range(len(tower.layers))]
+        self.input_shape = (None, None, input_size_per_time_step)
+
+    @staticmethod
+    def _npz_path(path) -> Path:
+        path = Path(str(path))
+        return path if path.suffix == ".npz" else path.with_suffix(".npz")
+
+    def save_weights(self, path) -> None:
+        arrays = {}
+        for layer in self.layers:
+            kernel, bias = layer.get_weights()
+            arrays["{}/kernel".format(layer.name)] = kernel
+            arrays["{}/bias".format(layer.name)] = bias
+        try:
+            import h5py  # optional: Keras-compatible container when available
+        except ImportError:
+            numpy.savez(str(self._npz_path(path)), **arrays)
+            return
+        with h5py.File(str(path), "w") as f:
+            f.attrs["layer_names"] = [layer.name.encode("utf8") for layer in self.layers]
+            for layer in self.layers:
+                group = f.create_group(layer.name)
+                names = ["{}/kernel:0".format(layer.name), "{}/bias:0".format(layer.name)]
+                group.attrs["weight_names"] = [n.encode("utf8") for n in names]
+                group.create_dataset(names[0], data=arrays["{}/kernel".format(layer.name)])
+                group.create_dataset(names[1], data=arrays["{}/bias".format(layer.name)])
+
+    def load_weights(self, path) -> None:
+        npz = self._npz_path(path)
+        if npz.exists():
+            with numpy.load(str(npz)) as arrays:
+                for layer in self.layers:
+                    layer.set_weights([arrays["{}/kernel".format(layer.name)], arrays["{}/bias".format(layer.name)]])
+            return
+        try:
+            import h5py
+        except ImportError:
+            raise IOError("{} not found and h5py is unavailable to read {}".format(npz, path))
+        with h5py.File(str(path), "r") as f:
+            root = f["model_weights"] if "model_weights" in f else f
+            for layer in self.layers:
+                group = root[layer.name]
+                names = [n.decode("utf8") if isinstance(n, bytes) else n for n in group.attrs["weight_names"]]
+                layer.set_weights([numpy.asarray(group[names[0]]), numpy.asarray(group[names[1]])])
+
+
+class _Prefetcher:
+    """Keras' fit_generator pulls batches on a background thread with a bounded queue
+    (net.py:550); this keeps host batch assembly overlapped with the device step."""
+    _END = object()
+
+    def __init__(self, iterable: Iterable, depth: int = 10):
+        self._queue: "queue.Queue" = queue.Queue(maxsize=depth)
+        self._error: Optional[BaseException] = None
+        self._stop = threading.Event()
+        self._thread = threading.Thread(target=self._run, args=(iter(iterable),), daemon=True)
+        self._thread.start()
+
+    def _run(self, iterator):
+        try:
+            for item in iterator:
+                while not self._stop.is_set():
+                    try:
+                        self._queue.put(item, timeout=0.1)
+                        break
+                    except queue.Full:
+                        continue
+                if self._stop.is_set():
+                    return
+        except BaseException as e:  # surfaced on the consumer side
+            self._error = e
+        self._queue.put(self._END)
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        item = self._queue.get()
+        if item is self._END:
+            self._queue.put(self._END)
+            if self._error is not None:
+                raise self._error
+            raise StopIteration
+        return item
+
+    def close(self):
+        self._stop.set()
+
+
+class Wav2Letter:
+    """Speech-recognition network based on wav2letter (https://arxiv.org/pdf/1609.03193v2.pdf)."""
+
+    class InputNames:
+        input_batch = "input_batch"
+        label_batch = "label_batch"
+        prediction_lengths = "prediction_lenghts"
+        label_lengths = "label_lenghts"
+
+    def __init__(self,
+                 input_size_per_time_step: int,
+                 allowed_characters: List[chr],
+                 use_raw_wave_input: bool = False,
+                 activation: str = "relu",
+                 output_activation: str = "softmax",
+                 optimizer: Optional[Adam] = None,
+                 dropout: Optional[float] = None,
+                 load_model_from_directory: Optional[Path] = None,
+                 load_epoch: Optional[int] = None,
+                 allowed_characters_for_loaded_model: Optional[List[chr]] = None,
+                 frozen_layer_count: int = 0,
+                 reinitialize_trainable_loaded_layers: bool = False,
+                 use_asg: bool = False,
+                 asg_transition_probabilities: Optional[ndarray] = None,
+                 asg_initial_probabilities: Optional[ndarray] = None,
+                 kenlm_directory: Path = None,
+                 *,
+                 main_filter_count: int = 250,
+                 out_filter_count: int = 2000,
+                 compute_dtype: str = "bf16x2",
+                 device=None,
+                 seed: Optional[int] = None):
+        if frozen_layer_count > 0 and load_model_from_directory is None:
+            raise ValueError("Layers cannot be frozen if model is trained from scratch.")
+        if use_raw_wave_input:
+            raise NotImplementedError("raw-wave input (wave_conv k250 s160) is not built yet (SURVEY.md §8f-4).")
+        if dropout is not None:
+            raise NotImplementedError("dropout is not built yet (SURVEY.md §8f-2).")
+        if compute_dtype not in ("bf16", "bf16x2"):
+            raise ValueError("compute_dtype must be 'bf16' or 'bf16x2'")
+
+        self.kenlm_directory = kenlm_directory
+        self.grapheme_encoding = AsgGraphemeEncoding(allowed_characters=allowed_characters) \
+            if use_asg else CtcGraphemeEncoding(allowed_characters=allowed_characters)
+        self.asg_transition_probabilities = asg_transition_probabilities
+        self.asg_initial_probabilities = asg_initial_probabilities
+        self.use_asg = use_asg
+        self.frozen_layer_count = frozen_layer_count
+        self.output_activation = output_activation
+        self.activation = activation
+        self.use_raw_wave_input = use_raw_wave_input
+        self.input_size_per_time_step = input_size_per_time_step
+        self.optimizer = optimizer if optimizer is not None else Adam(1e-4)
+        self.load_epoch = load_epoch
+        self.dropout = dropout
+        self.main_filter_count = main_filter_count
+        self.out_filter_count = out_filter_count
+        self.compute_dtype = compute_dtype
+        self.seed = seed
+        self._device = device
+        self.predictive_net = self.create_predictive_net()
+        self.prediction_phase_flag = 0.
+
+        if self.kenlm_directory is not None:
+            expected_characters = list(
+                single(read_text(self.kenlm_directory / "vocabulary", encoding='utf8').splitlines()).lower())
+            if allowed_characters != expected_characters:
+                raise ValueError("Allowed characters {} differ from those expected by kenlm decoder: {}".
+                                 format(allowed_characters, expected_characters))
+            raise NotImplementedError("KenLM beam-search decoding needs the reference's patched TensorFlow "
+                                      "(net.py:420-422) and is not built (SURVEY.md §8f-4).")
+
+        if load_model_from_directory is not None:
+            self.load_weights(
+                allowed_characters_for_loaded_model, load_epoch, load_model_from_directory,
+                loaded_first_layers_count=frozen_layer_count if reinitialize_trainable_loaded_layers else None)
+
+    # ------------------------------------------------------------------ construction
+    def create_predictive_net(self) -> PredictiveNet:
+        """The 11-layer Conv1D tower of reference net.py:291-341 as a `ConvTower` on one B200."""
+        import torch
+        from speechless_b200.engine import ConvTower, wav2letter_layers
+
+        if not torch.cuda.is_available():
+            raise RuntimeError("speechless_b200.Wav2Letter needs a CUDA device (B200); there is no CPU fallback.")
+        device = torch.device(self._device) if self._device is not None else torch.device(
+            "cuda", torch.cuda.current_device())
+        layers = wav2letter_layers(self.input_size_per_time_step, self.grapheme_encoding.grapheme_set_size,
+                                   activation=self.activation, output_activation=self.output_activation,
+                                   main_filter_count=self.main_filter_count,
+                                   out_filter_count=self.out_filter_count)
+        if self.frozen_layer_count > 0:
+            log("All but {} layers frozen.".format(len(layers) - self.frozen_layer_count))
+        self.tower = ConvTower(layers, device, PREC_BF16X2 if self.compute_dtype == "bf16x2" else PREC_BF16,
+                               frozen_layer_count=self.frozen_layer_count)
+        self.tower.init_glorot(self.seed)
+        return PredictiveNet(self.tower, self.input_size_per_time_step)
+
+    @property
+    def input_to_prediction_length_ratio(self) -> int:
+        """Factor by which striding shortens the output (reference net.py:343-348)."""
+        return reduce(lambda x, y: x * y, [layer.strides[0] for layer in self.predictive_net.layers], 1)
+
+    # ------------------------------------------------------------------ weight loading (net.py:184-269)
+    @staticmethod
+    def indices_to_load_by_target_index(allowed_characters_for_loaded_model: List[chr],
+                                        allowed_characters: List[chr]) -> List[Optional[int]]:
+        load_character_set = set(allowed_characters_for_loaded_model)
+        target_character_set = set(allowed_characters)
+        ignored = load_character_set - target_character_set
+        if ignored:
+            log("Ignoring characters {} from loaded model.".format(sorted(ignored)))
+        extra = target_character_set - load_character_set
+        if extra:
+            log("Initializing extra characters {} not found in model.".format(sorted(extra)))
+
+        character_mapping = [
+            single_or_none([index for index, character in enumerate(allowed_characters_for_loaded_model)
+                            if character == target_character])
+            for target_character in allowed_characters]
+        log("Character mapping: {}".format(character_mapping))
+        return character_mapping
+
+    def load_weights(self, allowed_characters_for_loaded_model: List[chr], load_epoch: int,
+                     load_model_from_directory: Path, loaded_first_layers_count: Optional[int] = None):
+        if allowed_characters_for_loaded_model is None:
+            self.predictive_net.load_weights(str(Path(load_model_from_directory) / self.model_file_name(load_epoch)))
+            return
+
+        layer_count = len(self.predictive_net.layers)
+        if loaded_first_layers_count is None:
+            loaded_first_layers_count = layer_count
+
+        original_wav2letter = Wav2Letter(input_size_per_time_step=self.input_size_per_time_step,
+                                         allowed_characters=allowed_characters_for_loaded_model,
+                                         use_raw_wave_input=self.use_raw_wave_input,
+                                         activation=self.activation,
+                                         output_activation=self.output_activation,
+                                         optimizer=self.optimizer,
+                                         dropout=self.dropout,
+                                         load_model_from_directory=load_model_from_directory,
+                                         load_epoch=load_epoch,
+                                         frozen_layer_count=self.frozen_layer_count,
+                                         use_asg=self.use_asg,
+                                         asg_initial_probabilities=self.asg_initial_probabilities,
+                                         asg_transition_probabilities=self.asg_transition_probabilities,
+                                         main_filter_count=self.main_filter_count,
+                                         out_filter_count=self.out_filter_count,
+                                         compute_dtype=self.compute_dtype, device=self._device)
+
+        log("Loading first {} layers of {}, epoch {}, reinitializing the last {}.".format(
+            loaded_first_layers_count, load_model_from_directory, load_epoch,
+            layer_count - loaded_first_layers_count))
+
+        for index, layer in enumerate(self.predictive_net.layers[:loaded_first_layers_count]):
+            original_weights, original_biases = original_wav2letter.predictive_net.layers[index].get_weights()
+
+            if index == layer_count - 1:
+                # re-index the grapheme axis of output_conv for the new alphabet (net.py:240-267)
+                mapping = self.indices_to_load_by_target_index(allowed_characters_for_loaded_model,
+                                                               self.grapheme_encoding.allowed_characters)
+                blank = self.grapheme_encoding.ctc_blank
+
+                def source_index(target_grapheme_index: int) -> Optional[int]:
+                    if target_grapheme_index == blank:
+                        return original_wav2letter.grapheme_encoding.ctc_blank
+                    return mapping[target_grapheme_index]
+
+                sources = [source_index(g) for g in range(self.grapheme_encoding.grapheme_set_size)]
+                k, cin, _ = original_weights.shape
+                # NB the reference tests `if index`, so source index 0 (its first character) is
+                # treated like a missing character and zero-initialised (net.py:254,258); kept.
+                new_weights = zeros((k, cin, len(sources)), dtype=original_weights.dtype)
+                new_biases = zeros((len(sources),), dtype=original_biases.dtype)
+                for target, source in enumerate(sources):
+                    if source:
+                        new_weights[:, :, target] = original_weights[:, :, source]
+                        new_biases[target] = original_biases[source]
+                original_weights, original_biases = new_weights, new_biases
+
+            layer.set_weights([original_weights, original_biases])
+
+    # ------------------------------------------------------------------ inference (net.py:350-357, 485-498)
+    def prediction_batch(self, input_batch: ndarray) -> ndarray:
+        """Grapheme probabilities (B, ceil(T/ratio), V) for a zero-padded spectrogram batch (B, T, F)."""
+        ws = self.tower.upload(input_batch)
+        self.tower.forward(ws)
+        return ws.probs.cpu().numpy()
+
+    def logits_batch(self, input_batch: ndarray) -> ndarray:
+        """Pre-softmax activations of output_conv — not part of the reference surface; parity tests use it."""
+        ws = self.tower.upload(input_batch)
+        self.tower.forward(ws, want_logits=True)
+        return ws.logits.cpu().numpy()
+
+    def predict_batch_greedily(self, spectrograms: List[ndarray]) -> List[str]:
+        input_batch, prediction_lengths = self._input_batch_and_prediction_lengths(spectrograms)
+        return self.grapheme_encoding.decode_prediction_batch(self.prediction_batch(input_batch),
+                                                              prediction_lengths=prediction_lengths)
+
+    def get_predicted_graphemes_and_loss_batch(self, input_by_name: Dict[str, ndarray]) -> Tuple[ndarray, ndarray]:
+        """One fused device pass: greedy-decoded graphemes (dense, -1 padded, as tf.sparse_to_dense
+        in net.py:436) and the per-example CTC loss (B, 1) (net.py:456-459)."""
+        if self.use_asg:
+            raise NotImplementedError("ASG is not yet implemented.")
+        names = Wav2Letter.InputNames
+        tower = self.tower
+        ws = tower.upload(input_by_name[names.input_batch])
+        tower.forward(ws)
+        tower.set_labels(ws, input_by_name[names.label_batch], input_by_name[names.prediction_lengths],
+                         input_by_name[names.label_lengths])
+        loss = tower.ctc(ws, want_grad=False)
+        decoded, decoded_lengths = tower.greedy_decode(ws, merge_repeated=True)
+        decoded = decoded.cpu().numpy()
+        width = max(int(decoded_lengths.max().item()), 1)
+        return decoded[:, :width], loss.cpu().numpy().reshape(-1, 1)
+
+    def test_and_predict_batch(self, labeled_spectrogram_batch: List[LabeledSpectrogram]) -> ExpectationsVsPredictions:
+        input_by_name, dummy_labels = self._inputs_for_loss_net(labeled_spectrogram_batch)
+        predicted_graphemes, loss_batch = self.get_predicted_graphemes_and_loss_batch(input_by_name)
+
+        # blank labels are returned as -1 (net.py:467-468)
+        predicted_graphemes = predicted_graphemes.copy()
+        predicted_graphemes[predicted_graphemes < 0] = self.grapheme_encoding.ctc_blank
+
+        prediction_lengths = list(numpy.squeeze(input_by_name[Wav2Letter.InputNames.prediction_lengths], axis=1))
+        losses = list(numpy.squeeze(loss_batch, axis=1))
+
+        # repeats were already merged on the device, so merging is disabled here (net.py:473-475)
+        predictions = self.grapheme_encoding.decode_grapheme_batch(predicted_graphemes, prediction_lengths,
+                                                                   merge_repeated=False)
+        return ExpectationsVsPredictions(
+            [ExpectationVsPrediction(predicted=predicted, expected=expected, loss=float(loss))
+             for predicted, expected, loss in
+             zip(predictions, (e.label for e in labeled_spectrogram_batch), losses)])
+
+    def test_and_predict(self, labeled_spectrogram: LabeledSpectrogram) -> ExpectationVsPrediction:
+        # the reference duplicates the example because TF fails on batches of size 1 (net.py:491-495)
+        return self.test_and_predict_batch([labeled_spectrogram, labeled_spectrogram]).results[0]
+
+    def predict(self, labeled_spectrogram: LabeledSpectrogram) -> str:
+        return self.test_and_predict(labeled_spectrogram).predicted
+
+    def test_and_predict_batch_with_log(self, index: int, batch: List[LabeledSpectrogram]) -> ExpectationsVsPredictions:
+        result = self.test_and_predict_batch(batch)
+        log(str(result) + " (batch {})".format(index))
+        return result
+
+    def test_and_predict_batches(self, labeled_spectrogram_batches: Iterable[
+        List[LabeledSpectrogram]]) -> ExpectationsVsPredictionsInBatches:
+        return ExpectationsVsPredictionsInBatches([self.test_and_predict_batch_with_log(index, batch)
+                                                   for index, batch in enumerate(labeled_spectrogram_batches)])
+
+    def test_and_predict_batches_with_log(
+            self, corpus_name: str, batches: Iterable[List[LabeledSpectrogram]]) -> ExpectationsVsPredictionsInBatches:
+        result = self.test_and_predict_batches(batches)
+        log("{}: {}".format(corpus_name, result))
+        return result
+
+    def test_and_predict_grouped_batches(self, grouped_labeled_spectrogram_batches: Dict[str, Iterable[
+        List[LabeledSpectrogram]]]) -> ExpectationsVsPredictionsInGroupedBatches:
+        return ExpectationsVsPredictionsInGroupedBatches(
+            OrderedDict((corpus_name, self.test_and_predict_batches_with_log(corpus_name=corpus_name,
+                                                                             batches=labeled_spectrogram_batches))
+                        for corpus_name, labeled_spectrogram_batches in grouped_labeled_spectrogram_batches.items()))
+
+    # ------------------------------------------------------------------ training (net.py:541-576)
+    def train_on_batch(self, input_by_name: Dict[str, ndarray], global_batch_size: Optional[int] = None,
+                       allreduce: Optional[Callable] = None) -> float:
+        """One optimisation step on this GPU's shard: forward, CTC loss + gradient, backward,
+        (gradient all-reduce), Keras-2 Adam.  Objective = mean over the *global* batch (net.py:389).
+        Returns this shard's contribution to that mean."""
+        if self.use_asg:
+            raise NotImplementedError("ASG is not yet implemented.")
+        names = Wav2Letter.InputNames
+        tower = self.tower
+        ws = tower.upload(input_by_name[names.input_batch])
+        tower.forward(ws)
+        tower.set_labels(ws, input_by_name[names.label_batch], input_by_name[names.prediction_lengths],
+                         input_by_name[names.label_lengths])
+        batch_size = global_batch_size if global_batch_size is not None else ws.B
+        loss = tower.ctc(ws, want_grad=True, grad_scale=1.0 / batch_size)
+        tower.backward(ws)
+        loss_sum = loss.sum()
+        if allreduce is not None:
+            allreduce(tower.grads, loss_sum)
+        self.optimizer.iterations += 1
+        tower.adam_step(self.optimizer.lr, self.optimizer.beta_1, self.optimizer.beta_2, self.optimizer.epsilon,
+                        self.optimizer.iterations)
+        return float(loss_sum.item()) / batch_size
+
+    def train(self,
+              labeled_spectrogram_batches: Iterable[List[LabeledSpectrogram]],
+              preview_labeled_spectrogram_batch: List[LabeledSpectrogram],
+              tensor_board_log_directory: Path,
+              net_directory: Path,
+              batches_per_epoch: int,
+              *,
+              epochs: int = 100000000):
+        """Same schedule as the reference's `fit_generator` call (net.py:550-556): log the preview
+        batch, then epochs of `batches_per_epoch` steps starting at `load_epoch`, calling the
+        callbacks of `create_callbacks` at every epoch end.  `epochs` (keyword-only, default as in
+        the reference) bounds the run for tests; a finite batch iterable ends training quietly."""
+        print_preview_batch = lambda: log(self.test_and_predict_batch(preview_labeled_spectrogram_batch))
+        print_preview_batch()
+        callbacks = self.create_callbacks(callback=print_preview_batch,
+                                          tensor_board_log_directory=tensor_board_log_directory,
+                                          net_directory=net_directory)
+        initial_epoch = self.load_epoch if (self.load_epoch is not None) else 0
+        batches = _Prefetcher(self._loss_inputs_generator(labeled_spectrogram_batches))
+        try:
+            for epoch in range(initial_epoch, epochs):
+                losses = []
+                started = time.time()
+                for _ in range(batches_per_epoch):
+                    try:
+                        input_by_name, _dummy = next(batches)
+                    except StopIteration:
+                        return
+                    losses.append(self.train_on_batch(input_by_name))
+                logs = {"loss": sum(losses) / len(losses), "seconds": time.time() - started}
+                for on_epoch_end in callbacks:
+                    on_epoch_end(epoch, logs)
+        finally:
+            batches.close()
+
+    @staticmethod
+    def model_file_name(epoch: int) -> str:
+        return "weights-epoch{}.h5".format(epoch)
+
+    def create_callbacks(self, callback: Callable[[], None], tensor_board_log_directory: Path, net_directory: Path,
+                         callback_step: int = 1, save_step: int = 1) -> List[Callable]:
+        """Epoch-end hooks with the reference's semantics (net.py:562-576): run `callback` every
+        `callback_step` epochs, save `weights-epoch{N}` every `save_step` epochs for N > 0.  The
+        TensorBoard callback becomes a JSON-lines scalar log in `tensor_board_log_directory`."""
+
+        def custom_callback(epoch: int, logs=()):
+            if epoch % callback_step == 0:
+                callback()
+            if epoch % save_step == 0 and epoch > 0:
+                mkdir(net_directory)
+                self.predictive_net.save_weights(str(Path(net_directory) / self.model_file_name(epoch)))
+
+        def scalar_log(epoch: int, logs=()):
+            if tensor_board_log_directory is None:
+                return
+            mkdir(tensor_board_log_directory)
+            with (Path(tensor_board_log_directory) / "scalars.jsonl").open("a") as f:
+                f.write(json.dumps(dict(epoch=epoch, **dict(logs))) + "\n")
+
+        return [scalar_log, custom_callback]
+
+    # ------------------------------------------------------------------ batching (net.py:500-511, 578-607)
+    def _loss_inputs_generator(self, labeled_spectrogram_batches: Iterable[List[LabeledSpectrogram]]) -> Iterable[
+        Tuple[Dict, ndarray]]:
+        for labeled_spectrogram_batch in labeled_spectrogram_batches:
+            yield self._inputs_for_loss_net(labeled_spectrogram_batch)
+
+    def _inputs_for_loss_net(self, labeled_spectrogram_batch: List[LabeledSpectrogram]) -> Tuple[
+        Dict[str, ndarray], ndarray]:
+        batch_size = len(labeled_spectrogram_batch)
+        dummy_labels_for_dummy_loss_function = zeros((batch_size,))
+        training_input_dictionary = self._input_dictionary_for_loss_net(
+            labeled_spectrogram_batch=labeled_spectrogram_batch)
+        return training_input_dictionary, dummy_labels_for_dummy_loss_function
+
+    def _input_batch_and_prediction_lengths(self, spectrograms: List[ndarray]) -> Tuple[ndarray, List[int]]:
+        """Zero-pad to the longest utterance; prediction length = T // ratio (floor, net.py:582)
+        although the tower emits ceil(T / ratio) frames.  Padded frames are NOT masked."""
+        batch_size = len(spectrograms)
+        input_size_per_time_step = spectrograms[0].shape[1]
+        input_lengths = [spectrogram.shape[0] for spectrogram in spectrograms]
+        prediction_lengths = [s // self.input_to_prediction_length_ratio for s in input_lengths]
+        input_batch = zeros((batch_size, max(input_lengths), input_size_per_time_step), dtype=numpy.float32)
+        for index, spectrogram in enumerate(spectrograms):
+            input_batch[index, :spectrogram.shape[0], :spectrogram.shape[1]] = spectrogram
+        return input_batch, prediction_lengths
+
+    def _prediction_length_batch(self, prediction_lengths: List[int], batch_size: int) -> ndarray:
+        return reshape(array(prediction_lengths), (batch_size, 1))
+
+    def _input_dictionary_for_loss_net(self, labeled_spectrogram_batch: List[LabeledSpectrogram]) -> Dict[str, ndarray]:
+        spectrograms = [x.z_normalized_transposed_spectrogram() for x in labeled_spectrogram_batch]
+        labels = [x.label for x in labeled_spectrogram_batch]
+        input_batch, prediction_lengths = self._input_batch_and_prediction_lengths(spectrograms)
+        label_lengths = reshape(array([len(label) for label in labels]), (len(labeled_spectrogram_batch), 1))
+        return {
+            Wav2Letter.InputNames.input_batch: input_batch,
+            Wav2Letter.InputNames.prediction_lengths: self._prediction_length_batch(prediction_lengths,
+                                                                                    batch_size=len(spectrograms)),
+            Wav2Letter.InputNames.label_batch: self.grapheme_encoding.encode_label_batch(labels),
+            Wav2Letter.InputNames.label_lengths: label_lengths,
+            'keras_learning_phase': array([True])
+        }

@@ -559,7 +559,99 @@ static bool test_adam() {
   return report("adam 3 steps (update)", compare(gu, ru, 2e-3), gu, ru);
 }
 
+// ---------------- perf mode: every conv kernel at the bench shapes, CUDA-event timed ----------------
+struct PerfLayer {
+  const char* name;
+  int cin, cout, k, s;
+};
+static bool run_perf(int B, int T, int prec, int iters) {
+  const PerfLayer layers[] = {{"striding_conv", 128, 250, 48, 2}, {"inner_conv", 250, 250, 7, 1},
+                              {"big_conv_1", 250, 2000, 32, 1},   {"big_conv_2", 2000, 2000, 1, 1},
+                              {"output_conv", 2000, 29, 1, 1}};
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  int t_in = T;
+  printf("perf: B=%d T=%d prec=%d (%s)\n", B, T, prec, prec == 1 ? "bf16" : "bf16x2 3-term");
+  for (const auto& L : layers) {
+    int T_out, pad_l;
+    same_pad(t_in, L.k, L.s, &T_out, &pad_l);
+    const int T_alloc = (t_in + L.s - 1) / L.s * L.s;
+    const int cip = round64(L.cin), cop = round64(L.cout);
+    Dev<uint16_t> xp(static_cast<size_t>(B) * T_alloc * cip * prec), yp(static_cast<size_t>(B) * T_out * cop * prec),
+        dxp(static_cast<size_t>(B) * T_alloc * cip * prec);
+    Dev<uint16_t> wf(static_cast<size_t>(L.k) * cop * cip * prec), wd(static_cast<size_t>(L.k) * cop * cip * prec);
+    Dev<float> bias(cop), dw(static_cast<size_t>(L.k) * cop * cip), db(cop), probs(static_cast<size_t>(B) * T_out * 32),
+        logp(static_cast<size_t>(B) * T_out * 64);
+    // fill operands with small random bf16 values (bit patterns via a float pack)
+    {
+      auto hx = randn(static_cast<size_t>(B) * t_in * L.cin, 1.f);
+      Dev<float> dx(hx.size());
+      dx.up(hx);
+      SLCK(sl_pack_activation(dx.p, xp.p, B, t_in, L.cin, T_alloc, cip, prec, nullptr));
+      auto hy = randn(static_cast<size_t>(B) * T_out * L.cout, 1.f);
+      Dev<float> dy(hy.size());
+      dy.up(hy);
+      SLCK(sl_pack_activation(dy.p, yp.p, B, T_out, L.cout, T_out, cop, prec, nullptr));
+      auto hw = randn(static_cast<size_t>(L.k) * L.cin * L.cout, 0.05f);
+      Dev<float> dwk(hw.size());
+      dwk.up(hw);
+      SLCK(sl_pack_weights(dwk.p, wf.p, wd.p, L.k, L.cin, L.cout, cip, cop, prec, nullptr));
+    }
+    const double flops = 2.0 * L.k * L.cin * L.cout * static_cast<double>(T_out) * B;
+    const bool is_out = L.cout == 29;
+    auto time_it = [&](const char* what, auto fn) -> bool {
+      for (int i = 0; i < 2; ++i)
+        if (fn() != 0) return false;
+      CK(cudaEventRecord(e0));
+      for (int i = 0; i < iters; ++i)
+        if (fn() != 0) return false;
+      CK(cudaEventRecord(e1));
+      CK(cudaEventSynchronize(e1));
+      float ms = 0;
+      CK(cudaEventElapsedTime(&ms, e0, e1));
+      ms /= iters;
+      printf("  %-14s %-6s %8.3f ms  %7.1f TFLOP/s (algorithmic)\n", L.name, what, ms, flops / ms / 1e9);
+      return true;
+    };
+    bool ok = true;
+    Dev<uint16_t> y2(static_cast<size_t>(B) * T_out * cop * prec);
+    if (is_out)
+      ok &= time_it("fwd", [&] {
+        return sl_conv1d_fwd(xp.p, wf.p, bias.p, nullptr, probs.p, nullptr, logp.p, B, t_in, T_alloc, L.cin, L.cout,
+                             L.k, L.s, SL_ACT_SOFTMAX, prec, nullptr);
+      });
+    else
+      ok &= time_it("fwd", [&] {
+        return sl_conv1d_fwd(xp.p, wf.p, bias.p, y2.p, nullptr, nullptr, nullptr, B, t_in, T_alloc, L.cin, L.cout, L.k,
+                             L.s, SL_ACT_RELU, prec, nullptr);
+      });
+    if (L.s == 1)
+      ok &= time_it("dgrad", [&] {
+        return sl_conv1d_dgrad(yp.p, wd.p, xp.p, dxp.p, B, t_in, L.cin, L.cout, L.k, prec, nullptr);
+      });
+    ok &= time_it("wgrad", [&] {
+      return sl_conv1d_wgrad(xp.p, yp.p, dw.p, db.p, B, t_in, T_alloc, L.cin, L.cout, L.k, L.s, prec, 1, nullptr);
+    });
+    if (!ok) {
+      char buf[1024];
+      sl_last_error(buf, sizeof buf);
+      printf("  perf failure: %s\n", buf);
+      return false;
+    }
+    SLCK(sl_sync_check());
+    t_in = T_out;
+  }
+  return true;
+}
+
 int main(int argc, char** argv) {
+  if (argc > 1 && std::string(argv[1]) == "perf") {
+    const int B = argc > 2 ? atoi(argv[2]) : 64;
+    const int T = argc > 3 ? atoi(argv[3]) : 1251;
+    const int prec = argc > 4 ? atoi(argv[4]) : 1;
+    return run_perf(B, T, prec, 5) ? 0 : 1;
+  }
   const std::string filter = argc > 1 ? argv[1] : "";
   auto want = [&](const char* n) { return filter.empty() || std::string(n).find(filter) != std::string::npos; };
   int dev_count = 0;
