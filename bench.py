@@ -196,6 +196,7 @@ def run_ours(args):
     net = Wav2Letter(128, alphabet, main_filter_count=main, out_filter_count=out, compute_dtype=dtype,
                      device=device, seed=0)
     tower = net.tower
+    tower.overlap_backward = bool(args.overlap_backward)
     inputs, _ = net._inputs_for_loss_net(examples)
     names = Wav2Letter.InputNames
     host_x = torch.from_numpy(inputs[names.input_batch]).pin_memory()
@@ -342,6 +343,7 @@ def main():
     parser.add_argument("--batch-per-gpu", type=int, default=None)
     parser.add_argument("--dtype", default=None, choices=["bf16", "bf16x2"])
     parser.add_argument("--no-cpu-baseline", action="store_true")
+    parser.add_argument("--overlap-backward", type=int, default=0, help="run wgrad on a side stream (experiment)")
     args = parser.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -62,32 +62,34 @@ int sl_unpack_activation(const void* x_packed, float* x, int B, int T, int C,
                          int T_alloc, int c_pad, int prec, void* stream);
 
 /* Keras kernel layout (k, Cin, Cout) fp32 (net.py:251-255,264-265) ->
- *   w_fwd  (k, cout_pad, [hi cin_pad | lo cin_pad]) bf16   B operand of fwd
- *   w_dgrad(k, cin_pad,  [hi cout_pad| lo cout_pad]) bf16  B operand of dgrad (may be NULL) */
-int sl_pack_weights(const float* w_keras, void* w_fwd, void* w_dgrad, int k,
-                    int Cin, int Cout, int cin_pad, int cout_pad, int prec,
-                    void* stream);
+ *   w_fwd (k, cout_pad, [hi cin_pad | lo cin_pad]) bf16: the B operand of the forward GEMM
+ *   (K-major) and, read MN-major, of the input-gradient GEMM — one copy serves both. */
+int sl_pack_weights(const float* w_keras, void* w_fwd, int k, int Cin, int Cout,
+                    int cin_pad, int cout_pad, int prec, void* stream);
 
 /* ---- Conv1D tower (replaces keras.layers.Conv1D(padding="same"), net.py:304-305) ---- */
 
 /* y = act(bias + conv1d_same(x, w)).  x_packed (B,T_in_alloc,..), w_fwd from
  * sl_pack_weights, bias fp32 (Cout).  T_out = ceil(T_in/stride); pad_l per TF
  * SAME rule is computed inside.
- *  act NONE/RELU : y_packed (B,T_out,[hi cout_pad|lo]) bf16
+ *  act NONE/RELU : y_packed (B,T_out,[hi cout_pad|lo]) bf16; optional
+ *                  relu_mask_out (B,T_out,cout_pad/8) bytes: bit c%8 of byte c/8
+ *                  is set iff y[b,t,c] > 0 — the ReLU derivative kept for backward
  *  act SOFTMAX   : probs (B,T_out,Cout) fp32  [net.py:328-330]; optional
  *                  logits (B,T_out,Cout) fp32 (pre-softmax, for parity tests) and
  *                  logp (B,T_out,64) fp32 = log_softmax(log(p+1e-8)), the
  *                  quantity tf.nn.ctc_loss consumes after K.ctc_batch_cost. */
 int sl_conv1d_fwd(const void* x_packed, const void* w_fwd, const float* bias,
-                  void* y_packed, float* probs, float* logits, float* logp,
-                  int B, int T_in, int T_in_alloc, int Cin, int Cout, int k,
-                  int stride, int act, int prec, void* stream);
+                  void* y_packed, void* relu_mask_out, float* probs, float* logits,
+                  float* logp, int B, int T_in, int T_in_alloc, int Cin, int Cout,
+                  int k, int stride, int act, int prec, void* stream);
 
 /* dX = conv1d_same_backward_input(dY, w) masked by the ReLU of the layer below
  * (TF autodiff of net.py:304-305; stride 1 only — the strided first layer needs
- * no dX).  x_saved = packed output of the layer below (post-ReLU), or NULL. */
-int sl_conv1d_dgrad(const void* dy_packed, const void* w_dgrad,
-                    const void* x_saved, void* dx_packed, int B, int T,
+ * no dX).  relu_mask = the relu_mask_out the layer below wrote in its forward
+ * pass ((B,T,cin_pad/8) bytes), or NULL for a linear layer below. */
+int sl_conv1d_dgrad(const void* dy_packed, const void* w_fwd,
+                    const void* relu_mask, void* dx_packed, int B, int T,
                     int Cin, int Cout, int k, int prec, void* stream);
 
 /* dW (k,cout_pad,cin_pad) fp32 += sum_{b,t} x[b,t*s+j-pad_l,ci]*dy[b,t,co];
@@ -105,10 +107,9 @@ int sl_weights_keras_to_internal(const float* w_keras, float* w_int, int k,
 int sl_weights_internal_to_keras(const float* w_int, float* w_keras, int k,
                                  int Cin, int Cout, int cin_pad, int cout_pad,
                                  void* stream);
-/* internal fp32 master (k,cout_pad,cin_pad) -> packed bf16 w_fwd / w_dgrad */
-int sl_pack_weights_internal(const float* w_int, void* w_fwd, void* w_dgrad,
-                             int k, int cin_pad, int cout_pad, int prec,
-                             void* stream);
+/* internal fp32 master (k,cout_pad,cin_pad) -> packed bf16 w_fwd */
+int sl_pack_weights_internal(const float* w_int, void* w_fwd, int k, int cin_pad,
+                             int cout_pad, int prec, void* stream);
 
 /* ---- CTC (replaces K.ctc_batch_cost -> tf.nn.ctc_loss, net.py:402-406) ---- */
 
@@ -143,6 +144,16 @@ int sl_ctc_greedy_decode(const float* probs, const int32_t* input_len,
 int sl_adam_step(float* p, const float* g, float* m, float* v, size_t n,
                  float lr, float beta1, float beta2, float eps, int t,
                  void* stream);
+
+/* Same update fused with the refresh of the bf16 operands: for each of the n_layers kernels
+ * placed at floats [w_begin, w_end) of the flat buffer (internal layout, rows of cin_pad),
+ * the updated weights are re-emitted into w_fwd[i] (NULL = skip).  The *_host arrays are
+ * HOST arrays of length n_layers (<= 16). */
+int sl_adam_step_fused(float* p, const float* g, float* m, float* v, size_t n,
+                       const size_t* w_begin_host, const size_t* w_end_host,
+                       void* const* w_fwd_host, const int* cin_pad_host, int n_layers,
+                       int prec, float lr, float beta1, float beta2, float eps, int t,
+                       void* stream);
 
 #ifdef __cplusplus
 }

@@ -24,7 +24,9 @@ int pack_activation_launch(const float*, void*, int, int, int, int, int, int, cu
 int unpack_activation_launch(const void*, float*, int, int, int, int, int, int, cudaStream_t);
 int keras_to_internal_launch(const float*, float*, int, int, int, int, int, cudaStream_t);
 int internal_to_keras_launch(const float*, float*, int, int, int, int, int, cudaStream_t);
-int pack_weights_internal_launch(const float*, void*, void*, int, int, int, int, cudaStream_t);
+int pack_weights_internal_launch(const float*, void*, int, int, int, int, cudaStream_t);
+int adam_fused_launch(float*, const float*, float*, float*, size_t, const size_t*, const size_t*, void* const*,
+                      const int*, int, int, float, float, float, float, int, cudaStream_t);
 int bias_grad_launch(const void*, float*, size_t, int, int, int, cudaStream_t);
 int adam_launch(float*, const float*, float*, float*, size_t, float, float, float, float, int,
                 cudaStream_t);
@@ -138,31 +140,31 @@ int sl_weights_internal_to_keras(const float* w_int, float* w_keras, int k, int 
   return internal_to_keras_launch(w_int, w_keras, k, Cin, Cout, cin_pad, cout_pad,
                                   static_cast<cudaStream_t>(stream));
 }
-int sl_pack_weights_internal(const float* w_int, void* w_fwd, void* w_dgrad, int k, int cin_pad,
-                             int cout_pad, int prec, void* stream) {
-  SL_REQUIRE(w_int, "null pointer");
+int sl_pack_weights_internal(const float* w_int, void* w_fwd, int k, int cin_pad, int cout_pad, int prec,
+                             void* stream) {
+  SL_REQUIRE(w_int && w_fwd, "null pointer");
   SL_REQUIRE(cin_pad % 64 == 0 && cout_pad % 64 == 0 && k > 0, "bad shape");
-  return pack_weights_internal_launch(w_int, w_fwd, w_dgrad, k, cin_pad, cout_pad, planes_of(prec),
+  return pack_weights_internal_launch(w_int, w_fwd, k, cin_pad, cout_pad, planes_of(prec),
                                       static_cast<cudaStream_t>(stream));
 }
 
-int sl_pack_weights(const float* w_keras, void* w_fwd, void* w_dgrad, int k, int Cin, int Cout,
-                    int cin_pad, int cout_pad, int prec, void* stream) {
+int sl_pack_weights(const float* w_keras, void* w_fwd, int k, int Cin, int Cout, int cin_pad, int cout_pad,
+                    int prec, void* stream) {
   // convenience path (tests, weight loading): via a temporary internal master copy
-  SL_REQUIRE(w_keras, "null pointer");
+  SL_REQUIRE(w_keras && w_fwd, "null pointer");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   float* tmp = nullptr;
   const size_t bytes = static_cast<size_t>(k) * cin_pad * cout_pad * sizeof(float);
   SL_CUDA(cudaMallocAsync(&tmp, bytes, s));
   int rc = keras_to_internal_launch(w_keras, tmp, k, Cin, Cout, cin_pad, cout_pad, s);
-  if (rc == 0) rc = pack_weights_internal_launch(tmp, w_fwd, w_dgrad, k, cin_pad, cout_pad, planes_of(prec), s);
+  if (rc == 0) rc = pack_weights_internal_launch(tmp, w_fwd, k, cin_pad, cout_pad, planes_of(prec), s);
   cudaFreeAsync(tmp, s);
   return rc;
 }
 
 int sl_conv1d_fwd(const void* x_packed, const void* w_fwd, const float* bias, void* y_packed,
-                  float* probs, float* logits, float* logp, int B, int T_in, int T_in_alloc, int Cin,
-                  int Cout, int k, int stride, int act, int prec, void* stream) {
+                  void* relu_mask_out, float* probs, float* logits, float* logp, int B, int T_in,
+                  int T_in_alloc, int Cin, int Cout, int k, int stride, int act, int prec, void* stream) {
   SL_REQUIRE(x_packed && w_fwd, "null pointer");
   SL_REQUIRE(B > 0 && T_in > 0 && Cin > 0 && Cout > 0 && k > 0, "bad shape");
   SL_REQUIRE(stride == 1 || stride == 2, "stride must be 1 or 2");
@@ -210,15 +212,17 @@ int sl_conv1d_fwd(const void* x_packed, const void* w_fwd, const float* bias, vo
     p.relu = act == SL_ACT_RELU;
     p.y_planes = planes;
     p.y_lo_off = cout_pad;
+    p.mask_bits_out = static_cast<uint8_t*>(relu_mask_out);
+    p.mask_row_bytes = cout_pad / 8;
     rc = make_act_map3(&p.tmY, y_packed, planes * cout_pad, T_out, B, 128);
     if (rc) return rc;
   }
-  return conv_gemm_launch(p, bn, epi, num_sms(), static_cast<cudaStream_t>(stream));
+  return conv_gemm_launch(p, bn, epi, false, num_sms(), static_cast<cudaStream_t>(stream));
 }
 
-int sl_conv1d_dgrad(const void* dy_packed, const void* w_dgrad, const void* x_saved, void* dx_packed,
+int sl_conv1d_dgrad(const void* dy_packed, const void* w_fwd, const void* relu_mask, void* dx_packed,
                     int B, int T, int Cin, int Cout, int k, int prec, void* stream) {
-  SL_REQUIRE(dy_packed && w_dgrad && dx_packed, "null pointer");
+  SL_REQUIRE(dy_packed && w_fwd && dx_packed, "null pointer");
   SL_REQUIRE(B > 0 && T > 0 && Cin > 0 && Cout > 0 && k > 0, "bad shape");
   SL_REQUIRE(prec == SL_PREC_BF16 || prec == SL_PREC_BF16X2, "bad precision");
   const int planes = planes_of(prec);
@@ -232,7 +236,9 @@ int sl_conv1d_dgrad(const void* dy_packed, const void* w_dgrad, const void* x_sa
   SL_REQUIRE(cin_pad % bn == 0 && (bn == 64 || bn == 128 || bn == 256), "unsupported channel count");
   int rc = make_act_load_map(&p.tmA, dy_packed, planes * cout_pad, 1, T, B, 128);
   if (rc) return rc;
-  rc = make_weight_map(&p.tmB, w_dgrad, planes * cout_pad, cin_pad, k, bn);
+  // B[n = ci][k = co] comes straight from the forward layout (k, cout_pad, [hi|lo] cin_pad):
+  // boxes of 64 co rows x 64 ci, consumed MN-major
+  rc = make_weight_map(&p.tmB, w_fwd, planes * cin_pad, cout_pad, k, 64);
   if (rc) return rc;
   rc = make_act_map3(&p.tmY, dx_packed, planes * cin_pad, T, B, 128);
   if (rc) return rc;
@@ -244,7 +250,7 @@ int sl_conv1d_dgrad(const void* dy_packed, const void* w_dgrad, const void* x_sa
   p.chunks = cout_pad / 64;
   p.terms = planes == 2 ? 3 : 1;
   p.a_lo_off = cout_pad;
-  p.b_lo_off = cout_pad;
+  p.b_lo_off = cin_pad;
   p.stride = 1;
   p.pad_l = k - 1 - pad_l;  // dX[u] = sum_j dY[u + pad_l - j] W[j]  
   p.tap_reverse = 1;
@@ -253,10 +259,9 @@ int sl_conv1d_dgrad(const void* dy_packed, const void* w_dgrad, const void* x_sa
   p.relu = 0;
   p.y_planes = planes;
   p.y_lo_off = cin_pad;
-  p.mask = reinterpret_cast<const __nv_bfloat16*>(x_saved);
-  p.mask_row_stride = static_cast<long long>(planes) * cin_pad;
-  p.mask_utt_stride = p.mask_row_stride * T;
-  return conv_gemm_launch(p, bn, EPI_PACKED, num_sms(), static_cast<cudaStream_t>(stream));
+  p.mask_bits_in = static_cast<const uint8_t*>(relu_mask);
+  p.mask_row_bytes = cin_pad / 8;
+  return conv_gemm_launch(p, bn, EPI_PACKED, true, num_sms(), static_cast<cudaStream_t>(stream));
 }
 
 int sl_conv1d_wgrad(const void* x_packed, const void* dy_packed, float* dw, float* db, int B, int T_in,
@@ -296,14 +301,35 @@ int sl_conv1d_wgrad(const void* x_packed, const void* dy_packed, float* dw, floa
   p.cout_pad = cout_pad;
   p.cin_pad = cin_pad;
   p.dy_c_total = planes * cout_pad;
-  // K split: aim for >= 4 waves of work units, each with at least 8 pipeline steps
+  {
+    // fp32 view of dW for the TMA (reduce-)store epilogue
+    const uint64_t dims[3] = {static_cast<uint64_t>(cin_pad), static_cast<uint64_t>(cout_pad),
+                              static_cast<uint64_t>(k)};
+    const uint64_t strides[2] = {static_cast<uint64_t>(cin_pad) * 4, static_cast<uint64_t>(cin_pad) * cout_pad * 4};
+    const uint32_t box[3] = {32, 128, 1};
+    rc = make_tmap(&p.tmDW, TMAP_F32, 3, dw, dims, strides, box, true);
+    if (rc) return rc;
+  }
+  // K split: minimise  waves x (pipeline steps per unit + epilogue)  over the split count
   const int base_units = k * p.m_tiles * p.n_tiles;
   const int k_total = B * p.tchunks;
-  int ksplit = (4 * num_sms() + base_units - 1) / base_units;
-  if (ksplit > k_total / 8) ksplit = k_total / 8;
-  if (ksplit < 1) ksplit = 1;
-  // no empty splits: ceil(k_total / ksplit) * (ksplit - 1) < k_total
-  while (ksplit > 1 && ((k_total + ksplit - 1) / ksplit) * (ksplit - 1) >= k_total) --ksplit;
+  int ksplit = 1;
+  {
+    const int sms = num_sms();
+    const double step_cycles = 512.0 * bn / 256.0 * p.terms;  // 4 MMAs of 128 x bn x 16 per stage
+    const double epilogue_cycles = 1500.0 * bn / 32.0 / 8.0 + 2000.0;
+    double best = 1e300;
+    for (int ks = 1; ks <= k_total && ks <= 256; ++ks) {
+      const int per = (k_total + ks - 1) / ks;
+      if (per * (ks - 1) >= k_total) continue;  // would leave an empty split
+      const int waves = (base_units * ks + sms - 1) / sms;
+      const double cost = waves * (per * step_cycles + epilogue_cycles);
+      if (cost < best * 0.98) {  // prefer fewer splits (less reduction traffic) on near ties
+        best = cost;
+        ksplit = ks;
+      }
+    }
+  }
   p.ksplit = ksplit;
   p.use_atomics = (ksplit > 1 || accumulate) ? 1 : 0;
   const size_t dw_bytes = static_cast<size_t>(k) * cout_pad * cin_pad * sizeof(float);
@@ -349,6 +375,25 @@ int sl_adam_step(float* p, const float* g, float* m, float* v, size_t n, float l
              "Adam buffers must be 16-byte aligned");
   if (n == 0) return SL_OK;
   return adam_launch(p, g, m, v, n, lr, beta1, beta2, eps, t, static_cast<cudaStream_t>(stream));
+}
+
+int sl_adam_step_fused(float* p, const float* g, float* m, float* v, size_t n, const size_t* w_begin_host,
+                       const size_t* w_end_host, void* const* w_fwd_host, const int* cin_pad_host, int n_layers,
+                       int prec, float lr, float beta1, float beta2, float eps, int t, void* stream) {
+  SL_REQUIRE(p && g && m && v && w_begin_host && w_end_host && w_fwd_host && cin_pad_host, "null pointer");
+  SL_REQUIRE(t >= 1, "Adam step counter is 1-based");
+  SL_REQUIRE(n % 4 == 0, "flat buffer length must be a multiple of 4");
+  SL_REQUIRE(n_layers >= 0 && n_layers <= 16, "at most 16 layers");
+  SL_REQUIRE((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) |
+              reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) % 16 == 0,
+             "Adam buffers must be 16-byte aligned");
+  for (int i = 0; i < n_layers; ++i)
+    SL_REQUIRE(w_begin_host[i] % 4 == 0 && w_end_host[i] % 4 == 0 && cin_pad_host[i] % 64 == 0 &&
+                   w_end_host[i] <= n && w_begin_host[i] <= w_end_host[i],
+               "bad layer placement");
+  if (n == 0) return SL_OK;
+  return adam_fused_launch(p, g, m, v, n, w_begin_host, w_end_host, w_fwd_host, cin_pad_host, n_layers,
+                           planes_of(prec), lr, beta1, beta2, eps, t, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

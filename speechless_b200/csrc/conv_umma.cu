@@ -48,7 +48,9 @@ struct Cfg {
       kStages * STAGE_BYTES + 2 * STAGING_BYTES + BN * 4 + 256 + 1024 /*align slack*/;
 };
 
-template <int BN, int EPI>
+// BMN: the B operand is MN-major (input gradient: B[n = ci][k = co] read straight from the
+// forward weight layout (k, co, ci), ci contiguous) instead of K-major.
+template <int BN, int EPI, bool BMN>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   using C = Cfg<BN>;
@@ -127,7 +129,16 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
               uint8_t* b_s = a_s + A_BYTES;
               mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
               tma_load_4d(&p.tmA, &full_bar[stage], a_s, a_c, par, t0 + q, b);
-              tma_load_3d(&p.tmB, &full_bar[stage], b_s, b_c, n0, wtap);
+              if (BMN) {
+                // 64 contraction rows (co) x 64 output channels (ci) per box
+                const int n_c = n0 + (term == 1 ? p.b_lo_off : 0);
+#pragma unroll
+                for (int i = 0; i < BN / 64; ++i)
+                  tma_load_3d(&p.tmB, &full_bar[stage], b_s + i * (BLOCK_K * 128), n_c + 64 * i,
+                              chunk * BLOCK_K, wtap);
+              } else {
+                tma_load_3d(&p.tmB, &full_bar[stage], b_s, b_c, n0, wtap);
+              }
               if (++stage == C::kStages) {
                 stage = 0;
                 phase ^= 1;
@@ -139,7 +150,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BN, 0, 0);
+    constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BN, 0, BMN ? 1 : 0);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
@@ -158,7 +169,10 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             const uint64_t da = make_smem_desc_sw128(a_addr + k * UMMA_K * 2, 16, 1024);
-            const uint64_t db = make_smem_desc_sw128(b_addr + k * UMMA_K * 2, 16, 1024);
+            // MN-major B: 16 contraction rows = two 8-row swizzle atoms (2048 B); 64-channel
+            // groups are BLOCK_K * 128 B apart (leading byte offset)
+            const uint64_t db = BMN ? make_smem_desc_sw128(b_addr + k * 2048, BLOCK_K * 128, 1024)
+                                    : make_smem_desc_sw128(b_addr + k * UMMA_K * 2, 16, 1024);
             umma_bf16(tmem_d, da, db, idesc, (ks | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
@@ -224,23 +238,27 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
 #pragma unroll
             for (int i = 0; i < 64; ++i) v[i] = fmaxf(v[i], 0.f);
           }
-          if (p.mask != nullptr && row_valid) {
-            // ReLU backward: zero where the saved (post-ReLU) activation is not > 0
-            const uint4* mp = reinterpret_cast<const uint4*>(
-                p.mask + static_cast<size_t>(b) * p.mask_utt_stride +
-                static_cast<size_t>(t) * p.mask_row_stride + n0 + c * 64);
+          if (p.mask_bits_in != nullptr && row_valid) {
+            // ReLU backward: keep the gradient only where the forward output was > 0
+            const uint2 mb = __ldg(reinterpret_cast<const uint2*>(
+                p.mask_bits_in + (static_cast<size_t>(b) * p.T_out + t) * p.mask_row_bytes +
+                ((n0 + c * 64) >> 3)));
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const uint4 m = __ldg(mp + j);
-              const uint32_t w[4] = {m.x, m.y, m.z, m.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                // bf16 > 0  <=>  sign bit clear and magnitude non-zero
-                const uint32_t lo16 = w[e] & 0xFFFFu, hi16 = w[e] >> 16;
-                if (!(lo16 != 0 && (lo16 & 0x8000u) == 0)) v[j * 8 + e * 2] = 0.f;
-                if (!(hi16 != 0 && (hi16 & 0x8000u) == 0)) v[j * 8 + e * 2 + 1] = 0.f;
-              }
+            for (int i = 0; i < 32; ++i) {
+              if (!((mb.x >> i) & 1u)) v[i] = 0.f;
+              if (!((mb.y >> i) & 1u)) v[32 + i] = 0.f;
             }
+          }
+          if (p.mask_bits_out != nullptr && row_valid) {
+            uint2 mb = make_uint2(0u, 0u);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              mb.x |= (v[i] > 0.f ? 1u : 0u) << i;
+              mb.y |= (v[32 + i] > 0.f ? 1u : 0u) << i;
+            }
+            *reinterpret_cast<uint2*>(p.mask_bits_out +
+                                      (static_cast<size_t>(b) * p.T_out + t) * p.mask_row_bytes +
+                                      ((n0 + c * 64) >> 3)) = mb;
           }
           for (int plane = 0; plane < p.y_planes; ++plane) {
             uint32_t packed[32];
@@ -340,37 +358,40 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   }
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool BMN>
 int launch(const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
   using C = Cfg<BN>;
   static bool configured = false;  // benign race: attribute set is idempotent
   if (!configured) {
-    SL_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, EPI>,
+    SL_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, EPI, BMN>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     configured = true;
   }
   const int num_tiles = p.B * p.m_tiles_per_utt * p.n_tiles;
   const int grid = num_tiles < num_sms ? num_tiles : num_sms;
-  conv_gemm_kernel<BN, EPI><<<grid, kThreads, C::SMEM_BYTES, stream>>>(p);
+  conv_gemm_kernel<BN, EPI, BMN><<<grid, kThreads, C::SMEM_BYTES, stream>>>(p);
   SL_CUDA(cudaGetLastError());
   return 0;
 }
 
 }  // namespace
 
-int conv_gemm_launch(const ConvGemmParams& p, int block_n, int epi, int num_sms,
+int conv_gemm_launch(const ConvGemmParams& p, int block_n, int epi, bool b_mn_major, int num_sms,
                      cudaStream_t stream) {
   if (epi == EPI_SOFTMAX) {
-    SL_REQUIRE(block_n == 64, "softmax epilogue needs a 64-wide tile");
-    return launch<64, EPI_SOFTMAX>(p, num_sms, stream);
+    SL_REQUIRE(block_n == 64 && !b_mn_major, "softmax epilogue needs a 64-wide K-major tile");
+    return launch<64, EPI_SOFTMAX, false>(p, num_sms, stream);
   }
   switch (block_n) {
     case 64:
-      return launch<64, EPI_PACKED>(p, num_sms, stream);
+      return b_mn_major ? launch<64, EPI_PACKED, true>(p, num_sms, stream)
+                        : launch<64, EPI_PACKED, false>(p, num_sms, stream);
     case 128:
-      return launch<128, EPI_PACKED>(p, num_sms, stream);
+      return b_mn_major ? launch<128, EPI_PACKED, true>(p, num_sms, stream)
+                        : launch<128, EPI_PACKED, false>(p, num_sms, stream);
     case 256:
-      return launch<256, EPI_PACKED>(p, num_sms, stream);
+      return b_mn_major ? launch<256, EPI_PACKED, true>(p, num_sms, stream)
+                        : launch<256, EPI_PACKED, false>(p, num_sms, stream);
     default:
       set_error("conv_gemm: unsupported block_n");
       return 1;

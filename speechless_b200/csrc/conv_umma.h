@@ -9,7 +9,8 @@ enum { EPI_PACKED = 0, EPI_SOFTMAX = 1 };
 // Forward / input-gradient implicit GEMM (conv_umma.cu)
 struct ConvGemmParams {
   CUtensorMap tmA;  // activations, rank 4 {C_total, stride, T_alloc/stride, B}, box {64,1,128,1}
-  CUtensorMap tmB;  // weights, rank 3 {K_total (contiguous), N rows, taps}, box {64, BN, 1}
+  CUtensorMap tmB;  // weights (k, cout, cin), rank 3 {cin_total, cout, taps}: box {64, BN, 1} (fwd: K-major B)
+                    // or box {64, 64, 1} (dgrad: MN-major B, 64 cout rows of contraction)
   CUtensorMap tmY;  // packed bf16 output, rank 3 {C_total, T_out, B}, box {64,128,1}
   int B;
   int T_out;
@@ -28,22 +29,25 @@ struct ConvGemmParams {
   int relu;
   int y_planes;  // 1 or 2 (hi | lo)
   int y_lo_off;
-  const __nv_bfloat16* mask;  // saved post-ReLU activation of the layer below (dgrad) or null
-  long long mask_row_stride;
-  long long mask_utt_stride;
+  // ReLU sign bitmask, 1 bit per (frame, channel), rows of mask_row_bytes = C_pad / 8 bytes:
+  // written by the forward epilogue (y > 0), consumed by the dgrad epilogue of the layer above
+  const uint8_t* mask_bits_in;
+  uint8_t* mask_bits_out;
+  int mask_row_bytes;
   float* probs;   // EPI_SOFTMAX outputs
   float* logits;
   float* logp;
   int V;
 };
 
-int conv_gemm_launch(const ConvGemmParams& p, int block_n, int epi, int num_sms,
+int conv_gemm_launch(const ConvGemmParams& p, int block_n, int epi, bool b_mn_major, int num_sms,
                      cudaStream_t stream);
 
 // Weight-gradient GEMM (wgrad_umma.cu): both operands MN-major, contraction over time
 struct WgradParams {
   CUtensorMap tmDY;  // rank 3 {Cout_total, T_out, B}, box {64, 64, 1}
   CUtensorMap tmX;   // rank 4 {Cin_total, stride, T_alloc/stride, B}, box {64, 1, 64, 1}
+  CUtensorMap tmDW;  // fp32 rank 3 {cin_pad, cout_pad, taps}, box {32, 128, 1}: TMA (reduce-)store target
   float* dw;         // (taps, cout_pad, cin_pad) fp32
   int B;
   int T_out;
@@ -60,7 +64,7 @@ struct WgradParams {
   int cout_pad;
   int cin_pad;
   int dy_c_total;  // channel extent of the dY tensor map (an OOB coordinate for zero tiles)
-  int use_atomics;  // 1: red.add into dw, 0: plain stores
+  int use_atomics;  // 1: TMA reduce-add into dw (split K / accumulate), 0: plain TMA store
 };
 
 int wgrad_launch(const WgradParams& p, int block_n, int num_sms, cudaStream_t stream);

@@ -97,56 +97,115 @@ __global__ void pack_w_fwd_kernel(const float* __restrict__ wi, __nv_bfloat16* _
   }
 }
 
-// internal fp32 (k,cout_pad,cin_pad) -> w_dgrad bf16 (k,cin_pad,planes*cout_pad): per-tap
-// transpose through a 32x33 smem tile (both sides coalesced)
-__global__ void pack_w_dgrad_kernel(const float* __restrict__ wi, __nv_bfloat16* __restrict__ wd,
-                                    int cin_pad, int cout_pad, int planes) {
-  __shared__ float tile[32][33];
-  const int j = blockIdx.z;
-  const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
-  const float* src = wi + static_cast<size_t>(j) * cout_pad * cin_pad;
-  for (int r = threadIdx.y; r < 32; r += blockDim.y)
-    tile[r][threadIdx.x] = src[static_cast<size_t>(co0 + r) * cin_pad + ci0 + threadIdx.x];
-  __syncthreads();
-  __nv_bfloat16* dst = wd + static_cast<size_t>(j) * cin_pad * (static_cast<size_t>(planes) * cout_pad);
-  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-    const float v = tile[threadIdx.x][r];  // (co = co0 + tx, ci = ci0 + r)
-    __nv_bfloat16* row = dst + static_cast<size_t>(ci0 + r) * (static_cast<size_t>(planes) * cout_pad);
-    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-    row[co0 + threadIdx.x] = hi;
-    if (planes == 2) row[cout_pad + co0 + threadIdx.x] = __float2bfloat16_rn(v - __bfloat162float(hi));
+// db[c] += sum over rows of dy (hi + lo planes).  256 threads; each thread owns one 16-byte
+// vector (8 channels) of the packed row and walks rows with 4 loads in flight; row lanes are
+// folded through smem and one thread per channel group issues the atomics.
+__global__ void bias_grad_kernel(const __nv_bfloat16* __restrict__ dy, float* __restrict__ db,
+                                 size_t rows, int c_pad, int planes, int C) {
+  __shared__ float red[256 * 8];
+  const int vpr = planes * c_pad / 8;              // 16-byte vectors per row
+  const int tpr = vpr < 256 ? vpr : 256;           // threads across one row
+  const int rpp = 256 / tpr;                       // rows per pass of the block
+  const int lane_col = threadIdx.x % tpr, lane_row = threadIdx.x / tpr;
+  const uint4* base = reinterpret_cast<const uint4*>(dy);
+  for (int cg = lane_col; cg < vpr; cg += tpr) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const size_t stride = static_cast<size_t>(gridDim.x) * rpp;
+    // (widths that do not divide 256 leave the last threads without a row lane)
+    size_t r = lane_row < rpp ? static_cast<size_t>(blockIdx.x) * rpp + lane_row : rows;
+    auto add = [&](const uint4& q) {
+      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        acc[2 * e] += __uint_as_float(w[e] << 16);
+        acc[2 * e + 1] += __uint_as_float(w[e] & 0xffff0000u);
+      }
+    };
+    for (; r + 3 * stride < rows; r += 4 * stride) {
+      const uint4 q0 = __ldg(base + r * vpr + cg);
+      const uint4 q1 = __ldg(base + (r + stride) * vpr + cg);
+      const uint4 q2 = __ldg(base + (r + 2 * stride) * vpr + cg);
+      const uint4 q3 = __ldg(base + (r + 3 * stride) * vpr + cg);
+      add(q0);
+      add(q1);
+      add(q2);
+      add(q3);
+    }
+    for (; r < rows; r += stride) add(__ldg(base + r * vpr + cg));
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 8; ++e) red[threadIdx.x * 8 + e] = acc[e];
+    __syncthreads();
+    if (lane_row == 0) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float s = 0.f;
+        for (int rr = 0; rr < rpp; ++rr) s += red[(rr * tpr + lane_col) * 8 + e];
+        const int channel = (cg * 8 + e) % c_pad;  // hi and lo planes fold onto the same channel
+        if (channel < C) atomicAdd(db + channel, s);
+      }
+    }
   }
 }
 
-// db[c] (+)= sum over rows of dy (hi + lo planes).  blockDim = (32, 8): 32 channel pairs
-// x 8 row lanes; grid = (c_pad/64, row_splits)
-__global__ void bias_grad_kernel(const __nv_bfloat16* __restrict__ dy, float* __restrict__ db,
-                                 size_t rows, int c_pad, int planes, int C) {
-  __shared__ float red[8][64];
-  const int c = blockIdx.x * 64 + threadIdx.x * 2;
-  const size_t row_elems = static_cast<size_t>(planes) * c_pad;
-  float s0 = 0.f, s1 = 0.f;
-  for (size_t r = blockIdx.y * static_cast<size_t>(blockDim.y) + threadIdx.y; r < rows;
-       r += static_cast<size_t>(gridDim.y) * blockDim.y) {
-    const __nv_bfloat16* p = dy + r * row_elems + c;
-    const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(p);
-    s0 += __bfloat162float(h.x);
-    s1 += __bfloat162float(h.y);
-    if (planes == 2) {
-      const __nv_bfloat162 l = *reinterpret_cast<const __nv_bfloat162*>(p + c_pad);
-      s0 += __bfloat162float(l.x);
-      s1 += __bfloat162float(l.y);
-    }
-  }
-  red[threadIdx.y][threadIdx.x * 2] = s0;
-  red[threadIdx.y][threadIdx.x * 2 + 1] = s1;
-  __syncthreads();
-  if (threadIdx.y == 0) {
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      float s = 0.f;
-      for (int r = 0; r < 8; ++r) s += red[r][threadIdx.x * 2 + e];
-      if (c + e < C) atomicAdd(db + c + e, s);
+// per-layer placement of the kernels inside the flat fp32 parameter buffer
+struct AdamLayer {
+  unsigned long long begin, end;  // float offsets of the layer's kernel [begin, end)
+  __nv_bfloat16* w_fwd;           // (rows, planes * cin_pad) bf16 or null
+  int cin_pad;
+};
+struct AdamLayers {
+  AdamLayer layer[16];
+  int count;
+  int planes;
+};
+
+// Keras-2 Adam over the whole flat buffer, fused with the refresh of the bf16
+// tensor-core operands: the master layout (k, cout_pad, cin_pad) is the forward operand's
+// layout, so each float4 of updated weights is re-emitted as bf16 (hi | lo planes) in place.
+__global__ void adam_fused_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                  float* __restrict__ m, float* __restrict__ v, size_t n4, float lr_t,
+                                  float b1, float b2, float eps, const __grid_constant__ AdamLayers L) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    const float4 gg = reinterpret_cast<const float4*>(g)[i];
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+#define SL_ADAM1(f)                            \
+  mm.f = b1 * mm.f + (1.f - b1) * gg.f;        \
+  vv.f = b2 * vv.f + (1.f - b2) * gg.f * gg.f; \
+  pp.f = pp.f - lr_t * mm.f / (sqrtf(vv.f) + eps);
+    SL_ADAM1(x) SL_ADAM1(y) SL_ADAM1(z) SL_ADAM1(w)
+#undef SL_ADAM1
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+    const unsigned long long idx = static_cast<unsigned long long>(i) * 4;
+    for (int l = 0; l < L.count; ++l) {
+      if (idx >= L.layer[l].begin && idx < L.layer[l].end) {
+        if (L.layer[l].w_fwd != nullptr) {
+          const unsigned long long local = idx - L.layer[l].begin;
+          const int cin_pad = L.layer[l].cin_pad;
+          const unsigned long long row = local / cin_pad;
+          const int c = static_cast<int>(local - row * cin_pad);
+          __nv_bfloat16* dst = L.layer[l].w_fwd + row * (static_cast<size_t>(L.planes) * cin_pad) + c;
+          const __nv_bfloat162 h0 = __floats2bfloat162_rn(pp.x, pp.y), h1 = __floats2bfloat162_rn(pp.z, pp.w);
+          uint2 hv;
+          hv.x = *reinterpret_cast<const uint32_t*>(&h0);
+          hv.y = *reinterpret_cast<const uint32_t*>(&h1);
+          *reinterpret_cast<uint2*>(dst) = hv;
+          if (L.planes == 2) {
+            const __nv_bfloat162 l0 = __floats2bfloat162_rn(pp.x - __bfloat162float(h0.x), pp.y - __bfloat162float(h0.y));
+            const __nv_bfloat162 l1 = __floats2bfloat162_rn(pp.z - __bfloat162float(h1.x), pp.w - __bfloat162float(h1.y));
+            uint2 lv;
+            lv.x = *reinterpret_cast<const uint32_t*>(&l0);
+            lv.y = *reinterpret_cast<const uint32_t*>(&l1);
+            *reinterpret_cast<uint2*>(dst + cin_pad) = lv;
+          }
+        }
+        break;
+      }
     }
   }
 }
@@ -222,30 +281,42 @@ int internal_to_keras_launch(const float* wi, float* wk, int k, int Cin, int Cou
   SL_CUDA(cudaGetLastError());
   return 0;
 }
-int pack_weights_internal_launch(const float* wi, void* wf, void* wd, int k, int cin_pad,
-                                 int cout_pad, int planes, cudaStream_t s) {
-  if (wf != nullptr) {
-    const size_t rows = static_cast<size_t>(k) * cout_pad;
-    pack_w_fwd_kernel<<<grid_for(rows * (cin_pad / 2), 256), 256, 0, s>>>(
-        wi, reinterpret_cast<__nv_bfloat16*>(wf), rows, cin_pad, planes);
-    SL_CUDA(cudaGetLastError());
-  }
-  if (wd != nullptr) {
-    dim3 grid(cin_pad / 32, cout_pad / 32, k), block(32, 8);
-    pack_w_dgrad_kernel<<<grid, block, 0, s>>>(wi, reinterpret_cast<__nv_bfloat16*>(wd), cin_pad,
-                                               cout_pad, planes);
-    SL_CUDA(cudaGetLastError());
-  }
+int pack_weights_internal_launch(const float* wi, void* wf, int k, int cin_pad, int cout_pad,
+                                 int planes, cudaStream_t s) {
+  const size_t rows = static_cast<size_t>(k) * cout_pad;
+  pack_w_fwd_kernel<<<grid_for(rows * (cin_pad / 2), 256), 256, 0, s>>>(
+      wi, reinterpret_cast<__nv_bfloat16*>(wf), rows, cin_pad, planes);
+  SL_CUDA(cudaGetLastError());
   return 0;
 }
 int bias_grad_launch(const void* dy, float* db, size_t rows, int c_pad, int planes, int C,
                      cudaStream_t s) {
-  size_t splits = (rows + 255) / 256;
-  if (splits > 256) splits = 256;
-  if (splits < 1) splits = 1;
-  dim3 grid(c_pad / 64, static_cast<unsigned>(splits)), block(32, 8);
-  bias_grad_kernel<<<grid, block, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(dy), db, rows,
-                                          c_pad, planes, C);
+  const int vpr = planes * c_pad / 8;
+  const int rpp = vpr < 256 ? 256 / vpr : 1;
+  size_t blocks = (rows + static_cast<size_t>(rpp) * 8 - 1) / (static_cast<size_t>(rpp) * 8);
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  if (blocks < 1) blocks = 1;
+  bias_grad_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dy), db, rows, c_pad, planes, C);
+  SL_CUDA(cudaGetLastError());
+  return 0;
+}
+int adam_fused_launch(float* p, const float* g, float* m, float* v, size_t n, const size_t* begins,
+                      const size_t* ends, void* const* w_fwd, const int* cin_pads, int n_layers,
+                      int planes, float lr, float b1, float b2, float eps, int t, cudaStream_t s) {
+  AdamLayers L;
+  L.count = n_layers;
+  L.planes = planes;
+  for (int i = 0; i < n_layers; ++i) {
+    L.layer[i].begin = begins[i];
+    L.layer[i].end = ends[i];
+    L.layer[i].w_fwd = reinterpret_cast<__nv_bfloat16*>(w_fwd[i]);
+    L.layer[i].cin_pad = cin_pads[i];
+  }
+  const double lr_t = static_cast<double>(lr) * sqrt(1.0 - pow(static_cast<double>(b2), t)) /
+                      (1.0 - pow(static_cast<double>(b1), t));
+  adam_fused_kernel<<<grid_for(n / 4, 256), 256, 0, s>>>(p, g, m, v, n / 4, static_cast<float>(lr_t), b1,
+                                                         b2, eps, L);
   SL_CUDA(cudaGetLastError());
   return 0;
 }

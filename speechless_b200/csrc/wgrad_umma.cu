@@ -11,8 +11,10 @@
 //   D[128 co x BN ci] (TMEM fp32) += dY_tile^T[128 co x 64 t] * X_tile[64 t x BN ci]
 //
 // Work unit = (tap, 128-filter tile, BN-channel tile, K split); the K range of a unit
-// is a contiguous run of (utterance, 64-frame chunk) pairs.  Partial sums of different
-// K splits meet in HBM through fp32 red.add (dW is zeroed by the caller).
+// is a contiguous run of (utterance, 64-frame chunk) pairs.  The epilogue stages the fp32
+// accumulator through swizzled smem, 32 columns at a time, and hands it to TMA: a plain
+// tensor store, or cp.reduce.async.bulk.tensor (.add) when several K splits / layers of
+// accumulation meet in the same dW tile (dW is zeroed by the caller in that case).
 #include "conv_umma.h"
 
 namespace sl {
@@ -29,6 +31,8 @@ constexpr int BOX_BYTES = KT * 128;          // one 64-frame x 64-channel box
 constexpr int A_BYTES = 2 * BOX_BYTES;       // 128 filters
 constexpr int LBO = BOX_BYTES;               // byte stride between 64-channel groups
 constexpr int SBO = 1024;                    // byte stride between 8-frame groups
+constexpr int STAGING_BYTES = BLOCK_M * 128; // 128 filters x 32 fp32 columns
+constexpr int kEpiThreads = 128;
 
 template <int BN>
 struct WCfg {
@@ -36,7 +40,7 @@ struct WCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int kStages = BN >= 256 ? 4 : 6;
   static constexpr int TMEM_COLS = 2 * BN;
-  static constexpr int SMEM_BYTES = kStages * STAGE_BYTES + 256 + 1024;
+  static constexpr int SMEM_BYTES = kStages * STAGE_BYTES + 2 * STAGING_BYTES + 256 + 1024;
 };
 
 template <int BN>
@@ -46,7 +50,8 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::STAGE_BYTES);
+  uint8_t* staging = smem + C::kStages * C::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + 2 * STAGING_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + C::kStages;
   uint64_t* tmem_full = bars + 2 * C::kStages;
@@ -59,6 +64,7 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.tmDY);
     prefetch_tmap(&p.tmX);
+    prefetch_tmap(&p.tmDW);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::kStages; ++s) {
@@ -80,9 +86,8 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
 
-  // unit -> (split, n_tile, m_tile, tap): split fastest so that the CTAs that share a
-  // weight tile's red.add target run at different times only by accident, while CTAs
-  // running together read the same dY / X slabs from L2.
+  // unit -> (tap fastest, then m_tile, n_tile, split): CTAs running together work on the
+  // same K range, i.e. read the same dY / X slabs from L2, and reduce into different dW tiles.
   const int num_units = p.taps * p.m_tiles * p.n_tiles * p.ksplit;
   const int k_total = p.B * p.tchunks;  // (utterance, frame chunk) pairs
   const int k_per = (k_total + p.ksplit - 1) / p.ksplit;
@@ -188,7 +193,9 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
   } else if (warp >= 4) {
     const int ew = warp - 4;
     const int row = ew * 32 + lane;
+    const int et = threadIdx.x - 128;
     int it = 0;
+    uint32_t store_count = 0;
     for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
       int tap, mt, nt, k_begin, k_end;
       decode(unit, tap, mt, nt, k_begin, k_end);
@@ -197,35 +204,47 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
       mbar_wait(&tmem_full[as], aphase);
       tcgen05_fence_after();
       const bool has_data = k_end > k_begin;
-      const int co = mt * BLOCK_M + row;
-      const bool row_valid = co < p.cout_pad && has_data;
-      float* dst = p.dw + (static_cast<size_t>(tap) * p.cout_pad + co) * p.cin_pad + nt * BN;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) +
                              static_cast<uint32_t>(as * BN);
+      if (has_data) {
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        if (has_data) {
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
           tmem_ld_32x32(taddr + c * 32, r);
           tmem_ld_wait();
-        }
-        if (row_valid) {
-          if (p.use_atomics) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) atomicAdd(dst + c * 32 + i, __uint_as_float(r[i]));
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              *reinterpret_cast<float4*>(dst + c * 32 + i * 4) =
-                  make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
-                              __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+          if (c == BN / 32 - 1) {
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[as]);
           }
+          uint8_t* sbuf = staging + (store_count & 1) * STAGING_BYTES;
+          if (et == 0) tma_wait_group_read<1>();
+          named_bar_sync(1, kEpiThreads);
+          uint8_t* rowp = sbuf + row * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int phys = j ^ (row & 7);
+            *reinterpret_cast<uint4*>(rowp + phys * 16) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1, kEpiThreads);
+          if (et == 0) {
+            // rows beyond cout_pad (output_conv: 64 of 128) are clipped by the tensor map
+            if (p.use_atomics)
+              tma_reduce_add_3d(&p.tmDW, sbuf, nt * BN + c * 32, mt * BLOCK_M, tap);
+            else
+              tma_store_3d(&p.tmDW, sbuf, nt * BN + c * 32, mt * BLOCK_M, tap);
+            tma_commit_group();
+          }
+          ++store_count;
         }
+      } else {
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[as]);
       }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[as]);
     }
+    if (et == 0) tma_wait_group<0>();
   }
 
   tcgen05_fence_before();

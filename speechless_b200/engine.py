@@ -9,8 +9,8 @@ HBM layout
   params / grads / adam_m / adam_v : one flat fp32 buffer each; per layer the kernel in the
         *internal master layout* (k, cout_pad, cin_pad) followed by the bias (cout_pad).
         Channel pads are zero and stay zero (their gradients are exactly zero).
-  w_fwd[l]  (k, cout_pad, planes*cin_pad)  bf16   B operand of the forward implicit GEMM
-  w_dgrad[l](k, cin_pad,  planes*cout_pad) bf16   B operand of the input-gradient GEMM
+  w_fwd[l]  (k, cout_pad, planes*cin_pad)  bf16   B operand of the forward implicit GEMM (K-major)
+        and of the input-gradient GEMM (the same bytes read MN-major) — refreshed by the fused Adam kernel
   act[l]    (B, T', planes*cout_pad)       bf16   post-ReLU output of layer l (kept for backward)
   probs (B,T',V) fp32, logp (B,T',64) fp32, CTC lattices alpha/beta (B,T',S_pad) fp32.
 """
@@ -102,8 +102,10 @@ class _Workspace:
             t, _ = same_padding(t, layer.kernel, layer.stride)
             self.t_out.append(t)
         self.Tp = self.t_out[-1]
+        self.masks: List[torch.Tensor] = []  # ReLU sign bits of act[l], 1 bit per (frame, channel)
         for layer, t_out in zip(tower.layers[:-1], self.t_out[:-1]):
             self.acts.append(torch.empty((B, t_out, planes * layer.cout_pad), dtype=torch.bfloat16, device=dev))
+            self.masks.append(torch.empty((B, t_out, layer.cout_pad // 8), dtype=torch.uint8, device=dev))
         V = tower.layers[-1].cout
         self.probs = torch.empty((B, self.Tp, V), dtype=torch.float32, device=dev)
         self.logits = torch.empty((B, self.Tp, V), dtype=torch.float32, device=dev)
@@ -158,13 +160,15 @@ class ConvTower:
             self.adam_v: Optional[torch.Tensor] = None
             self.w_fwd = [torch.zeros((l.kernel, l.cout_pad, self.planes * l.cin_pad), dtype=torch.bfloat16,
                                       device=device) for l in layers]
-            self.w_dgrad: List[Optional[torch.Tensor]] = [None] * len(layers)
         self._workspaces: Dict[Tuple[int, int], _Workspace] = {}
         self._current: Optional[_Workspace] = None
         self.launches = 0  # kernels launched through the C-ABI (bench.py reports it)
         # optional per-kernel timing: list of (kind, layer name, start event, stop event) on the
         # launching stream; bench.py turns it on to measure roofline fractions live
         self.profile: Optional[list] = None
+        self.overlap_backward = False
+        self._adam_tables = None
+        self._side_stream = None
 
     # ------------------------------------------------------------------ helpers
     @property
@@ -231,21 +235,16 @@ class ConvTower:
                                                         self.stream))
             return [w_keras.cpu().numpy(), self._b(self.params, layer)[:layer.cout].cpu().numpy()]
 
-    def repack(self, indices: Optional[Sequence[int]] = None, with_dgrad: Optional[bool] = None) -> None:
-        """fp32 master -> bf16 tensor-core operands (after a weight load or an optimizer step)."""
+    def repack(self, indices: Optional[Sequence[int]] = None) -> None:
+        """fp32 master -> bf16 tensor-core operands (after a weight load; the optimizer step
+        refreshes them itself)."""
         with torch.cuda.device(self.device):
             for index in (range(len(self.layers)) if indices is None else indices):
                 layer = self.layers[index]
-                need_dgrad = self.w_dgrad[index] is not None if with_dgrad is None else with_dgrad
-                need_dgrad = need_dgrad and index > 0
-                if need_dgrad and self.w_dgrad[index] is None:
-                    self.w_dgrad[index] = torch.zeros((layer.kernel, layer.cin_pad, self.planes * layer.cout_pad),
-                                                      dtype=torch.bfloat16, device=self.device)
                 check(self.lib.sl_pack_weights_internal(ptr(self._w(self.params, layer)), ptr(self.w_fwd[index]),
-                                                        ptr(self.w_dgrad[index]) if need_dgrad else None,
                                                         layer.kernel, layer.cin_pad, layer.cout_pad, self.precision,
                                                         self.stream))
-                self.launches += 2 if need_dgrad else 1
+                self.launches += 1
 
     # ------------------------------------------------------------------ forward
     def workspace(self, B: int, T: int) -> _Workspace:
@@ -298,15 +297,16 @@ class ConvTower:
                 bias = self._b(self.params, layer)
                 if layer.activation == "softmax":
                     self._timed("fwd", layer.name, lambda: self.lib.sl_conv1d_fwd(
-                        ptr(x), ptr(self.w_fwd[index]), ptr(bias), None, ptr(ws.probs),
+                        ptr(x), ptr(self.w_fwd[index]), ptr(bias), None, None, ptr(ws.probs),
                         ptr(ws.logits) if want_logits else None, ptr(ws.logp), ws.B, t_in, t_alloc, layer.cin,
                         layer.cout, layer.kernel, layer.stride, ACT_SOFTMAX, self.precision, self.stream))
                 else:
                     y = ws.acts[index]
                     act = ACT_RELU if layer.activation == "relu" else ACT_NONE
+                    mask = ws.masks[index] if layer.activation == "relu" else None
                     self._timed("fwd", layer.name, lambda: self.lib.sl_conv1d_fwd(
-                        ptr(x), ptr(self.w_fwd[index]), ptr(bias), ptr(y), None, None, None, ws.B, t_in, t_alloc,
-                        layer.cin, layer.cout, layer.kernel, layer.stride, act, self.precision, self.stream))
+                        ptr(x), ptr(self.w_fwd[index]), ptr(bias), ptr(y), ptr(mask), None, None, None, ws.B, t_in,
+                        t_alloc, layer.cin, layer.cout, layer.kernel, layer.stride, act, self.precision, self.stream))
                     x, t_in, t_alloc = y, ws.t_out[index], ws.t_out[index]
                 self.launches += 1
         return ws
@@ -377,50 +377,79 @@ class ConvTower:
                 self.grads = torch.zeros_like(self.params)
                 self.adam_m = torch.zeros_like(self.params)
                 self.adam_v = torch.zeros_like(self.params)
-            missing = [i for i in range(max(1, self.first_trainable() + 1), len(self.layers))
-                       if self.w_dgrad[i] is None]
-            if missing:
-                self.repack(missing, with_dgrad=True)
 
     def backward(self, ws: Optional[_Workspace] = None) -> None:
-        """Fill self.grads from ws.dz_packed (set by ctc(want_grad=True))."""
+        """Fill self.grads from ws.dz_packed (set by ctc(want_grad=True)).
+
+        The chain dY_l -> dgrad_l -> dY_{l-1} runs on the current stream; with
+        `overlap_backward` the weight gradients (which only consume dY_l and the saved
+        activations) run on a side stream, so the partial last wave of one persistent kernel
+        is filled by CTAs of the other."""
         ws = ws or self._current
         self.ensure_training_state()
         first = self.first_trainable()
         with torch.cuda.device(self.device):
+            main = torch.cuda.current_stream(self.device)
+            side = None
+            if self.overlap_backward and self.profile is None:
+                if self._side_stream is None:
+                    self._side_stream = torch.cuda.Stream(device=self.device)
+                side = self._side_stream
             self.grads.zero_()
             dy = ws.dz_packed
             flip = 0
+            wgrad_done = None  # event: the wgrad that still reads the buffer the next dgrad overwrites
             for index in range(len(self.layers) - 1, first - 1, -1):
                 layer = self.layers[index]
                 x = ws.x_packed if index == 0 else ws.acts[index - 1]
                 t_in = ws.T if index == 0 else ws.t_out[index - 1]
                 t_alloc = ws.T_alloc if index == 0 else t_in
-                self._timed("wgrad", layer.name, lambda: self.lib.sl_conv1d_wgrad(
+                launch_wgrad = lambda: self._timed("wgrad", layer.name, lambda: self.lib.sl_conv1d_wgrad(
                     ptr(x), ptr(dy), ptr(self._w(self.grads, layer)), ptr(self._b(self.grads, layer)), ws.B, t_in,
                     t_alloc, layer.cin, layer.cout, layer.kernel, layer.stride, self.precision, 1, self.stream))
+                previous_wgrad_done = wgrad_done
+                if side is None:
+                    launch_wgrad()
+                else:
+                    side.wait_event(main.record_event())
+                    with torch.cuda.stream(side):
+                        launch_wgrad()
+                        wgrad_done = side.record_event()
                 self.launches += 2
                 if index > first:
                     below = self.layers[index - 1]
                     dx = ws.dact[flip].view(-1)[:ws.B * t_in * self.planes * below.cout_pad].view(
                         ws.B, t_in, self.planes * below.cout_pad)
-                    mask = ws.acts[index - 1] if below.activation == "relu" else None
+                    mask = ws.masks[index - 1] if below.activation == "relu" else None
+                    if previous_wgrad_done is not None:
+                        main.wait_event(previous_wgrad_done)  # it reads the buffer dx aliases
                     self._timed("dgrad", layer.name, lambda: self.lib.sl_conv1d_dgrad(
-                        ptr(dy), ptr(self.w_dgrad[index]), ptr(mask), ptr(dx), ws.B, t_in, layer.cin, layer.cout,
+                        ptr(dy), ptr(self.w_fwd[index]), ptr(mask), ptr(dx), ws.B, t_in, layer.cin, layer.cout,
                         layer.kernel, self.precision, self.stream))
                     self.launches += 1
                     dy = dx
                     flip ^= 1
+            if side is not None:
+                main.wait_stream(side)
 
     def adam_step(self, lr: float, beta_1: float, beta_2: float, epsilon: float, iteration: int) -> None:
         """Keras-2 Adam over the whole flat buffer (frozen layers have zero gradients and zero
-        moments, so they do not move), then refresh the bf16 operands."""
+        moments, so they do not move) fused with the refresh of the bf16 operands."""
+        import ctypes
+        if self._adam_tables is None:
+            n = len(self.layers)
+            begins = (ctypes.c_size_t * n)(*[l.w_offset for l in self.layers])
+            ends = (ctypes.c_size_t * n)(*[l.w_offset + l.w_size for l in self.layers])
+            targets = (ctypes.c_void_p * n)(*[w.data_ptr() for w in self.w_fwd])
+            cin_pads = (ctypes.c_int * n)(*[l.cin_pad for l in self.layers])
+            self._adam_tables = (begins, ends, targets, cin_pads)
+        begins, ends, targets, cin_pads = self._adam_tables
         with torch.cuda.device(self.device):
-            self._timed("adam", "adam", lambda: self.lib.sl_adam_step(
-                ptr(self.params), ptr(self.grads), ptr(self.adam_m), ptr(self.adam_v), self.param_count, lr, beta_1,
-                beta_2, epsilon, iteration, self.stream))
+            self._timed("adam", "adam", lambda: self.lib.sl_adam_step_fused(
+                ptr(self.params), ptr(self.grads), ptr(self.adam_m), ptr(self.adam_v), self.param_count, begins, ends,
+                targets, cin_pads, len(self.layers), self.precision, lr, beta_1, beta_2, epsilon, iteration,
+                self.stream))
             self.launches += 1
-            self.repack(range(self.first_trainable(), len(self.layers)))
 
     def sync(self) -> None:
         torch.cuda.current_stream(self.device).synchronize()

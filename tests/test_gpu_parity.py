@@ -79,15 +79,20 @@ def test_conv_layer_matches_oracle(env, B, T, cin, cout, k, stride, prec):
     yp = torch.zeros((B, t_out, prec * cop), dtype=torch.bfloat16, device=dev)
     y = torch.zeros((B, t_out, cout), dtype=torch.float32, device=dev)
     check(lib.sl_pack_activation(ptr(xd), ptr(xp), B, T, cin, t_alloc, cip, prec, None))
-    check(lib.sl_pack_weights(ptr(wd), ptr(wf), None, k, cin, cout, cip, cop, prec, None))
-    check(lib.sl_conv1d_fwd(ptr(xp), ptr(wf), ptr(bd), ptr(yp), None, None, None, B, T, t_alloc, cin, cout, k, stride,
-                            1, prec, None))
+    check(lib.sl_pack_weights(ptr(wd), ptr(wf), k, cin, cout, cip, cop, prec, None))
+    mask = torch.zeros((B, t_out, cop // 8), dtype=torch.uint8, device=dev)
+    check(lib.sl_conv1d_fwd(ptr(xp), ptr(wf), ptr(bd), ptr(yp), ptr(mask), None, None, None, B, T, t_alloc, cin, cout,
+                            k, stride, 1, prec, None))
     check(lib.sl_unpack_activation(ptr(yp), ptr(y), B, t_out, cout, t_out, cop, prec, None))
     check(lib.sl_sync_check())
     want = np.maximum(env.oracle.conv1d_same(x.astype(np.float64), w.astype(np.float64), bias.astype(np.float64),
                                              stride), 0)
     # bf16x2: ~16 mantissa bits in, 16 out; bf16: 8 bits in/out (reported, not a parity claim)
     assert rel_err(y.cpu().numpy(), want) < (1e-4 if prec == 2 else 2e-2)
+    # the ReLU sign bitmask kept for backward agrees with the stored activation
+    bits = np.unpackbits(mask.cpu().numpy(), axis=2, bitorder="little")[..., :cout].astype(bool)
+    stored = y.cpu().numpy()
+    assert (bits == (stored > 0))[np.abs(want) > 1e-6].all()
     # channel padding of the packed output stays exactly zero
     assert float(yp.view(B, t_out, prec, cop)[..., cout:].abs().max()) == 0.0 or cout == cop
 

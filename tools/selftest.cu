@@ -233,7 +233,7 @@ static bool run_conv_fwd(const ConvCase& cc, int prec) {
   Dev<uint16_t> xp(static_cast<size_t>(B) * T_alloc * cip * prec);
   Dev<uint16_t> wf(static_cast<size_t>(k) * cop * cip * prec);
   SLCK(sl_pack_activation(dx.p, xp.p, B, T, Cin, T_alloc, cip, prec, nullptr));
-  SLCK(sl_pack_weights(dw.p, wf.p, nullptr, k, Cin, Cout, cip, cop, prec, nullptr));
+  SLCK(sl_pack_weights(dw.p, wf.p, k, Cin, Cout, cip, cop, prec, nullptr));
 
   // reference: bf16 mode multiplies bf16-rounded operands exactly; bf16x2 ~ fp32 operands
   std::vector<double> ref = prec == 1 ? cpu_conv(round_bf16(x), round_bf16(w), bias, B, T, Cin, Cout, k, s)
@@ -242,7 +242,7 @@ static bool run_conv_fwd(const ConvCase& cc, int prec) {
   char label[128];
   if (cc.act == SL_ACT_SOFTMAX) {
     Dev<float> probs(static_cast<size_t>(B) * T_out * Cout), logits(probs.n), logp(static_cast<size_t>(B) * T_out * 64);
-    SLCK(sl_conv1d_fwd(xp.p, wf.p, dbias.p, nullptr, probs.p, logits.p, logp.p, B, T, T_alloc, Cin, Cout,
+    SLCK(sl_conv1d_fwd(xp.p, wf.p, dbias.p, nullptr, nullptr, probs.p, logits.p, logp.p, B, T, T_alloc, Cin, Cout,
                        k, s, SL_ACT_SOFTMAX, prec, nullptr));
     SLCK(sl_sync_check());
     auto gl = logits.down(), gp = probs.down(), glp = logp.down();
@@ -271,8 +271,9 @@ static bool run_conv_fwd(const ConvCase& cc, int prec) {
     if (cc.act == SL_ACT_RELU)
       for (auto& v : ref) v = std::max(v, 0.0);
     Dev<uint16_t> yp(static_cast<size_t>(B) * T_out * cop * prec);
+    Dev<uint8_t> mask(static_cast<size_t>(B) * T_out * cop / 8);
     Dev<float> y(static_cast<size_t>(B) * T_out * Cout);
-    SLCK(sl_conv1d_fwd(xp.p, wf.p, dbias.p, yp.p, nullptr, nullptr, nullptr, B, T, T_alloc, Cin, Cout, k, s,
+    SLCK(sl_conv1d_fwd(xp.p, wf.p, dbias.p, yp.p, mask.p, nullptr, nullptr, nullptr, B, T, T_alloc, Cin, Cout, k, s,
                        cc.act, prec, nullptr));
     SLCK(sl_unpack_activation(yp.p, y.p, B, T_out, Cout, T_out, cop, prec, nullptr));
     SLCK(sl_sync_check());
@@ -280,7 +281,20 @@ static bool run_conv_fwd(const ConvCase& cc, int prec) {
     snprintf(label, sizeof label, "%s p%d", cc.name, prec);
     // bf16 output rounding: 2^-9 relative; split: 2^-17
     ok &= report(label, compare(got, ref, prec == 1 ? 6e-3 : 5e-5), got, ref);
-    // padded output channels must be exactly zero when bias pad is zero
+    if (cc.act == SL_ACT_RELU) {
+      // the ReLU bitmask must agree with the sign of the stored activation
+      auto mb = mask.down();
+      size_t bad = 0;
+      for (size_t r = 0; r < static_cast<size_t>(B) * T_out; ++r)
+        for (int c = 0; c < Cout; ++c) {
+          const bool bit = (mb[r * (cop / 8) + c / 8] >> (c % 8)) & 1;
+          const bool pos = got[r * Cout + c] > 0.f;
+          // values that round to zero in bf16 may legitimately differ
+          if (bit != pos && std::fabs(ref[r * Cout + c]) > 1e-30) ++bad;
+        }
+      printf("  %-26s relu bitmask mismatches %zu\n", label, bad);
+      ok &= bad == 0;
+    }
   }
   return ok;
 }
@@ -296,14 +310,18 @@ static bool run_dgrad(const ConvCase& cc, int prec) {
   ddy.up(dy);
   dw.up(w);
   dxs.up(xs);
-  Dev<uint16_t> dyp(static_cast<size_t>(B) * T * cop * prec), xsp(static_cast<size_t>(B) * T * cip * prec),
-      dxp(static_cast<size_t>(B) * T * cip * prec);
+  Dev<uint16_t> dyp(static_cast<size_t>(B) * T * cop * prec), dxp(static_cast<size_t>(B) * T * cip * prec);
   Dev<uint16_t> wd(static_cast<size_t>(k) * cip * cop * prec);
   Dev<float> dxo(static_cast<size_t>(B) * T * Cin);
   SLCK(sl_pack_activation(ddy.p, dyp.p, B, T, Cout, T, cop, prec, nullptr));
-  SLCK(sl_pack_activation(dxs.p, xsp.p, B, T, Cin, T, cip, prec, nullptr));
-  SLCK(sl_pack_weights(dw.p, nullptr, wd.p, k, Cin, Cout, cip, cop, prec, nullptr));
-  SLCK(sl_conv1d_dgrad(dyp.p, wd.p, cc.act == SL_ACT_RELU ? xsp.p : nullptr, dxp.p, B, T, Cin, Cout, k, prec,
+  std::vector<uint8_t> hmask(static_cast<size_t>(B) * T * cip / 8, 0);
+  for (size_t r = 0; r < static_cast<size_t>(B) * T; ++r)
+    for (int c = 0; c < Cin; ++c)
+      if (xs[r * Cin + c] > 0.f) hmask[r * (cip / 8) + c / 8] |= static_cast<uint8_t>(1u << (c % 8));
+  Dev<uint8_t> dmask(hmask.size());
+  dmask.up(hmask);
+  SLCK(sl_pack_weights(dw.p, wd.p, k, Cin, Cout, cip, cop, prec, nullptr));
+  SLCK(sl_conv1d_dgrad(dyp.p, wd.p, cc.act == SL_ACT_RELU ? dmask.p : nullptr, dxp.p, B, T, Cin, Cout, k, prec,
                        nullptr));
   SLCK(sl_unpack_activation(dxp.p, dxo.p, B, T, Cin, T, cip, prec, nullptr));
   SLCK(sl_sync_check());
@@ -311,7 +329,7 @@ static bool run_dgrad(const ConvCase& cc, int prec) {
                        : cpu_dgrad(dy, w, B, T, Cin, Cout, k);
   if (cc.act == SL_ACT_RELU)
     for (size_t i = 0; i < ref.size(); ++i)
-      if (!(bf16r(xs[i]) > 0.f)) ref[i] = 0.0;
+      if (!(xs[i] > 0.f)) ref[i] = 0.0;
   auto got = dxo.down();
   char label[128];
   snprintf(label, sizeof label, "%s dgrad p%d", cc.name, prec);
@@ -556,7 +574,36 @@ static bool test_adam() {
     gu[i] = got[i] - p[i];
     ru[i] = rp[i] - p[i];
   }
-  return report("adam 3 steps (update)", compare(gu, ru, 2e-3), gu, ru);
+  bool ok = report("adam 3 steps (update)", compare(gu, ru, 2e-3), gu, ru);
+  // fused variant: same update + bf16 re-emission of two "layers" (rows of 64 / 128 channels)
+  const size_t n2 = 64 * 64 + 16 + 32 * 128;
+  auto p2 = randn(n2), g2 = randn(n2, 0.1f);
+  Dev<float> fp(n2), fg(n2), fm(n2), fv(n2);
+  fp.up(p2);
+  fg.up(g2);
+  Dev<uint16_t> w0(64 * 64 * 2), w1(32 * 128 * 2);
+  const size_t begins[2] = {0, 64 * 64 + 16}, ends[2] = {64 * 64, n2};
+  void* targets[2] = {w0.p, w1.p};
+  const int cin_pads[2] = {64, 128};
+  SLCK(sl_adam_step_fused(fp.p, fg.p, fm.p, fv.p, n2, begins, ends, targets, cin_pads, 2, SL_PREC_BF16X2, 1e-4f,
+                          0.9f, 0.999f, 1e-8f, 1, nullptr));
+  Dev<float> back0(64 * 64), back1(32 * 128);
+  SLCK(sl_unpack_activation(w0.p, back0.p, 1, 64, 64, 64, 64, SL_PREC_BF16X2, nullptr));
+  SLCK(sl_unpack_activation(w1.p, back1.p, 1, 32, 128, 32, 128, SL_PREC_BF16X2, nullptr));
+  SLCK(sl_sync_check());
+  auto newp = fp.down();
+  auto bk0 = back0.down(), bk1 = back1.down();
+  std::vector<double> want0(newp.begin(), newp.begin() + 64 * 64), want1(newp.begin() + 64 * 64 + 16, newp.end());
+  ok &= report("adam fused: w_fwd layer 0", compare(bk0, want0, 2e-5), bk0, want0);
+  ok &= report("adam fused: w_fwd layer 1", compare(bk1, want1, 2e-5), bk1, want1);
+  std::vector<double> wantp(n2);
+  const double lr1 = 1e-4 * std::sqrt(1 - 0.999) / (1 - 0.9);
+  for (size_t i = 0; i < n2; ++i) {
+    const double mi = 0.1 * g2[i], vi = 0.001 * static_cast<double>(g2[i]) * g2[i];
+    wantp[i] = p2[i] - lr1 * mi / (std::sqrt(vi) + 1e-8);
+  }
+  ok &= report("adam fused: params", compare(newp, wantp, 1e-6), newp, wantp);
+  return ok;
 }
 
 // ---------------- perf mode: every conv kernel at the bench shapes, CUDA-event timed ----------------
@@ -596,7 +643,7 @@ static bool run_perf(int B, int T, int prec, int iters) {
       auto hw = randn(static_cast<size_t>(L.k) * L.cin * L.cout, 0.05f);
       Dev<float> dwk(hw.size());
       dwk.up(hw);
-      SLCK(sl_pack_weights(dwk.p, wf.p, wd.p, L.k, L.cin, L.cout, cip, cop, prec, nullptr));
+      SLCK(sl_pack_weights(dwk.p, wf.p, L.k, L.cin, L.cout, cip, cop, prec, nullptr));
     }
     const double flops = 2.0 * L.k * L.cin * L.cout * static_cast<double>(T_out) * B;
     const bool is_out = L.cout == 29;
@@ -616,19 +663,21 @@ static bool run_perf(int B, int T, int prec, int iters) {
     };
     bool ok = true;
     Dev<uint16_t> y2(static_cast<size_t>(B) * T_out * cop * prec);
+    Dev<uint8_t> pmask(static_cast<size_t>(B) * T_out * cop / 8), pmask_in(static_cast<size_t>(B) * T_alloc * cip / 8);
+    CK(cudaMemset(pmask_in.p, 0x5a, pmask_in.n));
     if (is_out)
       ok &= time_it("fwd", [&] {
-        return sl_conv1d_fwd(xp.p, wf.p, bias.p, nullptr, probs.p, nullptr, logp.p, B, t_in, T_alloc, L.cin, L.cout,
+        return sl_conv1d_fwd(xp.p, wf.p, bias.p, nullptr, nullptr, probs.p, nullptr, logp.p, B, t_in, T_alloc, L.cin, L.cout,
                              L.k, L.s, SL_ACT_SOFTMAX, prec, nullptr);
       });
     else
       ok &= time_it("fwd", [&] {
-        return sl_conv1d_fwd(xp.p, wf.p, bias.p, y2.p, nullptr, nullptr, nullptr, B, t_in, T_alloc, L.cin, L.cout, L.k,
+        return sl_conv1d_fwd(xp.p, wf.p, bias.p, y2.p, pmask.p, nullptr, nullptr, nullptr, B, t_in, T_alloc, L.cin, L.cout, L.k,
                              L.s, SL_ACT_RELU, prec, nullptr);
       });
     if (L.s == 1)
       ok &= time_it("dgrad", [&] {
-        return sl_conv1d_dgrad(yp.p, wd.p, xp.p, dxp.p, B, t_in, L.cin, L.cout, L.k, prec, nullptr);
+        return sl_conv1d_dgrad(yp.p, wf.p, pmask_in.p, dxp.p, B, t_in, L.cin, L.cout, L.k, prec, nullptr);
       });
     ok &= time_it("wgrad", [&] {
       return sl_conv1d_wgrad(xp.p, yp.p, dw.p, db.p, B, t_in, T_alloc, L.cin, L.cout, L.k, L.s, prec, 1, nullptr);
