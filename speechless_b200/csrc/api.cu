@@ -2,6 +2,7 @@
 #include "../../include/speechless_b200.h"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "conv_umma.h"
@@ -38,6 +39,10 @@ int ctc_greedy_launch(const float*, const int32_t*, int32_t*, int32_t*, int, int
                       cudaStream_t);
 
 static int round64(int c) { return (c + 63) & ~63; }
+static int dbg_mode() {
+  const char* e = std::getenv("SL_DBG_MODE");  // measurement aid for kernel bring-up; results are garbage
+  return e ? std::atoi(e) : 0;
+}
 static int planes_of(int prec) { return prec == SL_PREC_BF16X2 ? 2 : 1; }
 
 static int num_sms() {
@@ -86,6 +91,40 @@ static int make_weight_map(CUtensorMap* m, const void* base, int k_total, int ro
   const uint64_t strides[2] = {row_bytes, row_bytes * rows};
   const uint32_t box[3] = {64, static_cast<uint32_t>(box_rows), 1};
   return make_tmap(m, TMAP_BF16, 3, base, dims, strides, box, true);
+}
+
+static int grouped_tma() {
+  const char* e = std::getenv("SL_GROUPED_TMA");  // 0 disables the one-TMA-per-operand tensor maps
+  return e ? std::atoi(e) : 1;
+}
+// MN-major operands: 64-channel groups as their own tensor dimension so that one TMA box
+// {64 ch, rows, n groups} fills the whole [group][row][64 ch] operand tile.
+// activation (B, T_alloc, C_total), optionally with the stride-`stride` parity split
+static int make_act_group_map(CUtensorMap* m, const void* base, int c_total, int stride, int T_alloc, int B,
+                              int box_rows, int box_groups, bool parity_dim) {
+  const uint64_t row_bytes = static_cast<uint64_t>(c_total) * 2;
+  if (!parity_dim) {
+    const uint64_t dims[4] = {64, static_cast<uint64_t>(T_alloc), static_cast<uint64_t>(c_total / 64),
+                              static_cast<uint64_t>(B)};
+    const uint64_t strides[3] = {row_bytes, 128, row_bytes * T_alloc};
+    const uint32_t box[4] = {64, static_cast<uint32_t>(box_rows), static_cast<uint32_t>(box_groups), 1};
+    return make_tmap(m, TMAP_BF16, 4, base, dims, strides, box, true);
+  }
+  const uint64_t dims[5] = {64, static_cast<uint64_t>(stride), static_cast<uint64_t>(T_alloc / stride),
+                            static_cast<uint64_t>(c_total / 64), static_cast<uint64_t>(B)};
+  const uint64_t strides[4] = {row_bytes, row_bytes * stride, 128, row_bytes * T_alloc};
+  const uint32_t box[5] = {64, 1, static_cast<uint32_t>(box_rows), static_cast<uint32_t>(box_groups), 1};
+  return make_tmap(m, TMAP_BF16, 5, base, dims, strides, box, true);
+}
+// weights (taps, rows, K_total): {64, rows, K_total/64, taps}
+static int make_weight_group_map(CUtensorMap* m, const void* base, int k_total, int rows, int taps,
+                                 int box_rows, int box_groups) {
+  const uint64_t row_bytes = static_cast<uint64_t>(k_total) * 2;
+  const uint64_t dims[4] = {64, static_cast<uint64_t>(rows), static_cast<uint64_t>(k_total / 64),
+                            static_cast<uint64_t>(taps)};
+  const uint64_t strides[3] = {row_bytes, 128, row_bytes * rows};
+  const uint32_t box[4] = {64, static_cast<uint32_t>(box_rows), static_cast<uint32_t>(box_groups), 1};
+  return make_tmap(m, TMAP_BF16, 4, base, dims, strides, box, true);
 }
 
 }  // namespace sl
@@ -195,6 +234,7 @@ int sl_conv1d_fwd(const void* x_packed, const void* w_fwd, const float* bias, vo
   p.stride = stride;
   p.pad_l = pad_l;
   p.tap_reverse = 0;
+  p.dbg_mode = dbg_mode();
   p.bias = bias;
   p.n_valid = Cout;
   int epi = EPI_PACKED;
@@ -238,7 +278,9 @@ int sl_conv1d_dgrad(const void* dy_packed, const void* w_fwd, const void* relu_m
   if (rc) return rc;
   // B[n = ci][k = co] comes straight from the forward layout (k, cout_pad, [hi|lo] cin_pad):
   // boxes of 64 co rows x 64 ci, consumed MN-major
-  rc = make_weight_map(&p.tmB, w_fwd, planes * cin_pad, cout_pad, k, 64);
+  p.b_grouped = grouped_tma();
+  rc = p.b_grouped ? make_weight_group_map(&p.tmB, w_fwd, planes * cin_pad, cout_pad, k, 64, bn / 64)
+                   : make_weight_map(&p.tmB, w_fwd, planes * cin_pad, cout_pad, k, 64);
   if (rc) return rc;
   rc = make_act_map3(&p.tmY, dx_packed, planes * cin_pad, T, B, 128);
   if (rc) return rc;
@@ -254,6 +296,7 @@ int sl_conv1d_dgrad(const void* dy_packed, const void* w_fwd, const void* relu_m
   p.stride = 1;
   p.pad_l = k - 1 - pad_l;  // dX[u] = sum_j dY[u + pad_l - j] W[j]  
   p.tap_reverse = 1;
+  p.dbg_mode = dbg_mode();
   p.bias = nullptr;
   p.n_valid = Cin;
   p.relu = 0;
@@ -282,9 +325,12 @@ int sl_conv1d_wgrad(const void* x_packed, const void* dy_packed, float* dw, floa
   std::memset(&p, 0, sizeof(p));
   const int bn = cin_pad >= 256 ? 256 : cin_pad;
   SL_REQUIRE(cin_pad % bn == 0 && (bn == 64 || bn == 128 || bn == 256), "unsupported channel count");
-  int rc = make_act_map3(&p.tmDY, dy_packed, planes * cout_pad, T_out, B, 64);
+  p.grouped = grouped_tma();
+  int rc = p.grouped ? make_act_group_map(&p.tmDY, dy_packed, planes * cout_pad, 1, T_out, B, 64, 2, false)
+                     : make_act_map3(&p.tmDY, dy_packed, planes * cout_pad, T_out, B, 64);
   if (rc) return rc;
-  rc = make_act_load_map(&p.tmX, x_packed, planes * cin_pad, stride, T_in_alloc, B, 64);
+  rc = p.grouped ? make_act_group_map(&p.tmX, x_packed, planes * cin_pad, stride, T_in_alloc, B, 64, bn / 64, true)
+                 : make_act_load_map(&p.tmX, x_packed, planes * cin_pad, stride, T_in_alloc, B, 64);
   if (rc) return rc;
   p.dw = dw;
   p.B = B;
@@ -301,6 +347,7 @@ int sl_conv1d_wgrad(const void* x_packed, const void* dy_packed, float* dw, floa
   p.cout_pad = cout_pad;
   p.cin_pad = cin_pad;
   p.dy_c_total = planes * cout_pad;
+  p.dbg_mode = dbg_mode();
   {
     // fp32 view of dW for the TMA (reduce-)store epilogue
     const uint64_t dims[3] = {static_cast<uint64_t>(cin_pad), static_cast<uint64_t>(cout_pad),

@@ -103,6 +103,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      int issued = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int n_tile = tile / tiles_per_n;
         const int rem = tile - n_tile * tiles_per_n;
@@ -127,15 +128,29 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
               mbar_wait(&empty_bar[stage], phase ^ 1);
               uint8_t* a_s = smem + stage * C::STAGE_BYTES;
               uint8_t* b_s = a_s + A_BYTES;
+              if (p.dbg_mode == 1 && issued >= C::kStages) {  // measurement aid: MMA on stale tiles
+                mbar_arrive(&full_bar[stage]);
+                if (++stage == C::kStages) {
+                  stage = 0;
+                  phase ^= 1;
+                }
+                continue;
+              }
+              ++issued;
               mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
               tma_load_4d(&p.tmA, &full_bar[stage], a_s, a_c, par, t0 + q, b);
               if (BMN) {
                 // 64 contraction rows (co) x 64 output channels (ci) per box
                 const int n_c = n0 + (term == 1 ? p.b_lo_off : 0);
+                if (p.b_grouped) {
+                  // one box {64 ci, 64 co rows, BN/64 channel groups}: lands as [group][row][64]
+                  tma_load_4d(&p.tmB, &full_bar[stage], b_s, 0, chunk * BLOCK_K, n_c >> 6, wtap);
+                } else {
 #pragma unroll
-                for (int i = 0; i < BN / 64; ++i)
-                  tma_load_3d(&p.tmB, &full_bar[stage], b_s + i * (BLOCK_K * 128), n_c + 64 * i,
-                              chunk * BLOCK_K, wtap);
+                  for (int i = 0; i < BN / 64; ++i)
+                    tma_load_3d(&p.tmB, &full_bar[stage], b_s + i * (BLOCK_K * 128), n_c + 64 * i,
+                                chunk * BLOCK_K, wtap);
+                }
               } else {
                 tma_load_3d(&p.tmB, &full_bar[stage], b_s, b_c, n0, wtap);
               }

@@ -34,6 +34,8 @@ struct ConvGemmParams {
   const uint8_t* mask_bits_in;
   uint8_t* mask_bits_out;
   int mask_row_bytes;
+  int dbg_mode;   // bring-up only (env SL_DBG_MODE): 1 = stop issuing TMA loads after the first ring fill
+  int b_grouped;  // MN-major B: tmB is rank 4 {64, cout, cin_total/64, taps}, one box {64,64,BN/64,1} per stage
   float* probs;   // EPI_SOFTMAX outputs
   float* logits;
   float* logp;
@@ -65,6 +67,8 @@ struct WgradParams {
   int cin_pad;
   int dy_c_total;  // channel extent of the dY tensor map (an OOB coordinate for zero tiles)
   int use_atomics;  // 1: TMA reduce-add into dw (split K / accumulate), 0: plain TMA store
+  int dbg_mode;     // bring-up only (env SL_DBG_MODE)
+  int grouped;      // tmDY rank 4 {64, T_out, C/64, B} / tmX rank 5 {64, S, T/S, C/64, B}: one TMA per operand
 };
 
 int wgrad_launch(const WgradParams& p, int block_n, int num_sms, cudaStream_t stream);

@@ -35,19 +35,29 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-__device__ __forceinline__ float lse3(float a, float b, float c) {
-  const float m = fmaxf(a, fmaxf(b, c));
-  if (m == -INFINITY) return -INFINITY;
-  return m + __logf(__expf(a - m) + __expf(b - m) + __expf(c - m));
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
-__device__ __forceinline__ float lse2_accurate(float a, float b) {
-  const float m = fmaxf(a, b);
-  if (m == -INFINITY) return -INFINITY;
-  return m + logf(expf(a - m) + expf(b - m));
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// log2(2^a + 2^b + 2^c), branch free: all -inf -> -inf (lg2(0) = -inf)
+__device__ __forceinline__ float lse3_base2(float a, float b, float c) {
+  const float m = fmaxf(fmaxf(fmaxf(a, b), c), -1e30f);
+  return m + lg2_approx(ex2_approx(a - m) + ex2_approx(b - m) + ex2_approx(c - m));
 }
 
 // dir 0: alpha (forward in time); dir 1: beta, computed as the same recurrence on the
 // time- and state-reversed problem (the skip condition is symmetric).
+// The lattices are kept in BASE-2 logarithms (ex2/lg2 are the native SFU ops; the natural-log
+// inputs are rescaled once per frame), SPT consecutive states per thread.
 template <int SPT>
 __global__ void ctc_alpha_beta_kernel(const float* __restrict__ logp,
                                       const int32_t* __restrict__ labels,
@@ -55,7 +65,7 @@ __global__ void ctc_alpha_beta_kernel(const float* __restrict__ logp,
                                       const int32_t* __restrict__ label_len,
                                       float* __restrict__ loss, float* __restrict__ beta_loss,
                                       float* __restrict__ alpha, float* __restrict__ beta, int T,
-                                      int L_max, int blank, int S_stride) {
+                                      int L_max, int blank, int S_stride, int col_stride) {
   extern __shared__ uint8_t smem_raw[];
   const int dir = blockIdx.x & 1;
   const int b = blockIdx.x >> 1;
@@ -65,11 +75,10 @@ __global__ void ctc_alpha_beta_kernel(const float* __restrict__ logp,
   const int S = 2 * L + 1;
 
   // smem carve-up
-  float* lp_s = reinterpret_cast<float*>(smem_raw);              // [2][CHUNK][VP]
-  float* col = lp_s + 2 * CHUNK * VP;                            // [2][S_stride + 2]
-  int* ext = reinterpret_cast<int*>(col + 2 * (S_stride + 2));   // [S_stride]
+  float* lp_s = reinterpret_cast<float*>(smem_raw);              // ring of 2*CHUNK rows x VP
+  float* col = lp_s + 2 * CHUNK * VP;                            // [2][col_stride], 2 leading pads
+  int* ext = reinterpret_cast<int*>(col + 2 * col_stride);       // [S_stride]
 
-  const int col_stride = S_stride + 2;
   // extended label sequence in walking order (reversed for beta)
   for (int s = tid; s < S_stride; s += blockDim.x) {
     int e = blank;
@@ -83,7 +92,7 @@ __global__ void ctc_alpha_beta_kernel(const float* __restrict__ logp,
 
   const float* lp_b = logp + static_cast<size_t>(b) * T * VP;
   auto issue_chunk = [&](int c) {
-    // rows tt = c*CHUNK .. +CHUNK-1 in walking order -> buffer c & 1
+    // rows tt = c*CHUNK .. +CHUNK-1 in walking order -> ring rows (c & 1) * CHUNK ..
     float* dst = lp_s + (c & 1) * CHUNK * VP;
     for (int i = tid; i < CHUNK * (VP / 4); i += blockDim.x) {
       const int r = i / (VP / 4), piece = i % (VP / 4);
@@ -99,58 +108,66 @@ __global__ void ctc_alpha_beta_kernel(const float* __restrict__ logp,
   issue_chunk(1);
   __syncthreads();
 
-  // per-thread state bookkeeping
+  // per-thread state bookkeeping: symbol, skip permission, smem / global offsets
+  const int s0 = tid * SPT;
   int my_e[SPT];
-  bool my_skip[SPT];
+  bool my_skip[SPT], my_on[SPT];
+  int my_out[SPT];
 #pragma unroll
   for (int i = 0; i < SPT; ++i) {
-    const int s = tid * SPT + i;
+    const int s = s0 + i;
+    my_on[i] = s < S;
     my_e[i] = s < S_stride ? ext[s] : blank;
     my_skip[i] = (s >= 2 && s < S) ? (ext[s] != blank && ext[s] != ext[s - 2]) : false;
+    my_out[i] = dir ? (S - 1 - s) : s;
   }
 
-  float* out = (dir ? beta : alpha) + static_cast<size_t>(b) * T * S_stride;
+  float* out = (dir ? beta : alpha) + static_cast<size_t>(b) * T * S_stride +
+               (dir ? static_cast<size_t>(P > 0 ? P - 1 : 0) * S_stride : 0);
+  const ptrdiff_t out_step = dir ? -static_cast<ptrdiff_t>(S_stride) : static_cast<ptrdiff_t>(S_stride);
+  float* prev = col + col_stride + 2;  // column of step tt-1 (initially all -inf)
+  float* cur = col + 2;
 
   for (int tt = 0; tt < P; ++tt) {
     if ((tt & (CHUNK - 1)) == 0) {
       cp_async_wait<1>();
       __syncthreads();
     }
-    const float* lp_row = lp_s + ((tt / CHUNK) & 1) * CHUNK * VP + (tt & (CHUNK - 1)) * VP;
-    const float* prev = col + ((tt & 1) ^ 1) * col_stride + 2;
-    float* cur = col + (tt & 1) * col_stride + 2;
-    const int t = dir ? (P - 1 - tt) : tt;
-    float* out_row = out + static_cast<size_t>(t) * S_stride;
+    const float* lp_row = lp_s + (tt & (2 * CHUNK - 1)) * VP;
+    float val[SPT];
 #pragma unroll
     for (int i = 0; i < SPT; ++i) {
-      const int s = tid * SPT + i;
-      if (s < S) {
-        float val;
-        const float em = lp_row[my_e[i]];
-        if (tt == 0) {
-          val = (s <= 1) ? em : -INFINITY;
-        } else {
-          const float a0 = prev[s];
-          const float a1 = prev[s - 1];
-          const float a2 = my_skip[i] ? prev[s - 2] : -INFINITY;
-          val = lse3(a0, a1, a2) + em;
-        }
-        cur[s] = val;
-        out_row[dir ? (S - 1 - s) : s] = val;
+      const int s = s0 + i;
+      const float em = lp_row[my_e[i]] * LOG2E;
+      const float a0 = prev[s];
+      const float a1 = prev[s - 1];
+      const float a2 = my_skip[i] ? prev[s - 2] : -INFINITY;
+      val[i] = lse3_base2(a0, a1, a2) + em;
+      if (tt == 0) val[i] = (s <= 1) ? em : -INFINITY;
+    }
+#pragma unroll
+    for (int i = 0; i < SPT; ++i) {
+      if (my_on[i]) {
+        cur[s0 + i] = val[i];
+        out[my_out[i]] = val[i];
       }
     }
+    out += out_step;
     __syncthreads();
     if ((tt & (CHUNK - 1)) == CHUNK - 1) issue_chunk(tt / CHUNK + 2);
+    float* tmp = prev;
+    prev = cur;
+    cur = tmp;
   }
   cp_async_wait<0>();
 
   if (tid == 0) {
     float l = INFINITY;
     if (P > 0) {
-      const float* last = col + ((P - 1) & 1) * col_stride + 2;
-      const float a = last[S - 1];
-      const float c = S >= 2 ? last[S - 2] : -INFINITY;
-      l = -lse2_accurate(a, c);
+      const float a = prev[S - 1];  // prev = column of the last processed step
+      const float c = S >= 2 ? prev[S - 2] : -INFINITY;
+      const float m = fmaxf(a, c);
+      l = (m == -INFINITY) ? INFINITY : -(m + log2f(exp2f(a - m) + exp2f(c - m))) * LN2;
     }
     if (dir == 0)
       loss[b] = l;
@@ -163,6 +180,7 @@ __global__ void ctc_alpha_beta_kernel(const float* __restrict__ logp,
 //   u = log(p+eps), lp = log_softmax(u);  g_u(v) = exp(lp_v) - occ(v)
 //   occ(v) = sum_{s: e[s]=v} exp(alpha_t(s) + beta_t(s) - lp_t(v) + loss_b)
 //   dL/dp_v = g_u(v)/(p_v+eps);  dL/dz_v = p_v (dL/dp_v - sum_w p_w dL/dp_w)
+// alpha/beta arrive as base-2 logs; each lane reads 4 consecutive states (float4) per pass.
 __global__ void ctc_grad_kernel(const float* __restrict__ logp, const float* __restrict__ probs,
                                 const int32_t* __restrict__ labels,
                                 const int32_t* __restrict__ input_len,
@@ -182,6 +200,7 @@ __global__ void ctc_grad_kernel(const float* __restrict__ logp, const float* __r
   for (int i = threadIdx.x; i < L; i += blockDim.x) lab_s[i] = labels[static_cast<size_t>(b) * L_max + i];
   __syncthreads();
   const float loss_b = loss[b];
+  const float loss2 = loss_b * LOG2E;
   float* my_bins = bins + warp * VP;
   const int t_begin = blockIdx.x * frames_per_block;
   const int t_end = min(t_begin + frames_per_block, T);
@@ -194,19 +213,41 @@ __global__ void ctc_grad_kernel(const float* __restrict__ logp, const float* __r
       my_bins[lane] = 0.f;
       my_bins[lane + 32] = 0.f;
       __syncwarp();
-      const float* a_row = alpha + ro * S_stride;
-      const float* b_row = beta + ro * S_stride;
+      const float4* a_row = reinterpret_cast<const float4*>(alpha + ro * S_stride);
+      const float4* b_row = reinterpret_cast<const float4*>(beta + ro * S_stride);
       const float* lp_row = logp + ro * VP;
-      const float lp_blank = lp_row[blank];
+      const float lp_blank2 = lp_row[blank] * LOG2E;
       float blank_acc = 0.f;
-      for (int s = lane; s < S; s += 32) {
-        const float ab = a_row[s] + b_row[s];
-        if (s & 1) {
-          const int v = lab_s[s >> 1];
-          const float x = expf(ab - lp_row[v] + loss_b);
-          if (x != 0.f) atomicAdd(&my_bins[v], x);
-        } else {
-          blank_acc += expf(ab - lp_blank + loss_b);
+      for (int base = 0; base < S; base += 512) {
+        // up to 4 passes of 128 states issued together (8 x 16-byte loads in flight per lane)
+        float4 av[4], bv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int s = base + j * 128 + lane * 4;
+          if (s < S) {
+            av[j] = __ldg(a_row + (s >> 2));
+            bv[j] = __ldg(b_row + (s >> 2));
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int s = base + j * 128 + lane * 4;
+          if (s < S) {
+            const float ab[4] = {av[j].x + bv[j].x, av[j].y + bv[j].y, av[j].z + bv[j].z, av[j].w + bv[j].w};
+            // s is a multiple of 4: states s, s+2 are blanks, s+1, s+3 carry labels
+            blank_acc += ex2_approx(ab[0] - lp_blank2 + loss2);
+            if (s + 1 < S) {
+              const int v = lab_s[s >> 1];
+              const float x = ex2_approx(ab[1] - lp_row[v] * LOG2E + loss2);
+              if (x != 0.f) atomicAdd(&my_bins[v], x);
+            }
+            if (s + 2 < S) blank_acc += ex2_approx(ab[2] - lp_blank2 + loss2);
+            if (s + 3 < S) {
+              const int v = lab_s[(s >> 1) + 1];
+              const float x = ex2_approx(ab[3] - lp_row[v] * LOG2E + loss2);
+              if (x != 0.f) atomicAdd(&my_bins[v], x);
+            }
+          }
         }
       }
 #pragma unroll
@@ -314,19 +355,24 @@ int ctc_loss_launch(const float* logp, const float* probs, const int32_t* labels
   float* beta = alpha + lat;
   float* beta_loss = beta + lat;
 
-  // threads: one per state up to 1024, then 2 or 4 states per thread
+  // two consecutive states per thread (four beyond 2048 states)
   const int S_max = 2 * L_max + 1;
-  int spt = 1;
-  if (S_max > 1024) spt = 2;
+  int spt = S_max <= 64 ? 1 : 2;
   if (S_max > 2048) spt = 4;
   SL_REQUIRE(S_max <= 4096, "label too long (max 2047 characters)");
   int threads = ((S_max + spt - 1) / spt + 31) & ~31;
   if (threads < 64) threads = 64;
-  const size_t smem = (2 * CHUNK * VP + 2 * (S_stride + 2)) * sizeof(float) + S_stride * sizeof(int);
-#define SL_LAUNCH_AB(SPT)                                                                        \
-  ctc_alpha_beta_kernel<SPT><<<2 * B, threads, smem, stream>>>(logp, labels, input_len, label_len, \
-                                                               loss, beta_loss, alpha, beta, T,  \
-                                                               L_max, blank, S_stride)
+  const int col_stride = (threads * spt > S_stride ? threads * spt : S_stride) + 2;
+  const size_t smem = (2 * CHUNK * VP + 2 * col_stride) * sizeof(float) + S_stride * sizeof(int);
+#define SL_LAUNCH_AB(SPT)                                                                          \
+  do {                                                                                             \
+    if (smem > 48 * 1024)                                                                          \
+      SL_CUDA(cudaFuncSetAttribute(ctc_alpha_beta_kernel<SPT>,                                     \
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); \
+    ctc_alpha_beta_kernel<SPT><<<2 * B, threads, smem, stream>>>(logp, labels, input_len, label_len, \
+                                                                 loss, beta_loss, alpha, beta, T,  \
+                                                                 L_max, blank, S_stride, col_stride); \
+  } while (0)
   if (spt == 1)
     SL_LAUNCH_AB(1);
   else if (spt == 2)

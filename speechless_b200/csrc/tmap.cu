@@ -32,7 +32,7 @@ int make_tmap(CUtensorMap* out, TmapDtype dtype, int rank, const void* base, con
     return 2;
   }
   cuuint64_t gdims[5];
-  cuuint64_t gstrides[4];
+  cuuint64_t gstrides[4] = {0, 0, 0, 0};
   cuuint32_t gbox[5];
   cuuint32_t estr[5];
   for (int i = 0; i < rank; ++i) {

@@ -109,6 +109,7 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      int issued = 0;
       for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
         int tap, mt, nt, k_begin, k_end;
         decode(unit, tap, mt, nt, k_begin, k_end);
@@ -132,18 +133,36 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* a_s = smem + stage * C::STAGE_BYTES;
             uint8_t* b_s = a_s + A_BYTES;
-            mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              // filter groups beyond cout_pad (output_conv: 64 < 128) read as zeros via an
-              // out-of-range channel coordinate
-              const int c = (co0 + 64 * i < p.cout_pad) ? (co0 + 64 * i + dy_off) : p.dy_c_total;
-              tma_load_3d(&p.tmDY, &full_bar[stage], a_s + i * BOX_BYTES, c, tr, b);
+            if (p.dbg_mode == 1 && issued >= C::kStages) {  // measurement aid: MMA on stale tiles
+              mbar_arrive(&full_bar[stage]);
+              if (++stage == C::kStages) {
+                stage = 0;
+                phase ^= 1;
+              }
+              continue;
             }
+            ++issued;
+            mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+            if (p.grouped) {
+              // one TMA per operand: the 64-channel groups are a tensor dimension of their own,
+              // so a box {64 ch, 64 frames, n groups} lands as [group][frame][64 ch].  Groups past
+              // the tensor read as zeros; for output_conv (64 filters) the second group of the
+              // 128-row tile is zero or the lo plane, and those rows are clipped at the store.
+              tma_load_4d(&p.tmDY, &full_bar[stage], a_s, 0, tr, (co0 + dy_off) >> 6, b);
+              tma_load_5d(&p.tmX, &full_bar[stage], b_s, 0, par, tr + q, (ci0 + x_off) >> 6, b);
+            } else {
 #pragma unroll
-            for (int i = 0; i < BN / 64; ++i)
-              tma_load_4d(&p.tmX, &full_bar[stage], b_s + i * BOX_BYTES, ci0 + 64 * i + x_off, par,
-                          tr + q, b);
+              for (int i = 0; i < 2; ++i) {
+                // filter groups beyond cout_pad (output_conv: 64 < 128) read as zeros via an
+                // out-of-range channel coordinate
+                const int c = (co0 + 64 * i < p.cout_pad) ? (co0 + 64 * i + dy_off) : p.dy_c_total;
+                tma_load_3d(&p.tmDY, &full_bar[stage], a_s + i * BOX_BYTES, c, tr, b);
+              }
+#pragma unroll
+              for (int i = 0; i < BN / 64; ++i)
+                tma_load_4d(&p.tmX, &full_bar[stage], b_s + i * BOX_BYTES, ci0 + 64 * i + x_off, par,
+                            tr + q, b);
+            }
             if (++stage == C::kStages) {
               stage = 0;
               phase ^= 1;

@@ -31,6 +31,7 @@ class DataParallel:
     def __init__(self, backend: Optional[str] = None, bucket_bytes: int = 32 << 20):
         self.rank, self.world_size, self.local_rank = env_world()
         self.bucket_bytes = bucket_bytes
+        self._pending = []
         if self.world_size > 1 and not dist.is_initialized():
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
             os.environ.setdefault("MASTER_PORT", "29500")
@@ -61,6 +62,21 @@ class DataParallel:
             handles.append(dist.all_reduce(loss_sum, op=dist.ReduceOp.SUM, async_op=True))
         for handle in handles:
             handle.wait()
+
+    def allreduce_bucket_async(self, grads: torch.Tensor, begin: int, end: int) -> None:
+        """Start the SUM all-reduce of grads[begin:end] (called from `ConvTower.backward` as each
+        bucket's weight gradients are enqueued); `finish()` makes the compute stream wait."""
+        if self.active:
+            self._pending.append(dist.all_reduce(grads.view(-1)[begin:end], op=dist.ReduceOp.SUM, async_op=True))
+
+    def finish(self, loss_sum: Optional[torch.Tensor] = None) -> None:
+        if not self.active:
+            return
+        if loss_sum is not None:
+            self._pending.append(dist.all_reduce(loss_sum, op=dist.ReduceOp.SUM, async_op=True))
+        for handle in self._pending:
+            handle.wait()
+        self._pending = []
 
     def max_over_ranks(self, value: float) -> float:
         if not self.active:

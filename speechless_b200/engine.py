@@ -94,6 +94,11 @@ class _Workspace:
         self.T_alloc = round_up(T, first.stride)
         self.x_f32 = torch.empty((B, T, first.cin), dtype=torch.float32, device=dev)
         self.x_host = torch.empty((B, T, first.cin), dtype=torch.float32, pin_memory=True)
+        # second slot for the pipelined training loop (copy of batch i+1 overlaps step i)
+        self.x_slots = [self.x_f32, None]
+        self.host_slots = [self.x_host, None]
+        self.slot_copied = [None, None]   # event on the copy stream: slot holds the new batch
+        self.slot_consumed = [None, None]  # event on the compute stream: pack kernel has read the slot
         self.x_packed = torch.zeros((B, self.T_alloc, planes * first.cin_pad), dtype=torch.bfloat16, device=dev)
         self.t_out: List[int] = []
         self.acts: List[torch.Tensor] = []
@@ -168,6 +173,7 @@ class ConvTower:
         self.profile: Optional[list] = None
         self.overlap_backward = False
         self._adam_tables = None
+        self._copy_stream = None
         self._side_stream = None
 
     # ------------------------------------------------------------------ helpers
@@ -289,6 +295,55 @@ class ConvTower:
             self._current = ws
             return ws
 
+    def stage_async(self, input_batch, slot: int) -> _Workspace:
+        """Start the host->device copy of a (B,T,F) batch into input slot `slot` on the copy stream
+        (pinned torch tensors go straight to the DMA engine; numpy arrays are first gathered into a
+        pinned staging buffer by the calling host thread)."""
+        with torch.cuda.device(self.device):
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(device=self.device)
+            if isinstance(input_batch, torch.Tensor):
+                B, T, F = input_batch.shape
+            else:
+                input_batch = np.asarray(input_batch)
+                B, T, F = input_batch.shape
+            if F != self.layers[0].cin:
+                raise ValueError("expected {} features per time step, got {}".format(self.layers[0].cin, F))
+            ws = self.workspace(B, T)
+            if ws.x_slots[slot] is None:
+                ws.x_slots[slot] = torch.empty_like(ws.x_f32)
+            pinned = isinstance(input_batch, torch.Tensor) and input_batch.is_pinned() and \
+                input_batch.dtype == torch.float32 and input_batch.is_contiguous()
+            if not pinned:
+                if ws.host_slots[slot] is None:
+                    ws.host_slots[slot] = torch.empty_like(ws.x_host).pin_memory()
+                if ws.slot_copied[slot] is not None:
+                    ws.slot_copied[slot].synchronize()  # the previous DMA out of this staging buffer is done
+                source = input_batch if isinstance(input_batch, torch.Tensor) else torch.from_numpy(
+                    np.ascontiguousarray(input_batch, dtype=np.float32))
+                ws.host_slots[slot].copy_(source)
+                input_batch = ws.host_slots[slot]
+            copy = self._copy_stream
+            if ws.slot_consumed[slot] is not None:
+                copy.wait_event(ws.slot_consumed[slot])
+            with torch.cuda.stream(copy):
+                ws.x_slots[slot].copy_(input_batch, non_blocking=True)
+                ws.slot_copied[slot] = copy.record_event()
+            return ws
+
+    def consume_slot(self, ws: _Workspace, slot: int) -> _Workspace:
+        """Compute stream: wait for the slot's copy, pack it to bf16 and release the slot."""
+        with torch.cuda.device(self.device):
+            main = torch.cuda.current_stream(self.device)
+            main.wait_event(ws.slot_copied[slot])
+            first = self.layers[0]
+            check(self.lib.sl_pack_activation(ptr(ws.x_slots[slot]), ptr(ws.x_packed), ws.B, ws.T, first.cin,
+                                              ws.T_alloc, first.cin_pad, self.precision, self.stream))
+            ws.slot_consumed[slot] = main.record_event()
+            self.launches += 1
+            self._current = ws
+            return ws
+
     def forward(self, ws: Optional[_Workspace] = None, want_logits: bool = False) -> _Workspace:
         ws = ws or self._current
         with torch.cuda.device(self.device):
@@ -378,8 +433,31 @@ class ConvTower:
                 self.adam_m = torch.zeros_like(self.params)
                 self.adam_v = torch.zeros_like(self.params)
 
-    def backward(self, ws: Optional[_Workspace] = None) -> None:
+    def grad_buckets(self) -> List[Tuple[int, int, int]]:
+        """(first layer index, begin, end) float ranges of the flat gradient buffer, in the order
+        backward completes them: [output_conv + big_conv_2], [big_conv_1], [everything below]
+        (16 / 64 / 18 MB at reference widths)."""
+        n = len(self.layers)
+        first = self.first_trainable()
+        cuts = sorted({max(first, n - 2), max(first, n - 3), first})
+        cuts = [c for c in cuts if c < n]
+        buckets = []
+        end_layer = n
+        for start_layer in reversed(cuts):
+            if start_layer >= end_layer:
+                continue
+            begin = self.layers[start_layer].w_offset
+            last = self.layers[end_layer - 1]
+            buckets.append((start_layer, begin, last.b_offset + last.cout_pad))
+            end_layer = start_layer
+        return buckets
+
+    def backward(self, ws: Optional[_Workspace] = None, on_bucket_ready=None) -> None:
         """Fill self.grads from ws.dz_packed (set by ctc(want_grad=True)).
+
+        `on_bucket_ready(begin, end)` is called (on the launching stream) as soon as the weight
+        gradients of a bucket of `grad_buckets()` have been enqueued, so the data-parallel
+        all-reduce of the big top layers overlaps the backward pass of the layers below.
 
         The chain dY_l -> dgrad_l -> dY_{l-1} runs on the current stream; with
         `overlap_backward` the weight gradients (which only consume dY_l and the saved
@@ -399,6 +477,7 @@ class ConvTower:
             dy = ws.dz_packed
             flip = 0
             wgrad_done = None  # event: the wgrad that still reads the buffer the next dgrad overwrites
+            bucket_starts = {b[0]: (b[1], b[2]) for b in self.grad_buckets()} if on_bucket_ready else {}
             for index in range(len(self.layers) - 1, first - 1, -1):
                 layer = self.layers[index]
                 x = ws.x_packed if index == 0 else ws.acts[index - 1]
@@ -416,6 +495,10 @@ class ConvTower:
                         launch_wgrad()
                         wgrad_done = side.record_event()
                 self.launches += 2
+                if index in bucket_starts:
+                    if side is not None:
+                        main.wait_stream(side)
+                    on_bucket_ready(*bucket_starts[index])
                 if index > first:
                     below = self.layers[index - 1]
                     dx = ws.dact[flip].view(-1)[:ws.B * t_in * self.planes * below.cout_pad].view(

@@ -437,10 +437,12 @@ class Wav2Letter:
 
     # ------------------------------------------------------------------ training (net.py:541-576)
     def train_on_batch(self, input_by_name: Dict[str, ndarray], global_batch_size: Optional[int] = None,
-                       allreduce: Optional[Callable] = None) -> float:
+                       allreduce: Optional[Callable] = None, data_parallel=None) -> float:
         """One optimisation step on this GPU's shard: forward, CTC loss + gradient, backward,
         (gradient all-reduce), Keras-2 Adam.  Objective = mean over the *global* batch (net.py:389).
-        Returns this shard's contribution to that mean."""
+        Returns the batch-mean loss (the global one when an all-reduce hook is given).  `data_parallel` (a
+        `speechless_b200.distributed.DataParallel`) overlaps the bucketed all-reduce with backward;
+        `allreduce(grads, loss_sum)` is the plain, non-overlapped hook."""
         if self.use_asg:
             raise NotImplementedError("ASG is not yet implemented.")
         names = Wav2Letter.InputNames
@@ -451,14 +453,68 @@ class Wav2Letter:
                          input_by_name[names.label_lengths])
         batch_size = global_batch_size if global_batch_size is not None else ws.B
         loss = tower.ctc(ws, want_grad=True, grad_scale=1.0 / batch_size)
-        tower.backward(ws)
-        loss_sum = loss.sum()
-        if allreduce is not None:
-            allreduce(tower.grads, loss_sum)
+        if data_parallel is not None and data_parallel.active:
+            tower.backward(ws, on_bucket_ready=lambda begin, end: data_parallel.allreduce_bucket_async(
+                tower.grads, begin, end))
+            loss_sum = loss.sum()
+            data_parallel.finish(loss_sum)
+        else:
+            tower.backward(ws)
+            loss_sum = loss.sum()
+            if allreduce is not None:
+                allreduce(tower.grads, loss_sum)
         self.optimizer.iterations += 1
         tower.adam_step(self.optimizer.lr, self.optimizer.beta_1, self.optimizer.beta_2, self.optimizer.epsilon,
                         self.optimizer.iterations)
         return float(loss_sum.item()) / batch_size
+
+    def fit_batches(self, input_batches: Iterable[Dict[str, ndarray]], global_batch_size: Optional[int] = None,
+                    data_parallel=None) -> List[float]:
+        """Train on consecutive batches (the dictionaries `_inputs_for_loss_net` builds), pipelined:
+        the host->device copy of batch i+1 runs on a copy stream while batch i computes, and the
+        per-step loss is read back asynchronously — one host synchronisation at the end.  Returns
+        each step's (shard contribution to the) batch-mean loss.  Same arithmetic as calling
+        `train_on_batch` per batch."""
+        import torch
+        if self.use_asg:
+            raise NotImplementedError("ASG is not yet implemented.")
+        names = Wav2Letter.InputNames
+        tower = self.tower
+        iterator = iter(input_batches)
+        current = next(iterator, None)
+        if current is None:
+            return []
+        slot = 0
+        ws = tower.stage_async(current[names.input_batch], slot)
+        device_losses = []
+        batch_sizes = []
+        while current is not None:
+            upcoming = next(iterator, None)
+            next_ws = tower.stage_async(upcoming[names.input_batch], slot ^ 1) if upcoming is not None else None
+            tower.consume_slot(ws, slot)
+            tower.forward(ws)
+            tower.set_labels(ws, current[names.label_batch], current[names.prediction_lengths],
+                             current[names.label_lengths])
+            batch_size = global_batch_size if global_batch_size is not None else ws.B
+            loss = tower.ctc(ws, want_grad=True, grad_scale=1.0 / batch_size)
+            if data_parallel is not None and data_parallel.active:
+                tower.backward(ws, on_bucket_ready=lambda begin, end: data_parallel.allreduce_bucket_async(
+                    tower.grads, begin, end))
+                loss_sum = loss.sum()
+                data_parallel.finish(loss_sum)
+            else:
+                tower.backward(ws)
+                loss_sum = loss.sum()
+            self.optimizer.iterations += 1
+            tower.adam_step(self.optimizer.lr, self.optimizer.beta_1, self.optimizer.beta_2,
+                            self.optimizer.epsilon, self.optimizer.iterations)
+            host_loss = torch.empty((), dtype=torch.float32, pin_memory=True)
+            host_loss.copy_(loss_sum, non_blocking=True)  # device -> host read of the step's result
+            device_losses.append(host_loss)
+            batch_sizes.append(batch_size)
+            current, ws, slot = upcoming, next_ws, slot ^ 1
+        tower.sync()
+        return [float(l) / n for l, n in zip(device_losses, batch_sizes)]
 
     def train(self,
               labeled_spectrogram_batches: Iterable[List[LabeledSpectrogram]],
@@ -481,14 +537,10 @@ class Wav2Letter:
         batches = _Prefetcher(self._loss_inputs_generator(labeled_spectrogram_batches))
         try:
             for epoch in range(initial_epoch, epochs):
-                losses = []
                 started = time.time()
-                for _ in range(batches_per_epoch):
-                    try:
-                        input_by_name, _dummy = next(batches)
-                    except StopIteration:
-                        return
-                    losses.append(self.train_on_batch(input_by_name))
+                losses = self.fit_batches(inputs for inputs, _dummy in itertools.islice(batches, batches_per_epoch))
+                if len(losses) < batches_per_epoch:
+                    return  # the batch iterable is exhausted
                 logs = {"loss": sum(losses) / len(losses), "seconds": time.time() - started}
                 for on_epoch_end in callbacks:
                     on_epoch_end(epoch, logs)

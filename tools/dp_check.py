@@ -51,8 +51,7 @@ def main():
                                          allreduce=dp.allreduce))
     grads_dp = net.tower.grads.clone()
     params_dp = net.tower.params.clone()
-    loss_dp = torch.tensor(losses, device=device, dtype=torch.float64)
-    dist.all_reduce(loss_dp)  # sum of shard contributions = global mean
+    loss_dp = torch.tensor(losses, device=device, dtype=torch.float64)  # already the global batch mean
 
     # --- replicas identical?
     reference = params_dp.clone()
