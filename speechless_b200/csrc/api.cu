@@ -28,7 +28,6 @@ int internal_to_keras_launch(const float*, float*, int, int, int, int, int, cuda
 int pack_weights_internal_launch(const float*, void*, int, int, int, int, cudaStream_t);
 int adam_fused_launch(float*, const float*, float*, float*, size_t, const size_t*, const size_t*, void* const*,
                       const int*, int, int, float, float, float, float, int, cudaStream_t);
-int bias_grad_launch(const void*, float*, size_t, int, int, int, cudaStream_t);
 int adam_launch(float*, const float*, float*, float*, size_t, float, float, float, float, int,
                 cudaStream_t);
 size_t ctc_workspace_bytes(int B, int T, int L_max);
@@ -91,6 +90,32 @@ static int make_weight_map(CUtensorMap* m, const void* base, int k_total, int ro
   const uint64_t strides[2] = {row_bytes, row_bytes * rows};
   const uint32_t box[3] = {64, static_cast<uint32_t>(box_rows), 1};
   return make_tmap(m, TMAP_BF16, 3, base, dims, strides, box, true);
+}
+
+// Tail splitting of the persistent conv grid (see ConvGemmParams::tail_split)
+static void plan_tail(int total_tiles, int bn, bool allow, int* full_tiles, int* split) {
+  const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
+  const int rest = total_tiles % grid;
+  *full_tiles = total_tiles;
+  *split = 1;
+  const char* e = std::getenv("SL_TAIL_SPLIT");      // max split factor (0/1 = off)
+  const char* all = std::getenv("SL_TAIL_SPLIT_ALL");  // measurement aid: split EVERY tile by this factor
+  if (allow && all && std::atoi(all) > 1 && bn / std::atoi(all) >= 64) {
+    *full_tiles = 0;
+    *split = std::atoi(all);
+    return;
+  }
+  const int max_split = e ? std::atoi(e) : 4;
+  if (!allow || rest == 0 || max_split < 2) return;
+  double best = 1.0;  // cost of the partial wave in units of one full-width tile
+  for (int s = 2; s <= max_split && bn / s >= 64; s *= 2) {
+    const double cost = static_cast<double>((rest * s + grid - 1) / grid) / s;
+    if (cost < best - 1e-9) {
+      best = cost;
+      *split = s;
+    }
+  }
+  if (*split > 1) *full_tiles = total_tiles - rest;
 }
 
 static int grouped_tma() {
@@ -226,6 +251,11 @@ int sl_conv1d_fwd(const void* x_packed, const void* w_fwd, const float* bias, vo
   p.T_out = T_out;
   p.m_tiles_per_utt = (T_out + 127) / 128;
   p.n_tiles = cout_pad / bn;
+  plan_tail(B * p.m_tiles_per_utt * p.n_tiles, bn, act != SL_ACT_SOFTMAX, &p.full_tiles, &p.tail_split);
+  if (p.tail_split > 1) {
+    rc = make_weight_map(&p.tmBtail, w_fwd, planes * cin_pad, cout_pad, k, bn / p.tail_split);
+    if (rc) return rc;
+  }
   p.taps = k;
   p.chunks = cin_pad / 64;
   p.terms = planes == 2 ? 3 : 1;
@@ -288,6 +318,11 @@ int sl_conv1d_dgrad(const void* dy_packed, const void* w_fwd, const void* relu_m
   p.T_out = T;
   p.m_tiles_per_utt = (T + 127) / 128;
   p.n_tiles = cin_pad / bn;
+  plan_tail(B * p.m_tiles_per_utt * p.n_tiles, bn, p.b_grouped != 0, &p.full_tiles, &p.tail_split);
+  if (p.tail_split > 1) {
+    rc = make_weight_group_map(&p.tmBtail, w_fwd, planes * cin_pad, cout_pad, k, 64, bn / p.tail_split / 64);
+    if (rc) return rc;
+  }
   p.taps = k;
   p.chunks = cout_pad / 64;
   p.terms = planes == 2 ? 3 : 1;
@@ -381,13 +416,11 @@ int sl_conv1d_wgrad(const void* x_packed, const void* dy_packed, float* dw, floa
   p.use_atomics = (ksplit > 1 || accumulate) ? 1 : 0;
   const size_t dw_bytes = static_cast<size_t>(k) * cout_pad * cin_pad * sizeof(float);
   if (p.use_atomics && !accumulate) SL_CUDA(cudaMemsetAsync(dw, 0, dw_bytes, s));
-  rc = wgrad_launch(p, bn, num_sms(), s);
-  if (rc) return rc;
-  if (db != nullptr) {
-    if (!accumulate) SL_CUDA(cudaMemsetAsync(db, 0, static_cast<size_t>(Cout) * sizeof(float), s));
-    rc = bias_grad_launch(dy_packed, db, static_cast<size_t>(B) * T_out, cout_pad, planes, Cout, s);
-  }
-  return rc;
+  // bias gradient: fused into the wgrad kernel (column sums of the staged dY tiles)
+  p.db = db;
+  p.n_filters = Cout;
+  if (db != nullptr && !accumulate) SL_CUDA(cudaMemsetAsync(db, 0, static_cast<size_t>(Cout) * sizeof(float), s));
+  return wgrad_launch(p, bn, num_sms(), s);
 }
 
 size_t sl_ctc_workspace_bytes(int B, int T, int L_max) {

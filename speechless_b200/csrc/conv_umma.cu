@@ -48,6 +48,31 @@ struct Cfg {
       kStages * STAGE_BYTES + 2 * STAGING_BYTES + BN * 4 + 256 + 1024 /*align slack*/;
 };
 
+// Work item of the persistent loop: an output tile, or one of the tail_split narrow slices of a
+// tile of the last partial wave.
+struct WorkItem {
+  int b, t0, n0, width;
+};
+template <int BN>
+__device__ __forceinline__ WorkItem decode_item(const ConvGemmParams& p, int item) {
+  int tile = item, sub = 0, width = BN;
+  if (item >= p.full_tiles) {
+    const int r = item - p.full_tiles;
+    tile = p.full_tiles + r / p.tail_split;
+    sub = r - (r / p.tail_split) * p.tail_split;
+    width = BN / p.tail_split;
+  }
+  const int tiles_per_n = p.B * p.m_tiles_per_utt;
+  const int n_tile = tile / tiles_per_n;
+  const int rem = tile - n_tile * tiles_per_n;
+  WorkItem w;
+  w.b = rem / p.m_tiles_per_utt;
+  w.t0 = (rem - w.b * p.m_tiles_per_utt) * BLOCK_M;
+  w.n0 = n_tile * BN + sub * width;
+  w.width = width;
+  return w;
+}
+
 // BMN: the B operand is MN-major (input gradient: B[n = ci][k = co] read straight from the
 // forward weight layout (k, co, ci), ci contiguous) instead of K-major.
 template <int BN, int EPI, bool BMN>
@@ -72,6 +97,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.tmA);
     prefetch_tmap(&p.tmB);
+    if (p.tail_split > 1) prefetch_tmap(&p.tmBtail);
     if (EPI == EPI_PACKED) prefetch_tmap(&p.tmY);
   }
   if (warp == 1 && lane == 0) {
@@ -94,8 +120,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
 
-  const int tiles_per_n = p.B * p.m_tiles_per_utt;
-  const int num_tiles = tiles_per_n * p.n_tiles;
+  const int total_tiles = p.B * p.m_tiles_per_utt * p.n_tiles;
+  const int num_tiles = p.full_tiles + (total_tiles - p.full_tiles) * p.tail_split;  // work items
   const int ksteps = p.taps * p.chunks * p.terms;
 
   if (warp == 0) {
@@ -105,11 +131,10 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       uint32_t phase = 0;
       int issued = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int n_tile = tile / tiles_per_n;
-        const int rem = tile - n_tile * tiles_per_n;
-        const int b = rem / p.m_tiles_per_utt;
-        const int t0 = (rem - b * p.m_tiles_per_utt) * BLOCK_M;
-        const int n0 = n_tile * BN;
+        const WorkItem w = decode_item<BN>(p, tile);
+        const int b = w.b, t0 = w.t0, n0 = w.n0;
+        const CUtensorMap* tmB = w.width == BN ? &p.tmB : &p.tmBtail;
+        const uint32_t stage_tx = A_BYTES + w.width * (BLOCK_K * 2);
         for (int tap = 0; tap < p.taps; ++tap) {
           const int jp = tap - p.pad_l;  // signed frame offset of this tap
           int q, par;
@@ -137,22 +162,23 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
                 continue;
               }
               ++issued;
-              mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+              mbar_expect_tx(&full_bar[stage], stage_tx);
               tma_load_4d(&p.tmA, &full_bar[stage], a_s, a_c, par, t0 + q, b);
               if (BMN) {
                 // 64 contraction rows (co) x 64 output channels (ci) per box
                 const int n_c = n0 + (term == 1 ? p.b_lo_off : 0);
                 if (p.b_grouped) {
                   // one box {64 ci, 64 co rows, BN/64 channel groups}: lands as [group][row][64]
-                  tma_load_4d(&p.tmB, &full_bar[stage], b_s, 0, chunk * BLOCK_K, n_c >> 6, wtap);
+                  tma_load_4d(tmB, &full_bar[stage], b_s, 0, chunk * BLOCK_K, n_c >> 6, wtap);
                 } else {
 #pragma unroll
                   for (int i = 0; i < BN / 64; ++i)
-                    tma_load_3d(&p.tmB, &full_bar[stage], b_s + i * (BLOCK_K * 128), n_c + 64 * i,
-                                chunk * BLOCK_K, wtap);
+                    if (i * 64 < w.width)
+                      tma_load_3d(&p.tmB, &full_bar[stage], b_s + i * (BLOCK_K * 128), n_c + 64 * i,
+                                  chunk * BLOCK_K, wtap);
                 }
               } else {
-                tma_load_3d(&p.tmB, &full_bar[stage], b_s, b_c, n0, wtap);
+                tma_load_3d(tmB, &full_bar[stage], b_s, b_c, n0, wtap);
               }
               if (++stage == C::kStages) {
                 stage = 0;
@@ -165,11 +191,12 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BN, 0, BMN ? 1 : 0);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int width = tile >= p.full_tiles ? BN / p.tail_split : BN;
+      const uint32_t idesc = make_idesc_bf16(BLOCK_M, width, 0, BMN ? 1 : 0);
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(&tmem_empty[as], aphase ^ 1);
@@ -208,11 +235,9 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     int it = 0;
     uint32_t store_count = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int n_tile = tile / tiles_per_n;
-      const int rem = tile - n_tile * tiles_per_n;
-      const int b = rem / p.m_tiles_per_utt;
-      const int t0 = (rem - b * p.m_tiles_per_utt) * BLOCK_M;
-      const int n0 = n_tile * BN;
+      const WorkItem w = decode_item<BN>(p, tile);
+      const int b = w.b, t0 = w.t0, n0 = w.n0;
+      const int n_chunks = w.width / 64;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const int t = t0 + row;
@@ -221,7 +246,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       // stage the bias slice of this tile (previous tile's readers are past the
       // barrier below because every chunk iteration ends behind a named barrier)
       named_bar_sync(2, kEpiThreads);
-      for (int i = et; i < BN; i += kEpiThreads)
+      for (int i = et; i < w.width; i += kEpiThreads)
         bias_s[i] = (p.bias != nullptr && (n0 + i) < p.n_valid) ? p.bias[n0 + i] : 0.f;
       named_bar_sync(2, kEpiThreads);
 
@@ -232,12 +257,12 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
 
       if (EPI == EPI_PACKED) {
 #pragma unroll 1
-        for (int c = 0; c < BN / 64; ++c) {
+        for (int c = 0; c < n_chunks; ++c) {
           uint32_t r0[32], r1[32];
           tmem_ld_32x32(taddr + c * 64, r0);
           tmem_ld_32x32(taddr + c * 64 + 32, r1);
           tmem_ld_wait();
-          if (c == BN / 64 - 1) {
+          if (c == n_chunks - 1) {
             // accumulator fully drained: hand the TMEM stage back to the MMA warp
             tcgen05_fence_before();
             __syncwarp();
@@ -384,6 +409,10 @@ int launch(const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
   }
   const int num_tiles = p.B * p.m_tiles_per_utt * p.n_tiles;
   const int grid = num_tiles < num_sms ? num_tiles : num_sms;
+  if (p.full_tiles + (num_tiles - p.full_tiles) * p.tail_split < grid || p.tail_split < 1) {
+    set_error("conv_gemm: inconsistent tail split");
+    return 1;
+  }
   conv_gemm_kernel<BN, EPI, BMN><<<grid, kThreads, C::SMEM_BYTES, stream>>>(p);
   SL_CUDA(cudaGetLastError());
   return 0;

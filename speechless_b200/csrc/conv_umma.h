@@ -11,11 +11,16 @@ struct ConvGemmParams {
   CUtensorMap tmA;  // activations, rank 4 {C_total, stride, T_alloc/stride, B}, box {64,1,128,1}
   CUtensorMap tmB;  // weights (k, cout, cin), rank 3 {cin_total, cout, taps}: box {64, BN, 1} (fwd: K-major B)
                     // or box {64, 64, 1} (dgrad: MN-major B, 64 cout rows of contraction)
+  CUtensorMap tmBtail;  // as tmB with a box of BN / tail_split filters: the last partial wave's narrow tiles
   CUtensorMap tmY;  // packed bf16 output, rank 3 {C_total, T_out, B}, box {64,128,1}
   int B;
   int T_out;
   int m_tiles_per_utt;
   int n_tiles;
+  // tail splitting: the tiles of the last, partial wave of the persistent grid are cut into
+  // tail_split (1, 2 or 4) narrower tiles so that the wave costs 1/tail_split of a tile time
+  int full_tiles;  // tiles [0, full_tiles) are whole; the rest are split
+  int tail_split;
   int taps;
   int chunks;  // 64-channel chunks of the contraction dimension
   int terms;   // 1 = bf16, 3 = split bf16 (hi*hi + hi*lo + lo*hi)
@@ -51,6 +56,8 @@ struct WgradParams {
   CUtensorMap tmX;   // rank 4 {Cin_total, stride, T_alloc/stride, B}, box {64, 1, 64, 1}
   CUtensorMap tmDW;  // fp32 rank 3 {cin_pad, cout_pad, taps}, box {32, 128, 1}: TMA (reduce-)store target
   float* dw;         // (taps, cout_pad, cin_pad) fp32
+  float* db;         // (n_filters) fp32 bias gradient, accumulated with atomics; may be null
+  int n_filters;     // real (unpadded) filter count
   int B;
   int T_out;
   int taps;

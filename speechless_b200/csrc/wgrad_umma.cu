@@ -15,6 +15,12 @@
 // accumulator through swizzled smem, 32 columns at a time, and hands it to TMA: a plain
 // tensor store, or cp.reduce.async.bulk.tensor (.add) when several K splits / layers of
 // accumulation meet in the same dW tile (dW is zeroed by the caller in that case).
+//
+// Bias gradient, fused: db[co] = sum_{b,t} dY[b,t,co] is the column sum of the very dY tiles
+// the A operand streams through smem, so the otherwise idle warp 3 adds up staged tiles before
+// the slot is released (the empty barrier counts two arrivals: the MMA commit and warp 3).
+// The (tap, channel tile) units of one filter tile see the same dY tiles and share the work
+// round-robin by frame chunk; each unit ends with 128 atomics.
 #include "conv_umma.h"
 
 namespace sl {
@@ -69,7 +75,7 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::kStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], 2);  // tcgen05.commit of the MMA warp + the bias-gradient warp
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
@@ -208,6 +214,56 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
         }
       }
       if (ksteps == 0 && lane == 0) mbar_arrive(&tmem_full[as]);  // empty K range: nothing to add
+    }
+  } else if (warp == 3) {
+    // ===================== bias gradient (column sums of the staged dY tiles) =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    const int grp = lane >> 4;          // which 64-filter half of the 128-filter tile
+    const int sub = lane & 15;          // 4 consecutive filters: bytes [sub*8, sub*8+8) of the row
+    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+      int tap, mt, nt, k_begin, k_end;
+      decode(unit, tap, mt, nt, k_begin, k_end);
+      // All taps x channel tiles of one (filter tile, K split) stream the same dY tiles, so the
+      // column-sum work is dealt round-robin: this unit sums every `slices`-th frame chunk.
+      const int slices = p.taps * p.n_tiles;
+      const int my_slice = tap * p.n_tiles + nt;
+      const int ksteps = (k_end - k_begin) * p.terms;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      int term = 0;
+      int kk_mod = k_begin % slices;  // (frame chunk index) mod slices
+      for (int ks = 0; ks < ksteps; ++ks) {
+        mbar_wait(&full_bar[stage], phase);
+        const bool sel = p.db != nullptr && kk_mod == my_slice;
+        if (sel && term != 1) {  // terms 0 / 2 stage the hi / lo plane of dY; term 1 repeats hi
+          const uint8_t* a_s = smem + stage * C::STAGE_BYTES + grp * BOX_BYTES;
+#pragma unroll 8
+          for (int r = 0; r < KT; ++r) {
+            const int phys = (sub >> 1) ^ (r & 7);  // SWIZZLE_128B: 16-byte chunk index ^= row % 8
+            const uint2 q = *reinterpret_cast<const uint2*>(a_s + r * 128 + phys * 16 + (sub & 1) * 8);
+            acc[0] += __uint_as_float(q.x << 16);
+            acc[1] += __uint_as_float(q.x & 0xffff0000u);
+            acc[2] += __uint_as_float(q.y << 16);
+            acc[3] += __uint_as_float(q.y & 0xffff0000u);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);
+        if (++term == p.terms) {
+          term = 0;
+          if (++kk_mod == slices) kk_mod = 0;
+        }
+        if (++stage == C::kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if (p.db != nullptr) {
+        const int co = mt * BLOCK_M + grp * 64 + sub * 4;
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (co + e < p.n_filters) atomicAdd(p.db + co + e, acc[e]);
+      }
     }
   } else if (warp >= 4) {
     const int ew = warp - 4;

@@ -494,7 +494,7 @@ class ConvTower:
                     with torch.cuda.stream(side):
                         launch_wgrad()
                         wgrad_done = side.record_event()
-                self.launches += 2
+                self.launches += 1
                 if index in bucket_starts:
                     if side is not None:
                         main.wait_stream(side)

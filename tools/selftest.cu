@@ -737,6 +737,10 @@ int main(int argc, char** argv) {
       {"big2_k1_2000_2000", 1, 200, 2000, 2000, 1, 1, SL_ACT_RELU},
       {"out_k1_2000_29", 2, 151, 2000, 29, 1, 1, SL_ACT_SOFTMAX},
       {"out_k1_250_33", 1, 140, 250, 33, 1, 1, SL_ACT_SOFTMAX},
+      // > 148 tiles with a remainder: exercises the tail-split (narrow tile) path
+      {"tail4_k3_250", 10, 2000, 250, 250, 3, 1, SL_ACT_RELU},
+      {"tail2_k1_64_128", 10, 2000, 64, 128, 1, 1, SL_ACT_RELU},
+      {"tail_k1_250_2000", 3, 1000, 250, 2000, 1, 1, SL_ACT_RELU},
   };
   for (const auto& cc : fwd_cases)
     for (int prec = 1; prec <= 2; ++prec) {
@@ -749,6 +753,8 @@ int main(int argc, char** argv) {
       {"big1_k32_250_2000", 1, 150, 250, 2000, 32, 1, SL_ACT_RELU},
       {"big2_k1_2000_2000", 1, 200, 2000, 2000, 1, 1, SL_ACT_RELU},
       {"out_k1_2000_29", 2, 151, 2000, 29, 1, 1, SL_ACT_RELU},
+      {"tail4_k3_250", 10, 2000, 250, 250, 3, 1, SL_ACT_RELU},
+      {"tail2_k1_128_64", 10, 2000, 128, 64, 1, 1, SL_ACT_RELU},
   };
   for (const auto& cc : dg_cases)
     for (int prec = 1; prec <= 2; ++prec) {
