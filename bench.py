@@ -108,6 +108,17 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+def ncu_traffic(kernel_key, workload, dtype):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the named kernel from
+    the committed `ncu --set full` capture summary (profiles/ncu_traffic.json), or None."""
+    path = ROOT / "profiles" / "ncu_traffic.json"
+    if not path.exists():
+        return None
+    table = json.loads(path.read_text())
+    entry = table.get("{}|{}|{}".format(workload, dtype, kernel_key))
+    return entry["dram_bytes"] if entry else None
+
+
 def make_host_batch(args, rank):
     import numpy as np
     from speechless_b200 import english_frequent_characters as alphabet
@@ -324,7 +335,9 @@ def run_ours(args):
     terms = 3 if dtype == "bf16x2" else 1
     roofline = {
         "kernel": top["kernel"], "bound": "tensor", "achieved": top.get("tflops"), "peak": peak_tf, "unit": "TFLOP/s",
-        "frac": round(top["tflops"] / peak_tf, 4) if "tflops" in top else None, "traffic": None,
+        "frac": round(top["tflops"] / peak_tf, 4) if "tflops" in top else None,
+        "traffic": ncu_traffic(top["kernel"], args.workload, dtype),
+        "algorithmic_flops": flops.get((top_kind, top_name)),
         "peak_source": "{} ({})".format("bf16_tflops_sustained of MEASURED_PEAKS.json", peaks["source"]),
         "mma_terms_per_product": terms,
         "timing": "CUDA-event pair around each launch, {} instrumented steps right after the timed region "

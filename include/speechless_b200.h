@@ -90,7 +90,12 @@ int sl_conv1d_fwd(const void* x_packed, const void* w_fwd, const float* bias,
  * pass ((B,T,cin_pad/8) bytes), or NULL for a linear layer below. */
 int sl_conv1d_dgrad(const void* dy_packed, const void* w_fwd,
                     const void* relu_mask, void* dx_packed, int B, int T,
-                    int Cin, int Cout, int k, int prec, void* stream);
+                    int Cin, int Cout, int k, int prec, void* workspace,
+                    size_t workspace_bytes, void* stream);
+/* Optional fp32 scratch for the split-K variant (long tap loops whose tile count fills the
+ * persistent grid badly, e.g. big_conv_1); 0 = not wanted for this shape.  Passing
+ * workspace = NULL is always legal and selects the unsplit kernel. */
+size_t sl_conv1d_dgrad_workspace_bytes(int B, int T, int Cin, int Cout, int k);
 
 /* dW (k,cout_pad,cin_pad) fp32 += sum_{b,t} x[b,t*s+j-pad_l,ci]*dy[b,t,co];
  * db (Cout) fp32 = sum_{b,t} dy.  dW/db are overwritten (accumulate=0) or

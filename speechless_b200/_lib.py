@@ -26,7 +26,8 @@ SIGNATURES = {
     "sl_conv1d_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "sl_conv1d_dgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
-                                c_void_p]),
+                                c_void_p, c_size_t, c_void_p]),
+    "sl_conv1d_dgrad_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "sl_conv1d_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                 c_int, c_int, c_int, c_void_p]),
     "sl_weights_keras_to_internal": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),

@@ -26,6 +26,7 @@ int unpack_activation_launch(const void*, float*, int, int, int, int, int, int, 
 int keras_to_internal_launch(const float*, float*, int, int, int, int, int, cudaStream_t);
 int internal_to_keras_launch(const float*, float*, int, int, int, int, int, cudaStream_t);
 int pack_weights_internal_launch(const float*, void*, int, int, int, int, cudaStream_t);
+int dgrad_finalize_launch(const float*, const void*, void*, size_t, int, int, cudaStream_t);
 int adam_fused_launch(float*, const float*, float*, float*, size_t, const size_t*, const size_t*, void* const*,
                       const int*, int, int, float, float, float, float, int, cudaStream_t);
 int adam_launch(float*, const float*, float*, float*, size_t, float, float, float, float, int,
@@ -284,14 +285,46 @@ int sl_conv1d_fwd(const void* x_packed, const void* w_fwd, const float* bias, vo
     p.y_lo_off = cout_pad;
     p.mask_bits_out = static_cast<uint8_t*>(relu_mask_out);
     p.mask_row_bytes = cout_pad / 8;
-    rc = make_act_map3(&p.tmY, y_packed, planes * cout_pad, T_out, B, 128);
+    rc = make_act_map3(&p.tmY, y_packed, planes * cout_pad, T_out, B, 32);
     if (rc) return rc;
   }
   return conv_gemm_launch(p, bn, epi, false, num_sms(), static_cast<cudaStream_t>(stream));
 }
 
+// split-K plan of the input-gradient GEMM: worthwhile when the tile count leaves the last
+// wave of the persistent grid mostly empty and every tile is a long loop over many taps
+static int plan_dgrad_ksplit(int B, int T, int cin_pad, int cout_pad, int k) {
+  const char* e = std::getenv("SL_DGRAD_KSPLIT");
+  if (e) return std::atoi(e) > 1 ? std::atoi(e) : 1;
+  const int bn = cin_pad >= 256 ? 256 : cin_pad;
+  if (bn < 128 || k < 8) return 1;
+  const int tiles = B * ((T + 127) / 128) * (cin_pad / bn);
+  const int sms = num_sms();
+  if (tiles < sms) return 1;
+  const long long ksteps = static_cast<long long>(k) * (cout_pad / 64);
+  if (ksteps < 256) return 1;
+  int best = 1;
+  double best_cost = static_cast<double>((tiles + sms - 1) / sms);
+  for (int ks = 2; ks <= 8 && ks <= k / 4; ks *= 2) {
+    // each split item also pays a fixed epilogue + pipeline ramp (~3 % of a 1024-step tile)
+    const double cost = static_cast<double>((tiles * ks + sms - 1) / sms) / ks * (1.0 + 0.01 * ks);
+    if (cost < best_cost * 0.95) {
+      best_cost = cost;
+      best = ks;
+    }
+  }
+  return best;
+}
+
+size_t sl_conv1d_dgrad_workspace_bytes(int B, int T, int Cin, int Cout, int k) {
+  const int cin_pad = round64(Cin), cout_pad = round64(Cout);
+  if (plan_dgrad_ksplit(B, T, cin_pad, cout_pad, k) <= 1) return 0;
+  return static_cast<size_t>(B) * T * cin_pad * sizeof(float);
+}
+
 int sl_conv1d_dgrad(const void* dy_packed, const void* w_fwd, const void* relu_mask, void* dx_packed,
-                    int B, int T, int Cin, int Cout, int k, int prec, void* stream) {
+                    int B, int T, int Cin, int Cout, int k, int prec, void* workspace,
+                    size_t workspace_bytes, void* stream) {
   SL_REQUIRE(dy_packed && w_fwd && dx_packed, "null pointer");
   SL_REQUIRE(B > 0 && T > 0 && Cin > 0 && Cout > 0 && k > 0, "bad shape");
   SL_REQUIRE(prec == SL_PREC_BF16 || prec == SL_PREC_BF16X2, "bad precision");
@@ -312,7 +345,7 @@ int sl_conv1d_dgrad(const void* dy_packed, const void* w_fwd, const void* relu_m
   rc = p.b_grouped ? make_weight_group_map(&p.tmB, w_fwd, planes * cin_pad, cout_pad, k, 64, bn / 64)
                    : make_weight_map(&p.tmB, w_fwd, planes * cin_pad, cout_pad, k, 64);
   if (rc) return rc;
-  rc = make_act_map3(&p.tmY, dx_packed, planes * cin_pad, T, B, 128);
+  rc = make_act_map3(&p.tmY, dx_packed, planes * cin_pad, T, B, 32);
   if (rc) return rc;
   p.B = B;
   p.T_out = T;
@@ -339,6 +372,28 @@ int sl_conv1d_dgrad(const void* dy_packed, const void* w_fwd, const void* relu_m
   p.y_lo_off = cin_pad;
   p.mask_bits_in = static_cast<const uint8_t*>(relu_mask);
   p.mask_row_bytes = cin_pad / 8;
+  p.ksplit = 1;
+  const int ksplit = plan_dgrad_ksplit(B, T, cin_pad, cout_pad, k);
+  const size_t need = static_cast<size_t>(B) * T * cin_pad * sizeof(float);
+  if (ksplit > 1 && p.b_grouped && workspace != nullptr && workspace_bytes >= need) {
+    // split K over tap ranges: fp32 partial sums meet in `workspace` (TMA reduce-add), then one
+    // elementwise pass applies the ReLU mask and packs to bf16
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    SL_CUDA(cudaMemsetAsync(workspace, 0, need, s));
+    const uint64_t dims[3] = {static_cast<uint64_t>(cin_pad), static_cast<uint64_t>(T), static_cast<uint64_t>(B)};
+    const uint64_t strides[2] = {static_cast<uint64_t>(cin_pad) * 4, static_cast<uint64_t>(cin_pad) * 4 * T};
+    const uint32_t box[3] = {32, 32, 1};
+    rc = make_tmap(&p.tmY, TMAP_F32, 3, workspace, dims, strides, box, true);
+    if (rc) return rc;
+    p.ksplit = ksplit;
+    p.full_tiles = B * p.m_tiles_per_utt * p.n_tiles;
+    p.tail_split = 1;
+    p.mask_bits_in = nullptr;
+    rc = conv_gemm_launch(p, bn, EPI_F32, true, num_sms(), s);
+    if (rc) return rc;
+    return dgrad_finalize_launch(static_cast<const float*>(workspace), relu_mask, dx_packed,
+                                 static_cast<size_t>(B) * T, cin_pad, planes, s);
+  }
   return conv_gemm_launch(p, bn, EPI_PACKED, true, num_sms(), static_cast<cudaStream_t>(stream));
 }
 
@@ -388,7 +443,7 @@ int sl_conv1d_wgrad(const void* x_packed, const void* dy_packed, float* dw, floa
     const uint64_t dims[3] = {static_cast<uint64_t>(cin_pad), static_cast<uint64_t>(cout_pad),
                               static_cast<uint64_t>(k)};
     const uint64_t strides[2] = {static_cast<uint64_t>(cin_pad) * 4, static_cast<uint64_t>(cin_pad) * cout_pad * 4};
-    const uint32_t box[3] = {32, 128, 1};
+    const uint32_t box[3] = {32, 32, 1};
     rc = make_tmap(&p.tmDW, TMAP_F32, 3, dw, dims, strides, box, true);
     if (rc) return rc;
   }

@@ -36,6 +36,7 @@ constexpr int kThreads = 256;
 constexpr int kEpiThreads = 128;
 constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
 constexpr int STAGING_BYTES = BLOCK_M * 128;  // 128 rows x 128 B
+constexpr int WARP_STAGING_BYTES = 32 * 128;  // one epilogue warp's 32-row slab
 
 template <int BN>
 struct Cfg {
@@ -51,12 +52,21 @@ struct Cfg {
 // Work item of the persistent loop: an output tile, or one of the tail_split narrow slices of a
 // tile of the last partial wave.
 struct WorkItem {
-  int b, t0, n0, width;
+  int b, t0, n0, width, tap_begin, tap_end;
 };
 template <int BN>
 __device__ __forceinline__ WorkItem decode_item(const ConvGemmParams& p, int item) {
   int tile = item, sub = 0, width = BN;
-  if (item >= p.full_tiles) {
+  int tap_begin = 0, tap_end = p.taps;
+  if (p.ksplit > 1) {
+    // split-major order: CTAs running together share a tap range (the same weights in L2)
+    const int total = p.B * p.m_tiles_per_utt * p.n_tiles;
+    const int split = item / total;
+    tile = item - split * total;
+    const int per = (p.taps + p.ksplit - 1) / p.ksplit;
+    tap_begin = split * per;
+    tap_end = tap_begin + per < p.taps ? tap_begin + per : p.taps;
+  } else if (item >= p.full_tiles) {
     const int r = item - p.full_tiles;
     tile = p.full_tiles + r / p.tail_split;
     sub = r - (r / p.tail_split) * p.tail_split;
@@ -70,6 +80,8 @@ __device__ __forceinline__ WorkItem decode_item(const ConvGemmParams& p, int ite
   w.t0 = (rem - w.b * p.m_tiles_per_utt) * BLOCK_M;
   w.n0 = n_tile * BN + sub * width;
   w.width = width;
+  w.tap_begin = tap_begin;
+  w.tap_end = tap_end;
   return w;
 }
 
@@ -98,7 +110,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     prefetch_tmap(&p.tmA);
     prefetch_tmap(&p.tmB);
     if (p.tail_split > 1) prefetch_tmap(&p.tmBtail);
-    if (EPI == EPI_PACKED) prefetch_tmap(&p.tmY);
+    if (EPI != EPI_SOFTMAX) prefetch_tmap(&p.tmY);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::kStages; ++s) {
@@ -121,8 +133,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   const uint32_t tmem_base = *tmem_ptr_s;
 
   const int total_tiles = p.B * p.m_tiles_per_utt * p.n_tiles;
-  const int num_tiles = p.full_tiles + (total_tiles - p.full_tiles) * p.tail_split;  // work items
-  const int ksteps = p.taps * p.chunks * p.terms;
+  const int num_tiles = p.ksplit > 1 ? total_tiles * p.ksplit
+                                     : p.full_tiles + (total_tiles - p.full_tiles) * p.tail_split;  // work items
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -135,7 +147,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         const int b = w.b, t0 = w.t0, n0 = w.n0;
         const CUtensorMap* tmB = w.width == BN ? &p.tmB : &p.tmBtail;
         const uint32_t stage_tx = A_BYTES + w.width * (BLOCK_K * 2);
-        for (int tap = 0; tap < p.taps; ++tap) {
+        for (int tap = w.tap_begin; tap < w.tap_end; ++tap) {
           const int jp = tap - p.pad_l;  // signed frame offset of this tap
           int q, par;
           if (p.stride == 1) {
@@ -195,8 +207,9 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     uint32_t phase = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int width = tile >= p.full_tiles ? BN / p.tail_split : BN;
-      const uint32_t idesc = make_idesc_bf16(BLOCK_M, width, 0, BMN ? 1 : 0);
+      const WorkItem w = decode_item<BN>(p, tile);
+      const int ksteps = (w.tap_end - w.tap_begin) * p.chunks * p.terms;
+      const uint32_t idesc = make_idesc_bf16(BLOCK_M, w.width, 0, BMN ? 1 : 0);
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(&tmem_empty[as], aphase ^ 1);
@@ -226,6 +239,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           phase ^= 1;
         }
       }
+      if (ksteps == 0 && lane == 0) mbar_arrive(&tmem_full[as]);  // empty tap range (never planned)
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
@@ -234,6 +248,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     const int et = threadIdx.x - 128;
     int it = 0;
     uint32_t store_count = 0;
+    int staged_n0 = -1;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const WorkItem w = decode_item<BN>(p, tile);
       const int b = w.b, t0 = w.t0, n0 = w.n0;
@@ -243,19 +258,59 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       const int t = t0 + row;
       const bool row_valid = t < p.T_out;
 
-      // stage the bias slice of this tile (previous tile's readers are past the
-      // barrier below because every chunk iteration ends behind a named barrier)
-      named_bar_sync(2, kEpiThreads);
-      for (int i = et; i < w.width; i += kEpiThreads)
-        bias_s[i] = (p.bias != nullptr && (n0 + i) < p.n_valid) ? p.bias[n0 + i] : 0.f;
-      named_bar_sync(2, kEpiThreads);
+      // stage the bias slice of this tile; consecutive tiles of a CTA mostly share their filter
+      // range, so the (two-barrier) refill only runs when it changes
+      if (n0 != staged_n0) {
+        named_bar_sync(2, kEpiThreads);  // every warp is done reading the previous slice
+        for (int i = et; i < BN; i += kEpiThreads)
+          bias_s[i] = (p.bias != nullptr && (n0 + i) < p.n_valid) ? p.bias[n0 + i] : 0.f;
+        named_bar_sync(2, kEpiThreads);
+        staged_n0 = n0;
+      }
+      // ReLU bitmask of the whole row slice, fetched before the accumulator is ready
+      uint2 mask_in[BN / 64];
+      if (EPI == EPI_PACKED && p.mask_bits_in != nullptr && row_valid) {
+        const uint2* mp = reinterpret_cast<const uint2*>(
+            p.mask_bits_in + (static_cast<size_t>(b) * p.T_out + t) * p.mask_row_bytes + (n0 >> 3));
+#pragma unroll
+        for (int c = 0; c < BN / 64; ++c)
+          if (c < n_chunks) mask_in[c] = __ldg(mp + c);
+      }
 
       mbar_wait(&tmem_full[as], aphase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) +
                              static_cast<uint32_t>(as * BN);
 
-      if (EPI == EPI_PACKED) {
+      if (EPI == EPI_F32) {
+        // split-K partial sums: fp32 accumulator -> per-warp swizzled slab -> TMA reduce-add
+        const bool has_data = w.tap_end > w.tap_begin;
+#pragma unroll 1
+        for (int c = 0; c < (has_data ? w.width / 32 : 0); ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c * 32, r);
+          tmem_ld_wait();
+          uint8_t* sbuf = staging + ew * (2 * WARP_STAGING_BYTES) + (store_count & 1) * WARP_STAGING_BYTES;
+          if (lane == 0) tma_wait_group_read<1>();
+          __syncwarp();
+          uint8_t* rowp = sbuf + lane * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int phys = j ^ (lane & 7);
+            *reinterpret_cast<uint4*>(rowp + phys * 16) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_reduce_add_3d(&p.tmY, sbuf, n0 + c * 32, t0 + ew * 32, b);
+            tma_commit_group();
+          }
+          ++store_count;
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[as]);
+      } else if (EPI == EPI_PACKED) {
 #pragma unroll 1
         for (int c = 0; c < n_chunks; ++c) {
           uint32_t r0[32], r1[32];
@@ -280,9 +335,10 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           }
           if (p.mask_bits_in != nullptr && row_valid) {
             // ReLU backward: keep the gradient only where the forward output was > 0
-            const uint2 mb = __ldg(reinterpret_cast<const uint2*>(
-                p.mask_bits_in + (static_cast<size_t>(b) * p.T_out + t) * p.mask_row_bytes +
-                ((n0 + c * 64) >> 3)));
+            uint2 mb = mask_in[0];
+#pragma unroll
+            for (int cc = 1; cc < BN / 64; ++cc)
+              if (cc == c) mb = mask_in[cc];
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               if (!((mb.x >> i) & 1u)) v[i] = 0.f;
@@ -311,20 +367,22 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
                                         v[2 * i + 1] - bf16_round(v[2 * i + 1]));
               }
             }
-            uint8_t* sbuf = staging + (store_count & 1) * STAGING_BYTES;
-            if (et == 0) tma_wait_group_read<1>();  // the store that last read sbuf is done
-            named_bar_sync(1, kEpiThreads);
-            uint8_t* rowp = sbuf + row * 128;
+            // Each epilogue warp owns a 32-row slab: it stages and TMA-stores it on its own, so
+            // the four warps never wait for each other (bulk async-groups are per thread).
+            uint8_t* sbuf = staging + ew * (2 * WARP_STAGING_BYTES) + (store_count & 1) * WARP_STAGING_BYTES;
+            if (lane == 0) tma_wait_group_read<1>();  // the store that last read sbuf is done
+            __syncwarp();
+            uint8_t* rowp = sbuf + lane * 128;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const int phys = j ^ (row & 7);  // SWIZZLE_128B: 16-byte chunk index ^= row % 8
+              const int phys = j ^ (lane & 7);  // SWIZZLE_128B: 16-byte chunk index ^= row % 8
               *reinterpret_cast<uint4*>(rowp + phys * 16) =
                   make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
             }
             fence_proxy_async_smem();
-            named_bar_sync(1, kEpiThreads);
-            if (et == 0) {
-              tma_store_3d(&p.tmY, sbuf, n0 + c * 64 + (plane ? p.y_lo_off : 0), t0, b);
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_3d(&p.tmY, sbuf, n0 + c * 64 + (plane ? p.y_lo_off : 0), t0 + ew * 32, b);
               tma_commit_group();
             }
             ++store_count;
@@ -387,7 +445,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         }
       }
     }
-    if (EPI == EPI_PACKED && et == 0) tma_wait_group<0>();
+    if (EPI != EPI_SOFTMAX && lane == 0) tma_wait_group<0>();
   }
 
   tcgen05_fence_before();
@@ -407,9 +465,9 @@ int launch(const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     configured = true;
   }
-  const int num_tiles = p.B * p.m_tiles_per_utt * p.n_tiles;
+  const int num_tiles = p.B * p.m_tiles_per_utt * p.n_tiles * (p.ksplit > 1 ? p.ksplit : 1);
   const int grid = num_tiles < num_sms ? num_tiles : num_sms;
-  if (p.full_tiles + (num_tiles - p.full_tiles) * p.tail_split < grid || p.tail_split < 1) {
+  if (p.ksplit <= 1 && (p.full_tiles + (num_tiles - p.full_tiles) * p.tail_split < grid || p.tail_split < 1)) {
     set_error("conv_gemm: inconsistent tail split");
     return 1;
   }
@@ -425,6 +483,11 @@ int conv_gemm_launch(const ConvGemmParams& p, int block_n, int epi, bool b_mn_ma
   if (epi == EPI_SOFTMAX) {
     SL_REQUIRE(block_n == 64 && !b_mn_major, "softmax epilogue needs a 64-wide K-major tile");
     return launch<64, EPI_SOFTMAX, false>(p, num_sms, stream);
+  }
+  if (epi == EPI_F32) {
+    SL_REQUIRE(b_mn_major && (block_n == 128 || block_n == 256), "split-K epilogue is built for the dgrad tiles");
+    return block_n == 256 ? launch<256, EPI_F32, true>(p, num_sms, stream)
+                          : launch<128, EPI_F32, true>(p, num_sms, stream);
   }
   switch (block_n) {
     case 64:

@@ -4,7 +4,7 @@
 
 namespace sl {
 
-enum { EPI_PACKED = 0, EPI_SOFTMAX = 1 };
+enum { EPI_PACKED = 0, EPI_SOFTMAX = 1, EPI_F32 = 2 };
 
 // Forward / input-gradient implicit GEMM (conv_umma.cu)
 struct ConvGemmParams {
@@ -12,7 +12,8 @@ struct ConvGemmParams {
   CUtensorMap tmB;  // weights (k, cout, cin), rank 3 {cin_total, cout, taps}: box {64, BN, 1} (fwd: K-major B)
                     // or box {64, 64, 1} (dgrad: MN-major B, 64 cout rows of contraction)
   CUtensorMap tmBtail;  // as tmB with a box of BN / tail_split filters: the last partial wave's narrow tiles
-  CUtensorMap tmY;  // packed bf16 output, rank 3 {C_total, T_out, B}, box {64,128,1}
+  CUtensorMap tmY;  // packed bf16 output, rank 3 {C_total, T_out, B}, box {64,32,1}; EPI_F32: fp32 partial
+                    // sums {C_pad, T_out, B}, box {32,32,1}, written with TMA reduce-add
   int B;
   int T_out;
   int m_tiles_per_utt;
@@ -21,6 +22,9 @@ struct ConvGemmParams {
   // tail_split (1, 2 or 4) narrower tiles so that the wave costs 1/tail_split of a tile time
   int full_tiles;  // tiles [0, full_tiles) are whole; the rest are split
   int tail_split;
+  // split K (EPI_F32 only): every tile is computed by ksplit work items, each over a contiguous
+  // range of filter taps, whose fp32 partial sums meet in HBM through TMA reduce-add
+  int ksplit;
   int taps;
   int chunks;  // 64-channel chunks of the contraction dimension
   int terms;   // 1 = bf16, 3 = split bf16 (hi*hi + hi*lo + lo*hi)

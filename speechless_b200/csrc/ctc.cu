@@ -135,21 +135,47 @@ __global__ void ctc_alpha_beta_kernel(const float* __restrict__ logp,
     }
     const float* lp_row = lp_s + (tt & (2 * CHUNK - 1)) * VP;
     float val[SPT];
+    if (SPT == 2) {
+      // states s0 (even: blank) and s0+1 (label): two 8-byte loads cover prev[s0-2 .. s0+1]
+      const float2 lo = *reinterpret_cast<const float2*>(prev + s0 - 2);
+      const float2 hi = *reinterpret_cast<const float2*>(prev + s0);
+      const float em0 = lp_row[my_e[0]] * LOG2E;
+      const float em1 = lp_row[my_e[1]] * LOG2E;
+      val[0] = lse3_base2(hi.x, lo.y, my_skip[0] ? lo.x : -INFINITY) + em0;
+      val[1] = lse3_base2(hi.y, hi.x, my_skip[1] ? lo.y : -INFINITY) + em1;
+      if (tt == 0) {
+        val[0] = (s0 <= 1) ? em0 : -INFINITY;
+        val[1] = (s0 + 1 <= 1) ? em1 : -INFINITY;
+      }
+      if (my_on[1]) {
+        *reinterpret_cast<float2*>(cur + s0) = make_float2(val[0], val[1]);
+        if (dir == 0) {
+          *reinterpret_cast<float2*>(out + s0) = make_float2(val[0], val[1]);
+        } else {
+          out[my_out[0]] = val[0];
+          out[my_out[1]] = val[1];
+        }
+      } else if (my_on[0]) {
+        cur[s0] = val[0];
+        out[my_out[0]] = val[0];
+      }
+    } else {
 #pragma unroll
-    for (int i = 0; i < SPT; ++i) {
-      const int s = s0 + i;
-      const float em = lp_row[my_e[i]] * LOG2E;
-      const float a0 = prev[s];
-      const float a1 = prev[s - 1];
-      const float a2 = my_skip[i] ? prev[s - 2] : -INFINITY;
-      val[i] = lse3_base2(a0, a1, a2) + em;
-      if (tt == 0) val[i] = (s <= 1) ? em : -INFINITY;
-    }
+      for (int i = 0; i < SPT; ++i) {
+        const int s = s0 + i;
+        const float em = lp_row[my_e[i]] * LOG2E;
+        const float a0 = prev[s];
+        const float a1 = prev[s - 1];
+        const float a2 = my_skip[i] ? prev[s - 2] : -INFINITY;
+        val[i] = lse3_base2(a0, a1, a2) + em;
+        if (tt == 0) val[i] = (s <= 1) ? em : -INFINITY;
+      }
 #pragma unroll
-    for (int i = 0; i < SPT; ++i) {
-      if (my_on[i]) {
-        cur[s0 + i] = val[i];
-        out[my_out[i]] = val[i];
+      for (int i = 0; i < SPT; ++i) {
+        if (my_on[i]) {
+          cur[s0 + i] = val[i];
+          out[my_out[i]] = val[i];
+        }
       }
     }
     out += out_step;
@@ -201,7 +227,7 @@ __global__ void ctc_grad_kernel(const float* __restrict__ logp, const float* __r
   __syncthreads();
   const float loss_b = loss[b];
   const float loss2 = loss_b * LOG2E;
-  float* my_bins = bins + warp * VP;
+  float* my_bins = bins + warp * (2 * VP);  // [VP] occupancy bins | [VP] log-prob row
   const int t_begin = blockIdx.x * frames_per_block;
   const int t_end = min(t_begin + frames_per_block, T);
   const int row_elems = planes * 64;
@@ -210,13 +236,22 @@ __global__ void ctc_grad_kernel(const float* __restrict__ logp, const float* __r
     const size_t ro = static_cast<size_t>(b) * T + t;
     float dz[2] = {0.f, 0.f};  // symbols lane and lane + 32
     if (t < P && isfinite(loss_b)) {
+      // issue every independent load of this frame up front: the symbol row (to smem), the
+      // probabilities, then the lattice rows
+      const float* lp_g = logp + ro * VP;
+      const float lp_mine[2] = {lp_g[lane], lp_g[lane + 32]};
+      float pv_mine[2] = {0.f, 0.f};
+      if (lane < V) pv_mine[0] = probs[ro * V + lane];
+      if (lane + 32 < V) pv_mine[1] = probs[ro * V + lane + 32];
+      float* lp_row = my_bins + VP;  // per-warp copy of the log-prob row (base 2)
       my_bins[lane] = 0.f;
       my_bins[lane + 32] = 0.f;
+      lp_row[lane] = lp_mine[0] * LOG2E;
+      lp_row[lane + 32] = lp_mine[1] * LOG2E;
       __syncwarp();
       const float4* a_row = reinterpret_cast<const float4*>(alpha + ro * S_stride);
       const float4* b_row = reinterpret_cast<const float4*>(beta + ro * S_stride);
-      const float* lp_row = logp + ro * VP;
-      const float lp_blank2 = lp_row[blank] * LOG2E;
+      const float lp_blank2 = lp_row[blank];
       float blank_acc = 0.f;
       for (int base = 0; base < S; base += 512) {
         // up to 4 passes of 128 states issued together (8 x 16-byte loads in flight per lane)
@@ -238,13 +273,13 @@ __global__ void ctc_grad_kernel(const float* __restrict__ logp, const float* __r
             blank_acc += ex2_approx(ab[0] - lp_blank2 + loss2);
             if (s + 1 < S) {
               const int v = lab_s[s >> 1];
-              const float x = ex2_approx(ab[1] - lp_row[v] * LOG2E + loss2);
+              const float x = ex2_approx(ab[1] - lp_row[v] + loss2);
               if (x != 0.f) atomicAdd(&my_bins[v], x);
             }
             if (s + 2 < S) blank_acc += ex2_approx(ab[2] - lp_blank2 + loss2);
             if (s + 3 < S) {
               const int v = lab_s[(s >> 1) + 1];
-              const float x = ex2_approx(ab[3] - lp_row[v] * LOG2E + loss2);
+              const float x = ex2_approx(ab[3] - lp_row[v] + loss2);
               if (x != 0.f) atomicAdd(&my_bins[v], x);
             }
           }
@@ -260,8 +295,8 @@ __global__ void ctc_grad_kernel(const float* __restrict__ logp, const float* __r
         const int v = lane + 32 * h;
         if (v < V) {
           const float occ = (v == blank) ? blank_acc : my_bins[v];
-          pv[h] = probs[ro * V + v];
-          const float g = expf(lp_row[v]) - occ;
+          pv[h] = pv_mine[h];
+          const float g = expf(lp_mine[h]) - occ;
           dLdp[h] = g / (pv[h] + 1e-8f);
           dot += pv[h] * dLdp[h];
         }
@@ -384,10 +419,10 @@ int ctc_loss_launch(const float* logp, const float* probs, const int32_t* labels
 
   if (dlogits_packed != nullptr || dlogits_f32 != nullptr) {
     SL_REQUIRE(probs != nullptr, "gradient needs the softmax probabilities");
-    const int frames_per_block = 64;
+    const int frames_per_block = 16;  // 2 frames per warp: many short, independent chains in flight
     const int warps = 8;
     dim3 grid((T + frames_per_block - 1) / frames_per_block, B);
-    const size_t gsmem = ((L_max + 31) & ~31) * sizeof(int) + warps * VP * sizeof(float);
+    const size_t gsmem = ((L_max + 31) & ~31) * sizeof(int) + warps * 2 * VP * sizeof(float);
     ctc_grad_kernel<<<grid, warps * 32, gsmem, stream>>>(
         logp, probs, labels, input_len, label_len, loss, alpha, beta,
         reinterpret_cast<__nv_bfloat16*>(dlogits_packed), dlogits_f32, grad_scale, T, V, L_max,

@@ -243,6 +243,37 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+// split-K dgrad finalize: fp32 sums (rows, c_pad) -> ReLU mask -> packed bf16 (hi | lo).
+// One thread per 8 channels: two float4 loads, one mask byte, one (or two) 16-byte stores.
+__global__ void dgrad_finalize_kernel(const float* __restrict__ acc, const uint8_t* __restrict__ mask,
+                                      __nv_bfloat16* __restrict__ dx, size_t rows, int c_pad, int planes) {
+  const int groups = c_pad / 8;
+  const size_t total = rows * groups;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t row = i / groups;
+    const int g = static_cast<int>(i - row * groups);
+    const float4 a = *reinterpret_cast<const float4*>(acc + row * c_pad + g * 8);
+    const float4 b = *reinterpret_cast<const float4*>(acc + row * c_pad + g * 8 + 4);
+    float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    if (mask != nullptr) {
+      const unsigned m = mask[row * groups + g];
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (!((m >> e) & 1u)) v[e] = 0.f;
+    }
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      hi[e] = pack_bf16x2(v[2 * e], v[2 * e + 1]);
+      lo[e] = pack_bf16x2(v[2 * e] - bf16_round(v[2 * e]), v[2 * e + 1] - bf16_round(v[2 * e + 1]));
+    }
+    __nv_bfloat16* dst = dx + row * (static_cast<size_t>(planes) * c_pad) + g * 8;
+    *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    if (planes == 2) *reinterpret_cast<uint4*>(dst + c_pad) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
 inline int grid_for(size_t total, int block) {
   size_t g = (total + block - 1) / block;
   const size_t cap = 148 * 16;
@@ -286,6 +317,13 @@ int pack_weights_internal_launch(const float* wi, void* wf, int k, int cin_pad, 
   const size_t rows = static_cast<size_t>(k) * cout_pad;
   pack_w_fwd_kernel<<<grid_for(rows * (cin_pad / 2), 256), 256, 0, s>>>(
       wi, reinterpret_cast<__nv_bfloat16*>(wf), rows, cin_pad, planes);
+  SL_CUDA(cudaGetLastError());
+  return 0;
+}
+int dgrad_finalize_launch(const float* acc, const void* mask, void* dx, size_t rows, int c_pad, int planes,
+                          cudaStream_t s) {
+  dgrad_finalize_kernel<<<grid_for(rows * (c_pad / 8), 256), 256, 0, s>>>(
+      acc, reinterpret_cast<const uint8_t*>(mask), reinterpret_cast<__nv_bfloat16*>(dx), rows, c_pad, planes);
   SL_CUDA(cudaGetLastError());
   return 0;
 }

@@ -38,6 +38,7 @@ constexpr int A_BYTES = 2 * BOX_BYTES;       // 128 filters
 constexpr int LBO = BOX_BYTES;               // byte stride between 64-channel groups
 constexpr int SBO = 1024;                    // byte stride between 8-frame groups
 constexpr int STAGING_BYTES = BLOCK_M * 128; // 128 filters x 32 fp32 columns
+constexpr int WARP_STAGING_BYTES = 32 * 128; // one epilogue warp's 32-row slab
 constexpr int kEpiThreads = 128;
 
 template <int BN>
@@ -292,23 +293,24 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[as]);
           }
-          uint8_t* sbuf = staging + (store_count & 1) * STAGING_BYTES;
-          if (et == 0) tma_wait_group_read<1>();
-          named_bar_sync(1, kEpiThreads);
-          uint8_t* rowp = sbuf + row * 128;
+          // per-warp 32-row slab: no cross-warp barrier (see conv_umma.cu)
+          uint8_t* sbuf = staging + ew * (2 * WARP_STAGING_BYTES) + (store_count & 1) * WARP_STAGING_BYTES;
+          if (lane == 0) tma_wait_group_read<1>();
+          __syncwarp();
+          uint8_t* rowp = sbuf + lane * 128;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const int phys = j ^ (row & 7);
+            const int phys = j ^ (lane & 7);
             *reinterpret_cast<uint4*>(rowp + phys * 16) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
           }
           fence_proxy_async_smem();
-          named_bar_sync(1, kEpiThreads);
-          if (et == 0) {
+          __syncwarp();
+          if (lane == 0) {
             // rows beyond cout_pad (output_conv: 64 of 128) are clipped by the tensor map
             if (p.use_atomics)
-              tma_reduce_add_3d(&p.tmDW, sbuf, nt * BN + c * 32, mt * BLOCK_M, tap);
+              tma_reduce_add_3d(&p.tmDW, sbuf, nt * BN + c * 32, mt * BLOCK_M + ew * 32, tap);
             else
-              tma_store_3d(&p.tmDW, sbuf, nt * BN + c * 32, mt * BLOCK_M, tap);
+              tma_store_3d(&p.tmDW, sbuf, nt * BN + c * 32, mt * BLOCK_M + ew * 32, tap);
             tma_commit_group();
           }
           ++store_count;
@@ -319,7 +321,7 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
         if (lane == 0) mbar_arrive(&tmem_empty[as]);
       }
     }
-    if (et == 0) tma_wait_group<0>();
+    if (lane == 0) tma_wait_group<0>();
   }
 
   tcgen05_fence_before();

@@ -125,6 +125,7 @@ class _Workspace:
         self.dz_packed: Optional[torch.Tensor] = None
         self.dz_f32: Optional[torch.Tensor] = None
         self.dact: List[Optional[torch.Tensor]] = [None, None]
+        self.dgrad_ws: Optional[torch.Tensor] = None  # fp32 scratch of the split-K input gradient
 
     def ensure_backward(self, tower: "ConvTower"):
         if self.dz_packed is None:
@@ -506,10 +507,14 @@ class ConvTower:
                     mask = ws.masks[index - 1] if below.activation == "relu" else None
                     if previous_wgrad_done is not None:
                         main.wait_event(previous_wgrad_done)  # it reads the buffer dx aliases
+                    need = self.lib.sl_conv1d_dgrad_workspace_bytes(ws.B, t_in, layer.cin, layer.cout, layer.kernel)
+                    if need and (ws.dgrad_ws is None or ws.dgrad_ws.numel() < need):
+                        ws.dgrad_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+                    scratch = ws.dgrad_ws if need else None
                     self._timed("dgrad", layer.name, lambda: self.lib.sl_conv1d_dgrad(
                         ptr(dy), ptr(self.w_fwd[index]), ptr(mask), ptr(dx), ws.B, t_in, layer.cin, layer.cout,
-                        layer.kernel, self.precision, self.stream))
-                    self.launches += 1
+                        layer.kernel, self.precision, ptr(scratch), need, self.stream))
+                    self.launches += 2 if need else 1
                     dy = dx
                     flip ^= 1
             if side is not None:

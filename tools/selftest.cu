@@ -321,8 +321,11 @@ static bool run_dgrad(const ConvCase& cc, int prec) {
   Dev<uint8_t> dmask(hmask.size());
   dmask.up(hmask);
   SLCK(sl_pack_weights(dw.p, wd.p, k, Cin, Cout, cip, cop, prec, nullptr));
+  const size_t wsb = sl_conv1d_dgrad_workspace_bytes(B, T, Cin, Cout, k);
+  Dev<uint8_t> dws(wsb);
+  if (wsb) printf("  (split-K dgrad, %zu byte scratch)\n", wsb);
   SLCK(sl_conv1d_dgrad(dyp.p, wd.p, cc.act == SL_ACT_RELU ? dmask.p : nullptr, dxp.p, B, T, Cin, Cout, k, prec,
-                       nullptr));
+                       wsb ? dws.p : nullptr, wsb, nullptr));
   SLCK(sl_unpack_activation(dxp.p, dxo.p, B, T, Cin, T, cip, prec, nullptr));
   SLCK(sl_sync_check());
   auto ref = prec == 1 ? cpu_dgrad(round_bf16(dy), round_bf16(w), B, T, Cin, Cout, k)
@@ -663,6 +666,7 @@ static bool run_perf(int B, int T, int prec, int iters) {
     };
     bool ok = true;
     Dev<uint16_t> y2(static_cast<size_t>(B) * T_out * cop * prec);
+    Dev<uint8_t> dgws(L.s == 1 ? sl_conv1d_dgrad_workspace_bytes(B, t_in, L.cin, L.cout, L.k) : 0);
     Dev<uint8_t> pmask(static_cast<size_t>(B) * T_out * cop / 8), pmask_in(static_cast<size_t>(B) * T_alloc * cip / 8);
     CK(cudaMemset(pmask_in.p, 0x5a, pmask_in.n));
     if (is_out)
@@ -677,7 +681,8 @@ static bool run_perf(int B, int T, int prec, int iters) {
       });
     if (L.s == 1)
       ok &= time_it("dgrad", [&] {
-        return sl_conv1d_dgrad(yp.p, wf.p, pmask_in.p, dxp.p, B, t_in, L.cin, L.cout, L.k, prec, nullptr);
+        return sl_conv1d_dgrad(yp.p, wf.p, pmask_in.p, dxp.p, B, t_in, L.cin, L.cout, L.k, prec,
+                               dgws.n > 1 ? dgws.p : nullptr, dgws.n > 1 ? dgws.n : 0, nullptr);
       });
     ok &= time_it("wgrad", [&] {
       return sl_conv1d_wgrad(xp.p, yp.p, dw.p, db.p, B, t_in, T_alloc, L.cin, L.cout, L.k, L.s, prec, 1, nullptr);
@@ -755,6 +760,7 @@ int main(int argc, char** argv) {
       {"out_k1_2000_29", 2, 151, 2000, 29, 1, 1, SL_ACT_RELU},
       {"tail4_k3_250", 10, 2000, 250, 250, 3, 1, SL_ACT_RELU},
       {"tail2_k1_128_64", 10, 2000, 128, 64, 1, 1, SL_ACT_RELU},
+      {"splitk_k8_250_2000", 10, 2000, 250, 2000, 8, 1, SL_ACT_RELU},
   };
   for (const auto& cc : dg_cases)
     for (int prec = 1; prec <= 2; ++prec) {
