@@ -50,12 +50,31 @@ def library_path() -> Path:
     return Path(override) if override else Path(__file__).resolve().parent / _LIB_NAME
 
 
+def _try_build(path: Path) -> None:
+    """The built library normally travels with the tree; on a fresh checkout compile it once with
+    nvcc (sm_100a) if the toolchain is there.  Failure is not fatal here: load() raises."""
+    import shutil
+    import subprocess
+    csrc = path.parent / "csrc"
+    if not (csrc / "Makefile").exists() or shutil.which("make") is None:
+        return
+    if shutil.which("nvcc") is None and not Path("/usr/local/cuda/bin/nvcc").exists():
+        return
+    try:
+        subprocess.run(["make", "-C", str(csrc), "-j", str(os.cpu_count() or 4), "all"], check=True,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=900)
+    except Exception:
+        pass
+
+
 def load():
     """Load (once) and return the ctypes handle; raises RuntimeError when the library is absent."""
     global _lib
     if _lib is not None:
         return _lib
     path = library_path()
+    if not path.exists() and "SPEECHLESS_B200_LIB" not in os.environ:
+        _try_build(path)
     if not path.exists():
         raise RuntimeError(
             "{} not found at {} — build it with `python -c 'import __graft_entry__ as g; g.build()'` "
