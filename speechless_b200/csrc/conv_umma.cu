@@ -174,6 +174,26 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
                 continue;
               }
               ++issued;
+              if (p.dbg_mode >= 2 && issued > C::kStages) {
+                // measurement aids: 2 = keep only the A loads (what a shared-B / 2-CTA scheme would
+                // save), 3 = keep only the B loads (what reusing the A halo across taps would save)
+                if (p.dbg_mode == 2) {
+                  mbar_expect_tx(&full_bar[stage], A_BYTES);
+                  tma_load_4d(&p.tmA, &full_bar[stage], a_s, a_c, par, t0 + q, b);
+                } else {
+                  mbar_expect_tx(&full_bar[stage], stage_tx - A_BYTES);
+                  if (BMN)
+                    tma_load_4d(tmB, &full_bar[stage], b_s, 0, chunk * BLOCK_K,
+                                (n0 + (term == 1 ? p.b_lo_off : 0)) >> 6, wtap);
+                  else
+                    tma_load_3d(tmB, &full_bar[stage], b_s, b_c, n0, wtap);
+                }
+                if (++stage == C::kStages) {
+                  stage = 0;
+                  phase ^= 1;
+                }
+                continue;
+              }
               mbar_expect_tx(&full_bar[stage], stage_tx);
               tma_load_4d(&p.tmA, &full_bar[stage], a_s, a_c, par, t0 + q, b);
               if (BMN) {

@@ -508,7 +508,9 @@ class Wav2Letter:
             self.optimizer.iterations += 1
             tower.adam_step(self.optimizer.lr, self.optimizer.beta_1, self.optimizer.beta_2,
                             self.optimizer.epsilon, self.optimizer.iterations)
-            host_loss = torch.empty((), dtype=torch.float32, pin_memory=True)
+            if len(device_losses) % 64 == 0:  # pinned allocations are slow: one per 64 steps
+                host_block = torch.empty((64,), dtype=torch.float32, pin_memory=True)
+            host_loss = host_block[len(device_losses) % 64]
             host_loss.copy_(loss_sum, non_blocking=True)  # device -> host read of the step's result
             device_losses.append(host_loss)
             batch_sizes.append(batch_size)
