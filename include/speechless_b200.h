@@ -84,14 +84,23 @@ int sl_conv1d_fwd(const void* x_packed, const void* w_fwd, const float* bias,
                   float* logp, int B, int T_in, int T_in_alloc, int Cin, int Cout,
                   int k, int stride, int act, int prec, void* stream);
 
-/* dX = conv1d_same_backward_input(dY, w) masked by the ReLU of the layer below
+/* Inverted dropout in front of a Conv1D (keras.layers.Dropout, net.py:301-303), training
+ * phase: y = keep ? x/(1-p) : 0 on a packed (B,T,round64(C)) activation.  The keep decision
+ * of an element is a pure function of (seed, element index).  mask_out (B,T,round64(C)/8)
+ * bytes = keep bits AND relu_mask_in bits (if given): with out_scale = 1/(1-p) it is what
+ * sl_conv1d_dgrad of the consuming layer applies on its way down. */
+int sl_dropout_fwd(const void* x_packed, void* y_packed, const void* relu_mask_in,
+                   void* mask_out, int B, int T, int C, int prec, float p,
+                   uint64_t seed, void* stream);
+
+/* dX = out_scale * conv1d_same_backward_input(dY, w) masked by the ReLU of the layer below
  * (TF autodiff of net.py:304-305; stride 1 only — the strided first layer needs
  * no dX).  relu_mask = the relu_mask_out the layer below wrote in its forward
  * pass ((B,T,cin_pad/8) bytes), or NULL for a linear layer below. */
 int sl_conv1d_dgrad(const void* dy_packed, const void* w_fwd,
                     const void* relu_mask, void* dx_packed, int B, int T,
-                    int Cin, int Cout, int k, int prec, void* workspace,
-                    size_t workspace_bytes, void* stream);
+                    int Cin, int Cout, int k, int prec, float out_scale,
+                    void* workspace, size_t workspace_bytes, void* stream);
 /* Optional fp32 scratch for the split-K variant (long tap loops whose tile count fills the
  * persistent grid badly, e.g. big_conv_1); 0 = not wanted for this shape.  Passing
  * workspace = NULL is always legal and selects the unsplit kernel. */

@@ -26,7 +26,8 @@ int unpack_activation_launch(const void*, float*, int, int, int, int, int, int, 
 int keras_to_internal_launch(const float*, float*, int, int, int, int, int, cudaStream_t);
 int internal_to_keras_launch(const float*, float*, int, int, int, int, int, cudaStream_t);
 int pack_weights_internal_launch(const float*, void*, int, int, int, int, cudaStream_t);
-int dgrad_finalize_launch(const float*, const void*, void*, size_t, int, int, cudaStream_t);
+int dgrad_finalize_launch(const float*, const void*, void*, size_t, int, int, float, cudaStream_t);
+int dropout_launch(const void*, void*, const void*, void*, size_t, int, int, float, unsigned long long, cudaStream_t);
 int adam_fused_launch(float*, const float*, float*, float*, size_t, const size_t*, const size_t*, void* const*,
                       const int*, int, int, float, float, float, float, int, cudaStream_t);
 int adam_launch(float*, const float*, float*, float*, size_t, float, float, float, float, int,
@@ -266,6 +267,7 @@ int sl_conv1d_fwd(const void* x_packed, const void* w_fwd, const float* bias, vo
   p.pad_l = pad_l;
   p.tap_reverse = 0;
   p.dbg_mode = dbg_mode();
+  p.out_scale = 1.0f;
   p.bias = bias;
   p.n_valid = Cout;
   int epi = EPI_PACKED;
@@ -323,7 +325,7 @@ size_t sl_conv1d_dgrad_workspace_bytes(int B, int T, int Cin, int Cout, int k) {
 }
 
 int sl_conv1d_dgrad(const void* dy_packed, const void* w_fwd, const void* relu_mask, void* dx_packed,
-                    int B, int T, int Cin, int Cout, int k, int prec, void* workspace,
+                    int B, int T, int Cin, int Cout, int k, int prec, float out_scale, void* workspace,
                     size_t workspace_bytes, void* stream) {
   SL_REQUIRE(dy_packed && w_fwd && dx_packed, "null pointer");
   SL_REQUIRE(B > 0 && T > 0 && Cin > 0 && Cout > 0 && k > 0, "bad shape");
@@ -368,6 +370,7 @@ int sl_conv1d_dgrad(const void* dy_packed, const void* w_fwd, const void* relu_m
   p.bias = nullptr;
   p.n_valid = Cin;
   p.relu = 0;
+  p.out_scale = out_scale;
   p.y_planes = planes;
   p.y_lo_off = cin_pad;
   p.mask_bits_in = static_cast<const uint8_t*>(relu_mask);
@@ -392,7 +395,7 @@ int sl_conv1d_dgrad(const void* dy_packed, const void* w_fwd, const void* relu_m
     rc = conv_gemm_launch(p, bn, EPI_F32, true, num_sms(), s);
     if (rc) return rc;
     return dgrad_finalize_launch(static_cast<const float*>(workspace), relu_mask, dx_packed,
-                                 static_cast<size_t>(B) * T, cin_pad, planes, s);
+                                 static_cast<size_t>(B) * T, cin_pad, planes, out_scale, s);
   }
   return conv_gemm_launch(p, bn, EPI_PACKED, true, num_sms(), static_cast<cudaStream_t>(stream));
 }
@@ -510,6 +513,15 @@ int sl_adam_step(float* p, const float* g, float* m, float* v, size_t n, float l
              "Adam buffers must be 16-byte aligned");
   if (n == 0) return SL_OK;
   return adam_launch(p, g, m, v, n, lr, beta1, beta2, eps, t, static_cast<cudaStream_t>(stream));
+}
+
+int sl_dropout_fwd(const void* x_packed, void* y_packed, const void* relu_mask_in, void* mask_out, int B, int T,
+                   int C, int prec, float p, uint64_t seed, void* stream) {
+  SL_REQUIRE(x_packed && y_packed && mask_out, "null pointer");
+  SL_REQUIRE(B > 0 && T > 0 && C > 0, "bad shape");
+  SL_REQUIRE(p >= 0.0f && p < 1.0f, "dropout rate must be in [0, 1)");
+  return dropout_launch(x_packed, y_packed, relu_mask_in, mask_out, static_cast<size_t>(B) * T, round64(C),
+                        planes_of(prec), p, seed, static_cast<cudaStream_t>(stream));
 }
 
 int sl_adam_step_fused(float* p, const float* g, float* m, float* v, size_t n, const size_t* w_begin_host,

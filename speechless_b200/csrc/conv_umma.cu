@@ -365,6 +365,10 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
               if (!((mb.y >> i) & 1u)) v[32 + i] = 0.f;
             }
           }
+          if (p.out_scale != 1.0f) {
+#pragma unroll
+            for (int i = 0; i < 64; ++i) v[i] *= p.out_scale;
+          }
           if (p.mask_bits_out != nullptr && row_valid) {
             uint2 mb = make_uint2(0u, 0u);
 #pragma unroll

@@ -36,6 +36,7 @@ struct ConvGemmParams {
   const float* bias;
   int n_valid;  // number of real (unpadded) output channels: bias bound
   int relu;
+  float out_scale;  // multiplies the (masked) output: 1/(1-p) of a dropout layer sitting below (dgrad), else 1
   int y_planes;  // 1 or 2 (hi | lo)
   int y_lo_off;
   // ReLU sign bitmask, 1 bit per (frame, channel), rows of mask_row_bytes = C_pad / 8 bytes:

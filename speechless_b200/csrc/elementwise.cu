@@ -246,7 +246,8 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 // split-K dgrad finalize: fp32 sums (rows, c_pad) -> ReLU mask -> packed bf16 (hi | lo).
 // One thread per 8 channels: two float4 loads, one mask byte, one (or two) 16-byte stores.
 __global__ void dgrad_finalize_kernel(const float* __restrict__ acc, const uint8_t* __restrict__ mask,
-                                      __nv_bfloat16* __restrict__ dx, size_t rows, int c_pad, int planes) {
+                                      __nv_bfloat16* __restrict__ dx, size_t rows, int c_pad, int planes,
+                                      float out_scale) {
   const int groups = c_pad / 8;
   const size_t total = rows * groups;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -255,7 +256,8 @@ __global__ void dgrad_finalize_kernel(const float* __restrict__ acc, const uint8
     const int g = static_cast<int>(i - row * groups);
     const float4 a = *reinterpret_cast<const float4*>(acc + row * c_pad + g * 8);
     const float4 b = *reinterpret_cast<const float4*>(acc + row * c_pad + g * 8 + 4);
-    float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    float v[8] = {a.x * out_scale, a.y * out_scale, a.z * out_scale, a.w * out_scale,
+                  b.x * out_scale, b.y * out_scale, b.z * out_scale, b.w * out_scale};
     if (mask != nullptr) {
       const unsigned m = mask[row * groups + g];
 #pragma unroll
@@ -271,6 +273,58 @@ __global__ void dgrad_finalize_kernel(const float* __restrict__ acc, const uint8
     __nv_bfloat16* dst = dx + row * (static_cast<size_t>(planes) * c_pad) + g * 8;
     *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     if (planes == 2) *reinterpret_cast<uint4*>(dst + c_pad) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+// Inverted dropout on a packed activation (keras.layers.Dropout in front of striding_conv /
+// inner_conv_*, reference net.py:301-303): y = keep ? x / (1 - p) : 0, training phase only.
+// One thread per 8 channels; the keep decision of element i is bit-reproducible from
+// (seed, i): 16 random bits per element from a splitmix64 hash of the 4-element group index.
+// mask_out bit = keep & (relu_mask_in bit, if given): exactly what the input-gradient epilogue
+// of the consuming layer must multiply by (together with the 1/(1-p) scale).
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+__global__ void dropout_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                               const uint8_t* __restrict__ relu_mask_in, uint8_t* __restrict__ mask_out,
+                               size_t rows, int c_pad, int planes, unsigned threshold16, float scale,
+                               unsigned long long seed) {
+  const int groups = c_pad / 8;
+  const size_t total = rows * groups;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t row = i / groups;
+    const int g = static_cast<int>(i - row * groups);
+    const unsigned long long r0 = splitmix64(seed ^ (2 * i)), r1 = splitmix64(seed ^ (2 * i + 1));
+    unsigned keep = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (((r0 >> (16 * e)) & 0xffffu) >= threshold16) keep |= 1u << e;
+      if (((r1 >> (16 * e)) & 0xffffu) >= threshold16) keep |= 1u << (4 + e);
+    }
+    const size_t base = row * (static_cast<size_t>(planes) * c_pad) + g * 8;
+    const uint4 h = *reinterpret_cast<const uint4*>(x + base);
+    uint4 l = make_uint4(0u, 0u, 0u, 0u);
+    if (planes == 2) l = *reinterpret_cast<const uint4*>(x + base + c_pad);
+    const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+    uint32_t ho[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float v0 = __uint_as_float(hw[e] << 16) + __uint_as_float(lw[e] << 16);
+      float v1 = __uint_as_float(hw[e] & 0xffff0000u) + __uint_as_float(lw[e] & 0xffff0000u);
+      v0 = ((keep >> (2 * e)) & 1u) ? v0 * scale : 0.f;
+      v1 = ((keep >> (2 * e + 1)) & 1u) ? v1 * scale : 0.f;
+      ho[e] = pack_bf16x2(v0, v1);
+      lo[e] = pack_bf16x2(v0 - bf16_round(v0), v1 - bf16_round(v1));
+    }
+    *reinterpret_cast<uint4*>(y + base) = make_uint4(ho[0], ho[1], ho[2], ho[3]);
+    if (planes == 2) *reinterpret_cast<uint4*>(y + base + c_pad) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    unsigned m = keep;
+    if (relu_mask_in != nullptr) m &= relu_mask_in[row * groups + g];
+    mask_out[row * groups + g] = static_cast<uint8_t>(m);
   }
 }
 
@@ -321,9 +375,20 @@ int pack_weights_internal_launch(const float* wi, void* wf, int k, int cin_pad, 
   return 0;
 }
 int dgrad_finalize_launch(const float* acc, const void* mask, void* dx, size_t rows, int c_pad, int planes,
-                          cudaStream_t s) {
+                          float out_scale, cudaStream_t s) {
   dgrad_finalize_kernel<<<grid_for(rows * (c_pad / 8), 256), 256, 0, s>>>(
-      acc, reinterpret_cast<const uint8_t*>(mask), reinterpret_cast<__nv_bfloat16*>(dx), rows, c_pad, planes);
+      acc, reinterpret_cast<const uint8_t*>(mask), reinterpret_cast<__nv_bfloat16*>(dx), rows, c_pad, planes,
+      out_scale);
+  SL_CUDA(cudaGetLastError());
+  return 0;
+}
+int dropout_launch(const void* x, void* y, const void* relu_mask_in, void* mask_out, size_t rows, int c_pad,
+                   int planes, float p, unsigned long long seed, cudaStream_t s) {
+  const unsigned threshold16 = static_cast<unsigned>(p * 65536.0f + 0.5f);
+  dropout_kernel<<<grid_for(rows * (c_pad / 8), 256), 256, 0, s>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y),
+      reinterpret_cast<const uint8_t*>(relu_mask_in), reinterpret_cast<uint8_t*>(mask_out), rows, c_pad, planes,
+      threshold16, 1.0f / (1.0f - static_cast<float>(threshold16) / 65536.0f), seed);
   SL_CUDA(cudaGetLastError());
   return 0;
 }

@@ -325,7 +325,7 @@ static bool run_dgrad(const ConvCase& cc, int prec) {
   Dev<uint8_t> dws(wsb);
   if (wsb) printf("  (split-K dgrad, %zu byte scratch)\n", wsb);
   SLCK(sl_conv1d_dgrad(dyp.p, wd.p, cc.act == SL_ACT_RELU ? dmask.p : nullptr, dxp.p, B, T, Cin, Cout, k, prec,
-                       wsb ? dws.p : nullptr, wsb, nullptr));
+                       1.0f, wsb ? dws.p : nullptr, wsb, nullptr));
   SLCK(sl_unpack_activation(dxp.p, dxo.p, B, T, Cin, T, cip, prec, nullptr));
   SLCK(sl_sync_check());
   auto ref = prec == 1 ? cpu_dgrad(round_bf16(dy), round_bf16(w), B, T, Cin, Cout, k)
@@ -681,7 +681,7 @@ static bool run_perf(int B, int T, int prec, int iters) {
       });
     if (L.s == 1)
       ok &= time_it("dgrad", [&] {
-        return sl_conv1d_dgrad(yp.p, wf.p, pmask_in.p, dxp.p, B, t_in, L.cin, L.cout, L.k, prec,
+        return sl_conv1d_dgrad(yp.p, wf.p, pmask_in.p, dxp.p, B, t_in, L.cin, L.cout, L.k, prec, 1.0f,
                                dgws.n > 1 ? dgws.p : nullptr, dgws.n > 1 ? dgws.n : 0, nullptr);
       });
     ok &= time_it("wgrad", [&] {
