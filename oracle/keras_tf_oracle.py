@@ -124,12 +124,16 @@ class Wav2LetterOracle:
         self.weights = [np.asarray(w, dtype=self.dtype) for w in weights]
         self.biases = [np.asarray(b, dtype=self.dtype) for b in biases]
 
-    def forward(self, x: np.ndarray, keep: bool = False):
-        """x (B,T,F) -> probabilities (B, ceil(T/2), V); optionally the per-layer inputs and logits."""
+    def forward(self, x: np.ndarray, keep: bool = False, dropout_masks=None, dropout_scale: float = 1.0):
+        """x (B,T,F) -> probabilities (B, ceil(T/2), V); optionally the per-layer inputs and logits.
+        `dropout_masks[i]` (bool, shape of layer i's input) = keep mask of the Dropout layer in front
+        of layer i in the training phase (inverted dropout: kept values are scaled by dropout_scale)."""
         a = np.asarray(x, dtype=self.dtype)
         inputs = []
         logits = None
-        for (name, _, _, _, stride, act), w, b in zip(self.specs, self.weights, self.biases):
+        for index, ((name, _, _, _, stride, act), w, b) in enumerate(zip(self.specs, self.weights, self.biases)):
+            if dropout_masks is not None and dropout_masks.get(index) is not None:
+                a = a * dropout_masks[index] * dropout_scale
             inputs.append(a)
             z = conv1d_same(a, w, b, stride)
             if act == "relu":
@@ -141,9 +145,10 @@ class Wav2LetterOracle:
             return a, logits, inputs
         return a
 
-    def loss_and_gradients(self, x, labels: np.ndarray, prediction_lengths, label_lengths):
+    def loss_and_gradients(self, x, labels: np.ndarray, prediction_lengths, label_lengths, dropout_masks=None,
+                           dropout_scale: float = 1.0):
         """Mean-over-batch CTC objective (net.py:389) and its gradient wrt every kernel / bias."""
-        probs, logits, inputs = self.forward(x, keep=True)
+        probs, logits, inputs = self.forward(x, keep=True, dropout_masks=dropout_masks, dropout_scale=dropout_scale)
         B = probs.shape[0]
         losses, dlogits = ctc_batch_cost_with_logit_grad(probs, labels, prediction_lengths, label_lengths)
         d = dlogits / B  # objective = mean_b loss_b
@@ -155,6 +160,8 @@ class Wav2LetterOracle:
                 z_pos = conv1d_same(inputs[i], self.weights[i], self.biases[i], stride) > 0
                 d = d * z_pos
             dx, dws[i], dbs[i] = conv1d_same_backward(inputs[i], self.weights[i], d, stride)
+            if dropout_masks is not None and dropout_masks.get(i) is not None:
+                dx = dx * dropout_masks[i] * dropout_scale
             d = dx
         return losses, probs, logits, dws, dbs
 

@@ -72,9 +72,11 @@ __device__ __forceinline__ WorkItem decode_item(const ConvGemmParams& p, int ite
     sub = r - (r / p.tail_split) * p.tail_split;
     width = BN / p.tail_split;
   }
-  const int tiles_per_n = p.B * p.m_tiles_per_utt;
-  const int n_tile = tile / tiles_per_n;
-  const int rem = tile - n_tile * tiles_per_n;
+  // filter tile fastest: the n_tiles CTAs that share an activation tile run together, so the
+  // A operand comes from HBM once and from L2 afterwards (the weights are L2 resident anyway;
+  // with the filter tile slowest, big_conv_2 re-read its 164 MB input 8 times from HBM)
+  const int n_tile = tile % p.n_tiles;
+  const int rem = tile / p.n_tiles;
   WorkItem w;
   w.b = rem / p.m_tiles_per_utt;
   w.t0 = (rem - w.b * p.m_tiles_per_utt) * BLOCK_M;

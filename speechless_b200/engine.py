@@ -126,6 +126,11 @@ class _Workspace:
         self.dz_f32: Optional[torch.Tensor] = None
         self.dact: List[Optional[torch.Tensor]] = [None, None]
         self.dgrad_ws: Optional[torch.Tensor] = None  # fp32 scratch of the split-K input gradient
+        # training-phase dropout: dropped copy of a layer's input and the combined (keep & ReLU) mask
+        self.xdrop: Dict[int, torch.Tensor] = {}
+        self.bwd_mask: Dict[int, torch.Tensor] = {}
+        self.layer_inputs: List[Optional[torch.Tensor]] = [None] * len(tower.layers)
+        self.dropout_seeds: Dict[int, int] = {}
 
     def ensure_backward(self, tower: "ConvTower"):
         if self.dz_packed is None:
@@ -141,7 +146,8 @@ class ConvTower:
     """Weights + kernels of the 11-layer tower, CTC objective and Keras-2 Adam on one GPU."""
 
     def __init__(self, layers: List[LayerSpec], device: torch.device, precision: int = PREC_BF16X2,
-                 frozen_layer_count: int = 0):
+                 frozen_layer_count: int = 0, dropout: Optional[float] = None,
+                 dropout_layers: Sequence[int] = (), dropout_seed: int = 0):
         if not torch.cuda.is_available():
             raise RuntimeError("speechless_b200 needs a CUDA device (B200); there is no CPU fallback.")
         self.lib = _lib.load()
@@ -150,6 +156,15 @@ class ConvTower:
         self.precision = precision
         self.planes = 2 if precision == PREC_BF16X2 else 1
         self.frozen_layer_count = frozen_layer_count
+        # inverted dropout in front of the listed conv layers, training phase only (net.py:301-303);
+        # the kernel quantises p to 16 bits, the scale below matches it exactly
+        self.dropout = dropout if dropout else None
+        self.dropout_layers = set(dropout_layers) if self.dropout else set()
+        self.dropout_seed = dropout_seed
+        self.dropout_step = 0
+        if self.dropout is not None and not (0.0 < self.dropout < 1.0):
+            raise ValueError("dropout rate must be in (0, 1)")
+        self.dropout_scale = 1.0 / (1.0 - int(self.dropout * 65536.0 + 0.5) / 65536.0) if self.dropout else 1.0
         for layer in layers:
             if layer.activation not in ("relu", "linear", "softmax"):
                 raise NotImplementedError("activation '{}' has no sm_100a epilogue".format(layer.activation))
@@ -345,11 +360,36 @@ class ConvTower:
             self._current = ws
             return ws
 
-    def forward(self, ws: Optional[_Workspace] = None, want_logits: bool = False) -> _Workspace:
+    def _dropout_seed(self, index: int) -> int:
+        mixed = (self.dropout_seed * 0x9E3779B97F4A7C15 + self.dropout_step * 0xD1B54A32D192ED03 +
+                 (index + 1) * 0x8CB92BA72F3D8DD7) & 0xFFFFFFFFFFFFFFFF
+        return mixed
+
+    def forward(self, ws: Optional[_Workspace] = None, want_logits: bool = False,
+                training: bool = False) -> _Workspace:
+        """`training=True` is Keras' learning phase 1: dropout (if configured) is active."""
         ws = ws or self._current
+        drop = training and self.dropout is not None
+        if drop:
+            self.dropout_step += 1
         with torch.cuda.device(self.device):
             x, t_in, t_alloc = ws.x_packed, ws.T, ws.T_alloc
             for index, layer in enumerate(self.layers):
+                if drop and index in self.dropout_layers:
+                    if index not in ws.xdrop:
+                        ws.xdrop[index] = torch.zeros_like(x)  # zero: keeps the T_alloc padding rows zero
+                        ws.bwd_mask[index] = torch.empty((ws.B, t_alloc, layer.cin_pad // 8), dtype=torch.uint8,
+                                                         device=self.device)
+                    relu_below = ws.masks[index - 1] if index > 0 and self.layers[index - 1].activation == "relu" \
+                        else None
+                    seed = self._dropout_seed(index)
+                    ws.dropout_seeds[index] = seed
+                    check(self.lib.sl_dropout_fwd(ptr(x), ptr(ws.xdrop[index]), ptr(relu_below),
+                                                  ptr(ws.bwd_mask[index]), ws.B, t_alloc, layer.cin, self.precision,
+                                                  float(self.dropout), seed, self.stream))
+                    self.launches += 1
+                    x = ws.xdrop[index]
+                ws.layer_inputs[index] = x
                 bias = self._b(self.params, layer)
                 if layer.activation == "softmax":
                     self._timed("fwd", layer.name, lambda: self.lib.sl_conv1d_fwd(
@@ -481,7 +521,7 @@ class ConvTower:
             bucket_starts = {b[0]: (b[1], b[2]) for b in self.grad_buckets()} if on_bucket_ready else {}
             for index in range(len(self.layers) - 1, first - 1, -1):
                 layer = self.layers[index]
-                x = ws.x_packed if index == 0 else ws.acts[index - 1]
+                x = ws.layer_inputs[index]  # the tensor the forward conv actually read (dropped or not)
                 t_in = ws.T if index == 0 else ws.t_out[index - 1]
                 t_alloc = ws.T_alloc if index == 0 else t_in
                 launch_wgrad = lambda: self._timed("wgrad", layer.name, lambda: self.lib.sl_conv1d_wgrad(
@@ -504,7 +544,11 @@ class ConvTower:
                     below = self.layers[index - 1]
                     dx = ws.dact[flip].view(-1)[:ws.B * t_in * self.planes * below.cout_pad].view(
                         ws.B, t_in, self.planes * below.cout_pad)
-                    mask = ws.masks[index - 1] if below.activation == "relu" else None
+                    dropped = x is ws.xdrop.get(index)
+                    if dropped:  # keep & ReLU bits written by the dropout kernel; scale 1/(1-p)
+                        mask, out_scale = ws.bwd_mask[index], self.dropout_scale
+                    else:
+                        mask, out_scale = (ws.masks[index - 1] if below.activation == "relu" else None), 1.0
                     if previous_wgrad_done is not None:
                         main.wait_event(previous_wgrad_done)  # it reads the buffer dx aliases
                     need = self.lib.sl_conv1d_dgrad_workspace_bytes(ws.B, t_in, layer.cin, layer.cout, layer.kernel)
@@ -513,7 +557,7 @@ class ConvTower:
                     scratch = ws.dgrad_ws if need else None
                     self._timed("dgrad", layer.name, lambda: self.lib.sl_conv1d_dgrad(
                         ptr(dy), ptr(self.w_fwd[index]), ptr(mask), ptr(dx), ws.B, t_in, layer.cin, layer.cout,
-                        layer.kernel, self.precision, ptr(scratch), need, self.stream))
+                        layer.kernel, self.precision, out_scale, ptr(scratch), need, self.stream))
                     self.launches += 2 if need else 1
                     dy = dx
                     flip ^= 1

@@ -12,8 +12,10 @@ Differences that are deliberate and documented in DESIGN.md:
 * batches of size 1 work (the reference needs the duplication workaround of net.py:492-495,
   which is kept so results are identical either way);
 * weights are saved as `.npz` keyed by the Keras layer names when `h5py` is unavailable;
-* `dropout`, `use_raw_wave_input` and `kenlm_directory` raise `NotImplementedError`
-  (SURVEY.md §8f "next" rows); `use_asg=True` raises at loss time exactly like the reference.
+* `use_raw_wave_input` and `kenlm_directory` raise `NotImplementedError` (SURVEY.md §8f "next"
+  rows); `use_asg=True` raises at loss time exactly like the reference;
+* `dropout` masks come from a counter-based hash, so they cannot equal TF's bit for bit; the
+  arithmetic given the masks is what the parity tests check.
 """
 import itertools
 import json
@@ -73,13 +75,36 @@ class _ConvLayerView:
         self._tower.set_layer_weights(self._index, kernel, bias)
 
 
+class _DropoutLayerView:
+    """Stands for the `keras.layers.Dropout` the reference inserts in front of striding_conv and
+    inner_conv_1..7 (net.py:301-303); it counts as a layer for `frozen_layer_count` (net.py:338-339)."""
+
+    def __init__(self, name: str, rate: float):
+        self.name = name
+        self.rate = rate
+        self.trainable = True
+
+    def get_weights(self) -> List[ndarray]:
+        return []
+
+    def set_weights(self, weights: List[ndarray]) -> None:
+        if weights:
+            raise ValueError("Dropout layers have no weights")
+
+
 class PredictiveNet:
     """Shim for the Keras `Sequential` the reference exposes as `Wav2Letter.predictive_net`
     (net.py:168, used by main.py:121 and load_weights :212,237-269)."""
 
     def __init__(self, tower, input_size_per_time_step: int):
         self._tower = tower
-        self.layers = [_ConvLayerView(tower, index) for index in range(len(tower.layers))]
+        self.conv_layers = [_ConvLayerView(tower, index) for index in range(len(tower.layers))]
+        # the reference's layer list interleaves Dropout layers when dropout is configured
+        self.layers = []
+        for index, view in enumerate(self.conv_layers):
+            if index in tower.dropout_layers:
+                self.layers.append(_DropoutLayerView("dropout_before_{}".format(view.name), tower.dropout))
+            self.layers.append(view)
         self.input_shape = (None, None, input_size_per_time_step)
 
     @staticmethod
@@ -89,7 +114,7 @@ class PredictiveNet:
 
     def save_weights(self, path) -> None:
         arrays = {}
-        for layer in self.layers:
+        for layer in self.conv_layers:
             kernel, bias = layer.get_weights()
             arrays["{}/kernel".format(layer.name)] = kernel
             arrays["{}/bias".format(layer.name)] = bias
@@ -99,8 +124,8 @@ class PredictiveNet:
             numpy.savez(str(self._npz_path(path)), **arrays)
             return
         with h5py.File(str(path), "w") as f:
-            f.attrs["layer_names"] = [layer.name.encode("utf8") for layer in self.layers]
-            for layer in self.layers:
+            f.attrs["layer_names"] = [layer.name.encode("utf8") for layer in self.conv_layers]
+            for layer in self.conv_layers:
                 group = f.create_group(layer.name)
                 names = ["{}/kernel:0".format(layer.name), "{}/bias:0".format(layer.name)]
                 group.attrs["weight_names"] = [n.encode("utf8") for n in names]
@@ -111,7 +136,7 @@ class PredictiveNet:
         npz = self._npz_path(path)
         if npz.exists():
             with numpy.load(str(npz)) as arrays:
-                for layer in self.layers:
+                for layer in self.conv_layers:
                     layer.set_weights([arrays["{}/kernel".format(layer.name)], arrays["{}/bias".format(layer.name)]])
             return
         try:
@@ -120,7 +145,7 @@ class PredictiveNet:
             raise IOError("{} not found and h5py is unavailable to read {}".format(npz, path))
         with h5py.File(str(path), "r") as f:
             root = f["model_weights"] if "model_weights" in f else f
-            for layer in self.layers:
+            for layer in self.conv_layers:
                 group = root[layer.name]
                 names = [n.decode("utf8") if isinstance(n, bytes) else n for n in group.attrs["weight_names"]]
                 layer.set_weights([numpy.asarray(group[names[0]]), numpy.asarray(group[names[1]])])
@@ -205,8 +230,6 @@ class Wav2Letter:
             raise ValueError("Layers cannot be frozen if model is trained from scratch.")
         if use_raw_wave_input:
             raise NotImplementedError("raw-wave input (wave_conv k250 s160) is not built yet (SURVEY.md §8f-4).")
-        if dropout is not None:
-            raise NotImplementedError("dropout is not built yet (SURVEY.md §8f-2).")
         if compute_dtype not in ("bf16", "bf16x2"):
             raise ValueError("compute_dtype must be 'bf16' or 'bf16x2'")
 
@@ -260,17 +283,29 @@ class Wav2Letter:
                                    activation=self.activation, output_activation=self.output_activation,
                                    main_filter_count=self.main_filter_count,
                                    out_filter_count=self.out_filter_count)
+        # Dropout sits in front of striding_conv and inner_conv_1..7, never before the last three
+        # layers (never_dropout, net.py:326-330)
+        dropout_layers = list(range(len(layers) - 3)) if self.dropout else []
+        # `layers[:frozen_layer_count]` of the reference counts the interleaved Dropout layers too
+        combined_count = len(layers) + len(dropout_layers)
         if self.frozen_layer_count > 0:
-            log("All but {} layers frozen.".format(len(layers) - self.frozen_layer_count))
+            log("All but {} layers frozen.".format(combined_count - self.frozen_layer_count))
+        combined_index, frozen_convs = 0, 0
+        for index in range(len(layers)):
+            combined_index += 1 if index in dropout_layers else 0
+            if combined_index < self.frozen_layer_count:
+                frozen_convs += 1
+            combined_index += 1
         self.tower = ConvTower(layers, device, PREC_BF16X2 if self.compute_dtype == "bf16x2" else PREC_BF16,
-                               frozen_layer_count=self.frozen_layer_count)
+                               frozen_layer_count=frozen_convs, dropout=self.dropout, dropout_layers=dropout_layers,
+                               dropout_seed=self.seed if self.seed is not None else 0)
         self.tower.init_glorot(self.seed)
         return PredictiveNet(self.tower, self.input_size_per_time_step)
 
     @property
     def input_to_prediction_length_ratio(self) -> int:
         """Factor by which striding shortens the output (reference net.py:343-348)."""
-        return reduce(lambda x, y: x * y, [layer.strides[0] for layer in self.predictive_net.layers], 1)
+        return reduce(lambda x, y: x * y, [layer.strides[0] for layer in self.predictive_net.conv_layers], 1)
 
     # ------------------------------------------------------------------ weight loading (net.py:184-269)
     @staticmethod
@@ -324,6 +359,8 @@ class Wav2Letter:
             layer_count - loaded_first_layers_count))
 
         for index, layer in enumerate(self.predictive_net.layers[:loaded_first_layers_count]):
+            if isinstance(layer, _DropoutLayerView):
+                continue  # (the reference would fail to unpack a Dropout layer's empty weight list here)
             original_weights, original_biases = original_wav2letter.predictive_net.layers[index].get_weights()
 
             if index == layer_count - 1:
@@ -448,7 +485,7 @@ class Wav2Letter:
         names = Wav2Letter.InputNames
         tower = self.tower
         ws = tower.upload(input_by_name[names.input_batch])
-        tower.forward(ws)
+        tower.forward(ws, training=True)  # learning phase 1: dropout active (net.py:597-606)
         tower.set_labels(ws, input_by_name[names.label_batch], input_by_name[names.prediction_lengths],
                          input_by_name[names.label_lengths])
         batch_size = global_batch_size if global_batch_size is not None else ws.B
@@ -492,7 +529,7 @@ class Wav2Letter:
             upcoming = next(iterator, None)
             next_ws = tower.stage_async(upcoming[names.input_batch], slot ^ 1) if upcoming is not None else None
             tower.consume_slot(ws, slot)
-            tower.forward(ws)
+            tower.forward(ws, training=True)
             tower.set_labels(ws, current[names.label_batch], current[names.prediction_lengths],
                              current[names.label_lengths])
             batch_size = global_batch_size if global_batch_size is not None else ws.B

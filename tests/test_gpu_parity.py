@@ -383,8 +383,6 @@ def test_error_behaviour(env):
     with pytest.raises(ValueError, match="features per time step"):
         net.prediction_batch(np.zeros((1, 10, 64), dtype=np.float32))
     with pytest.raises(NotImplementedError):
-        env.Wav2Letter(128, env.alphabet, dropout=0.1)
-    with pytest.raises(NotImplementedError):
         env.Wav2Letter(128, env.alphabet, use_raw_wave_input=True)
     asg = env.Wav2Letter(128, env.alphabet, use_asg=True, main_filter_count=64, out_filter_count=64, device="cuda:0")
     with pytest.raises(NotImplementedError, match="ASG"):
@@ -467,3 +465,75 @@ def test_fit_batches_pipeline_equals_stepwise(env):
         for u, v in zip(la.get_weights(), lb.get_weights()):
             assert np.abs(u - v).max() < 2e-4  # 5 Adam steps of 1e-4; reduction order differs
     assert pipelined.fit_batches(iter([])) == []
+
+
+def test_dropout_statistics_and_parity_given_masks(env):
+    """Dropout (reference net.py:133,301-303): the masks come from a counter hash, so they cannot
+    match TF's bit for bit; what must hold is (i) Bernoulli(1-p) keep statistics, (ii) inference
+    ignores dropout, (iii) given the masks the device drew, loss and gradients equal the oracle's."""
+    torch = env.torch
+    from speechless_b200.synthetic import synthetic_batch
+    p = 0.3
+    net = env.Wav2Letter(128, env.alphabet, dropout=p, main_filter_count=64, out_filter_count=128, seed=31,
+                         device="cuda:0")
+    names_ = [l.name for l in net.predictive_net.layers]
+    assert names_[:4] == ["dropout_before_striding_conv", "striding_conv", "dropout_before_inner_conv_1", "inner_conv_1"]
+    assert len(names_) == 19 and names_[-3:] == ["big_conv_1", "big_conv_2", "output_conv"]
+    rng = np.random.default_rng(3)
+    for layer in net.predictive_net.conv_layers:
+        kernel, bias = layer.get_weights()
+        layer.set_weights([kernel, (rng.standard_normal(bias.shape) * 0.1).astype(np.float32)])
+    ref = env.oracle.Wav2LetterOracle(128, 29, 64, 128, dtype=np.float64)
+    weights = [layer.get_weights() for layer in net.predictive_net.conv_layers]
+    ref.set_weights([w for w, _ in weights], [b for _, b in weights])
+    batch = synthetic_batch(3, [161, 140, 118], env.alphabet, seed=4, label_length=9)
+    inputs, _ = net._inputs_for_loss_net(batch)
+    names = env.Wav2Letter.InputNames
+    x = inputs[names.input_batch]
+    # (ii) prediction phase: no dropout
+    assert np.abs(net.prediction_batch(x) - ref.forward(x)).max() < 1e-4
+    # training-phase forward + backward on the device
+    tower = net.tower
+    ws = tower.upload(x)
+    tower.forward(ws, training=True)
+    tower.set_labels(ws, inputs[names.label_batch], inputs[names.prediction_lengths], inputs[names.label_lengths])
+    loss = tower.ctc(ws, want_grad=True, grad_scale=1.0 / 3)
+    tower.backward(ws)
+    tower.sync()
+    # recover the keep masks the device drew: layer 0 from the dropped input, others from keep & relu bits
+    scale = tower.dropout_scale
+    masks = {}
+    first = tower.layers[0]
+    dropped0 = ws.xdrop[0].float().view(3, ws.T_alloc, 2, first.cin_pad).sum(dim=2)[:, :ws.T, :first.cin].cpu().numpy()
+    masks[0] = np.where(np.abs(x) > 1e-6, np.abs(dropped0) > 0, True)
+    kept_fraction = [masks[0][np.abs(x) > 1e-6].mean()]
+    acts = None
+    for index in range(1, 8):
+        layer = tower.layers[index]
+        bits = np.unpackbits(ws.bwd_mask[index].cpu().numpy(), axis=2, bitorder="little")[..., :layer.cin].astype(bool)
+        relu = np.unpackbits(ws.masks[index - 1].cpu().numpy(), axis=2, bitorder="little")[..., :layer.cin].astype(bool)
+        assert not (bits & ~relu).any()  # combined mask = keep AND relu
+        # where the ReLU bit is off the activation is zero and the keep bit is irrelevant: call it kept
+        masks[index] = bits | ~relu
+        kept_fraction.append(bits[relu].mean())
+    # (i) keep statistics: p quantised to 16 bits, > 1e4 samples per layer
+    for fraction in kept_fraction:
+        assert abs(fraction - (1 - p)) < 0.02, kept_fraction
+    # (iii) parity given the masks
+    losses, _, _, dws, dbs = ref.loss_and_gradients(x.astype(np.float64), inputs[names.label_batch],
+                                                    inputs[names.prediction_lengths][:, 0],
+                                                    inputs[names.label_lengths][:, 0], dropout_masks=masks,
+                                                    dropout_scale=scale)
+    assert np.abs(loss.cpu().numpy() / losses - 1).max() < 1e-4
+    saved = tower.params.clone()
+    tower.params.copy_(tower.grads)
+    for index, layer in enumerate(tower.layers):
+        dw, db = tower.get_layer_weights(index)
+        assert rel_err(dw, dws[index]) < 5e-3, layer.name
+        assert rel_err(db, dbs[index]) < 5e-3, layer.name
+    tower.params.copy_(saved)
+    # two training passes draw different masks; the seed makes runs reproducible
+    seeds_first = dict(ws.dropout_seeds)
+    tower.forward(ws, training=True)
+    assert ws.dropout_seeds != seeds_first
+    assert np.isfinite(net.train_on_batch(inputs))
