@@ -120,6 +120,22 @@ static void plan_tail(int total_tiles, int bn, bool allow, int* full_tiles, int*
   if (*split > 1) *full_tiles = total_tiles - rest;
 }
 
+// halo mode plan (ConvGemmParams::halo): SL_HALO=0 disables, SL_HALO_BASE selects the descriptor
+// base-offset convention (bring-up)
+static int make_act_load_map(CUtensorMap* m, const void* base, int c_total, int stride, int T_alloc, int B,
+                             int box_rows);
+static int plan_halo(ConvGemmParams* p, const void* act, int c_total, int T_alloc, int B, int taps, int stride) {
+  const char* e = std::getenv("SL_HALO");
+  const int want = e ? std::atoi(e) : 0;
+  p->halo = 0;
+  if (!want || stride != 1 || taps < 2 || 128 + taps - 1 > 256) return 0;
+  p->halo = 1;
+  p->halo_rows = 128 + taps - 1;
+  const char* b = std::getenv("SL_HALO_BASE");
+  p->halo_base_mode = b ? std::atoi(b) : 0;
+  return make_act_load_map(&p->tmAhalo, act, c_total, 1, T_alloc, B, p->halo_rows);
+}
+
 static int grouped_tma() {
   const char* e = std::getenv("SL_GROUPED_TMA");  // 0 disables the one-TMA-per-operand tensor maps
   return e ? std::atoi(e) : 1;
@@ -249,6 +265,8 @@ int sl_conv1d_fwd(const void* x_packed, const void* w_fwd, const float* bias, vo
   if (rc) return rc;
   rc = make_weight_map(&p.tmB, w_fwd, planes * cin_pad, cout_pad, k, bn);
   if (rc) return rc;
+  rc = plan_halo(&p, x_packed, planes * cin_pad, T_in_alloc, B, k, stride);
+  if (rc) return rc;
   p.B = B;
   p.T_out = T_out;
   p.m_tiles_per_utt = (T_out + 127) / 128;
@@ -348,6 +366,8 @@ int sl_conv1d_dgrad(const void* dy_packed, const void* w_fwd, const void* relu_m
                    : make_weight_map(&p.tmB, w_fwd, planes * cin_pad, cout_pad, k, 64);
   if (rc) return rc;
   rc = make_act_map3(&p.tmY, dx_packed, planes * cin_pad, T, B, 32);
+  if (rc) return rc;
+  rc = plan_halo(&p, dy_packed, planes * cout_pad, T, B, k, 1);
   if (rc) return rc;
   p.B = B;
   p.T_out = T;

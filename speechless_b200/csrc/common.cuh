@@ -239,6 +239,13 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uin
   return d;
 }
 
+// same, with the 3-bit "matrix base offset" field (bits [49,52)) for operands whose start address
+// is not aligned to the 1024-byte swizzle repeat
+__device__ __forceinline__ uint64_t make_smem_desc_sw128_off(uint32_t smem_addr, uint32_t lbo_bytes,
+                                                             uint32_t sbo_bytes, uint32_t base_offset) {
+  return make_smem_desc_sw128(smem_addr, lbo_bytes, sbo_bytes) | (static_cast<uint64_t>(base_offset & 7u) << 49);
+}
+
 // instruction descriptor, kind::f16: bf16 x bf16 -> fp32
 //   [4,6) c_format=1(F32) [7,10) a_format=1(BF16) [10,13) b_format=1(BF16)
 //   [15] a_major (0=K,1=MN) [16] b_major [17,23) N>>3 [24,29) M>>4

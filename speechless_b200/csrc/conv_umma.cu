@@ -46,7 +46,12 @@ struct Cfg {
   static constexpr int TMEM_COLS = (2 * BN) < 32 ? 32 : 2 * BN;
   // stages | 2 staging buffers | bias | barriers
   static constexpr int SMEM_BYTES =
-      kStages * STAGE_BYTES + 2 * STAGING_BYTES + BN * 4 + 256 + 1024 /*align slack*/;
+      kStages * STAGE_BYTES + 2 * STAGING_BYTES + BN * 4 + 512 + 1024 /*align slack*/;
+  // halo mode re-carves the stage region: two halo buffers of HALO_BYTES, then B-only stages
+  static constexpr int HALO_BYTES = 32768;  // up to 256 frames x 128 B
+  static constexpr int kStagesB = (kStages * STAGE_BYTES - 2 * HALO_BYTES) / B_BYTES > 8
+                                      ? 8
+                                      : (kStages * STAGE_BYTES - 2 * HALO_BYTES) / B_BYTES;
 };
 
 // Work item of the persistent loop: an output tile, or one of the tail_split narrow slices of a
@@ -99,11 +104,16 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   uint8_t* staging = smem + C::kStages * C::STAGE_BYTES;
   float* bias_s = reinterpret_cast<float*>(staging + 2 * STAGING_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + BN);
+  // barrier block: [0,8) full, [8,16) empty (ring of A+B stages, or of B-only stages in halo
+  // mode), [16,18) halo full, [18,20) halo empty, [20,22) tmem full, [22,24) tmem empty
   uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + C::kStages;
-  uint64_t* tmem_full = bars + 2 * C::kStages;
-  uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* empty_bar = bars + 8;
+  uint64_t* halo_full = bars + 16;
+  uint64_t* halo_empty = bars + 18;
+  uint64_t* tmem_full = bars + 20;
+  uint64_t* tmem_empty = bars + 22;
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 24);
+  static_assert(C::kStages <= 8 && C::kStagesB <= 8 && C::kStagesB >= 2, "barrier block layout");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -111,15 +121,18 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.tmA);
     prefetch_tmap(&p.tmB);
+    if (p.halo) prefetch_tmap(&p.tmAhalo);
     if (p.tail_split > 1) prefetch_tmap(&p.tmBtail);
     if (EPI != EPI_SOFTMAX) prefetch_tmap(&p.tmY);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < C::kStages; ++s) {
+    for (int s = 0; s < 8; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
+      mbar_init(&halo_full[a], 1);
+      mbar_init(&halo_empty[a], 1);
       mbar_init(&tmem_full[a], 1);
       mbar_init(&tmem_empty[a], 4);
     }
@@ -144,11 +157,47 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       int stage = 0;
       uint32_t phase = 0;
       int issued = 0;
+      int hbuf = 0;
+      uint32_t hphase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const WorkItem w = decode_item<BN>(p, tile);
         const int b = w.b, t0 = w.t0, n0 = w.n0;
         const CUtensorMap* tmB = w.width == BN ? &p.tmB : &p.tmBtail;
         const uint32_t stage_tx = A_BYTES + w.width * (BLOCK_K * 2);
+        if (p.halo) {
+          // chunk-major: one halo tile per (chunk, term), then one B tile per tap
+          uint8_t* b_ring = smem + 2 * C::HALO_BYTES;
+          const uint32_t b_tx = w.width * (BLOCK_K * 2);
+          for (int chunk = 0; chunk < p.chunks; ++chunk) {
+            for (int term = 0; term < p.terms; ++term) {
+              const int a_c = chunk * BLOCK_K + (term == 2 ? p.a_lo_off : 0);
+              const int b_c = chunk * BLOCK_K + (term == 1 ? p.b_lo_off : 0);
+              mbar_wait(&halo_empty[hbuf], hphase ^ 1);
+              mbar_expect_tx(&halo_full[hbuf], p.halo_rows * 128);
+              tma_load_4d(&p.tmAhalo, &halo_full[hbuf], smem + hbuf * C::HALO_BYTES, a_c, 0, t0 - p.pad_l, b);
+              if (++hbuf == 2) {
+                hbuf = 0;
+                hphase ^= 1;
+              }
+              for (int tap = w.tap_begin; tap < w.tap_end; ++tap) {
+                const int wtap = p.tap_reverse ? (p.taps - 1 - tap) : tap;
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* b_s = b_ring + stage * C::B_BYTES;
+                mbar_expect_tx(&full_bar[stage], b_tx);
+                if (BMN)
+                  tma_load_4d(tmB, &full_bar[stage], b_s, 0, chunk * BLOCK_K,
+                              (n0 + (term == 1 ? p.b_lo_off : 0)) >> 6, wtap);
+                else
+                  tma_load_3d(tmB, &full_bar[stage], b_s, b_c, n0, wtap);
+                if (++stage == C::kStagesB) {
+                  stage = 0;
+                  phase ^= 1;
+                }
+              }
+            }
+          }
+          continue;
+        }
         for (int tap = w.tap_begin; tap < w.tap_end; ++tap) {
           const int jp = tap - p.pad_l;  // signed frame offset of this tap
           int q, par;
@@ -228,6 +277,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
+    int hbuf = 0;
+    uint32_t hphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const WorkItem w = decode_item<BN>(p, tile);
       const int ksteps = (w.tap_end - w.tap_begin) * p.chunks * p.terms;
@@ -237,6 +288,47 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       mbar_wait(&tmem_empty[as], aphase ^ 1);
       tcgen05_fence_after();
       const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * BN);
+      if (p.halo) {
+        const uint32_t b_ring = smem_u32(smem + 2 * C::HALO_BYTES);
+        const int ntaps = w.tap_end - w.tap_begin;
+        uint32_t first = 1;
+        for (int ct = 0; ct < p.chunks * p.terms; ++ct) {
+          mbar_wait(&halo_full[hbuf], hphase);
+          const uint32_t halo_addr = smem_u32(smem + hbuf * C::HALO_BYTES);
+          for (int ti = 0; ti < ntaps; ++ti) {
+            mbar_wait(&full_bar[stage], phase);
+            tcgen05_fence_after();
+            if (lane == 0) {
+              // tap j reads halo rows [j, j + 128): start address advanced by j rows of 128 B
+              const uint32_t a_addr = halo_addr + static_cast<uint32_t>(w.tap_begin + ti) * 128u;
+              const uint32_t b_addr = b_ring + stage * C::B_BYTES;
+#pragma unroll
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                const uint32_t aa = a_addr + k * UMMA_K * 2;
+                const uint64_t da = make_smem_desc_sw128_off(aa, 16, 1024, p.halo_base_mode ? (aa >> 7) & 7u : 0u);
+                const uint64_t db = BMN ? make_smem_desc_sw128(b_addr + k * 2048, BLOCK_K * 128, 1024)
+                                        : make_smem_desc_sw128(b_addr + k * UMMA_K * 2, 16, 1024);
+                umma_bf16(tmem_d, da, db, idesc, first ? 0u : 1u);
+                first = 0;
+              }
+              umma_commit(&empty_bar[stage]);
+              if (ti == ntaps - 1) umma_commit(&halo_empty[hbuf]);
+              if (ti == ntaps - 1 && ct == p.chunks * p.terms - 1) umma_commit(&tmem_full[as]);
+            }
+            __syncwarp();
+            if (++stage == C::kStagesB) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          if (++hbuf == 2) {
+            hbuf = 0;
+            hphase ^= 1;
+          }
+        }
+        if (ksteps == 0 && lane == 0) mbar_arrive(&tmem_full[as]);
+        continue;
+      }
       for (int ks = 0; ks < ksteps; ++ks) {
         mbar_wait(&full_bar[stage], phase);
         tcgen05_fence_after();

@@ -11,6 +11,7 @@ struct ConvGemmParams {
   CUtensorMap tmA;  // activations, rank 4 {C_total, stride, T_alloc/stride, B}, box {64,1,128,1}
   CUtensorMap tmB;  // weights (k, cout, cin), rank 3 {cin_total, cout, taps}: box {64, BN, 1} (fwd: K-major B)
                     // or box {64, 64, 1} (dgrad: MN-major B, 64 cout rows of contraction)
+  CUtensorMap tmAhalo;  // halo mode: as tmA with a box of 128 + taps - 1 frames (one load serves every tap)
   CUtensorMap tmBtail;  // as tmB with a box of BN / tail_split filters: the last partial wave's narrow tiles
   CUtensorMap tmY;  // packed bf16 output, rank 3 {C_total, T_out, B}, box {64,32,1}; EPI_F32: fp32 partial
                     // sums {C_pad, T_out, B}, box {32,32,1}, written with TMA reduce-add
@@ -25,6 +26,12 @@ struct ConvGemmParams {
   // split K (EPI_F32 only): every tile is computed by ksplit work items, each over a contiguous
   // range of filter taps, whose fp32 partial sums meet in HBM through TMA reduce-add
   int ksplit;
+  // halo mode (stride 1, taps > 1): the A operand of tap j is the same smem tile shifted by j
+  // rows, so one halo tile of 128 + taps - 1 frames is loaded per 64-channel chunk and every tap's
+  // MMA reads it through a descriptor whose start address is advanced by j * 128 bytes
+  int halo;            // 0 = one A box per (tap, chunk)
+  int halo_rows;       // 128 + taps - 1
+  int halo_base_mode;  // bring-up: 0 = descriptor base_offset 0, 1 = (start address >> 7) & 7
   int taps;
   int chunks;  // 64-channel chunks of the contraction dimension
   int terms;   // 1 = bf16, 3 = split bf16 (hi*hi + hi*lo + lo*hi)
@@ -69,6 +76,12 @@ struct WgradParams {
   int m_tiles;  // ceil(cout_pad / 128)
   int n_tiles;  // cin_pad / BN
   int ksplit;
+  // halo mode (stride 1, taps > 1): the A operand of tap j is the same smem tile shifted by j
+  // rows, so one halo tile of 128 + taps - 1 frames is loaded per 64-channel chunk and every tap's
+  // MMA reads it through a descriptor whose start address is advanced by j * 128 bytes
+  int halo;            // 0 = one A box per (tap, chunk)
+  int halo_rows;       // 128 + taps - 1
+  int halo_base_mode;  // bring-up: 0 = descriptor base_offset 0, 1 = (start address >> 7) & 7
   int tchunks;  // ceil(T_out / 64)
   int terms;
   int dy_lo_off;
