@@ -125,12 +125,19 @@ static void plan_tail(int total_tiles, int bn, bool allow, int* full_tiles, int*
 static int make_act_load_map(CUtensorMap* m, const void* base, int c_total, int stride, int T_alloc, int B,
                              int box_rows);
 static int plan_halo(ConvGemmParams* p, const void* act, int c_total, int T_alloc, int B, int taps, int stride) {
+  // default: on for long filters (big_conv_1, k = 32: -4 % bf16, -15 % split-bf16 on its input
+  // gradient); for k = 7 the extra halo buffers cost more than the saved loads (measured).
+  // SL_HALO=0 disables, SL_HALO=1 forces it for every stride-1 layer with more than one tap.
   const char* e = std::getenv("SL_HALO");
-  const int want = e ? std::atoi(e) : 0;
+  const int mode = e ? std::atoi(e) : -1;
   p->halo = 0;
-  if (!want || stride != 1 || taps < 2 || 128 + taps - 1 > 256) return 0;
+  if (mode == 0 || stride != 1 || taps < 2 || 128 + taps - 1 > 256) return 0;
+  if (mode < 0 && taps < 16) return 0;
   p->halo = 1;
   p->halo_rows = 128 + taps - 1;
+  // measured on B200: the descriptor start address may simply be advanced by whole 128-byte rows
+  // (the swizzle is a function of the absolute smem address); setting the "base offset" field to
+  // (address >> 7) & 7 instead gives wrong results.  SL_HALO_BASE=1 reproduces that experiment.
   const char* b = std::getenv("SL_HALO_BASE");
   p->halo_base_mode = b ? std::atoi(b) : 0;
   return make_act_load_map(&p->tmAhalo, act, c_total, 1, T_alloc, B, p->halo_rows);
