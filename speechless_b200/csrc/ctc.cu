@@ -15,6 +15,8 @@
 //      gradient through log(p+1e-8) and the softmax to the pre-softmax logits, writing
 //      the packed bf16 tile the output_conv wgrad/dgrad kernels consume.
 //   3. (host) nothing: the loss per utterance is written by the alpha CTA.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace sl {
@@ -192,6 +194,180 @@ __global__ void ctc_alpha_beta_kernel(const float* __restrict__ logp,
     if (P > 0) {
       const float a = prev[S - 1];  // prev = column of the last processed step
       const float c = S >= 2 ? prev[S - 2] : -INFINITY;
+      const float m = fmaxf(a, c);
+      l = (m == -INFINITY) ? INFINITY : -(m + log2f(exp2f(a - m) + exp2f(c - m))) * LN2;
+    }
+    if (dir == 0)
+      loss[b] = l;
+    else
+      beta_loss[b] = l;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Wavefront variant of the alpha/beta recurrence: no block-wide barrier inside the time loop.
+//
+// Warp w owns the 32*SPT consecutive lattice states [w*32*SPT, ...), lane l the SPT states
+// s0 = (w*32 + l)*SPT ...  A state needs the previous column's values of itself and of its two left
+// neighbours: the lane's own registers plus the last two states of lane l-1 (warp shuffle); lane 0
+// takes them from the previous warp through a small smem ring (edge values + progress counters), so
+// the warps form a pipeline skewed by one time step and nobody waits in steady state.  A loader
+// warp (the last one) streams the log-prob rows into a 128-frame smem ring with cp.async and
+// publishes how many rows are ready; it reuses a ring slot only after every compute warp has passed
+// it.  Spins are bounded (trap, never hang).
+constexpr int LP_RING = 128;  // frames of log-probs resident in smem
+constexpr int EDGE_RING = 16;
+
+__device__ __forceinline__ int ld_volatile_s32(const int* p) {
+  int v;
+  asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(ptx::smem_u32(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_volatile_s32(int* p, int v) {
+  asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(ptx::smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ void spin_until_at_least(const int* p, int target) {
+  unsigned spins = 0;
+  while (ld_volatile_s32(p) < target) {
+    if (++spins > (1u << 26)) {
+      printf("speechless_b200: CTC wavefront wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+
+template <int SPT>
+__global__ void ctc_alpha_beta_wave_kernel(const float* __restrict__ logp,
+                                           const int32_t* __restrict__ labels,
+                                           const int32_t* __restrict__ input_len,
+                                           const int32_t* __restrict__ label_len,
+                                           float* __restrict__ loss, float* __restrict__ beta_loss,
+                                           float* __restrict__ alpha, float* __restrict__ beta, int T,
+                                           int L_max, int blank, int S_stride) {
+  extern __shared__ uint8_t smem_raw[];
+  const int dir = blockIdx.x & 1;
+  const int b = blockIdx.x >> 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_compute = (blockDim.x >> 5) - 1;  // the last warp is the loader
+  const int L = label_len[b];
+  const int P = min(input_len[b], T);
+  const int S = 2 * L + 1;
+  const int n_active = (S + 32 * SPT - 1) / (32 * SPT);  // warps that own at least one state
+
+  float* lp_s = reinterpret_cast<float*>(smem_raw);                         // [LP_RING][VP]
+  float2* edge = reinterpret_cast<float2*>(lp_s + LP_RING * VP);            // [n_compute][EDGE_RING]
+  float* final_col = reinterpret_cast<float*>(edge + n_compute * EDGE_RING);  // [n_compute * 32 * SPT]
+  int* done = reinterpret_cast<int*>(final_col + n_compute * 32 * SPT);     // [n_compute] steps completed
+  int* lp_ready = done + n_compute;                                         // rows of logp available
+
+  for (int i = threadIdx.x; i <= n_compute; i += blockDim.x) done[i] = 0;  // (includes lp_ready)
+  __syncthreads();
+
+  const float* lp_b = logp + static_cast<size_t>(b) * T * VP;
+  if (warp == n_compute) {
+    // ===================== loader warp =====================
+    const int chunks = (P + CHUNK - 1) / CHUNK;
+    for (int c = 0; c < chunks; ++c) {
+      if (c >= LP_RING / CHUNK) {
+        // the ring slot of chunk c still holds chunk c - 4: every active warp must be past it
+        const int need = (c - LP_RING / CHUNK + 1) * CHUNK;
+        for (int w = lane; w < n_active; w += 32) spin_until_at_least(&done[w], need);
+        __syncwarp();
+      }
+      float* dst = lp_s + (c % (LP_RING / CHUNK)) * CHUNK * VP;
+      for (int i = lane; i < CHUNK * (VP / 4); i += 32) {
+        const int r = i / (VP / 4), piece = i % (VP / 4);
+        const int tt = c * CHUNK + r;
+        if (tt < P) {
+          const int t = dir ? (P - 1 - tt) : tt;
+          cp_async16(dst + r * VP + piece * 4, lp_b + static_cast<size_t>(t) * VP + piece * 4);
+        }
+      }
+      cp_async_commit();
+      cp_async_wait<0>();
+      __threadfence_block();
+      __syncwarp();
+      if (lane == 0) st_volatile_s32(lp_ready, min(P, (c + 1) * CHUNK));
+    }
+  } else if (warp < n_active) {
+    // ===================== compute warps =====================
+    const int s0 = (warp * 32 + lane) * SPT;
+    int my_e[SPT], my_out[SPT];
+    bool my_skip[SPT], my_on[SPT];
+#pragma unroll
+    for (int i = 0; i < SPT; ++i) {
+      const int s = s0 + i;
+      my_on[i] = s < S;
+      auto symbol = [&](int st) {  // extended label sequence in walking order (reversed for beta)
+        const int so = dir ? (S - 1 - st) : st;
+        return (so & 1) ? labels[static_cast<size_t>(b) * L_max + (so >> 1)] : blank;
+      };
+      my_e[i] = my_on[i] ? symbol(s) : blank;
+      my_skip[i] = (my_on[i] && s >= 2) ? (my_e[i] != blank && my_e[i] != symbol(s - 2)) : false;
+      my_out[i] = dir ? (S - 1 - s) : s;
+    }
+    float prev[SPT];
+#pragma unroll
+    for (int i = 0; i < SPT; ++i) prev[i] = -INFINITY;
+    float* out = (dir ? beta : alpha) + static_cast<size_t>(b) * T * S_stride +
+                 (dir ? static_cast<size_t>(P > 0 ? P - 1 : 0) * S_stride : 0);
+    const ptrdiff_t out_step = dir ? -static_cast<ptrdiff_t>(S_stride) : static_cast<ptrdiff_t>(S_stride);
+    const bool last_warp = warp == n_active - 1;
+
+    for (int tt = 0; tt < P; ++tt) {
+      if ((tt & (CHUNK - 1)) == 0) spin_until_at_least(lp_ready, min(P, tt + CHUNK));
+      const float* lp_row = lp_s + (tt & (LP_RING - 1)) * VP;
+      float em[SPT];
+#pragma unroll
+      for (int i = 0; i < SPT; ++i) em[i] = lp_row[my_e[i]] * LOG2E;
+      // values of states s0-1, s0-2 at the previous step
+      float left1 = __shfl_up_sync(0xffffffffu, prev[SPT - 1], 1);
+      float left0 = __shfl_up_sync(0xffffffffu, prev[SPT - 2 >= 0 ? SPT - 2 : 0], 1);
+      if (lane == 0) {
+        left1 = -INFINITY;
+        left0 = -INFINITY;
+        if (warp > 0 && tt > 0) {
+          spin_until_at_least(&done[warp - 1], tt);  // the previous warp finished step tt-1
+          const float2 e = edge[(warp - 1) * EDGE_RING + ((tt - 1) & (EDGE_RING - 1))];
+          left0 = e.x;
+          left1 = e.y;
+        }
+      }
+      float cur[SPT];
+#pragma unroll
+      for (int i = 0; i < SPT; ++i) {
+        const float a0 = prev[i];
+        const float a1 = i >= 1 ? prev[i - 1] : left1;
+        const float a2raw = i >= 2 ? prev[i - 2] : (i == 1 ? left1 : left0);
+        const float a2 = my_skip[i] ? a2raw : -INFINITY;
+        cur[i] = lse3_base2(a0, a1, a2) + em[i];
+        if (tt == 0) cur[i] = (s0 + i <= 1) ? em[i] : -INFINITY;
+        if (!my_on[i]) cur[i] = -INFINITY;
+      }
+#pragma unroll
+      for (int i = 0; i < SPT; ++i)
+        if (my_on[i]) out[my_out[i]] = cur[i];
+      out += out_step;
+      if (lane == 31 && !last_warp) {
+        // slot tt % R was read by the next warp during its step tt - R + 1
+        if (tt >= EDGE_RING) spin_until_at_least(&done[warp + 1], tt - EDGE_RING + 2);
+        edge[warp * EDGE_RING + (tt & (EDGE_RING - 1))] = make_float2(cur[SPT - 2 >= 0 ? SPT - 2 : 0], cur[SPT - 1]);
+        __threadfence_block();
+      }
+      __syncwarp();
+      if (lane == 31) st_volatile_s32(&done[warp], tt + 1);
+#pragma unroll
+      for (int i = 0; i < SPT; ++i) prev[i] = cur[i];
+    }
+#pragma unroll
+    for (int i = 0; i < SPT; ++i) final_col[s0 + i] = prev[i];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float l = INFINITY;
+    if (P > 0) {
+      const float a = final_col[S - 1];
+      const float c = S >= 2 ? final_col[S - 2] : -INFINITY;
       const float m = fmaxf(a, c);
       l = (m == -INFINITY) ? INFINITY : -(m + log2f(exp2f(a - m) + exp2f(c - m))) * LN2;
     }
@@ -397,6 +573,23 @@ int ctc_loss_launch(const float* logp, const float* probs, const int32_t* labels
   SL_REQUIRE(S_max <= 4096, "label too long (max 2047 characters)");
   int threads = ((S_max + spt - 1) / spt + 31) & ~31;
   if (threads < 64) threads = 64;
+  const char* wave_env = std::getenv("SL_CTC_WAVE");
+  const int wspt = S_max <= 31 * 64 ? 2 : 4;  // wavefront kernel: 2 states per lane (4 beyond 1984 states)
+  const int n_compute = (S_max + 32 * wspt - 1) / (32 * wspt);
+  if (!(wave_env && std::atoi(wave_env) == 0) && n_compute <= 31) {  // + one loader warp <= 1024 threads
+    const int wthreads = (n_compute + 1) * 32;
+    const size_t wsmem = LP_RING * VP * sizeof(float) + static_cast<size_t>(n_compute) * EDGE_RING * sizeof(float2) +
+                         static_cast<size_t>(n_compute) * 32 * wspt * sizeof(float) + (n_compute + 1) * sizeof(int);
+    if (wspt == 2)
+      ctc_alpha_beta_wave_kernel<2><<<2 * B, wthreads, wsmem, stream>>>(logp, labels, input_len, label_len, loss,
+                                                                        beta_loss, alpha, beta, T, L_max, blank,
+                                                                        S_stride);
+    else
+      ctc_alpha_beta_wave_kernel<4><<<2 * B, wthreads, wsmem, stream>>>(logp, labels, input_len, label_len, loss,
+                                                                        beta_loss, alpha, beta, T, L_max, blank,
+                                                                        S_stride);
+    SL_CUDA(cudaGetLastError());
+  } else {
   const int col_stride = (threads * spt > S_stride ? threads * spt : S_stride) + 2;
   const size_t smem = (2 * CHUNK * VP + 2 * col_stride) * sizeof(float) + S_stride * sizeof(int);
 #define SL_LAUNCH_AB(SPT)                                                                          \
@@ -416,6 +609,7 @@ int ctc_loss_launch(const float* logp, const float* probs, const int32_t* labels
     SL_LAUNCH_AB(4);
 #undef SL_LAUNCH_AB
   SL_CUDA(cudaGetLastError());
+  }
 
   if (dlogits_packed != nullptr || dlogits_f32 != nullptr) {
     SL_REQUIRE(probs != nullptr, "gradient needs the softmax probabilities");

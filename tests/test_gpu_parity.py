@@ -537,3 +537,27 @@ def test_dropout_statistics_and_parity_given_masks(env):
     tower.forward(ws, training=True)
     assert ws.dropout_seeds != seeds_first
     assert np.isfinite(net.train_on_batch(inputs))
+
+
+def test_long_form_60s_utterances(env):
+    """BASELINE config 5 shape class: 60 s utterances (T = 7501 -> T' = 3751, P = 3750), labels of 900
+    characters (S = 1801 lattice states, two states per thread), small widths so the oracle finishes."""
+    from speechless_b200.synthetic import synthetic_batch
+    net, ref = make_pair(env, main=64, out=128, seed=77)
+    batch = synthetic_batch(2, [7501, 6003], env.alphabet, seed=5)
+    assert len(batch[0].label) == 900
+    inputs, _ = net._inputs_for_loss_net(batch)
+    names = env.Wav2Letter.InputNames
+    x = inputs[names.input_batch]
+    probs_ref = ref.forward(x)
+    assert probs_ref.shape == (2, 3751, 29)
+    pred = inputs[names.prediction_lengths][:, 0]
+    assert list(pred) == [3750, 3001]
+    losses = env.oracle.ctc_batch_cost(probs_ref, inputs[names.label_batch], pred, inputs[names.label_lengths][:, 0])
+    result = net.test_and_predict_batch(batch)
+    assert np.abs(np.array([r.loss for r in result.results]) / losses - 1).max() < 1e-4
+    assert np.abs(net.prediction_batch(x) - probs_ref).max() < 1e-4
+    before = net.train_on_batch(inputs)
+    assert abs(before / losses.mean() - 1) < 1e-4
+    after = net.test_and_predict_batch(batch).average_loss
+    assert np.isfinite(after) and after < before
