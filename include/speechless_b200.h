@@ -152,6 +152,21 @@ int sl_ctc_greedy_decode(const float* probs, const int32_t* input_len,
                          int32_t* out, int32_t* out_len, int B, int T, int V,
                          int blank, int merge_repeated, void* stream);
 
+/* ---- audio front end (replaces the librosa pipeline of labeled_example.py:99-140) ---- */
+/* audio (B, audio_stride) fp32 raw samples (sample_counts[b] valid each) ->
+ * out[b, t, m] for t < 1 + sample_counts[b]/hop: mel projection (mel_t = transposed Slaney
+ * filterbank (257, 128) fp32) of the power level 10 log10 |STFT|^2 floored at -150 dB, with
+ * librosa.stft semantics (periodic Hann window, center=True, reflect padding).  Rows beyond
+ * an utterance's frame count are left untouched.  Reference defaults only (512 / 128 / 128). */
+int sl_spectrogram(const float* audio, const int32_t* sample_counts, const float* mel_t,
+                   float* out, int B, int audio_stride, int T_max, int n_fft,
+                   int hop_length, int n_mels, void* stream);
+/* In place, per utterance: (x - mean) / std over the valid (frame_counts[b] x F) block
+ * (labeled_example.py:28-29), zeros beyond it (the batch padding of net.py:583-585).
+ * moments_ws: 2*B doubles of scratch. */
+int sl_z_normalize(float* x, const int32_t* frame_counts, void* moments_ws, int B,
+                   int T_max, int F, void* stream);
+
 /* ---- optimizer (replaces keras.optimizers.Adam, net.py:132,389) ---- */
 /* Keras-2 Adam on a flat fp32 buffer: t = step (1-based);
  * lr_t = lr*sqrt(1-b2^t)/(1-b1^t); p -= lr_t*m/(sqrt(v)+eps). */

@@ -27,6 +27,8 @@ int keras_to_internal_launch(const float*, float*, int, int, int, int, int, cuda
 int internal_to_keras_launch(const float*, float*, int, int, int, int, int, cudaStream_t);
 int pack_weights_internal_launch(const float*, void*, int, int, int, int, cudaStream_t);
 int dgrad_finalize_launch(const float*, const void*, void*, size_t, int, int, float, cudaStream_t);
+int spectrogram_launch(const float*, const int32_t*, const float*, float*, int, int, int, cudaStream_t);
+int z_normalize_launch(float*, const int32_t*, double*, int, int, int, cudaStream_t);
 int dropout_launch(const void*, void*, const void*, void*, size_t, int, int, float, unsigned long long, cudaStream_t);
 int adam_fused_launch(float*, const float*, float*, float*, size_t, const size_t*, const size_t*, void* const*,
                       const int*, int, int, float, float, float, float, int, cudaStream_t);
@@ -540,6 +542,24 @@ int sl_adam_step(float* p, const float* g, float* m, float* v, size_t n, float l
              "Adam buffers must be 16-byte aligned");
   if (n == 0) return SL_OK;
   return adam_launch(p, g, m, v, n, lr, beta1, beta2, eps, t, static_cast<cudaStream_t>(stream));
+}
+
+int sl_spectrogram(const float* audio, const int32_t* sample_counts, const float* mel_t, float* out, int B,
+                   int audio_stride, int T_max, int n_fft, int hop_length, int n_mels, void* stream) {
+  SL_REQUIRE(audio && sample_counts && mel_t && out, "null pointer");
+  SL_REQUIRE(B > 0 && audio_stride > 0 && T_max > 0, "bad shape");
+  SL_REQUIRE(n_fft == 512 && hop_length == 128 && n_mels == 128,
+             "the front end is built for the reference defaults: n_fft 512, hop 128, 128 mel bins");
+  return spectrogram_launch(audio, sample_counts, mel_t, out, B, audio_stride, T_max,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int sl_z_normalize(float* x, const int32_t* frame_counts, void* moments_ws, int B, int T_max, int F, void* stream) {
+  SL_REQUIRE(x && frame_counts && moments_ws, "null pointer");
+  SL_REQUIRE(B > 0 && T_max > 0 && F > 0, "bad shape");
+  SL_REQUIRE(reinterpret_cast<uintptr_t>(moments_ws) % 8 == 0, "moments workspace must be 8-byte aligned");
+  return z_normalize_launch(x, frame_counts, static_cast<double*>(moments_ws), B, T_max, F,
+                            static_cast<cudaStream_t>(stream));
 }
 
 int sl_dropout_fwd(const void* x_packed, void* y_packed, const void* relu_mask_in, void* mask_out, int B, int T,

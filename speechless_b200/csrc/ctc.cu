@@ -206,6 +206,7 @@ __global__ void ctc_alpha_beta_kernel(const float* __restrict__ logp,
 
 // ---------------------------------------------------------------------------------------------
 // Wavefront variant of the alpha/beta recurrence: no block-wide barrier inside the time loop.
+// (Opt-in experiment, SL_CTC_WAVE=1: correct, but slower than the barrier kernel — see the launcher.)
 //
 // Warp w owns the 32*SPT consecutive lattice states [w*32*SPT, ...), lane l the SPT states
 // s0 = (w*32 + l)*SPT ...  A state needs the previous column's values of itself and of its two left
@@ -228,12 +229,8 @@ __device__ __forceinline__ void st_volatile_s32(int* p, int v) {
 }
 __device__ __forceinline__ void spin_until_at_least(const int* p, int target) {
   unsigned spins = 0;
-  while (ld_volatile_s32(p) < target) {
-    if (++spins > (1u << 26)) {
-      printf("speechless_b200: CTC wavefront wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-      __trap();
-    }
-  }
+  while (ld_volatile_s32(p) < target)
+    if (++spins > (1u << 26)) __trap();  // a protocol bug must fail, not hang
 }
 
 template <int SPT>
@@ -255,12 +252,16 @@ __global__ void ctc_alpha_beta_wave_kernel(const float* __restrict__ logp,
   const int n_active = (S + 32 * SPT - 1) / (32 * SPT);  // warps that own at least one state
 
   float* lp_s = reinterpret_cast<float*>(smem_raw);                         // [LP_RING][VP]
-  float2* edge = reinterpret_cast<float2*>(lp_s + LP_RING * VP);            // [n_compute][EDGE_RING]
+  // edge ring: {value of state s_last-1, value of s_last, step + 1, 0} written with ONE 16-byte
+  // store, so the payload and its sequence tag become visible together and the hot loop needs no
+  // memory fence (a fence would also wait for the global lattice stores in flight)
+  uint4* edge = reinterpret_cast<uint4*>(lp_s + LP_RING * VP);              // [n_compute][EDGE_RING]
   float* final_col = reinterpret_cast<float*>(edge + n_compute * EDGE_RING);  // [n_compute * 32 * SPT]
   int* done = reinterpret_cast<int*>(final_col + n_compute * 32 * SPT);     // [n_compute] steps completed
   int* lp_ready = done + n_compute;                                         // rows of logp available
 
   for (int i = threadIdx.x; i <= n_compute; i += blockDim.x) done[i] = 0;  // (includes lp_ready)
+  for (int i = threadIdx.x; i < n_compute * EDGE_RING; i += blockDim.x) edge[i] = make_uint4(0u, 0u, 0u, 0u);
   __syncthreads();
 
   const float* lp_b = logp + static_cast<size_t>(b) * T * VP;
@@ -320,19 +321,29 @@ __global__ void ctc_alpha_beta_wave_kernel(const float* __restrict__ logp,
       float em[SPT];
 #pragma unroll
       for (int i = 0; i < SPT; ++i) em[i] = lp_row[my_e[i]] * LOG2E;
-      // values of states s0-1, s0-2 at the previous step
+      // values of states s0-1, s0-2 at the previous step.  Every poll below is executed by the
+      // whole warp on one address (warp-uniform trip counts): single-lane spin loops leave the
+      // warp diverged, and every later shuffle then pays for a re-convergence.
       float left1 = __shfl_up_sync(0xffffffffu, prev[SPT - 1], 1);
       float left0 = __shfl_up_sync(0xffffffffu, prev[SPT - 2 >= 0 ? SPT - 2 : 0], 1);
-      if (lane == 0) {
-        left1 = -INFINITY;
-        left0 = -INFINITY;
-        if (warp > 0 && tt > 0) {
-          spin_until_at_least(&done[warp - 1], tt);  // the previous warp finished step tt-1
-          const float2 e = edge[(warp - 1) * EDGE_RING + ((tt - 1) & (EDGE_RING - 1))];
-          left0 = e.x;
-          left1 = e.y;
-        }
+      float edge0 = -INFINITY, edge1 = -INFINITY;
+      if (warp > 0 && tt > 0) {
+        // poll the slot of step tt-1 until its tag says so (payload and tag share one 16-byte word)
+        const uint32_t slot = ptx::smem_u32(&edge[(warp - 1) * EDGE_RING + ((tt - 1) & (EDGE_RING - 1))]);
+        uint4 e;
+        unsigned spins = 0;
+        do {
+          asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(e.x), "=r"(e.y), "=r"(e.z), "=r"(e.w)
+                       : "r"(slot)
+                       : "memory");
+          if (++spins > (1u << 26)) __trap();
+        } while (e.z != static_cast<uint32_t>(tt));
+        edge0 = __uint_as_float(e.x);
+        edge1 = __uint_as_float(e.y);
       }
+      left0 = lane == 0 ? edge0 : left0;
+      left1 = lane == 0 ? edge1 : left1;
       float cur[SPT];
 #pragma unroll
       for (int i = 0; i < SPT; ++i) {
@@ -344,18 +355,25 @@ __global__ void ctc_alpha_beta_wave_kernel(const float* __restrict__ logp,
         if (tt == 0) cur[i] = (s0 + i <= 1) ? em[i] : -INFINITY;
         if (!my_on[i]) cur[i] = -INFINITY;
       }
+      // publish this warp's last two states for the next warp, then report the step as done (the
+      // report lets the previous warp overwrite the slot lane 0 just read, hence the __syncwarp)
+      if (!last_warp) {
+        // slot tt % R was read by the next warp during its step tt - R + 1 (uniform poll)
+        if (tt >= EDGE_RING) spin_until_at_least(&done[warp + 1], tt - EDGE_RING + 2);
+        if (lane == 31) {
+          const uint32_t slot = ptx::smem_u32(&edge[warp * EDGE_RING + (tt & (EDGE_RING - 1))]);
+          asm volatile("st.volatile.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(slot),
+                       "r"(__float_as_uint(cur[SPT - 2 >= 0 ? SPT - 2 : 0])), "r"(__float_as_uint(cur[SPT - 1])),
+                       "r"(static_cast<uint32_t>(tt + 1)), "r"(0u)
+                       : "memory");
+        }
+      }
+      __syncwarp();
+      if (lane == 31) st_volatile_s32(&done[warp], tt + 1);  // progress: back-pressure and ring reuse only
 #pragma unroll
       for (int i = 0; i < SPT; ++i)
         if (my_on[i]) out[my_out[i]] = cur[i];
       out += out_step;
-      if (lane == 31 && !last_warp) {
-        // slot tt % R was read by the next warp during its step tt - R + 1
-        if (tt >= EDGE_RING) spin_until_at_least(&done[warp + 1], tt - EDGE_RING + 2);
-        edge[warp * EDGE_RING + (tt & (EDGE_RING - 1))] = make_float2(cur[SPT - 2 >= 0 ? SPT - 2 : 0], cur[SPT - 1]);
-        __threadfence_block();
-      }
-      __syncwarp();
-      if (lane == 31) st_volatile_s32(&done[warp], tt + 1);
 #pragma unroll
       for (int i = 0; i < SPT; ++i) prev[i] = cur[i];
     }
@@ -576,9 +594,13 @@ int ctc_loss_launch(const float* logp, const float* probs, const int32_t* labels
   const char* wave_env = std::getenv("SL_CTC_WAVE");
   const int wspt = S_max <= 31 * 64 ? 2 : 4;  // wavefront kernel: 2 states per lane (4 beyond 1984 states)
   const int n_compute = (S_max + 32 * wspt - 1) / (32 * wspt);
-  if (!(wave_env && std::atoi(wave_env) == 0) && n_compute <= 31) {  // + one loader warp <= 1024 threads
+  // Measured on B200 (B=64, P=625, S=301): the wavefront kernel needs 0.21 ms, the block-barrier
+  // kernel below 0.11 ms — a lone warp per scheduler executes its ~160 dependent instructions per
+  // step at ~4 cycles each, while the barrier version interleaves warps.  The wavefront variant
+  // therefore stays opt-in (SL_CTC_WAVE=1) as a documented experiment.
+  if (wave_env && std::atoi(wave_env) == 1 && n_compute <= 31) {  // + one loader warp <= 1024 threads
     const int wthreads = (n_compute + 1) * 32;
-    const size_t wsmem = LP_RING * VP * sizeof(float) + static_cast<size_t>(n_compute) * EDGE_RING * sizeof(float2) +
+    const size_t wsmem = LP_RING * VP * sizeof(float) + static_cast<size_t>(n_compute) * EDGE_RING * sizeof(uint4) +
                          static_cast<size_t>(n_compute) * 32 * wspt * sizeof(float) + (n_compute + 1) * sizeof(int);
     if (wspt == 2)
       ctc_alpha_beta_wave_kernel<2><<<2 * B, wthreads, wsmem, stream>>>(logp, labels, input_len, label_len, loss,

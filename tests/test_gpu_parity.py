@@ -561,3 +561,50 @@ def test_long_form_60s_utterances(env):
     assert abs(before / losses.mean() - 1) < 1e-4
     after = net.test_and_predict_batch(batch).average_loss
     assert np.isfinite(after) and after < before
+
+
+def test_gpu_spectrogram_front_end(env, tmp_path):
+    """audio -> STFT -> power level -> mel -> z-normalised (T, 128) on the GPU against
+    the numpy restatement of the librosa pipeline (labeled_example.py:99-140), then straight into the
+    tower without leaving HBM."""
+    from oracle import spectrogram_oracle as so
+    from speechless_b200.frontend import SpectrogramFrontEnd, slaney_mel_filterbank
+    from speechless_b200.labeled_example import CachedLabeledSpectrogram, LabeledExample
+    assert np.abs(slaney_mel_filterbank() - so.mel_filterbank()).max() < 1e-12
+    rng = np.random.default_rng(5)
+
+    def clip(seconds, seed):
+        t = np.arange(int(16000 * seconds)) / 16000
+        r = np.random.default_rng(seed)
+        return (0.3 * np.sin(2 * np.pi * (200 + 50 * seed) * t) + 0.2 * np.sin(2 * np.pi * 2500 * t * (1 + 0.3 * t)) +
+                0.05 * r.standard_normal(t.shape)).astype(np.float32)
+
+    audios = [clip(1.3, 1), clip(0.41, 2), clip(2.0, 3), rng.standard_normal(777).astype(np.float32)]
+    front = SpectrogramFrontEnd(device="cuda:0")
+    got = front.z_normalized_transposed_spectrograms(audios)
+    for audio, z in zip(audios, got):
+        want = so.z_normalized_transposed_spectrogram(audio.astype(np.float64))
+        assert z.shape == want.shape == (1 + len(audio) // 128, 128)
+        # fp32 FFT + fp32 log vs fp64: values are O(1) after z-normalisation
+        assert np.abs(z - want).max() < 2e-3
+        assert abs(z.mean()) < 1e-4 and abs(z.std() - 1) < 1e-4
+    batch, frames = front.batch_on_device(audios)
+    assert batch.shape == (4, max(frames), 128)
+    for row, n in enumerate(frames):
+        assert float(batch[row, n:].abs().max()) == 0.0 if n < batch.shape[1] else True
+    # device-resident hand-over to the tower == the host path
+    net = env.Wav2Letter(128, env.alphabet, main_filter_count=64, out_filter_count=64, seed=1, device="cuda:0")
+    ws = net.tower.upload(batch)
+    net.tower.forward(ws)
+    host_input, _ = net._input_batch_and_prediction_lengths(got)
+    assert np.abs(ws.probs.cpu().numpy() - net.prediction_batch(host_input)).max() < 1e-6
+    # the reference-shaped example classes
+    example = LabeledExample(get_raw_audio=lambda: audios[0], id="clip-0", label="hello")
+    cached = CachedLabeledSpectrogram(example, tmp_path / "cache")
+    first = cached.z_normalized_transposed_spectrogram()
+    assert cached.is_cached() and (tmp_path / "cache" / "clip-0.npy").exists()
+    assert np.array_equal(cached.z_normalized_transposed_spectrogram(), first)
+    assert np.abs(first - got[0]).max() < 1e-6
+    assert isinstance(net.predict(cached), str)
+    with pytest.raises(NotImplementedError):
+        SpectrogramFrontEnd(hop_length=160)
