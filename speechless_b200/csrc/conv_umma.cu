@@ -577,11 +577,14 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
 template <int BN, int EPI, bool BMN>
 int launch(const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
   using C = Cfg<BN>;
-  static bool configured = false;  // benign race: attribute set is idempotent
-  if (!configured) {
+  // the opt-in shared-memory size is a per-device function attribute
+  static unsigned long long configured = 0;  // bit d: set for device d (benign race: idempotent)
+  int dev = 0;
+  SL_CUDA(cudaGetDevice(&dev));
+  if (!((configured >> (dev & 63)) & 1ull)) {
     SL_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, EPI, BMN>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    configured = true;
+    configured |= 1ull << (dev & 63);
   }
   const int num_tiles = p.B * p.m_tiles_per_utt * p.n_tiles * (p.ksplit > 1 ? p.ksplit : 1);
   const int grid = num_tiles < num_sms ? num_tiles : num_sms;

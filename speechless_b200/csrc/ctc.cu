@@ -137,31 +137,6 @@ __global__ void ctc_alpha_beta_kernel(const float* __restrict__ logp,
     }
     const float* lp_row = lp_s + (tt & (2 * CHUNK - 1)) * VP;
     float val[SPT];
-    if (SPT == 2) {
-      // states s0 (even: blank) and s0+1 (label): two 8-byte loads cover prev[s0-2 .. s0+1]
-      const float2 lo = *reinterpret_cast<const float2*>(prev + s0 - 2);
-      const float2 hi = *reinterpret_cast<const float2*>(prev + s0);
-      const float em0 = lp_row[my_e[0]] * LOG2E;
-      const float em1 = lp_row[my_e[1]] * LOG2E;
-      val[0] = lse3_base2(hi.x, lo.y, my_skip[0] ? lo.x : -INFINITY) + em0;
-      val[1] = lse3_base2(hi.y, hi.x, my_skip[1] ? lo.y : -INFINITY) + em1;
-      if (tt == 0) {
-        val[0] = (s0 <= 1) ? em0 : -INFINITY;
-        val[1] = (s0 + 1 <= 1) ? em1 : -INFINITY;
-      }
-      if (my_on[1]) {
-        *reinterpret_cast<float2*>(cur + s0) = make_float2(val[0], val[1]);
-        if (dir == 0) {
-          *reinterpret_cast<float2*>(out + s0) = make_float2(val[0], val[1]);
-        } else {
-          out[my_out[0]] = val[0];
-          out[my_out[1]] = val[1];
-        }
-      } else if (my_on[0]) {
-        cur[s0] = val[0];
-        out[my_out[0]] = val[0];
-      }
-    } else {
 #pragma unroll
       for (int i = 0; i < SPT; ++i) {
         const int s = s0 + i;
@@ -179,7 +154,6 @@ __global__ void ctc_alpha_beta_kernel(const float* __restrict__ logp,
           out[my_out[i]] = val[i];
         }
       }
-    }
     out += out_step;
     __syncthreads();
     if ((tt & (CHUNK - 1)) == CHUNK - 1) issue_chunk(tt / CHUNK + 2);
@@ -588,6 +562,10 @@ int ctc_loss_launch(const float* logp, const float* probs, const int32_t* labels
   const int S_max = 2 * L_max + 1;
   int spt = S_max <= 64 ? 1 : 2;
   if (S_max > 2048) spt = 4;
+  if (const char* e = std::getenv("SL_CTC_SPT")) {  // tuning aid: states per thread (1, 2 or 4)
+    const int v = std::atoi(e);
+    if ((v == 1 || v == 2 || v == 4) && (S_max + v - 1) / v <= 1024) spt = v;
+  }
   SL_REQUIRE(S_max <= 4096, "label too long (max 2047 characters)");
   int threads = ((S_max + spt - 1) / spt + 31) & ~31;
   if (threads < 64) threads = 64;

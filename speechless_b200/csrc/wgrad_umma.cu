@@ -335,11 +335,13 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
 template <int BN>
 int launch(const WgradParams& p, int num_sms, cudaStream_t stream) {
   using C = WCfg<BN>;
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;  // bit d: attribute set for device d
+  int dev = 0;
+  SL_CUDA(cudaGetDevice(&dev));
+  if (!((configured >> (dev & 63)) & 1ull)) {
     SL_CUDA(cudaFuncSetAttribute(wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  C::SMEM_BYTES));
-    configured = true;
+    configured |= 1ull << (dev & 63);
   }
   const int num_units = p.taps * p.m_tiles * p.n_tiles * p.ksplit;
   const int grid = num_units < num_sms ? num_units : num_sms;
