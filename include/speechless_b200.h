@@ -57,6 +57,16 @@ int sl_sync_check(void);
  * (T_alloc >= T rows per utterance, rows T..T_alloc zero).  */
 int sl_pack_activation(const float* x, void* x_packed, int B, int T, int C,
                        int T_alloc, int c_pad, int prec, void* stream);
+/* Raw-wave front layer (net.py:310-312 `wave_conv`: Conv1D k=250, strides=160,
+ * padding="same", with the training-phase Dropout of net.py:301-303 in front):
+ * lays the receptive field of every output frame out as one packed row,
+ * y[b][t][j*C + c] = x[b][t*stride + j - pad_l][c] (TF SAME padding, zeros
+ * outside), T_out = ceil(T/stride) rows of c_pad >= k*C channels, so that the
+ * layer runs as a 1-tap sl_conv1d_fwd / sl_conv1d_wgrad over k*C channels.
+ * drop_p > 0 applies inverted dropout per source sample (hash of seed). */
+int sl_window_activation(const float* x, void* x_windowed, int B, int T, int C,
+                         int k, int stride, int c_pad, int prec, float drop_p,
+                         unsigned long long seed, void* stream);
 /* inverse (debug / tests): packed -> fp32 (B,T,C) (hi + lo) */
 int sl_unpack_activation(const void* x_packed, float* x, int B, int T, int C,
                          int T_alloc, int c_pad, int prec, void* stream);

@@ -99,10 +99,12 @@ def glorot_uniform(rng: np.random.Generator, k: int, cin: int, cout: int, dtype=
 # The tower (net.py:291-341)
 # --------------------------------------------------------------------------------------
 def wav2letter_layer_specs(input_size: int, grapheme_set_size: int, main_filter_count: int = 250,
-                           out_filter_count: int = 2000):
-    """(name, cin, cout, kernel, stride, activation) for the 11 Conv1D layers of net.py:307-331."""
+                           out_filter_count: int = 2000, use_raw_wave_input: bool = False):
+    """(name, cin, cout, kernel, stride, activation) for the 11 Conv1D layers of net.py:307-331,
+    preceded by `wave_conv` (k250, s160, net.py:310-312) when `use_raw_wave_input`."""
     m, o = main_filter_count, out_filter_count
-    specs = [("striding_conv", input_size, m, 48, 2, "relu")]
+    specs = [("wave_conv", input_size, m, 250, 160, "relu")] if use_raw_wave_input else []
+    specs += [("striding_conv", m if use_raw_wave_input else input_size, m, 48, 2, "relu")]
     specs += [("inner_conv_{}".format(i), m, m, 7, 1, "relu") for i in range(1, 8)]
     specs += [("big_conv_1", m, o, 32, 1, "relu"), ("big_conv_2", o, o, 1, 1, "relu"),
               ("output_conv", o, grapheme_set_size, 1, 1, "softmax")]
@@ -113,8 +115,10 @@ class Wav2LetterOracle:
     """numpy restatement of the predictive net + CTC objective, with manual backprop."""
 
     def __init__(self, input_size: int, grapheme_set_size: int, main_filter_count: int = 250,
-                 out_filter_count: int = 2000, seed: int = 0, dtype=np.float64):
-        self.specs = wav2letter_layer_specs(input_size, grapheme_set_size, main_filter_count, out_filter_count)
+                 out_filter_count: int = 2000, seed: int = 0, dtype=np.float64,
+                 use_raw_wave_input: bool = False):
+        self.specs = wav2letter_layer_specs(input_size, grapheme_set_size, main_filter_count, out_filter_count,
+                                            use_raw_wave_input)
         self.dtype = dtype
         rng = np.random.default_rng(seed)
         self.weights = [glorot_uniform(rng, k, cin, cout).astype(dtype) for (_, cin, cout, k, _, _) in self.specs]

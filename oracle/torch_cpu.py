@@ -18,8 +18,10 @@ from oracle.keras_tf_oracle import EPSILON, same_padding, wav2letter_layer_specs
 
 class TorchCpuWav2Letter:
     def __init__(self, input_size: int, grapheme_set_size: int, main_filter_count: int = 250,
-                 out_filter_count: int = 2000, seed: int = 0, dtype=torch.float32, lr: float = 1e-4):
-        self.specs = wav2letter_layer_specs(input_size, grapheme_set_size, main_filter_count, out_filter_count)
+                 out_filter_count: int = 2000, seed: int = 0, dtype=torch.float32, lr: float = 1e-4,
+                 use_raw_wave_input: bool = False):
+        self.specs = wav2letter_layer_specs(input_size, grapheme_set_size, main_filter_count, out_filter_count,
+                                            use_raw_wave_input)
         self.dtype = dtype
         g = torch.Generator().manual_seed(seed)
         self.kernels: List[torch.Tensor] = []  # Keras layout (k, Cin, Cout)

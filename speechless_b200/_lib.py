@@ -21,6 +21,8 @@ SIGNATURES = {
     "sl_last_error": (c_int, [c_char_p, c_size_t]),
     "sl_sync_check": (c_int, []),
     "sl_pack_activation": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "sl_window_activation": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
+                                     ctypes.c_uint64, c_void_p]),
     "sl_unpack_activation": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "sl_pack_weights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "sl_conv1d_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

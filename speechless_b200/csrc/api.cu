@@ -23,6 +23,8 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
 // launchers implemented in the other translation units
 int pack_activation_launch(const float*, void*, int, int, int, int, int, int, cudaStream_t);
 int unpack_activation_launch(const void*, float*, int, int, int, int, int, int, cudaStream_t);
+int window_activation_launch(const float*, void*, int, int, int, int, int, int, int, int, int, float,
+                             unsigned long long, cudaStream_t);
 int keras_to_internal_launch(const float*, float*, int, int, int, int, int, cudaStream_t);
 int internal_to_keras_launch(const float*, float*, int, int, int, int, int, cudaStream_t);
 int pack_weights_internal_launch(const float*, void*, int, int, int, int, cudaStream_t);
@@ -206,6 +208,18 @@ int sl_pack_activation(const float* x, void* x_packed, int B, int T, int C, int 
   SL_REQUIRE(c_pad % 64 == 0 && c_pad >= C, "c_pad must be a multiple of 64 and >= C");
   return pack_activation_launch(x, x_packed, B, T, C, T_alloc, c_pad, planes_of(prec),
                                 static_cast<cudaStream_t>(stream));
+}
+
+int sl_window_activation(const float* x, void* x_windowed, int B, int T, int C, int k, int stride, int c_pad,
+                         int prec, float drop_p, unsigned long long seed, void* stream) {
+  SL_REQUIRE(x && x_windowed, "null pointer");
+  SL_REQUIRE(B > 0 && T > 0 && C > 0 && k > 0 && stride > 0, "bad shape");
+  SL_REQUIRE(c_pad % 64 == 0 && c_pad >= k * C, "c_pad must be a multiple of 64 and >= k*C");
+  SL_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "dropout rate must be in [0, 1)");
+  int T_out, pad_l;
+  same_padding(T, k, stride, &T_out, &pad_l);
+  return window_activation_launch(x, x_windowed, B, T, C, k, stride, T_out, pad_l, c_pad, planes_of(prec), drop_p,
+                                  seed, static_cast<cudaStream_t>(stream));
 }
 
 int sl_unpack_activation(const void* x_packed, float* x, int B, int T, int C, int T_alloc, int c_pad,

@@ -30,11 +30,60 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
     }                                                                  \
   } while (0)
 
+
+// ----------------------------------------------------------------------------------
+// host side: kernel launch with programmatic dependent launch (PDL)
+// ----------------------------------------------------------------------------------
+// Hot-path kernels call ptx::pdl_launch_dependents() first thing and ptx::pdl_wait() before they
+// touch global memory, so they can be launched with the programmatic-stream-serialization
+// attribute: the next kernel's CTAs are then scheduled (and run their barrier / TMEM / descriptor
+// setup) while the tail of this one drains.  Measured on B200 (profiles/README.md): no gain for the
+// conv / wgrad / elementwise kernels (5.22-5.28 ms/step either way: the stream is always full, so
+// launches are already hidden) and a 0.17 ms LOSS for the CTC lattice kernel (its 128 latency-bound
+// CTAs get packed onto the few SMs with free slots while output_conv still runs, instead of one
+// per SM).  The attribute is therefore off by default; SL_PDL=<bitmask of PdlClass> turns it on
+// per kernel class (without the attribute the device-side instructions are no-ops).
+#include <cstdlib>
+#include <utility>
+namespace sl {
+enum PdlClass { PDL_CONV = 1, PDL_WGRAD = 2, PDL_CTC = 4, PDL_ELEMENTWISE = 8 };
+inline int pdl_mask() {  // SL_PDL: bitmask of PdlClass values (tuning aid)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("SL_PDL");
+    v = e ? std::atoi(e) : 0;
+  }
+  return v;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(int pdl_class, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl_mask() & pdl_class) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+}  // namespace sl
+
 // ----------------------------------------------------------------------------------
 // device side
 // ----------------------------------------------------------------------------------
 namespace sl {
 namespace ptx {
+
+// programmatic dependent launch: let the next grid in the stream start its prologue / wait until
+// the previous grid has completed and its writes are visible (no-ops without the launch attribute)
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

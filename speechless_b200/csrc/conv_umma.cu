@@ -118,6 +118,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.tmA);
     prefetch_tmap(&p.tmB);
@@ -146,6 +147,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
+  pdl_wait();  // setup above overlapped the previous kernel's tail; its outputs are visible from here
 
   const int total_tiles = p.B * p.m_tiles_per_utt * p.n_tiles;
   const int num_tiles = p.ksplit > 1 ? total_tiles * p.ksplit
@@ -592,8 +594,7 @@ int launch(const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
     set_error("conv_gemm: inconsistent tail split");
     return 1;
   }
-  conv_gemm_kernel<BN, EPI, BMN><<<grid, kThreads, C::SMEM_BYTES, stream>>>(p);
-  SL_CUDA(cudaGetLastError());
+  SL_CUDA(launch_pdl(PDL_CONV, conv_gemm_kernel<BN, EPI, BMN>, dim3(grid), dim3(kThreads), C::SMEM_BYTES, stream, p));
   return 0;
 }
 

@@ -69,6 +69,8 @@ __global__ void ctc_alpha_beta_kernel(const float* __restrict__ logp,
                                       float* __restrict__ alpha, float* __restrict__ beta, int T,
                                       int L_max, int blank, int S_stride, int col_stride) {
   extern __shared__ uint8_t smem_raw[];
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();  // logp comes from the output_conv kernel right before
   const int dir = blockIdx.x & 1;
   const int b = blockIdx.x >> 1;
   const int tid = threadIdx.x;
@@ -384,6 +386,8 @@ __global__ void ctc_grad_kernel(const float* __restrict__ logp, const float* __r
                                 float* __restrict__ dz_f32, float grad_scale, int T, int V,
                                 int L_max, int blank, int S_stride, int planes, int frames_per_block) {
   extern __shared__ uint8_t smem_raw[];
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();  // alpha / beta / loss come from the lattice kernel right before
   int* lab_s = reinterpret_cast<int*>(smem_raw);                    // [L_max]
   float* bins = reinterpret_cast<float*>(lab_s + ((L_max + 31) & ~31));  // [warps][VP]
   const int b = blockIdx.y;
@@ -598,9 +602,9 @@ int ctc_loss_launch(const float* logp, const float* probs, const int32_t* labels
     if (smem > 48 * 1024)                                                                          \
       SL_CUDA(cudaFuncSetAttribute(ctc_alpha_beta_kernel<SPT>,                                     \
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); \
-    ctc_alpha_beta_kernel<SPT><<<2 * B, threads, smem, stream>>>(logp, labels, input_len, label_len, \
-                                                                 loss, beta_loss, alpha, beta, T,  \
-                                                                 L_max, blank, S_stride, col_stride); \
+    SL_CUDA(launch_pdl(PDL_CTC, ctc_alpha_beta_kernel<SPT>, dim3(2 * B), dim3(threads), smem, stream, logp, labels, \
+                       input_len, label_len, loss, beta_loss, alpha, beta, T, L_max, blank, S_stride,  \
+                       col_stride));                                                               \
   } while (0)
   if (spt == 1)
     SL_LAUNCH_AB(1);
@@ -618,11 +622,10 @@ int ctc_loss_launch(const float* logp, const float* probs, const int32_t* labels
     const int warps = 8;
     dim3 grid((T + frames_per_block - 1) / frames_per_block, B);
     const size_t gsmem = ((L_max + 31) & ~31) * sizeof(int) + warps * 2 * VP * sizeof(float);
-    ctc_grad_kernel<<<grid, warps * 32, gsmem, stream>>>(
-        logp, probs, labels, input_len, label_len, loss, alpha, beta,
-        reinterpret_cast<__nv_bfloat16*>(dlogits_packed), dlogits_f32, grad_scale, T, V, L_max,
-        blank, S_stride, planes, frames_per_block);
-    SL_CUDA(cudaGetLastError());
+    SL_CUDA(launch_pdl(PDL_CTC, ctc_grad_kernel, grid, dim3(warps * 32), gsmem, stream, logp, probs, labels, input_len,
+                       label_len, static_cast<const float*>(loss), static_cast<const float*>(alpha),
+                       static_cast<const float*>(beta), reinterpret_cast<__nv_bfloat16*>(dlogits_packed),
+                       dlogits_f32, grad_scale, T, V, L_max, blank, S_stride, planes, frames_per_block));
   }
   return 0;
 }

@@ -9,6 +9,8 @@ namespace {
 // (B,T,C) fp32 -> (B,T_alloc,planes*c_pad) bf16; one thread per pair of channels
 __global__ void pack_activation_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                        int B, int T, int C, int T_alloc, int c_pad, int planes) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   const size_t pairs_per_row = c_pad / 2;
   const size_t total = static_cast<size_t>(B) * T_alloc * pairs_per_row;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -166,6 +168,8 @@ struct AdamLayers {
 __global__ void adam_fused_kernel(float* __restrict__ p, const float* __restrict__ g,
                                   float* __restrict__ m, float* __restrict__ v, size_t n4, float lr_t,
                                   float b1, float b2, float eps, const __grid_constant__ AdamLayers L) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     float4 pp = reinterpret_cast<float4*>(p)[i];
@@ -248,6 +252,8 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 __global__ void dgrad_finalize_kernel(const float* __restrict__ acc, const uint8_t* __restrict__ mask,
                                       __nv_bfloat16* __restrict__ dx, size_t rows, int c_pad, int planes,
                                       float out_scale) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   const int groups = c_pad / 8;
   const size_t total = rows * groups;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -292,6 +298,8 @@ __global__ void dropout_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat1
                                const uint8_t* __restrict__ relu_mask_in, uint8_t* __restrict__ mask_out,
                                size_t rows, int c_pad, int planes, unsigned threshold16, float scale,
                                unsigned long long seed) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   const int groups = c_pad / 8;
   const size_t total = rows * groups;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -328,6 +336,47 @@ __global__ void dropout_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat1
   }
 }
 
+// Raw-wave input (reference net.py:310-312: Conv1D "wave_conv", k = 250, stride 160, SAME padding):
+// the strided long filter becomes a plain GEMM once every output frame's receptive field is laid
+// out as a row.  (B,T,C) fp32 -> (B,T_out,planes*c_pad) bf16 with row[t][j*C + c] = x[t*stride + j
+// - pad_l][c] (zero outside [0,T) and for columns >= k*C), so that wave_conv runs through the same
+// tcgen05 kernels as a 1-tap convolution over k*C input channels.  The training-phase Dropout in
+// front of wave_conv (net.py:301-303) is applied here: the keep decision is a function of the
+// *source* sample, so a dropped sample is dropped in every window that contains it.
+__global__ void window_activation_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int B,
+                                         int T, int C, int k, int stride, int T_out, int pad_l, int c_pad,
+                                         int planes, unsigned threshold16, float scale,
+                                         unsigned long long seed) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
+  const size_t total = static_cast<size_t>(B) * T_out * c_pad;
+  const int kc = k * C;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int col = static_cast<int>(i % c_pad);
+    const size_t row = i / c_pad;
+    const int t = static_cast<int>(row % T_out);
+    const int b = static_cast<int>(row / T_out);
+    float v = 0.f;
+    if (col < kc) {
+      const int j = col / C, c = col - j * C;
+      const int ts = t * stride + j - pad_l;
+      if (ts >= 0 && ts < T) {
+        const size_t src = (static_cast<size_t>(b) * T + ts) * C + c;
+        v = x[src];
+        if (threshold16 != 0) {
+          const unsigned long long r = splitmix64(seed ^ (src >> 2));
+          v = ((r >> (16 * (src & 3))) & 0xffffu) >= threshold16 ? v * scale : 0.f;
+        }
+      }
+    }
+    __nv_bfloat16* dst = y + row * (static_cast<size_t>(planes) * c_pad) + col;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    dst[0] = hi;
+    if (planes == 2) dst[c_pad] = __float2bfloat16_rn(v - __bfloat162float(hi));
+  }
+}
+
 inline int grid_for(size_t total, int block) {
   size_t g = (total + block - 1) / block;
   const size_t cap = 148 * 16;
@@ -339,9 +388,8 @@ inline int grid_for(size_t total, int block) {
 int pack_activation_launch(const float* x, void* y, int B, int T, int C, int T_alloc, int c_pad,
                            int planes, cudaStream_t s) {
   const size_t total = static_cast<size_t>(B) * T_alloc * (c_pad / 2);
-  pack_activation_kernel<<<grid_for(total, 256), 256, 0, s>>>(
-      x, reinterpret_cast<__nv_bfloat16*>(y), B, T, C, T_alloc, c_pad, planes);
-  SL_CUDA(cudaGetLastError());
+  SL_CUDA(launch_pdl(PDL_ELEMENTWISE, pack_activation_kernel, dim3(grid_for(total, 256)), dim3(256), 0, s, x,
+                     reinterpret_cast<__nv_bfloat16*>(y), B, T, C, T_alloc, c_pad, planes));
   return 0;
 }
 int unpack_activation_launch(const void* y, float* x, int B, int T, int C, int T_alloc, int c_pad,
@@ -376,10 +424,9 @@ int pack_weights_internal_launch(const float* wi, void* wf, int k, int cin_pad, 
 }
 int dgrad_finalize_launch(const float* acc, const void* mask, void* dx, size_t rows, int c_pad, int planes,
                           float out_scale, cudaStream_t s) {
-  dgrad_finalize_kernel<<<grid_for(rows * (c_pad / 8), 256), 256, 0, s>>>(
-      acc, reinterpret_cast<const uint8_t*>(mask), reinterpret_cast<__nv_bfloat16*>(dx), rows, c_pad, planes,
-      out_scale);
-  SL_CUDA(cudaGetLastError());
+  SL_CUDA(launch_pdl(PDL_ELEMENTWISE, dgrad_finalize_kernel, dim3(grid_for(rows * (c_pad / 8), 256)), dim3(256), 0, s, acc,
+                     reinterpret_cast<const uint8_t*>(mask), reinterpret_cast<__nv_bfloat16*>(dx), rows, c_pad,
+                     planes, out_scale));
   return 0;
 }
 int dropout_launch(const void* x, void* y, const void* relu_mask_in, void* mask_out, size_t rows, int c_pad,
@@ -389,6 +436,16 @@ int dropout_launch(const void* x, void* y, const void* relu_mask_in, void* mask_
       reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y),
       reinterpret_cast<const uint8_t*>(relu_mask_in), reinterpret_cast<uint8_t*>(mask_out), rows, c_pad, planes,
       threshold16, 1.0f / (1.0f - static_cast<float>(threshold16) / 65536.0f), seed);
+  SL_CUDA(cudaGetLastError());
+  return 0;
+}
+int window_activation_launch(const float* x, void* y, int B, int T, int C, int k, int stride, int T_out, int pad_l,
+                             int c_pad, int planes, float p, unsigned long long seed, cudaStream_t s) {
+  const unsigned threshold16 = p > 0.f ? static_cast<unsigned>(p * 65536.0f + 0.5f) : 0u;
+  const size_t total = static_cast<size_t>(B) * T_out * c_pad;
+  window_activation_kernel<<<grid_for(total, 256), 256, 0, s>>>(
+      x, reinterpret_cast<__nv_bfloat16*>(y), B, T, C, k, stride, T_out, pad_l, c_pad, planes, threshold16,
+      1.0f / (1.0f - static_cast<float>(threshold16) / 65536.0f), seed);
   SL_CUDA(cudaGetLastError());
   return 0;
 }
@@ -418,9 +475,8 @@ int adam_fused_launch(float* p, const float* g, float* m, float* v, size_t n, co
   }
   const double lr_t = static_cast<double>(lr) * sqrt(1.0 - pow(static_cast<double>(b2), t)) /
                       (1.0 - pow(static_cast<double>(b1), t));
-  adam_fused_kernel<<<grid_for(n / 4, 256), 256, 0, s>>>(p, g, m, v, n / 4, static_cast<float>(lr_t), b1,
-                                                         b2, eps, L);
-  SL_CUDA(cudaGetLastError());
+  SL_CUDA(launch_pdl(PDL_ELEMENTWISE, adam_fused_kernel, dim3(grid_for(n / 4, 256)), dim3(256), 0, s, p, g, m, v, n / 4,
+                     static_cast<float>(lr_t), b1, b2, eps, L));
   return 0;
 }
 int adam_launch(float* p, const float* g, float* m, float* v, size_t n, float lr, float b1, float b2,

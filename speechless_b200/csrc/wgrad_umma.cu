@@ -68,6 +68,7 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.tmDY);
     prefetch_tmap(&p.tmX);
@@ -92,6 +93,7 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
+  pdl_wait();  // the previous kernel's outputs (dY, the zeroed / partially reduced dW) are visible from here
 
   // unit -> (tap fastest, then m_tile, n_tile, split): CTAs running together work on the
   // same K range, i.e. read the same dY / X slabs from L2, and reduce into different dW tiles.
@@ -345,8 +347,7 @@ int launch(const WgradParams& p, int num_sms, cudaStream_t stream) {
   }
   const int num_units = p.taps * p.m_tiles * p.n_tiles * p.ksplit;
   const int grid = num_units < num_sms ? num_units : num_sms;
-  wgrad_kernel<BN><<<grid, kThreads, C::SMEM_BYTES, stream>>>(p);
-  SL_CUDA(cudaGetLastError());
+  SL_CUDA(launch_pdl(PDL_WGRAD, wgrad_kernel<BN>, dim3(grid), dim3(kThreads), C::SMEM_BYTES, stream, p));
   return 0;
 }
 

@@ -38,10 +38,25 @@ class LayerSpec:
     activation: str  # "relu" | "linear" | "softmax"
     w_offset: int = 0  # offsets into the flat parameter buffer (floats)
     b_offset: int = 0
+    # `windowed`: the layer's receptive fields are laid out as rows first (sl_window_activation), so
+    # the GEMM sees one tap over kernel*cin channels at stride 1 (raw-wave `wave_conv`, net.py:310-312)
+    windowed: bool = False
+
+    @property
+    def gemm_cin(self) -> int:
+        return self.kernel * self.cin if self.windowed else self.cin
+
+    @property
+    def gemm_kernel(self) -> int:
+        return 1 if self.windowed else self.kernel
+
+    @property
+    def gemm_stride(self) -> int:
+        return 1 if self.windowed else self.stride
 
     @property
     def cin_pad(self) -> int:
-        return round_up(self.cin, 64)
+        return round_up(self.gemm_cin, 64)
 
     @property
     def cout_pad(self) -> int:
@@ -49,16 +64,21 @@ class LayerSpec:
 
     @property
     def w_size(self) -> int:
-        return self.kernel * self.cout_pad * self.cin_pad
+        return self.gemm_kernel * self.cout_pad * self.cin_pad
 
 
 def wav2letter_layers(input_size_per_time_step: int, grapheme_set_size: int, activation: str = "relu",
                       output_activation: str = "softmax", main_filter_count: int = 250,
-                      out_filter_count: int = 2000) -> List[LayerSpec]:
+                      out_filter_count: int = 2000, use_raw_wave_input: bool = False) -> List[LayerSpec]:
     """The 11 Conv1D layers of `Wav2Letter.create_predictive_net` (reference net.py:307-331):
-    striding_conv k48 s2, inner_conv_1..7 k7, big_conv_1 k32, big_conv_2 k1, output_conv k1."""
+    striding_conv k48 s2, inner_conv_1..7 k7, big_conv_1 k32, big_conv_2 k1, output_conv k1;
+    with `use_raw_wave_input` a twelfth, `wave_conv` k250 s160, in front (net.py:310-312)."""
     m, o = main_filter_count, out_filter_count
-    layers = [LayerSpec("striding_conv", input_size_per_time_step, m, 48, 2, activation)]
+    layers = []
+    if use_raw_wave_input:
+        layers.append(LayerSpec("wave_conv", input_size_per_time_step, m, 250, 160, activation, windowed=True))
+    layers.append(LayerSpec("striding_conv", m if use_raw_wave_input else input_size_per_time_step, m, 48, 2,
+                            activation))
     layers += [LayerSpec("inner_conv_{}".format(i), m, m, 7, 1, activation) for i in range(1, 8)]
     layers += [LayerSpec("big_conv_1", m, o, 32, 1, activation),
                LayerSpec("big_conv_2", o, o, 1, 1, activation),
@@ -91,7 +111,10 @@ class _Workspace:
         dev, planes = tower.device, tower.planes
         first = tower.layers[0]
         self.B, self.T = B, T
-        self.T_alloc = round_up(T, first.stride)
+        # T0: rows per utterance of the packed first-layer operand (frames, or receptive-field rows
+        # of a windowed raw-wave layer)
+        self.T0 = same_padding(T, first.kernel, first.stride)[0] if first.windowed else T
+        self.T_alloc = round_up(self.T0, first.gemm_stride)
         self.x_f32 = torch.empty((B, T, first.cin), dtype=torch.float32, device=dev)
         self.x_host = torch.empty((B, T, first.cin), dtype=torch.float32, pin_memory=True)
         # second slot for the pipelined training loop (copy of batch i+1 overlaps step i)
@@ -131,6 +154,7 @@ class _Workspace:
         self.bwd_mask: Dict[int, torch.Tensor] = {}
         self.layer_inputs: List[Optional[torch.Tensor]] = [None] * len(tower.layers)
         self.dropout_seeds: Dict[int, int] = {}
+        self.input_dropped = False  # raw-wave input: dropout was applied while packing
 
     def ensure_backward(self, tower: "ConvTower"):
         if self.dz_packed is None:
@@ -168,9 +192,10 @@ class ConvTower:
         for layer in layers:
             if layer.activation not in ("relu", "linear", "softmax"):
                 raise NotImplementedError("activation '{}' has no sm_100a epilogue".format(layer.activation))
-            if layer.stride not in (1, 2):
-                raise NotImplementedError("stride {} is not supported (raw-wave input is out of scope)".format(
-                    layer.stride))
+            if layer.gemm_stride not in (1, 2):
+                raise NotImplementedError("stride {} needs a windowed layer".format(layer.stride))
+        if any(layer.windowed for layer in layers[1:]):
+            raise NotImplementedError("only the first layer can be windowed")
         if layers[-1].activation != "softmax":
             raise NotImplementedError("the output layer must be a softmax (CTC objective)")
         self.param_count = layers[-1].b_offset + layers[-1].cout_pad
@@ -179,7 +204,7 @@ class ConvTower:
             self.grads: Optional[torch.Tensor] = None
             self.adam_m: Optional[torch.Tensor] = None
             self.adam_v: Optional[torch.Tensor] = None
-            self.w_fwd = [torch.zeros((l.kernel, l.cout_pad, self.planes * l.cin_pad), dtype=torch.bfloat16,
+            self.w_fwd = [torch.zeros((l.gemm_kernel, l.cout_pad, self.planes * l.cin_pad), dtype=torch.bfloat16,
                                       device=device) for l in layers]
         self._workspaces: Dict[Tuple[int, int], _Workspace] = {}
         self._current: Optional[_Workspace] = None
@@ -238,9 +263,10 @@ class ConvTower:
                 layer.name, (layer.kernel, layer.cin, layer.cout), (layer.cout,), kernel.shape, bias.shape))
         with torch.cuda.device(self.device):
             w_keras = torch.from_numpy(kernel).to(self.device)
-            check(self.lib.sl_weights_keras_to_internal(ptr(w_keras), ptr(self._w(self.params, layer)), layer.kernel,
-                                                        layer.cin, layer.cout, layer.cin_pad, layer.cout_pad,
-                                                        self.stream))
+            # (k, Cin, Cout) row-major is also (1, k*Cin, Cout): a windowed layer needs no reshuffle
+            check(self.lib.sl_weights_keras_to_internal(ptr(w_keras), ptr(self._w(self.params, layer)),
+                                                        layer.gemm_kernel, layer.gemm_cin, layer.cout, layer.cin_pad,
+                                                        layer.cout_pad, self.stream))
             b = self._b(self.params, layer)
             b.zero_()
             b[:layer.cout].copy_(torch.from_numpy(bias).to(self.device))
@@ -252,9 +278,9 @@ class ConvTower:
         layer = self.layers[index]
         with torch.cuda.device(self.device):
             w_keras = torch.empty((layer.kernel, layer.cin, layer.cout), dtype=torch.float32, device=self.device)
-            check(self.lib.sl_weights_internal_to_keras(ptr(self._w(self.params, layer)), ptr(w_keras), layer.kernel,
-                                                        layer.cin, layer.cout, layer.cin_pad, layer.cout_pad,
-                                                        self.stream))
+            check(self.lib.sl_weights_internal_to_keras(ptr(self._w(self.params, layer)), ptr(w_keras),
+                                                        layer.gemm_kernel, layer.gemm_cin, layer.cout, layer.cin_pad,
+                                                        layer.cout_pad, self.stream))
             return [w_keras.cpu().numpy(), self._b(self.params, layer)[:layer.cout].cpu().numpy()]
 
     def repack(self, indices: Optional[Sequence[int]] = None) -> None:
@@ -264,8 +290,8 @@ class ConvTower:
             for index in (range(len(self.layers)) if indices is None else indices):
                 layer = self.layers[index]
                 check(self.lib.sl_pack_weights_internal(ptr(self._w(self.params, layer)), ptr(self.w_fwd[index]),
-                                                        layer.kernel, layer.cin_pad, layer.cout_pad, self.precision,
-                                                        self.stream))
+                                                        layer.gemm_kernel, layer.cin_pad, layer.cout_pad,
+                                                        self.precision, self.stream))
                 self.launches += 1
 
     # ------------------------------------------------------------------ forward
@@ -280,8 +306,25 @@ class ConvTower:
             self._workspaces[key] = ws
         return ws
 
-    def upload(self, input_batch) -> _Workspace:
-        """Host (B,T,F) float array (any float dtype, net.py:583) or a device fp32 tensor -> packed bf16."""
+    def _pack_input(self, ws: _Workspace, x: torch.Tensor, training: bool) -> None:
+        """fp32 (B,T,F) on the device -> packed bf16 operand of the first layer."""
+        first = self.layers[0]
+        if first.windowed:
+            drop = training and self.dropout is not None and 0 in self.dropout_layers
+            # forward(training=True) advances dropout_step before it derives the other layers' seeds
+            seed = self._dropout_seed(0, self.dropout_step + 1) if drop else 0
+            check(self.lib.sl_window_activation(ptr(x), ptr(ws.x_packed), ws.B, ws.T, first.cin, first.kernel,
+                                                first.stride, first.cin_pad, self.precision,
+                                                float(self.dropout) if drop else 0.0, seed, self.stream))
+            ws.input_dropped = drop
+        else:
+            check(self.lib.sl_pack_activation(ptr(x), ptr(ws.x_packed), ws.B, ws.T, first.cin, ws.T_alloc,
+                                              first.cin_pad, self.precision, self.stream))
+        self.launches += 1
+
+    def upload(self, input_batch, training: bool = False) -> _Workspace:
+        """Host (B,T,F) float array (any float dtype, net.py:583) or a device fp32 tensor -> packed bf16.
+        `training` only matters for raw-wave input, whose input dropout is applied while packing."""
         with torch.cuda.device(self.device):
             if isinstance(input_batch, torch.Tensor) and input_batch.is_cuda:
                 B, T, F = input_batch.shape
@@ -305,9 +348,7 @@ class ConvTower:
             first = self.layers[0]
             if F != first.cin:
                 raise ValueError("expected {} features per time step, got {}".format(first.cin, F))
-            check(self.lib.sl_pack_activation(ptr(x), ptr(ws.x_packed), B, T, F, ws.T_alloc, first.cin_pad,
-                                              self.precision, self.stream))
-            self.launches += 1
+            self._pack_input(ws, x, training)
             self._current = ws
             return ws
 
@@ -347,21 +388,19 @@ class ConvTower:
                 ws.slot_copied[slot] = copy.record_event()
             return ws
 
-    def consume_slot(self, ws: _Workspace, slot: int) -> _Workspace:
+    def consume_slot(self, ws: _Workspace, slot: int, training: bool = False) -> _Workspace:
         """Compute stream: wait for the slot's copy, pack it to bf16 and release the slot."""
         with torch.cuda.device(self.device):
             main = torch.cuda.current_stream(self.device)
             main.wait_event(ws.slot_copied[slot])
-            first = self.layers[0]
-            check(self.lib.sl_pack_activation(ptr(ws.x_slots[slot]), ptr(ws.x_packed), ws.B, ws.T, first.cin,
-                                              ws.T_alloc, first.cin_pad, self.precision, self.stream))
+            self._pack_input(ws, ws.x_slots[slot], training)
             ws.slot_consumed[slot] = main.record_event()
-            self.launches += 1
             self._current = ws
             return ws
 
-    def _dropout_seed(self, index: int) -> int:
-        mixed = (self.dropout_seed * 0x9E3779B97F4A7C15 + self.dropout_step * 0xD1B54A32D192ED03 +
+    def _dropout_seed(self, index: int, step: Optional[int] = None) -> int:
+        step = self.dropout_step if step is None else step
+        mixed = (self.dropout_seed * 0x9E3779B97F4A7C15 + step * 0xD1B54A32D192ED03 +
                  (index + 1) * 0x8CB92BA72F3D8DD7) & 0xFFFFFFFFFFFFFFFF
         return mixed
 
@@ -373,9 +412,11 @@ class ConvTower:
         if drop:
             self.dropout_step += 1
         with torch.cuda.device(self.device):
-            x, t_in, t_alloc = ws.x_packed, ws.T, ws.T_alloc
+            x, t_in, t_alloc = ws.x_packed, ws.T0, ws.T_alloc
             for index, layer in enumerate(self.layers):
-                if drop and index in self.dropout_layers:
+                if drop and layer.windowed and index in self.dropout_layers and not ws.input_dropped:
+                    raise RuntimeError("raw-wave input dropout is applied while packing: upload(training=True)")
+                if drop and index in self.dropout_layers and not layer.windowed:
                     if index not in ws.xdrop:
                         ws.xdrop[index] = torch.zeros_like(x)  # zero: keeps the T_alloc padding rows zero
                         ws.bwd_mask[index] = torch.empty((ws.B, t_alloc, layer.cin_pad // 8), dtype=torch.uint8,
@@ -385,7 +426,7 @@ class ConvTower:
                     seed = self._dropout_seed(index)
                     ws.dropout_seeds[index] = seed
                     check(self.lib.sl_dropout_fwd(ptr(x), ptr(ws.xdrop[index]), ptr(relu_below),
-                                                  ptr(ws.bwd_mask[index]), ws.B, t_alloc, layer.cin, self.precision,
+                                                  ptr(ws.bwd_mask[index]), ws.B, t_alloc, layer.gemm_cin, self.precision,
                                                   float(self.dropout), seed, self.stream))
                     self.launches += 1
                     x = ws.xdrop[index]
@@ -394,15 +435,16 @@ class ConvTower:
                 if layer.activation == "softmax":
                     self._timed("fwd", layer.name, lambda: self.lib.sl_conv1d_fwd(
                         ptr(x), ptr(self.w_fwd[index]), ptr(bias), None, None, ptr(ws.probs),
-                        ptr(ws.logits) if want_logits else None, ptr(ws.logp), ws.B, t_in, t_alloc, layer.cin,
-                        layer.cout, layer.kernel, layer.stride, ACT_SOFTMAX, self.precision, self.stream))
+                        ptr(ws.logits) if want_logits else None, ptr(ws.logp), ws.B, t_in, t_alloc, layer.gemm_cin,
+                        layer.cout, layer.gemm_kernel, layer.gemm_stride, ACT_SOFTMAX, self.precision, self.stream))
                 else:
                     y = ws.acts[index]
                     act = ACT_RELU if layer.activation == "relu" else ACT_NONE
                     mask = ws.masks[index] if layer.activation == "relu" else None
                     self._timed("fwd", layer.name, lambda: self.lib.sl_conv1d_fwd(
                         ptr(x), ptr(self.w_fwd[index]), ptr(bias), ptr(y), ptr(mask), None, None, None, ws.B, t_in,
-                        t_alloc, layer.cin, layer.cout, layer.kernel, layer.stride, act, self.precision, self.stream))
+                        t_alloc, layer.gemm_cin, layer.cout, layer.gemm_kernel, layer.gemm_stride, act, self.precision,
+                        self.stream))
                     x, t_in, t_alloc = y, ws.t_out[index], ws.t_out[index]
                 self.launches += 1
         return ws
@@ -522,11 +564,12 @@ class ConvTower:
             for index in range(len(self.layers) - 1, first - 1, -1):
                 layer = self.layers[index]
                 x = ws.layer_inputs[index]  # the tensor the forward conv actually read (dropped or not)
-                t_in = ws.T if index == 0 else ws.t_out[index - 1]
+                t_in = ws.T0 if index == 0 else ws.t_out[index - 1]
                 t_alloc = ws.T_alloc if index == 0 else t_in
                 launch_wgrad = lambda: self._timed("wgrad", layer.name, lambda: self.lib.sl_conv1d_wgrad(
                     ptr(x), ptr(dy), ptr(self._w(self.grads, layer)), ptr(self._b(self.grads, layer)), ws.B, t_in,
-                    t_alloc, layer.cin, layer.cout, layer.kernel, layer.stride, self.precision, 1, self.stream))
+                    t_alloc, layer.gemm_cin, layer.cout, layer.gemm_kernel, layer.gemm_stride, self.precision, 1,
+                    self.stream))
                 previous_wgrad_done = wgrad_done
                 if side is None:
                     launch_wgrad()

@@ -12,8 +12,10 @@ Differences that are deliberate and documented in DESIGN.md:
 * batches of size 1 work (the reference needs the duplication workaround of net.py:492-495,
   which is kept so results are identical either way);
 * weights are saved as `.npz` keyed by the Keras layer names when `h5py` is unavailable;
-* `use_raw_wave_input` and `kenlm_directory` raise `NotImplementedError` (SURVEY.md §8f "next"
-  rows); `use_asg=True` raises at loss time exactly like the reference;
+* `use_raw_wave_input=True` adds `wave_conv` (k250 s160, net.py:310-312) in front; its receptive
+  fields are laid out as rows on the device so it runs on the same tensor-core kernels;
+* `kenlm_directory` raises `NotImplementedError` (it needs the reference's patched
+  TensorFlow); `use_asg=True` raises at loss time exactly like the reference;
 * `dropout` masks come from a counter-based hash, so they cannot equal TF's bit for bit; the
   arithmetic given the masks is what the parity tests check.
 """
@@ -228,8 +230,6 @@ class Wav2Letter:
                  seed: Optional[int] = None):
         if frozen_layer_count > 0 and load_model_from_directory is None:
             raise ValueError("Layers cannot be frozen if model is trained from scratch.")
-        if use_raw_wave_input:
-            raise NotImplementedError("raw-wave input (wave_conv k250 s160) is not built yet (SURVEY.md §8f-4).")
         if compute_dtype not in ("bf16", "bf16x2"):
             raise ValueError("compute_dtype must be 'bf16' or 'bf16x2'")
 
@@ -282,8 +282,9 @@ class Wav2Letter:
         layers = wav2letter_layers(self.input_size_per_time_step, self.grapheme_encoding.grapheme_set_size,
                                    activation=self.activation, output_activation=self.output_activation,
                                    main_filter_count=self.main_filter_count,
-                                   out_filter_count=self.out_filter_count)
-        # Dropout sits in front of striding_conv and inner_conv_1..7, never before the last three
+                                   out_filter_count=self.out_filter_count,
+                                   use_raw_wave_input=self.use_raw_wave_input)
+        # Dropout sits in front of (wave_conv,) striding_conv and inner_conv_1..7, never before the last three
         # layers (never_dropout, net.py:326-330)
         dropout_layers = list(range(len(layers) - 3)) if self.dropout else []
         # `layers[:frozen_layer_count]` of the reference counts the interleaved Dropout layers too
@@ -484,7 +485,7 @@ class Wav2Letter:
             raise NotImplementedError("ASG is not yet implemented.")
         names = Wav2Letter.InputNames
         tower = self.tower
-        ws = tower.upload(input_by_name[names.input_batch])
+        ws = tower.upload(input_by_name[names.input_batch], training=True)
         tower.forward(ws, training=True)  # learning phase 1: dropout active (net.py:597-606)
         tower.set_labels(ws, input_by_name[names.label_batch], input_by_name[names.prediction_lengths],
                          input_by_name[names.label_lengths])
@@ -528,7 +529,7 @@ class Wav2Letter:
         while current is not None:
             upcoming = next(iterator, None)
             next_ws = tower.stage_async(upcoming[names.input_batch], slot ^ 1) if upcoming is not None else None
-            tower.consume_slot(ws, slot)
+            tower.consume_slot(ws, slot, training=True)
             tower.forward(ws, training=True)
             tower.set_labels(ws, current[names.label_batch], current[names.prediction_lengths],
                              current[names.label_lengths])

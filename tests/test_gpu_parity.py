@@ -382,8 +382,6 @@ def test_error_behaviour(env):
     assert single.loss == pytest.approx(net.test_and_predict(ok).loss, rel=1e-6)
     with pytest.raises(ValueError, match="features per time step"):
         net.prediction_batch(np.zeros((1, 10, 64), dtype=np.float32))
-    with pytest.raises(NotImplementedError):
-        env.Wav2Letter(128, env.alphabet, use_raw_wave_input=True)
     asg = env.Wav2Letter(128, env.alphabet, use_asg=True, main_filter_count=64, out_filter_count=64, device="cuda:0")
     with pytest.raises(NotImplementedError, match="ASG"):
         asg.test_and_predict_batch([ok, ok])
@@ -608,3 +606,112 @@ def test_gpu_spectrogram_front_end(env, tmp_path):
     assert isinstance(net.predict(cached), str)
     with pytest.raises(NotImplementedError):
         SpectrogramFrontEnd(hop_length=160)
+
+
+# ------------------------------------------------------------------ raw-wave input
+@pytest.mark.parametrize("T,C,k,stride,prec", [(1000, 1, 250, 160, 2), (961, 1, 250, 160, 1), (77, 3, 5, 4, 2)])
+def test_window_activation_matches_numpy(env, T, C, k, stride, prec):
+    """sl_window_activation lays TF-SAME receptive fields out as rows (net.py:310-312 wave_conv)."""
+    torch, lib, ptr, check = env.torch, env.lib, env._lib.ptr, env._lib.check
+    B = 2
+    rng = np.random.default_rng(T)
+    x = rng.standard_normal((B, T, C)).astype(np.float32)
+    t_out, pad_l, pad_r = env.oracle.same_padding(T, k, stride)
+    c_pad = -(-k * C // 64) * 64
+    planes = 2 if prec == 2 else 1
+    xd = torch.from_numpy(x).cuda()
+    out = torch.full((B, t_out, planes * c_pad), 7.0, dtype=torch.bfloat16, device="cuda")
+    check(lib.sl_window_activation(ptr(xd), ptr(out), B, T, C, k, stride, c_pad, prec, 0.0, 0,
+                                   torch.cuda.current_stream().cuda_stream))
+    got = out.float().view(B, t_out, planes, c_pad).sum(dim=2).cpu().numpy()
+    xp = np.pad(x, ((0, 0), (pad_l, pad_r + stride), (0, 0)))
+    want = np.zeros((B, t_out, c_pad), dtype=np.float32)
+    for t in range(t_out):
+        want[:, t, :k * C] = xp[:, t * stride:t * stride + k, :].reshape(B, k * C)
+    assert np.abs(got - want).max() <= (2.0 ** -16 if prec == 2 else 2.0 ** -8) * np.abs(want).max()
+    assert np.all(got[:, :, k * C:] == 0)
+    # dropout per source sample: a dropped sample is zero in every window that contains it
+    p = 0.25
+    check(lib.sl_window_activation(ptr(xd), ptr(out), B, T, C, k, stride, c_pad, prec, p, 1234,
+                                   torch.cuda.current_stream().cuda_stream))
+    dropped = out.float().view(B, t_out, planes, c_pad).sum(dim=2).cpu().numpy()
+    scale = 1.0 / (1.0 - int(p * 65536 + 0.5) / 65536)
+    keep_by_sample = {}
+    for b in range(B):
+        for t in range(t_out):
+            for j in range(0, k, max(k // 7, 1)):
+                ts = t * stride + j - pad_l
+                if 0 <= ts < T:
+                    for c in range(C):
+                        kept = dropped[b, t, j * C + c] != 0 or want[b, t, j * C + c] == 0
+                        assert keep_by_sample.setdefault((b, ts, c), kept) == kept
+                        if kept:
+                            assert abs(dropped[b, t, j * C + c] - want[b, t, j * C + c] * scale) <= \
+                                2.0 ** -7 * abs(want[b, t, j * C + c] * scale) + 1e-6
+    rate = 1.0 - np.mean(list(keep_by_sample.values()))
+    assert abs(rate - p) < 0.08
+
+
+def test_raw_wave_input_tower_matches_oracle(env):
+    """use_raw_wave_input=True: wave_conv (k250, s160) in front, ratio 320; logits, loss and all
+    gradients (wave_conv's included) against the fp64 oracle."""
+    net = env.Wav2Letter(1, env.alphabet, use_raw_wave_input=True, main_filter_count=64, out_filter_count=128,
+                         seed=3, device="cuda:0")
+    assert net.input_to_prediction_length_ratio == 320
+    assert [layer.name for layer in net.predictive_net.layers][:2] == ["wave_conv", "striding_conv"]
+    assert net.predictive_net.layers[0].get_weights()[0].shape == (250, 1, 64)
+    rng = np.random.default_rng(8)
+    for layer in net.predictive_net.layers:
+        kernel, bias = layer.get_weights()
+        layer.set_weights([kernel, (rng.standard_normal(bias.shape) * 0.1).astype(np.float32)])
+    ref = env.oracle.Wav2LetterOracle(1, len(env.alphabet) + 1, 64, 128, dtype=np.float64, use_raw_wave_input=True)
+    weights = [layer.get_weights() for layer in net.predictive_net.layers]
+    ref.set_weights([w for w, _ in weights], [b for _, b in weights])
+
+    B, T = 3, 9000
+    x = rng.standard_normal((B, T, 1)).astype(np.float32)
+    x[1, 7777:] = 0
+    x[2, 6401:] = 0
+    probs_ref, logits_ref, _ = ref.forward(x, keep=True)
+    logits = net.logits_batch(x)
+    assert logits.shape == logits_ref.shape == (B, 29, 29)  # ceil(ceil(9000/160)/2) frames
+    assert rel_err(logits, logits_ref) < 1e-3
+
+    prediction_lengths = np.array([[9000 // 320], [7777 // 320], [6401 // 320]], dtype=np.int64)
+    labels = rng.integers(0, 28, size=(B, 6)).astype(np.int32)
+    label_lengths = np.array([[6], [5], [4]], dtype=np.int64)
+    labels[1, 5:] = -1
+    labels[2, 4:] = -1
+    tower = net.tower
+    ws = tower.upload(x)
+    tower.forward(ws)
+    tower.set_labels(ws, labels, prediction_lengths, label_lengths)
+    loss = tower.ctc(ws, want_grad=True, grad_scale=1.0 / B)
+    tower.backward(ws)
+    tower.sync()
+    losses, _, _, dws, dbs = ref.loss_and_gradients(x.astype(np.float64), labels, prediction_lengths[:, 0],
+                                                    label_lengths[:, 0])
+    assert np.abs(loss.cpu().numpy() / losses - 1).max() < 1e-4
+    saved = tower.params.clone()
+    tower.params.copy_(tower.grads)
+    for index, layer in enumerate(tower.layers):
+        dw, db = tower.get_layer_weights(index)
+        assert rel_err(dw, dws[index]) < 5e-3, layer.name
+        assert rel_err(db, dbs[index]) < 5e-3, layer.name
+    tower.params.copy_(saved)
+    # the 6 pad columns of wave_conv's 256-wide operand hold real samples? no: they are zero, and
+    # so is their gradient
+    first = tower.layers[0]
+    g = tower.grads[first.w_offset:first.w_offset + first.w_size].view(1, first.cout_pad, first.cin_pad)
+    assert float(g[:, :, 250:].abs().max()) == 0.0
+
+    # a few optimisation steps with input dropout on the raw samples
+    drop = env.Wav2Letter(1, env.alphabet, use_raw_wave_input=True, dropout=0.1, main_filter_count=64,
+                          out_filter_count=128, seed=3, device="cuda:0")
+    names = env.Wav2Letter.InputNames
+    inputs = {names.input_batch: x, names.label_batch: labels, names.prediction_lengths: prediction_lengths,
+              names.label_lengths: label_lengths}
+    first_loss = drop.train_on_batch(inputs)
+    for _ in range(30):
+        last_loss = drop.train_on_batch(inputs)
+    assert np.isfinite(first_loss) and last_loss < first_loss

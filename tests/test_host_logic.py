@@ -126,3 +126,18 @@ def test_synthetic_shapes():
     batch = synthetic_batch(2, [30, 41], english_frequent_characters, seed=1)
     assert batch[1].z_normalized_transposed_spectrogram().shape == (41, 128)
     assert all(c in english_frequent_characters for c in batch[0].label)
+
+
+def test_layer_table_with_raw_wave_input():
+    """wave_conv k250 s160 in front (net.py:310-316); as a GEMM it is one tap over 250*Cin channels."""
+    from speechless_b200.engine import same_padding, wav2letter_layers
+    layers = wav2letter_layers(1, 29, use_raw_wave_input=True)
+    assert [l.name for l in layers][:2] == ["wave_conv", "striding_conv"] and len(layers) == 12
+    wave, striding = layers[0], layers[1]
+    assert (wave.cin, wave.cout, wave.kernel, wave.stride, wave.windowed) == (1, 250, 250, 160, True)
+    assert (wave.gemm_cin, wave.gemm_kernel, wave.gemm_stride, wave.cin_pad) == (250, 1, 1, 256)
+    assert wave.w_size == 256 * 256 and striding.cin == 250 and striding.w_offset == wave.w_size + 256
+    assert same_padding(160000, 250, 160) == (1000, 45)  # TF SAME: total 90 -> (45, 45)
+    assert same_padding(160001, 250, 160) == (1001, 124)
+    plain = wav2letter_layers(128, 29)
+    assert len(plain) == 11 and not any(l.windowed for l in plain)

@@ -19,7 +19,8 @@ def _torch_conv_same(x, w, b, stride):
     return y.transpose(1, 2).numpy()
 
 
-@pytest.mark.parametrize("T,k,stride", [(37, 48, 2), (38, 48, 2), (50, 7, 1), (41, 32, 1), (9, 1, 1), (5, 7, 1)])
+@pytest.mark.parametrize("T,k,stride", [(37, 48, 2), (38, 48, 2), (50, 7, 1), (41, 32, 1), (9, 1, 1), (5, 7, 1),
+                                         (1000, 250, 160), (961, 250, 160), (90, 250, 160)])  # + wave_conv (net.py:310-312)
 def test_conv1d_same_matches_torch(T, k, stride):
     rng = np.random.default_rng(T * 100 + k)
     x = rng.standard_normal((2, T, 5))
@@ -30,7 +31,7 @@ def test_conv1d_same_matches_torch(T, k, stride):
 
 def test_conv1d_backward_matches_autograd():
     rng = np.random.default_rng(5)
-    for (T, k, stride) in [(21, 48, 2), (20, 7, 1), (13, 32, 1)]:
+    for (T, k, stride) in [(21, 48, 2), (20, 7, 1), (13, 32, 1), (700, 250, 160)]:
         x = rng.standard_normal((2, T, 3))
         w = rng.standard_normal((k, 3, 4))
         b = rng.standard_normal(4)
@@ -154,3 +155,18 @@ def test_padding_bleed_is_reproduced():
     embedded = ref.forward(padded)[0, :50]
     changed = np.where(np.abs(alone - embedded).max(axis=1) > 1e-12)[0]
     assert len(changed) > 0 and changed.min() >= 50 - 37  # only the last <= 37 valid frames move
+
+
+def test_raw_wave_tower_numpy_matches_torch_restatement():
+    """use_raw_wave_input (net.py:310-316): 12 layers, ratio 320; numpy and torch restatements agree."""
+    specs = oracle.wav2letter_layer_specs(1, 29, 16, 24, use_raw_wave_input=True)
+    assert [s[0] for s in specs][:2] == ["wave_conv", "striding_conv"]
+    assert specs[0][1:5] == (1, 16, 250, 160) and specs[1][1] == 16
+    assert int(np.prod([s[4] for s in specs])) == 320
+    ref = oracle.Wav2LetterOracle(1, 29, 16, 24, dtype=np.float64, use_raw_wave_input=True)
+    cpu = TorchCpuWav2Letter(1, 29, 16, 24, dtype=torch.float64, use_raw_wave_input=True)
+    cpu.set_weights(ref.weights, ref.biases)
+    x = np.random.default_rng(1).standard_normal((2, 2500, 1))
+    probs = ref.forward(x)
+    assert probs.shape == (2, 8, 29)  # ceil(ceil(2500/160)/2)
+    assert np.abs(probs - cpu.forward(torch.as_tensor(x)).detach().numpy()).max() < 1e-12
