@@ -81,8 +81,10 @@ int sl_pack_weights(const float* w_keras, void* w_fwd, int k, int Cin, int Cout,
 
 /* y = act(bias + conv1d_same(x, w)).  x_packed (B,T_in_alloc,..), w_fwd from
  * sl_pack_weights, bias fp32 (Cout).  T_out = ceil(T_in/stride); pad_l per TF
- * SAME rule is computed inside.
- *  act NONE/RELU : y_packed (B,T_out,[hi cout_pad|lo]) bf16; optional
+ * SAME rule is computed inside.  T_out_alloc >= T_out (0 = T_out) is the row
+ * allocation per utterance of y_packed: a stride-2 consumer wants an even
+ * number of rows, the extra row must be (and stays) zero.
+ *  act NONE/RELU : y_packed (B,T_out_alloc,[hi cout_pad|lo]) bf16; optional
  *                  relu_mask_out (B,T_out,cout_pad/8) bytes: bit c%8 of byte c/8
  *                  is set iff y[b,t,c] > 0 — the ReLU derivative kept for backward
  *  act SOFTMAX   : probs (B,T_out,Cout) fp32  [net.py:328-330]; optional
@@ -91,26 +93,31 @@ int sl_pack_weights(const float* w_keras, void* w_fwd, int k, int Cin, int Cout,
  *                  quantity tf.nn.ctc_loss consumes after K.ctc_batch_cost. */
 int sl_conv1d_fwd(const void* x_packed, const void* w_fwd, const float* bias,
                   void* y_packed, void* relu_mask_out, float* probs, float* logits,
-                  float* logp, int B, int T_in, int T_in_alloc, int Cin, int Cout,
-                  int k, int stride, int act, int prec, void* stream);
+                  float* logp, int B, int T_in, int T_in_alloc, int T_out_alloc,
+                  int Cin, int Cout, int k, int stride, int act, int prec,
+                  void* stream);
 
 /* Inverted dropout in front of a Conv1D (keras.layers.Dropout, net.py:301-303), training
- * phase: y = keep ? x/(1-p) : 0 on a packed (B,T,round64(C)) activation.  The keep decision
- * of an element is a pure function of (seed, element index).  mask_out (B,T,round64(C)/8)
- * bytes = keep bits AND relu_mask_in bits (if given): with out_scale = 1/(1-p) it is what
+ * phase: y = keep ? x/(1-p) : 0 on a packed (B,T_alloc,round64(C)) activation (rows T..T_alloc
+ * of y are written as zeros).  The keep decision of an element is a pure function of
+ * (seed, b, t, c).  mask_out (B,T,round64(C)/8) bytes = keep bits AND relu_mask_in bits
+ * (if given; same dense (B,T,..) layout): with out_scale = 1/(1-p) it is what
  * sl_conv1d_dgrad of the consuming layer applies on its way down. */
 int sl_dropout_fwd(const void* x_packed, void* y_packed, const void* relu_mask_in,
-                   void* mask_out, int B, int T, int C, int prec, float p,
-                   uint64_t seed, void* stream);
+                   void* mask_out, int B, int T, int T_alloc, int C, int prec,
+                   float p, uint64_t seed, void* stream);
 
 /* dX = out_scale * conv1d_same_backward_input(dY, w) masked by the ReLU of the layer below
- * (TF autodiff of net.py:304-305; stride 1 only — the strided first layer needs
- * no dX).  relu_mask = the relu_mask_out the layer below wrote in its forward
- * pass ((B,T,cin_pad/8) bytes), or NULL for a linear layer below. */
+ * (TF autodiff of net.py:304-305).  T = frames of dX (the layer's input), dY has
+ * ceil(T/stride) frames; stride 2 (striding_conv behind a raw-wave layer, net.py:310-316)
+ * runs as one stride-1 problem per output parity.  relu_mask = the relu_mask_out the
+ * layer below wrote in its forward pass ((B,T,cin_pad/8) bytes), or NULL for a
+ * linear layer below. */
 int sl_conv1d_dgrad(const void* dy_packed, const void* w_fwd,
                     const void* relu_mask, void* dx_packed, int B, int T,
-                    int Cin, int Cout, int k, int prec, float out_scale,
-                    void* workspace, size_t workspace_bytes, void* stream);
+                    int Cin, int Cout, int k, int stride, int prec,
+                    float out_scale, void* workspace, size_t workspace_bytes,
+                    void* stream);
 /* Optional fp32 scratch for the split-K variant (long tap loops whose tile count fills the
  * persistent grid badly, e.g. big_conv_1); 0 = not wanted for this shape.  Passing
  * workspace = NULL is always legal and selects the unsplit kernel. */

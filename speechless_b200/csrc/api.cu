@@ -31,7 +31,8 @@ int pack_weights_internal_launch(const float*, void*, int, int, int, int, cudaSt
 int dgrad_finalize_launch(const float*, const void*, void*, size_t, int, int, float, cudaStream_t);
 int spectrogram_launch(const float*, const int32_t*, const float*, float*, int, int, int, cudaStream_t);
 int z_normalize_launch(float*, const int32_t*, double*, int, int, int, cudaStream_t);
-int dropout_launch(const void*, void*, const void*, void*, size_t, int, int, float, unsigned long long, cudaStream_t);
+int dropout_launch(const void*, void*, const void*, void*, int, int, int, int, int, float, unsigned long long,
+                   cudaStream_t);
 int adam_fused_launch(float*, const float*, float*, float*, size_t, const size_t*, const size_t*, void* const*,
                       const int*, int, int, float, float, float, float, int, cudaStream_t);
 int adam_launch(float*, const float*, float*, float*, size_t, float, float, float, float, int,
@@ -77,12 +78,13 @@ static int make_act_load_map(CUtensorMap* m, const void* base, int c_total, int 
   const uint32_t box[4] = {64, 1, static_cast<uint32_t>(box_rows), 1};
   return make_tmap(m, TMAP_BF16, 4, base, dims, strides, box, true);
 }
-// rank-3 view {C_total, T, B}
-static int make_act_map3(CUtensorMap* m, const void* base, int c_total, int T, int B, int box_rows) {
+// rank-3 view {C_total, T, B} of a tensor with T_alloc >= T rows per utterance, every row_step-th row
+static int make_act_map3(CUtensorMap* m, const void* base, int c_total, int T, int B, int box_rows,
+                         int T_alloc = 0, int row_step = 1) {
   const uint64_t row_bytes = static_cast<uint64_t>(c_total) * 2;
   const uint64_t dims[3] = {static_cast<uint64_t>(c_total), static_cast<uint64_t>(T),
                             static_cast<uint64_t>(B)};
-  const uint64_t strides[2] = {row_bytes, row_bytes * T};
+  const uint64_t strides[2] = {row_bytes * row_step, row_bytes * (T_alloc > 0 ? T_alloc : T)};
   const uint32_t box[3] = {64, static_cast<uint32_t>(box_rows), 1};
   return make_tmap(m, TMAP_BF16, 3, base, dims, strides, box, true);
 }
@@ -268,7 +270,8 @@ int sl_pack_weights(const float* w_keras, void* w_fwd, int k, int Cin, int Cout,
 
 int sl_conv1d_fwd(const void* x_packed, const void* w_fwd, const float* bias, void* y_packed,
                   void* relu_mask_out, float* probs, float* logits, float* logp, int B, int T_in,
-                  int T_in_alloc, int Cin, int Cout, int k, int stride, int act, int prec, void* stream) {
+                  int T_in_alloc, int T_out_alloc, int Cin, int Cout, int k, int stride, int act, int prec,
+                  void* stream) {
   SL_REQUIRE(x_packed && w_fwd, "null pointer");
   SL_REQUIRE(B > 0 && T_in > 0 && Cin > 0 && Cout > 0 && k > 0, "bad shape");
   SL_REQUIRE(stride == 1 || stride == 2, "stride must be 1 or 2");
@@ -278,6 +281,8 @@ int sl_conv1d_fwd(const void* x_packed, const void* w_fwd, const float* bias, vo
   const int cin_pad = round64(Cin), cout_pad = round64(Cout);
   int T_out, pad_l;
   same_padding(T_in, k, stride, &T_out, &pad_l);
+  if (T_out_alloc <= 0) T_out_alloc = T_out;
+  SL_REQUIRE(T_out_alloc >= T_out, "T_out_alloc must cover the output frames");
 
   ConvGemmParams p;
   std::memset(&p, 0, sizeof(p));
@@ -305,7 +310,10 @@ int sl_conv1d_fwd(const void* x_packed, const void* w_fwd, const float* bias, vo
   p.b_lo_off = cin_pad;
   p.stride = stride;
   p.pad_l = pad_l;
-  p.tap_reverse = 0;
+  p.w_tap0 = 0;
+  p.w_tap_step = 1;
+  p.mask_T = T_out;
+  p.out_t_scale = 1;
   p.dbg_mode = dbg_mode();
   p.out_scale = 1.0f;
   p.bias = bias;
@@ -327,7 +335,7 @@ int sl_conv1d_fwd(const void* x_packed, const void* w_fwd, const float* bias, vo
     p.y_lo_off = cout_pad;
     p.mask_bits_out = static_cast<uint8_t*>(relu_mask_out);
     p.mask_row_bytes = cout_pad / 8;
-    rc = make_act_map3(&p.tmY, y_packed, planes * cout_pad, T_out, B, 32);
+    rc = make_act_map3(&p.tmY, y_packed, planes * cout_pad, T_out, B, 32, T_out_alloc);
     if (rc) return rc;
   }
   return conv_gemm_launch(p, bn, epi, false, num_sms(), static_cast<cudaStream_t>(stream));
@@ -364,22 +372,17 @@ size_t sl_conv1d_dgrad_workspace_bytes(int B, int T, int Cin, int Cout, int k) {
   return static_cast<size_t>(B) * T * cin_pad * sizeof(float);
 }
 
-int sl_conv1d_dgrad(const void* dy_packed, const void* w_fwd, const void* relu_mask, void* dx_packed,
-                    int B, int T, int Cin, int Cout, int k, int prec, float out_scale, void* workspace,
-                    size_t workspace_bytes, void* stream) {
-  SL_REQUIRE(dy_packed && w_fwd && dx_packed, "null pointer");
-  SL_REQUIRE(B > 0 && T > 0 && Cin > 0 && Cout > 0 && k > 0, "bad shape");
-  SL_REQUIRE(prec == SL_PREC_BF16 || prec == SL_PREC_BF16X2, "bad precision");
-  const int planes = planes_of(prec);
-  const int cin_pad = round64(Cin), cout_pad = round64(Cout);
-  int T_out, pad_l;
-  same_padding(T, k, 1, &T_out, &pad_l);
-
+// one launch of the input-gradient GEMM: the output rows u = out_scale_t * v + out_off (v = 0..rows-1)
+// of dX, filter taps w_tap0, w_tap0 + w_step, ... (n_taps of them), dY frames shifted by i - a_pad
+static int dgrad_launch_rows(const void* dy_packed, const void* w_fwd, const void* relu_mask, void* dx_packed, int B,
+                             int T, int T_dy, int cin_pad, int cout_pad, int Cin, int k, int planes, float out_scale,
+                             int rows, int row_step, int row_off, int n_taps, int w_tap0, int w_step, int a_pad,
+                             void* workspace, size_t workspace_bytes, bool allow_ksplit, cudaStream_t s) {
   ConvGemmParams p;
   std::memset(&p, 0, sizeof(p));
   const int bn = cin_pad >= 256 ? 256 : cin_pad;
   SL_REQUIRE(cin_pad % bn == 0 && (bn == 64 || bn == 128 || bn == 256), "unsupported channel count");
-  int rc = make_act_load_map(&p.tmA, dy_packed, planes * cout_pad, 1, T, B, 128);
+  int rc = make_act_load_map(&p.tmA, dy_packed, planes * cout_pad, 1, T_dy, B, 128);
   if (rc) return rc;
   // B[n = ci][k = co] comes straight from the forward layout (k, cout_pad, [hi|lo] cin_pad):
   // boxes of 64 co rows x 64 ci, consumed MN-major
@@ -387,27 +390,29 @@ int sl_conv1d_dgrad(const void* dy_packed, const void* w_fwd, const void* relu_m
   rc = p.b_grouped ? make_weight_group_map(&p.tmB, w_fwd, planes * cin_pad, cout_pad, k, 64, bn / 64)
                    : make_weight_map(&p.tmB, w_fwd, planes * cin_pad, cout_pad, k, 64);
   if (rc) return rc;
-  rc = make_act_map3(&p.tmY, dx_packed, planes * cin_pad, T, B, 32);
+  const char* dx_rows = static_cast<const char*>(dx_packed) + static_cast<size_t>(row_off) * planes * cin_pad * 2;
+  rc = make_act_map3(&p.tmY, dx_rows, planes * cin_pad, rows, B, 32, T, row_step);
   if (rc) return rc;
-  rc = plan_halo(&p, dy_packed, planes * cout_pad, T, B, k, 1);
+  rc = plan_halo(&p, dy_packed, planes * cout_pad, T_dy, B, n_taps, 1);
   if (rc) return rc;
   p.B = B;
-  p.T_out = T;
-  p.m_tiles_per_utt = (T + 127) / 128;
+  p.T_out = rows;
+  p.m_tiles_per_utt = (rows + 127) / 128;
   p.n_tiles = cin_pad / bn;
   plan_tail(B * p.m_tiles_per_utt * p.n_tiles, bn, p.b_grouped != 0, &p.full_tiles, &p.tail_split);
   if (p.tail_split > 1) {
     rc = make_weight_group_map(&p.tmBtail, w_fwd, planes * cin_pad, cout_pad, k, 64, bn / p.tail_split / 64);
     if (rc) return rc;
   }
-  p.taps = k;
+  p.taps = n_taps;
   p.chunks = cout_pad / 64;
   p.terms = planes == 2 ? 3 : 1;
   p.a_lo_off = cout_pad;
   p.b_lo_off = cin_pad;
   p.stride = 1;
-  p.pad_l = k - 1 - pad_l;  // dX[u] = sum_j dY[u + pad_l - j] W[j]  
-  p.tap_reverse = 1;
+  p.pad_l = a_pad;
+  p.w_tap0 = w_tap0;
+  p.w_tap_step = w_step;
   p.dbg_mode = dbg_mode();
   p.bias = nullptr;
   p.n_valid = Cin;
@@ -417,13 +422,15 @@ int sl_conv1d_dgrad(const void* dy_packed, const void* w_fwd, const void* relu_m
   p.y_lo_off = cin_pad;
   p.mask_bits_in = static_cast<const uint8_t*>(relu_mask);
   p.mask_row_bytes = cin_pad / 8;
+  p.mask_T = T;
+  p.out_t_scale = row_step;
+  p.out_t_off = row_off;
   p.ksplit = 1;
-  const int ksplit = plan_dgrad_ksplit(B, T, cin_pad, cout_pad, k);
+  const int ksplit = allow_ksplit ? plan_dgrad_ksplit(B, T, cin_pad, cout_pad, k) : 1;
   const size_t need = static_cast<size_t>(B) * T * cin_pad * sizeof(float);
   if (ksplit > 1 && p.b_grouped && workspace != nullptr && workspace_bytes >= need) {
     // split K over tap ranges: fp32 partial sums meet in `workspace` (TMA reduce-add), then one
     // elementwise pass applies the ReLU mask and packs to bf16
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
     SL_CUDA(cudaMemsetAsync(workspace, 0, need, s));
     const uint64_t dims[3] = {static_cast<uint64_t>(cin_pad), static_cast<uint64_t>(T), static_cast<uint64_t>(B)};
     const uint64_t strides[2] = {static_cast<uint64_t>(cin_pad) * 4, static_cast<uint64_t>(cin_pad) * 4 * T};
@@ -439,7 +446,48 @@ int sl_conv1d_dgrad(const void* dy_packed, const void* w_fwd, const void* relu_m
     return dgrad_finalize_launch(static_cast<const float*>(workspace), relu_mask, dx_packed,
                                  static_cast<size_t>(B) * T, cin_pad, planes, out_scale, s);
   }
-  return conv_gemm_launch(p, bn, EPI_PACKED, true, num_sms(), static_cast<cudaStream_t>(stream));
+  return conv_gemm_launch(p, bn, EPI_PACKED, true, num_sms(), s);
+}
+
+int sl_conv1d_dgrad(const void* dy_packed, const void* w_fwd, const void* relu_mask, void* dx_packed,
+                    int B, int T, int Cin, int Cout, int k, int stride, int prec, float out_scale,
+                    void* workspace, size_t workspace_bytes, void* stream) {
+  SL_REQUIRE(dy_packed && w_fwd && dx_packed, "null pointer");
+  SL_REQUIRE(B > 0 && T > 0 && Cin > 0 && Cout > 0 && k > 0, "bad shape");
+  SL_REQUIRE(stride == 1 || stride == 2, "stride must be 1 or 2");
+  SL_REQUIRE(prec == SL_PREC_BF16 || prec == SL_PREC_BF16X2, "bad precision");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int planes = planes_of(prec);
+  const int cin_pad = round64(Cin), cout_pad = round64(Cout);
+  int T_out, pad_l;
+  same_padding(T, k, stride, &T_out, &pad_l);
+  if (stride == 1) {
+    // dX[u] = sum_j dY[u + pad_l - j] W[j]  (SURVEY.md A.1): taps walked backwards
+    return dgrad_launch_rows(dy_packed, w_fwd, relu_mask, dx_packed, B, T, T_out, cin_pad, cout_pad, Cin, k, planes,
+                             out_scale, T, 1, 0, k, k - 1, -1, k - 1 - pad_l, workspace, workspace_bytes, true, s);
+  }
+  // stride 2: y[v'] = sum_j x[2 v' + j - pad_l] W[j], so the rows u = 2 v + r of dX only see the taps
+  // j = jmax_r, jmax_r - 2, ... with (r + pad_l - j) even: dX[2v + r] = sum_i dY[v + c_r + i] W[jmax_r - 2 i],
+  // c_r = (r + pad_l - jmax_r) / 2 — one stride-1 problem per output parity, written to every other row
+  for (int r = 0; r < 2; ++r) {
+    const int rows = (T - r + 1) / 2;
+    if (rows <= 0) continue;
+    int jmax = k - 1;
+    if (((r + pad_l - jmax) & 1) != 0) --jmax;
+    if (jmax < 0) {  // k == 1: this parity receives no gradient at all
+      const size_t row_bytes = static_cast<size_t>(planes) * cin_pad * 2;
+      for (int b = 0; b < B; ++b)
+        SL_CUDA(cudaMemset2DAsync(static_cast<char*>(dx_packed) + (static_cast<size_t>(b) * T + r) * row_bytes,
+                                  2 * row_bytes, 0, row_bytes, static_cast<size_t>(rows), s));
+      continue;
+    }
+    const int n_taps = jmax / 2 + 1;
+    const int c_r = (r + pad_l - jmax) / 2;  // exact: the numerator is even
+    const int rc = dgrad_launch_rows(dy_packed, w_fwd, relu_mask, dx_packed, B, T, T_out, cin_pad, cout_pad, Cin, k,
+                                     planes, out_scale, rows, 2, r, n_taps, jmax, -2, -c_r, nullptr, 0, false, s);
+    if (rc) return rc;
+  }
+  return 0;
 }
 
 int sl_conv1d_wgrad(const void* x_packed, const void* dy_packed, float* dw, float* db, int B, int T_in,
@@ -576,12 +624,12 @@ int sl_z_normalize(float* x, const int32_t* frame_counts, void* moments_ws, int 
 }
 
 int sl_dropout_fwd(const void* x_packed, void* y_packed, const void* relu_mask_in, void* mask_out, int B, int T,
-                   int C, int prec, float p, uint64_t seed, void* stream) {
+                   int T_alloc, int C, int prec, float p, uint64_t seed, void* stream) {
   SL_REQUIRE(x_packed && y_packed && mask_out, "null pointer");
-  SL_REQUIRE(B > 0 && T > 0 && C > 0, "bad shape");
+  SL_REQUIRE(B > 0 && T > 0 && C > 0 && T_alloc >= T, "bad shape");
   SL_REQUIRE(p >= 0.0f && p < 1.0f, "dropout rate must be in [0, 1)");
-  return dropout_launch(x_packed, y_packed, relu_mask_in, mask_out, static_cast<size_t>(B) * T, round64(C),
-                        planes_of(prec), p, seed, static_cast<cudaStream_t>(stream));
+  return dropout_launch(x_packed, y_packed, relu_mask_in, mask_out, B, T, T_alloc, round64(C), planes_of(prec), p,
+                        seed, static_cast<cudaStream_t>(stream));
 }
 
 int sl_adam_step_fused(float* p, const float* g, float* m, float* v, size_t n, const size_t* w_begin_host,

@@ -182,7 +182,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
                 hphase ^= 1;
               }
               for (int tap = w.tap_begin; tap < w.tap_end; ++tap) {
-                const int wtap = p.tap_reverse ? (p.taps - 1 - tap) : tap;
+                const int wtap = p.w_tap0 + tap * p.w_tap_step;
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 uint8_t* b_s = b_ring + stage * C::B_BYTES;
                 mbar_expect_tx(&full_bar[stage], b_tx);
@@ -210,7 +210,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             q = jp >= 0 ? jp / p.stride : -((-jp + p.stride - 1) / p.stride);
             par = jp - q * p.stride;
           }
-          const int wtap = p.tap_reverse ? (p.taps - 1 - tap) : tap;
+          const int wtap = p.w_tap0 + tap * p.w_tap_step;
           for (int chunk = 0; chunk < p.chunks; ++chunk) {
             for (int term = 0; term < p.terms; ++term) {
               const int a_c = chunk * BLOCK_K + (term == 2 ? p.a_lo_off : 0);
@@ -387,7 +387,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       uint2 mask_in[BN / 64];
       if (EPI == EPI_PACKED && p.mask_bits_in != nullptr && row_valid) {
         const uint2* mp = reinterpret_cast<const uint2*>(
-            p.mask_bits_in + (static_cast<size_t>(b) * p.T_out + t) * p.mask_row_bytes + (n0 >> 3));
+            p.mask_bits_in +
+            (static_cast<size_t>(b) * p.mask_T + (t * p.out_t_scale + p.out_t_off)) * p.mask_row_bytes + (n0 >> 3));
 #pragma unroll
         for (int c = 0; c < BN / 64; ++c)
           if (c < n_chunks) mask_in[c] = __ldg(mp + c);

@@ -39,7 +39,11 @@ struct ConvGemmParams {
   int b_lo_off;
   int stride;
   int pad_l;
-  int tap_reverse;  // dgrad walks the filter taps backwards
+  // loop tap i reads activation frames shifted by i - pad_l and the weights of filter tap
+  // w_tap0 + i * w_tap_step: forward (0, +1); input gradient (k-1, -1); input gradient of a
+  // stride-2 layer, one output parity at a time (largest tap of that parity, -2)
+  int w_tap0;
+  int w_tap_step;
   const float* bias;
   int n_valid;  // number of real (unpadded) output channels: bias bound
   int relu;
@@ -51,6 +55,11 @@ struct ConvGemmParams {
   const uint8_t* mask_bits_in;
   uint8_t* mask_bits_out;
   int mask_row_bytes;
+  // mask_bits_in row of output row t (tile space) = out_t_scale * t + out_t_off of mask_T rows per
+  // utterance (stride-2 input gradient: tile rows are the frames of one parity)
+  int mask_T;
+  int out_t_scale;
+  int out_t_off;
   int dbg_mode;   // bring-up only (env SL_DBG_MODE): 1 = stop issuing TMA loads after the first ring fill
   int b_grouped;  // MN-major B: tmB is rank 4 {64, cout, cin_total/64, taps}, one box {64,64,BN/64,1} per stage
   float* probs;   // EPI_SOFTMAX outputs

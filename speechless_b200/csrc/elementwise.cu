@@ -295,17 +295,25 @@ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
   return x ^ (x >> 31);
 }
 __global__ void dropout_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
-                               const uint8_t* __restrict__ relu_mask_in, uint8_t* __restrict__ mask_out,
-                               size_t rows, int c_pad, int planes, unsigned threshold16, float scale,
+                               const uint8_t* __restrict__ relu_mask_in, uint8_t* __restrict__ mask_out, int B,
+                               int T, int T_alloc, int c_pad, int planes, unsigned threshold16, float scale,
                                unsigned long long seed) {
   ptx::pdl_launch_dependents();
   ptx::pdl_wait();
   const int groups = c_pad / 8;
-  const size_t total = rows * groups;
+  const size_t total = static_cast<size_t>(B) * T_alloc * groups;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const size_t row = i / groups;
+    const size_t row = i / groups;  // row of the (B, T_alloc) activation
     const int g = static_cast<int>(i - row * groups);
+    const int b = static_cast<int>(row / T_alloc);
+    const int t = static_cast<int>(row - static_cast<size_t>(b) * T_alloc);
+    const size_t base = row * (static_cast<size_t>(planes) * c_pad) + g * 8;
+    if (t >= T) {  // allocation padding rows stay zero
+      *reinterpret_cast<uint4*>(y + base) = make_uint4(0u, 0u, 0u, 0u);
+      if (planes == 2) *reinterpret_cast<uint4*>(y + base + c_pad) = make_uint4(0u, 0u, 0u, 0u);
+      continue;
+    }
     const unsigned long long r0 = splitmix64(seed ^ (2 * i)), r1 = splitmix64(seed ^ (2 * i + 1));
     unsigned keep = 0;
 #pragma unroll
@@ -313,7 +321,6 @@ __global__ void dropout_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat1
       if (((r0 >> (16 * e)) & 0xffffu) >= threshold16) keep |= 1u << e;
       if (((r1 >> (16 * e)) & 0xffffu) >= threshold16) keep |= 1u << (4 + e);
     }
-    const size_t base = row * (static_cast<size_t>(planes) * c_pad) + g * 8;
     const uint4 h = *reinterpret_cast<const uint4*>(x + base);
     uint4 l = make_uint4(0u, 0u, 0u, 0u);
     if (planes == 2) l = *reinterpret_cast<const uint4*>(x + base + c_pad);
@@ -330,9 +337,10 @@ __global__ void dropout_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat1
     }
     *reinterpret_cast<uint4*>(y + base) = make_uint4(ho[0], ho[1], ho[2], ho[3]);
     if (planes == 2) *reinterpret_cast<uint4*>(y + base + c_pad) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    const size_t mrow = static_cast<size_t>(b) * T + t;  // masks are dense (B, T)
     unsigned m = keep;
-    if (relu_mask_in != nullptr) m &= relu_mask_in[row * groups + g];
-    mask_out[row * groups + g] = static_cast<uint8_t>(m);
+    if (relu_mask_in != nullptr) m &= relu_mask_in[mrow * groups + g];
+    mask_out[mrow * groups + g] = static_cast<uint8_t>(m);
   }
 }
 
@@ -429,13 +437,14 @@ int dgrad_finalize_launch(const float* acc, const void* mask, void* dx, size_t r
                      planes, out_scale));
   return 0;
 }
-int dropout_launch(const void* x, void* y, const void* relu_mask_in, void* mask_out, size_t rows, int c_pad,
-                   int planes, float p, unsigned long long seed, cudaStream_t s) {
+int dropout_launch(const void* x, void* y, const void* relu_mask_in, void* mask_out, int B, int T, int T_alloc,
+                   int c_pad, int planes, float p, unsigned long long seed, cudaStream_t s) {
   const unsigned threshold16 = static_cast<unsigned>(p * 65536.0f + 0.5f);
+  const size_t rows = static_cast<size_t>(B) * T_alloc;
   dropout_kernel<<<grid_for(rows * (c_pad / 8), 256), 256, 0, s>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y),
-      reinterpret_cast<const uint8_t*>(relu_mask_in), reinterpret_cast<uint8_t*>(mask_out), rows, c_pad, planes,
-      threshold16, 1.0f / (1.0f - static_cast<float>(threshold16) / 65536.0f), seed);
+      reinterpret_cast<const uint8_t*>(relu_mask_in), reinterpret_cast<uint8_t*>(mask_out), B, T, T_alloc, c_pad,
+      planes, threshold16, 1.0f / (1.0f - static_cast<float>(threshold16) / 65536.0f), seed);
   SL_CUDA(cudaGetLastError());
   return 0;
 }

@@ -131,8 +131,13 @@ class _Workspace:
             self.t_out.append(t)
         self.Tp = self.t_out[-1]
         self.masks: List[torch.Tensor] = []  # ReLU sign bits of act[l], 1 bit per (frame, channel)
-        for layer, t_out in zip(tower.layers[:-1], self.t_out[:-1]):
-            self.acts.append(torch.empty((B, t_out, planes * layer.cout_pad), dtype=torch.bfloat16, device=dev))
+        # rows allocated per utterance for act[l]: a stride-2 consumer reads it through an
+        # (even, odd) frame view, so an odd frame count gets one extra row that stays zero
+        self.t_alloc_out: List[int] = []
+        for index, (layer, t_out) in enumerate(zip(tower.layers[:-1], self.t_out[:-1])):
+            alloc = round_up(t_out, tower.layers[index + 1].gemm_stride)
+            self.t_alloc_out.append(alloc)
+            self.acts.append(torch.zeros((B, alloc, planes * layer.cout_pad), dtype=torch.bfloat16, device=dev))
             self.masks.append(torch.empty((B, t_out, layer.cout_pad // 8), dtype=torch.uint8, device=dev))
         V = tower.layers[-1].cout
         self.probs = torch.empty((B, self.Tp, V), dtype=torch.float32, device=dev)
@@ -419,14 +424,15 @@ class ConvTower:
                 if drop and index in self.dropout_layers and not layer.windowed:
                     if index not in ws.xdrop:
                         ws.xdrop[index] = torch.zeros_like(x)  # zero: keeps the T_alloc padding rows zero
-                        ws.bwd_mask[index] = torch.empty((ws.B, t_alloc, layer.cin_pad // 8), dtype=torch.uint8,
+                        ws.bwd_mask[index] = torch.empty((ws.B, t_in, layer.cin_pad // 8), dtype=torch.uint8,
                                                          device=self.device)
                     relu_below = ws.masks[index - 1] if index > 0 and self.layers[index - 1].activation == "relu" \
                         else None
                     seed = self._dropout_seed(index)
                     ws.dropout_seeds[index] = seed
                     check(self.lib.sl_dropout_fwd(ptr(x), ptr(ws.xdrop[index]), ptr(relu_below),
-                                                  ptr(ws.bwd_mask[index]), ws.B, t_alloc, layer.gemm_cin, self.precision,
+                                                  ptr(ws.bwd_mask[index]), ws.B, t_in, t_alloc, layer.gemm_cin,
+                                                  self.precision,
                                                   float(self.dropout), seed, self.stream))
                     self.launches += 1
                     x = ws.xdrop[index]
@@ -435,17 +441,18 @@ class ConvTower:
                 if layer.activation == "softmax":
                     self._timed("fwd", layer.name, lambda: self.lib.sl_conv1d_fwd(
                         ptr(x), ptr(self.w_fwd[index]), ptr(bias), None, None, ptr(ws.probs),
-                        ptr(ws.logits) if want_logits else None, ptr(ws.logp), ws.B, t_in, t_alloc, layer.gemm_cin,
-                        layer.cout, layer.gemm_kernel, layer.gemm_stride, ACT_SOFTMAX, self.precision, self.stream))
+                        ptr(ws.logits) if want_logits else None, ptr(ws.logp), ws.B, t_in, t_alloc, 0,
+                        layer.gemm_cin, layer.cout, layer.gemm_kernel, layer.gemm_stride, ACT_SOFTMAX, self.precision,
+                        self.stream))
                 else:
                     y = ws.acts[index]
                     act = ACT_RELU if layer.activation == "relu" else ACT_NONE
                     mask = ws.masks[index] if layer.activation == "relu" else None
                     self._timed("fwd", layer.name, lambda: self.lib.sl_conv1d_fwd(
                         ptr(x), ptr(self.w_fwd[index]), ptr(bias), ptr(y), ptr(mask), None, None, None, ws.B, t_in,
-                        t_alloc, layer.gemm_cin, layer.cout, layer.gemm_kernel, layer.gemm_stride, act, self.precision,
-                        self.stream))
-                    x, t_in, t_alloc = y, ws.t_out[index], ws.t_out[index]
+                        t_alloc, ws.t_alloc_out[index], layer.gemm_cin, layer.cout, layer.gemm_kernel,
+                        layer.gemm_stride, act, self.precision, self.stream))
+                    x, t_in, t_alloc = y, ws.t_out[index], ws.t_alloc_out[index]
                 self.launches += 1
         return ws
 
@@ -565,7 +572,7 @@ class ConvTower:
                 layer = self.layers[index]
                 x = ws.layer_inputs[index]  # the tensor the forward conv actually read (dropped or not)
                 t_in = ws.T0 if index == 0 else ws.t_out[index - 1]
-                t_alloc = ws.T_alloc if index == 0 else t_in
+                t_alloc = ws.T_alloc if index == 0 else ws.t_alloc_out[index - 1]
                 launch_wgrad = lambda: self._timed("wgrad", layer.name, lambda: self.lib.sl_conv1d_wgrad(
                     ptr(x), ptr(dy), ptr(self._w(self.grads, layer)), ptr(self._b(self.grads, layer)), ws.B, t_in,
                     t_alloc, layer.gemm_cin, layer.cout, layer.gemm_kernel, layer.gemm_stride, self.precision, 1,
@@ -594,14 +601,16 @@ class ConvTower:
                         mask, out_scale = (ws.masks[index - 1] if below.activation == "relu" else None), 1.0
                     if previous_wgrad_done is not None:
                         main.wait_event(previous_wgrad_done)  # it reads the buffer dx aliases
-                    need = self.lib.sl_conv1d_dgrad_workspace_bytes(ws.B, t_in, layer.cin, layer.cout, layer.kernel)
+                    need = 0 if layer.gemm_stride != 1 else self.lib.sl_conv1d_dgrad_workspace_bytes(
+                        ws.B, t_in, layer.gemm_cin, layer.cout, layer.gemm_kernel)
                     if need and (ws.dgrad_ws is None or ws.dgrad_ws.numel() < need):
                         ws.dgrad_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
                     scratch = ws.dgrad_ws if need else None
                     self._timed("dgrad", layer.name, lambda: self.lib.sl_conv1d_dgrad(
-                        ptr(dy), ptr(self.w_fwd[index]), ptr(mask), ptr(dx), ws.B, t_in, layer.cin, layer.cout,
-                        layer.kernel, self.precision, out_scale, ptr(scratch), need, self.stream))
-                    self.launches += 2 if need else 1
+                        ptr(dy), ptr(self.w_fwd[index]), ptr(mask), ptr(dx), ws.B, t_in, layer.gemm_cin, layer.cout,
+                        layer.gemm_kernel, layer.gemm_stride, self.precision, out_scale, ptr(scratch), need,
+                        self.stream))
+                    self.launches += 2 if (need or layer.gemm_stride == 2) else 1
                     dy = dx
                     flip ^= 1
             if side is not None:

@@ -76,14 +76,15 @@ def test_conv_layer_matches_oracle(env, B, T, cin, cout, k, stride, prec):
     xd, wd, bd = (torch.from_numpy(a).to(dev) for a in (x, w, bias))
     xp = torch.zeros((B, t_alloc, prec * cip), dtype=torch.bfloat16, device=dev)
     wf = torch.zeros((k, cop, prec * cip), dtype=torch.bfloat16, device=dev)
-    yp = torch.zeros((B, t_out, prec * cop), dtype=torch.bfloat16, device=dev)
+    t_out_alloc = t_out + (t_out & 1)  # as if a stride-2 layer consumed the output
+    yp = torch.zeros((B, t_out_alloc, prec * cop), dtype=torch.bfloat16, device=dev)
     y = torch.zeros((B, t_out, cout), dtype=torch.float32, device=dev)
     check(lib.sl_pack_activation(ptr(xd), ptr(xp), B, T, cin, t_alloc, cip, prec, None))
     check(lib.sl_pack_weights(ptr(wd), ptr(wf), k, cin, cout, cip, cop, prec, None))
     mask = torch.zeros((B, t_out, cop // 8), dtype=torch.uint8, device=dev)
-    check(lib.sl_conv1d_fwd(ptr(xp), ptr(wf), ptr(bd), ptr(yp), ptr(mask), None, None, None, B, T, t_alloc, cin, cout,
-                            k, stride, 1, prec, None))
-    check(lib.sl_unpack_activation(ptr(yp), ptr(y), B, t_out, cout, t_out, cop, prec, None))
+    check(lib.sl_conv1d_fwd(ptr(xp), ptr(wf), ptr(bd), ptr(yp), ptr(mask), None, None, None, B, T, t_alloc,
+                            t_out_alloc, cin, cout, k, stride, 1, prec, None))
+    check(lib.sl_unpack_activation(ptr(yp), ptr(y), B, t_out, cout, t_out_alloc, cop, prec, None))
     check(lib.sl_sync_check())
     want = np.maximum(env.oracle.conv1d_same(x.astype(np.float64), w.astype(np.float64), bias.astype(np.float64),
                                              stride), 0)
@@ -94,7 +95,46 @@ def test_conv_layer_matches_oracle(env, B, T, cin, cout, k, stride, prec):
     stored = y.cpu().numpy()
     assert (bits == (stored > 0))[np.abs(want) > 1e-6].all()
     # channel padding of the packed output stays exactly zero
-    assert float(yp.view(B, t_out, prec, cop)[..., cout:].abs().max()) == 0.0 or cout == cop
+    assert cout == cop or float(yp.view(B, t_out_alloc, prec, cop)[..., cout:].abs().max()) == 0.0
+    assert float(yp[:, t_out:].abs().max()) == 0.0 if t_out_alloc > t_out else True  # allocation row untouched
+
+
+@pytest.mark.parametrize("B,T,cin,cout,k,stride", [
+    (2, 57, 250, 250, 48, 2),   # striding_conv behind wave_conv (net.py:310-316): odd T, pads (23, 24)
+    (2, 300, 64, 128, 48, 2),   # even T, pads (23, 23); several M tiles per parity
+    (1, 33, 64, 64, 1, 2),      # k = 1: odd rows receive no gradient
+    (2, 131, 250, 250, 7, 1),   # stride 1 through the same entry point
+])
+@pytest.mark.parametrize("prec", [1, 2])
+def test_conv_input_gradient_matches_oracle(env, B, T, cin, cout, k, stride, prec):
+    """sl_conv1d_dgrad against the oracle's conv1d_same_backward, ReLU mask of the layer below applied."""
+    torch, lib, check, ptr = env.torch, env.lib, env._lib.check, env._lib.ptr
+    rng = np.random.default_rng(T * 7 + k)
+    t_out = -(-T // stride)
+    dy = rng.standard_normal((B, t_out, cout)).astype(np.float32)
+    w = (rng.standard_normal((k, cin, cout)) / np.sqrt(k * cout)).astype(np.float32)
+    below = rng.standard_normal((B, T, cin)) > 0  # ReLU derivative of the layer below
+    cip, cop = (cin + 63) // 64 * 64, (cout + 63) // 64 * 64
+    dev = "cuda:0"
+    dyd, wd = torch.from_numpy(dy).to(dev), torch.from_numpy(w).to(dev)
+    dyp = torch.zeros((B, t_out, prec * cop), dtype=torch.bfloat16, device=dev)
+    wf = torch.zeros((k, cop, prec * cip), dtype=torch.bfloat16, device=dev)
+    dxp = torch.full((B, T, prec * cip), 3.0, dtype=torch.bfloat16, device=dev)
+    dx = torch.zeros((B, T, cin), dtype=torch.float32, device=dev)
+    bits = np.zeros((B, T, cip), dtype=np.uint8)
+    bits[..., :cin] = below
+    mask = torch.from_numpy(np.packbits(bits, axis=2, bitorder="little")).to(dev)
+    check(lib.sl_pack_activation(ptr(dyd), ptr(dyp), B, t_out, cout, t_out, cop, prec, None))
+    check(lib.sl_pack_weights(ptr(wd), ptr(wf), k, cin, cout, cip, cop, prec, None))
+    check(lib.sl_conv1d_dgrad(ptr(dyp), ptr(wf), ptr(mask), ptr(dxp), B, T, cin, cout, k, stride, prec, 1.0, None, 0,
+                              None))
+    check(lib.sl_unpack_activation(ptr(dxp), ptr(dx), B, T, cin, T, cip, prec, None))
+    check(lib.sl_sync_check())
+    x_dummy = np.zeros((B, T, cin))
+    want, _, _ = env.oracle.conv1d_same_backward(x_dummy, w.astype(np.float64), dy.astype(np.float64), stride)
+    want = want * below
+    assert rel_err(dx.cpu().numpy(), want) < (1e-4 if prec == 2 else 2e-2)
+    assert cin == cip or float(dxp.view(B, T, prec, cip)[..., cin:].abs().max()) == 0.0
 
 
 # ------------------------------------------------------------------ tower forward

@@ -242,7 +242,7 @@ static bool run_conv_fwd(const ConvCase& cc, int prec) {
   char label[128];
   if (cc.act == SL_ACT_SOFTMAX) {
     Dev<float> probs(static_cast<size_t>(B) * T_out * Cout), logits(probs.n), logp(static_cast<size_t>(B) * T_out * 64);
-    SLCK(sl_conv1d_fwd(xp.p, wf.p, dbias.p, nullptr, nullptr, probs.p, logits.p, logp.p, B, T, T_alloc, Cin, Cout,
+    SLCK(sl_conv1d_fwd(xp.p, wf.p, dbias.p, nullptr, nullptr, probs.p, logits.p, logp.p, B, T, T_alloc, 0, Cin, Cout,
                        k, s, SL_ACT_SOFTMAX, prec, nullptr));
     SLCK(sl_sync_check());
     auto gl = logits.down(), gp = probs.down(), glp = logp.down();
@@ -273,7 +273,7 @@ static bool run_conv_fwd(const ConvCase& cc, int prec) {
     Dev<uint16_t> yp(static_cast<size_t>(B) * T_out * cop * prec);
     Dev<uint8_t> mask(static_cast<size_t>(B) * T_out * cop / 8);
     Dev<float> y(static_cast<size_t>(B) * T_out * Cout);
-    SLCK(sl_conv1d_fwd(xp.p, wf.p, dbias.p, yp.p, mask.p, nullptr, nullptr, nullptr, B, T, T_alloc, Cin, Cout, k, s,
+    SLCK(sl_conv1d_fwd(xp.p, wf.p, dbias.p, yp.p, mask.p, nullptr, nullptr, nullptr, B, T, T_alloc, 0, Cin, Cout, k, s,
                        cc.act, prec, nullptr));
     SLCK(sl_unpack_activation(yp.p, y.p, B, T_out, Cout, T_out, cop, prec, nullptr));
     SLCK(sl_sync_check());
@@ -324,7 +324,7 @@ static bool run_dgrad(const ConvCase& cc, int prec) {
   const size_t wsb = sl_conv1d_dgrad_workspace_bytes(B, T, Cin, Cout, k);
   Dev<uint8_t> dws(wsb);
   if (wsb) printf("  (split-K dgrad, %zu byte scratch)\n", wsb);
-  SLCK(sl_conv1d_dgrad(dyp.p, wd.p, cc.act == SL_ACT_RELU ? dmask.p : nullptr, dxp.p, B, T, Cin, Cout, k, prec,
+  SLCK(sl_conv1d_dgrad(dyp.p, wd.p, cc.act == SL_ACT_RELU ? dmask.p : nullptr, dxp.p, B, T, Cin, Cout, k, 1, prec,
                        1.0f, wsb ? dws.p : nullptr, wsb, nullptr));
   SLCK(sl_unpack_activation(dxp.p, dxo.p, B, T, Cin, T, cip, prec, nullptr));
   SLCK(sl_sync_check());
@@ -671,17 +671,17 @@ static bool run_perf(int B, int T, int prec, int iters) {
     CK(cudaMemset(pmask_in.p, 0x5a, pmask_in.n));
     if (is_out)
       ok &= time_it("fwd", [&] {
-        return sl_conv1d_fwd(xp.p, wf.p, bias.p, nullptr, nullptr, probs.p, nullptr, logp.p, B, t_in, T_alloc, L.cin, L.cout,
+        return sl_conv1d_fwd(xp.p, wf.p, bias.p, nullptr, nullptr, probs.p, nullptr, logp.p, B, t_in, T_alloc, 0, L.cin, L.cout,
                              L.k, L.s, SL_ACT_SOFTMAX, prec, nullptr);
       });
     else
       ok &= time_it("fwd", [&] {
-        return sl_conv1d_fwd(xp.p, wf.p, bias.p, y2.p, pmask.p, nullptr, nullptr, nullptr, B, t_in, T_alloc, L.cin, L.cout, L.k,
+        return sl_conv1d_fwd(xp.p, wf.p, bias.p, y2.p, pmask.p, nullptr, nullptr, nullptr, B, t_in, T_alloc, 0, L.cin, L.cout, L.k,
                              L.s, SL_ACT_RELU, prec, nullptr);
       });
     if (L.s == 1)
       ok &= time_it("dgrad", [&] {
-        return sl_conv1d_dgrad(yp.p, wf.p, pmask_in.p, dxp.p, B, t_in, L.cin, L.cout, L.k, prec, 1.0f,
+        return sl_conv1d_dgrad(yp.p, wf.p, pmask_in.p, dxp.p, B, t_in, L.cin, L.cout, L.k, 1, prec, 1.0f,
                                dgws.n > 1 ? dgws.p : nullptr, dgws.n > 1 ? dgws.n : 0, nullptr);
       });
     ok &= time_it("wgrad", [&] {
