@@ -138,6 +138,7 @@ static int plan_halo(ConvGemmParams* p, const void* act, int c_total, int T_allo
   p->halo = 0;
   if (mode == 0 || stride != 1 || taps < 2 || 128 + taps - 1 > 256) return 0;
   if (mode < 0 && taps < 16) return 0;
+  if (mode < 0 && p->ctas == 2) return 0;  // a CTA pair is faster without it (0.905 vs 0.95 ms, big_conv_1 forward)
   p->halo = 1;
   p->halo_rows = 128 + taps - 1;
   // measured on B200: the descriptor start address may simply be advanced by whole 128-byte rows
@@ -148,6 +149,14 @@ static int plan_halo(ConvGemmParams* p, const void* act, int c_total, int T_allo
   return make_act_load_map(&p->tmAhalo, act, c_total, 1, T_alloc, B, p->halo_rows);
 }
 
+// CTA pairs (ConvGemmParams::ctas, cta_group::2).  Measured on B200 (profiles/README.md): correct, but not
+// faster than single CTAs with A-halo reuse — big_conv_1 forward 0.905 ms either way without the halo for
+// the pair, 0.95 ms with it; the short inner / striding layers lose 10-15 % — so the pair kernel is
+// opt-in: SL_CTA2=1 uses it for every 256-filter tile, SL_CTA2=2 only for layers with >= 2 filter tiles.
+static int cta_pairs() {
+  const char* e = std::getenv("SL_CTA2");
+  return e ? std::atoi(e) : 0;
+}
 static int grouped_tma() {
   const char* e = std::getenv("SL_GROUPED_TMA");  // 0 disables the one-TMA-per-operand tensor maps
   return e ? std::atoi(e) : 1;
@@ -288,17 +297,25 @@ int sl_conv1d_fwd(const void* x_packed, const void* w_fwd, const float* bias, vo
   std::memset(&p, 0, sizeof(p));
   int bn = cout_pad >= 256 ? 256 : cout_pad;
   SL_REQUIRE(cout_pad % bn == 0 && (bn == 64 || bn == 128 || bn == 256), "unsupported filter count");
+  p.ctas = (bn == 256 && act != SL_ACT_SOFTMAX && dbg_mode() == 0 &&
+            (cta_pairs() == 1 || (cta_pairs() == 2 && cout_pad / bn >= 2))) ? 2 : 1;
   int rc = make_act_load_map(&p.tmA, x_packed, planes * cin_pad, stride, T_in_alloc, B, 128);
   if (rc) return rc;
-  rc = make_weight_map(&p.tmB, w_fwd, planes * cin_pad, cout_pad, k, bn);
+  rc = make_weight_map(&p.tmB, w_fwd, planes * cin_pad, cout_pad, k, bn / p.ctas);
   if (rc) return rc;
   rc = plan_halo(&p, x_packed, planes * cin_pad, T_in_alloc, B, k, stride);
   if (rc) return rc;
   p.B = B;
   p.T_out = T_out;
   p.m_tiles_per_utt = (T_out + 127) / 128;
+  p.m_units = (B * p.m_tiles_per_utt + p.ctas - 1) / p.ctas;
   p.n_tiles = cout_pad / bn;
-  plan_tail(B * p.m_tiles_per_utt * p.n_tiles, bn, act != SL_ACT_SOFTMAX, &p.full_tiles, &p.tail_split);
+  if (p.ctas == 2) {
+    p.full_tiles = p.m_units * p.n_tiles;
+    p.tail_split = 1;
+  } else {
+    plan_tail(B * p.m_tiles_per_utt * p.n_tiles, bn, act != SL_ACT_SOFTMAX, &p.full_tiles, &p.tail_split);
+  }
   if (p.tail_split > 1) {
     rc = make_weight_map(&p.tmBtail, w_fwd, planes * cin_pad, cout_pad, k, bn / p.tail_split);
     if (rc) return rc;
@@ -387,7 +404,9 @@ static int dgrad_launch_rows(const void* dy_packed, const void* w_fwd, const voi
   // B[n = ci][k = co] comes straight from the forward layout (k, cout_pad, [hi|lo] cin_pad):
   // boxes of 64 co rows x 64 ci, consumed MN-major
   p.b_grouped = grouped_tma();
-  rc = p.b_grouped ? make_weight_group_map(&p.tmB, w_fwd, planes * cin_pad, cout_pad, k, 64, bn / 64)
+  p.ctas = (bn == 256 && p.b_grouped && dbg_mode() == 0 &&
+            (cta_pairs() == 1 || (cta_pairs() == 2 && cin_pad / bn >= 2 && cout_pad >= 512))) ? 2 : 1;
+  rc = p.b_grouped ? make_weight_group_map(&p.tmB, w_fwd, planes * cin_pad, cout_pad, k, 64, bn / 64 / p.ctas)
                    : make_weight_map(&p.tmB, w_fwd, planes * cin_pad, cout_pad, k, 64);
   if (rc) return rc;
   const char* dx_rows = static_cast<const char*>(dx_packed) + static_cast<size_t>(row_off) * planes * cin_pad * 2;
@@ -398,8 +417,14 @@ static int dgrad_launch_rows(const void* dy_packed, const void* w_fwd, const voi
   p.B = B;
   p.T_out = rows;
   p.m_tiles_per_utt = (rows + 127) / 128;
+  p.m_units = (B * p.m_tiles_per_utt + p.ctas - 1) / p.ctas;
   p.n_tiles = cin_pad / bn;
-  plan_tail(B * p.m_tiles_per_utt * p.n_tiles, bn, p.b_grouped != 0, &p.full_tiles, &p.tail_split);
+  if (p.ctas == 2) {
+    p.full_tiles = p.m_units * p.n_tiles;
+    p.tail_split = 1;
+  } else {
+    plan_tail(B * p.m_tiles_per_utt * p.n_tiles, bn, p.b_grouped != 0, &p.full_tiles, &p.tail_split);
+  }
   if (p.tail_split > 1) {
     rc = make_weight_group_map(&p.tmBtail, w_fwd, planes * cin_pad, cout_pad, k, 64, bn / p.tail_split / 64);
     if (rc) return rc;
@@ -438,7 +463,7 @@ static int dgrad_launch_rows(const void* dy_packed, const void* w_fwd, const voi
     rc = make_tmap(&p.tmY, TMAP_F32, 3, workspace, dims, strides, box, true);
     if (rc) return rc;
     p.ksplit = ksplit;
-    p.full_tiles = B * p.m_tiles_per_utt * p.n_tiles;
+    p.full_tiles = p.m_units * p.n_tiles;
     p.tail_split = 1;
     p.mask_bits_in = nullptr;
     rc = conv_gemm_launch(p, bn, EPI_F32, true, num_sms(), s);

@@ -38,11 +38,14 @@ constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
 constexpr int STAGING_BYTES = BLOCK_M * 128;  // 128 rows x 128 B
 constexpr int WARP_STAGING_BYTES = 32 * 128;  // one epilogue warp's 32-row slab
 
-template <int BN>
+// CTAS = 2: CTA pair (cta_group::2).  The pair computes a 256-frame x BN-filter tile; each CTA stages
+// its own 128 frames of A and BN / 2 filters of B, and the leader's MMAs (M = 256) read both halves.
+template <int BN, int CTAS>
 struct Cfg {
-  static constexpr int B_BYTES = BN * BLOCK_K * 2;
+  static constexpr int BN_LOCAL = BN / CTAS;  // filters of the B tile this CTA stages
+  static constexpr int B_BYTES = BN_LOCAL * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int kStages = BN >= 256 ? 4 : 6;
+  static constexpr int kStages = (BN >= 256 && CTAS == 1) ? 4 : 6;
   static constexpr int TMEM_COLS = (2 * BN) < 32 ? 32 : 2 * BN;
   // stages | 2 staging buffers | bias | barriers
   static constexpr int SMEM_BYTES =
@@ -59,13 +62,16 @@ struct Cfg {
 struct WorkItem {
   int b, t0, n0, width, tap_begin, tap_end;
 };
-template <int BN>
-__device__ __forceinline__ WorkItem decode_item(const ConvGemmParams& p, int item) {
+// `rank`: this CTA's rank in its pair (0 without pairs); a pair works on the frame tiles
+// 2 * unit and 2 * unit + 1 of one filter tile.  The odd tile out (if any) gets b = p.B: its loads
+// are zero-filled and its stores clipped by the tensor maps.
+template <int BN, int CTAS>
+__device__ __forceinline__ WorkItem decode_item(const ConvGemmParams& p, int item, int rank) {
   int tile = item, sub = 0, width = BN;
   int tap_begin = 0, tap_end = p.taps;
   if (p.ksplit > 1) {
     // split-major order: CTAs running together share a tap range (the same weights in L2)
-    const int total = p.B * p.m_tiles_per_utt * p.n_tiles;
+    const int total = p.m_units * p.n_tiles;
     const int split = item / total;
     tile = item - split * total;
     const int per = (p.taps + p.ksplit - 1) / p.ksplit;
@@ -81,10 +87,14 @@ __device__ __forceinline__ WorkItem decode_item(const ConvGemmParams& p, int ite
   // A operand comes from HBM once and from L2 afterwards (the weights are L2 resident anyway;
   // with the filter tile slowest, big_conv_2 re-read its 164 MB input 8 times from HBM)
   const int n_tile = tile % p.n_tiles;
-  const int rem = tile / p.n_tiles;
+  const int rem = (tile / p.n_tiles) * CTAS + rank;
   WorkItem w;
   w.b = rem / p.m_tiles_per_utt;
   w.t0 = (rem - w.b * p.m_tiles_per_utt) * BLOCK_M;
+  if (CTAS > 1 && w.b >= p.B) {
+    w.b = p.B;
+    w.t0 = 0;
+  }
   w.n0 = n_tile * BN + sub * width;
   w.width = width;
   w.tap_begin = tap_begin;
@@ -94,10 +104,45 @@ __device__ __forceinline__ WorkItem decode_item(const ConvGemmParams& p, int ite
 
 // BMN: the B operand is MN-major (input gradient: B[n = ci][k = co] read straight from the
 // forward weight layout (k, co, ci), ci contiguous) instead of K-major.
-template <int BN, int EPI, bool BMN>
+template <int CTAS>
+__device__ __forceinline__ void tma3(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+  if constexpr (CTAS == 2)
+    tma_load_3d_pair(m, mapa_u32(smem_u32(bar), 0), dst, c0, c1, c2);  // counted on the leader's barrier
+  else
+    tma_load_3d(m, bar, dst, c0, c1, c2);
+}
+template <int CTAS>
+__device__ __forceinline__ void tma4(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                     int c3) {
+  if constexpr (CTAS == 2)
+    tma_load_4d_pair(m, mapa_u32(smem_u32(bar), 0), dst, c0, c1, c2, c3);
+  else
+    tma_load_4d(m, bar, dst, c0, c1, c2, c3);
+}
+// MMA-retired signal: to this CTA's barrier, or to the barrier at the same offset in both CTAs of a pair
+template <int CTAS>
+__device__ __forceinline__ void commit(uint64_t* bar) {
+  if constexpr (CTAS == 2)
+    umma_commit_pair(bar);
+  else
+    umma_commit(bar);
+}
+// epilogue warp -> MMA issuer (always in the leader CTA): accumulator stage drained
+template <int CTAS>
+__device__ __forceinline__ void arrive_leader(uint64_t* bar) {
+  if constexpr (CTAS == 2)
+    mbar_arrive_cluster(mapa_u32(smem_u32(bar), 0));
+  else
+    mbar_arrive(bar);
+}
+
+template <int BN, int EPI, bool BMN, int CTAS>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, CTAS>;
+  const int rank = CTAS == 2 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int cta = CTAS == 2 ? static_cast<int>(blockIdx.x) / CTAS : static_cast<int>(blockIdx.x);  // work-item lane
+  const int n_ctas = static_cast<int>(gridDim.x) / CTAS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -135,21 +180,29 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       mbar_init(&halo_full[a], 1);
       mbar_init(&halo_empty[a], 1);
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 4);
+      mbar_init(&tmem_empty[a], 4 * CTAS);  // the epilogue warps of every CTA of the pair
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_ptr_s, C::TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (CTAS == 2) {
+      tmem_alloc_pair(tmem_ptr_s, C::TMEM_COLS);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_ptr_s, C::TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tcgen05_fence_before();
-  __syncthreads();
+  if constexpr (CTAS == 2)
+    cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them
+  else
+    __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
   pdl_wait();  // setup above overlapped the previous kernel's tail; its outputs are visible from here
 
-  const int total_tiles = p.B * p.m_tiles_per_utt * p.n_tiles;
+  const int total_tiles = p.m_units * p.n_tiles;
   const int num_tiles = p.ksplit > 1 ? total_tiles * p.ksplit
                                      : p.full_tiles + (total_tiles - p.full_tiles) * p.tail_split;  // work items
 
@@ -161,22 +214,24 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       int issued = 0;
       int hbuf = 0;
       uint32_t hphase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const WorkItem w = decode_item<BN>(p, tile);
+      for (int tile = cta; tile < num_tiles; tile += n_ctas) {
+        const WorkItem w = decode_item<BN, CTAS>(p, tile, rank);
         const int b = w.b, t0 = w.t0, n0 = w.n0;
         const CUtensorMap* tmB = w.width == BN ? &p.tmB : &p.tmBtail;
-        const uint32_t stage_tx = A_BYTES + w.width * (BLOCK_K * 2);
+        const int n_loc = n0 + rank * (w.width / CTAS);  // first filter of the B half this CTA stages
+        const bool expects = CTAS == 1 || rank == 0;     // a pair counts all its bytes on the leader's barrier
+        const uint32_t stage_tx = A_BYTES + (w.width / CTAS) * (BLOCK_K * 2);
         if (p.halo) {
           // chunk-major: one halo tile per (chunk, term), then one B tile per tap
           uint8_t* b_ring = smem + 2 * C::HALO_BYTES;
-          const uint32_t b_tx = w.width * (BLOCK_K * 2);
+          const uint32_t b_tx = (w.width / CTAS) * (BLOCK_K * 2);
           for (int chunk = 0; chunk < p.chunks; ++chunk) {
             for (int term = 0; term < p.terms; ++term) {
               const int a_c = chunk * BLOCK_K + (term == 2 ? p.a_lo_off : 0);
               const int b_c = chunk * BLOCK_K + (term == 1 ? p.b_lo_off : 0);
               mbar_wait(&halo_empty[hbuf], hphase ^ 1);
-              mbar_expect_tx(&halo_full[hbuf], p.halo_rows * 128);
-              tma_load_4d(&p.tmAhalo, &halo_full[hbuf], smem + hbuf * C::HALO_BYTES, a_c, 0, t0 - p.pad_l, b);
+              if (expects) mbar_expect_tx(&halo_full[hbuf], CTAS * p.halo_rows * 128);
+              tma4<CTAS>(&p.tmAhalo, &halo_full[hbuf], smem + hbuf * C::HALO_BYTES, a_c, 0, t0 - p.pad_l, b);
               if (++hbuf == 2) {
                 hbuf = 0;
                 hphase ^= 1;
@@ -185,12 +240,12 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
                 const int wtap = p.w_tap0 + tap * p.w_tap_step;
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 uint8_t* b_s = b_ring + stage * C::B_BYTES;
-                mbar_expect_tx(&full_bar[stage], b_tx);
+                if (expects) mbar_expect_tx(&full_bar[stage], CTAS * b_tx);
                 if (BMN)
-                  tma_load_4d(tmB, &full_bar[stage], b_s, 0, chunk * BLOCK_K,
-                              (n0 + (term == 1 ? p.b_lo_off : 0)) >> 6, wtap);
+                  tma4<CTAS>(tmB, &full_bar[stage], b_s, 0, chunk * BLOCK_K,
+                             (n_loc + (term == 1 ? p.b_lo_off : 0)) >> 6, wtap);
                 else
-                  tma_load_3d(tmB, &full_bar[stage], b_s, b_c, n0, wtap);
+                  tma3<CTAS>(tmB, &full_bar[stage], b_s, b_c, n_loc, wtap);
                 if (++stage == C::kStagesB) {
                   stage = 0;
                   phase ^= 1;
@@ -218,7 +273,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
               mbar_wait(&empty_bar[stage], phase ^ 1);
               uint8_t* a_s = smem + stage * C::STAGE_BYTES;
               uint8_t* b_s = a_s + A_BYTES;
-              if (p.dbg_mode == 1 && issued >= C::kStages) {  // measurement aid: MMA on stale tiles
+              if (CTAS == 1 && p.dbg_mode == 1 && issued >= C::kStages) {  // measurement aid: MMA on stale tiles
                 mbar_arrive(&full_bar[stage]);
                 if (++stage == C::kStages) {
                   stage = 0;
@@ -227,7 +282,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
                 continue;
               }
               ++issued;
-              if (p.dbg_mode >= 2 && issued > C::kStages) {
+              if (CTAS == 1 && p.dbg_mode >= 2 && issued > C::kStages) {
                 // measurement aids: 2 = keep only the A loads (what a shared-B / 2-CTA scheme would
                 // save), 3 = keep only the B loads (what reusing the A halo across taps would save)
                 if (p.dbg_mode == 2) {
@@ -247,14 +302,14 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
                 }
                 continue;
               }
-              mbar_expect_tx(&full_bar[stage], stage_tx);
-              tma_load_4d(&p.tmA, &full_bar[stage], a_s, a_c, par, t0 + q, b);
+              if (expects) mbar_expect_tx(&full_bar[stage], CTAS * stage_tx);
+              tma4<CTAS>(&p.tmA, &full_bar[stage], a_s, a_c, par, t0 + q, b);
               if (BMN) {
                 // 64 contraction rows (co) x 64 output channels (ci) per box
-                const int n_c = n0 + (term == 1 ? p.b_lo_off : 0);
-                if (p.b_grouped) {
-                  // one box {64 ci, 64 co rows, BN/64 channel groups}: lands as [group][row][64]
-                  tma_load_4d(tmB, &full_bar[stage], b_s, 0, chunk * BLOCK_K, n_c >> 6, wtap);
+                const int n_c = n_loc + (term == 1 ? p.b_lo_off : 0);
+                if (p.b_grouped || CTAS == 2) {
+                  // one box {64 ci, 64 co rows, BN_LOCAL/64 channel groups}: lands as [group][row][64]
+                  tma4<CTAS>(tmB, &full_bar[stage], b_s, 0, chunk * BLOCK_K, n_c >> 6, wtap);
                 } else {
 #pragma unroll
                   for (int i = 0; i < BN / 64; ++i)
@@ -263,7 +318,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
                                   chunk * BLOCK_K, wtap);
                 }
               } else {
-                tma_load_3d(tmB, &full_bar[stage], b_s, b_c, n0, wtap);
+                tma3<CTAS>(tmB, &full_bar[stage], b_s, b_c, n_loc, wtap);
               }
               if (++stage == C::kStages) {
                 stage = 0;
@@ -274,17 +329,17 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 && (CTAS == 1 || rank == 0)) {
     // ===================== MMA issuer =====================
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
     int hbuf = 0;
     uint32_t hphase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const WorkItem w = decode_item<BN>(p, tile);
+    for (int tile = cta; tile < num_tiles; tile += n_ctas, ++it) {
+      const WorkItem w = decode_item<BN, CTAS>(p, tile, rank);
       const int ksteps = (w.tap_end - w.tap_begin) * p.chunks * p.terms;
-      const uint32_t idesc = make_idesc_bf16(BLOCK_M, w.width, 0, BMN ? 1 : 0);
+      const uint32_t idesc = make_idesc_bf16(BLOCK_M * CTAS, w.width, 0, BMN ? 1 : 0);
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(&tmem_empty[as], aphase ^ 1);
@@ -310,12 +365,15 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
                 const uint64_t da = make_smem_desc_sw128_off(aa, 16, 1024, p.halo_base_mode ? (aa >> 7) & 7u : 0u);
                 const uint64_t db = BMN ? make_smem_desc_sw128(b_addr + k * 2048, BLOCK_K * 128, 1024)
                                         : make_smem_desc_sw128(b_addr + k * UMMA_K * 2, 16, 1024);
-                umma_bf16(tmem_d, da, db, idesc, first ? 0u : 1u);
+                if constexpr (CTAS == 2)
+                  umma_bf16_pair(tmem_d, da, db, idesc, first ? 0u : 1u);
+                else
+                  umma_bf16(tmem_d, da, db, idesc, first ? 0u : 1u);
                 first = 0;
               }
-              umma_commit(&empty_bar[stage]);
-              if (ti == ntaps - 1) umma_commit(&halo_empty[hbuf]);
-              if (ti == ntaps - 1 && ct == p.chunks * p.terms - 1) umma_commit(&tmem_full[as]);
+              commit<CTAS>(&empty_bar[stage]);
+              if (ti == ntaps - 1) commit<CTAS>(&halo_empty[hbuf]);
+              if (ti == ntaps - 1 && ct == p.chunks * p.terms - 1) commit<CTAS>(&tmem_full[as]);
             }
             __syncwarp();
             if (++stage == C::kStagesB) {
@@ -328,7 +386,10 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             hphase ^= 1;
           }
         }
-        if (ksteps == 0 && lane == 0) mbar_arrive(&tmem_full[as]);
+        if (ksteps == 0 && lane == 0) {
+          mbar_arrive(&tmem_full[as]);
+          if (CTAS == 2) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_full[as]), 1));
+        }
         continue;
       }
       for (int ks = 0; ks < ksteps; ++ks) {
@@ -344,10 +405,13 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             // groups are BLOCK_K * 128 B apart (leading byte offset)
             const uint64_t db = BMN ? make_smem_desc_sw128(b_addr + k * 2048, BLOCK_K * 128, 1024)
                                     : make_smem_desc_sw128(b_addr + k * UMMA_K * 2, 16, 1024);
-            umma_bf16(tmem_d, da, db, idesc, (ks | k) != 0 ? 1u : 0u);
+            if constexpr (CTAS == 2)
+              umma_bf16_pair(tmem_d, da, db, idesc, (ks | k) != 0 ? 1u : 0u);
+            else
+              umma_bf16(tmem_d, da, db, idesc, (ks | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
-          if (ks == ksteps - 1) umma_commit(&tmem_full[as]);
+          commit<CTAS>(&empty_bar[stage]);  // frees the smem slot (of both CTAs) when these MMAs retire
+          if (ks == ksteps - 1) commit<CTAS>(&tmem_full[as]);
         }
         __syncwarp();
         if (++stage == C::kStages) {
@@ -355,7 +419,10 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           phase ^= 1;
         }
       }
-      if (ksteps == 0 && lane == 0) mbar_arrive(&tmem_full[as]);  // empty tap range (never planned)
+      if (ksteps == 0 && lane == 0) {  // empty tap range (never planned)
+        mbar_arrive(&tmem_full[as]);
+        if (CTAS == 2) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_full[as]), 1));
+      }
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
@@ -365,14 +432,14 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     int it = 0;
     uint32_t store_count = 0;
     int staged_n0 = -1;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const WorkItem w = decode_item<BN>(p, tile);
+    for (int tile = cta; tile < num_tiles; tile += n_ctas, ++it) {
+      const WorkItem w = decode_item<BN, CTAS>(p, tile, rank);
       const int b = w.b, t0 = w.t0, n0 = w.n0;
       const int n_chunks = w.width / 64;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const int t = t0 + row;
-      const bool row_valid = t < p.T_out;
+      const bool row_valid = t < p.T_out && b < p.B;
 
       // stage the bias slice of this tile; consecutive tiles of a CTA mostly share their filter
       // range, so the (two-barrier) refill only runs when it changes
@@ -426,7 +493,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         }
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[as]);
+        if (lane == 0) arrive_leader<CTAS>(&tmem_empty[as]);
       } else if (EPI == EPI_PACKED) {
 #pragma unroll 1
         for (int c = 0; c < n_chunks; ++c) {
@@ -438,7 +505,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             // accumulator fully drained: hand the TMEM stage back to the MMA warp
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[as]);
+            if (lane == 0) arrive_leader<CTAS>(&tmem_empty[as]);
           }
           float v[64];
 #pragma unroll
@@ -517,7 +584,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         tmem_ld_wait();
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[as]);
+        if (lane == 0) arrive_leader<CTAS>(&tmem_empty[as]);
         if (row_valid) {
           float z[64];
 #pragma unroll
@@ -570,32 +637,71 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   }
 
   tcgen05_fence_before();
-  __syncthreads();
+  if constexpr (CTAS == 2)
+    cluster_sync_all();  // neither CTA may exit while the other can still signal its barriers
+  else
+    __syncthreads();
   if (warp == 2) {
     tcgen05_fence_after();
-    tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if constexpr (CTAS == 2)
+      tmem_dealloc_pair(tmem_base, C::TMEM_COLS);
+    else
+      tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
 }
 
-template <int BN, int EPI, bool BMN>
+template <int BN, int EPI, bool BMN, int CTAS>
 int launch(const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, CTAS>;
   // the opt-in shared-memory size is a per-device function attribute
   static unsigned long long configured = 0;  // bit d: set for device d (benign race: idempotent)
+  static int max_clusters[64] = {0};         // CTA pairs that can be co-resident on device d
   int dev = 0;
   SL_CUDA(cudaGetDevice(&dev));
   if (!((configured >> (dev & 63)) & 1ull)) {
-    SL_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, EPI, BMN>,
+    SL_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, EPI, BMN, CTAS>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     configured |= 1ull << (dev & 63);
   }
-  const int num_tiles = p.B * p.m_tiles_per_utt * p.n_tiles * (p.ksplit > 1 ? p.ksplit : 1);
+  const int num_tiles = p.m_units * p.n_tiles * (p.ksplit > 1 ? p.ksplit : 1);
+  if (CTAS == 2) {
+    if (p.tail_split != 1 || p.full_tiles != p.m_units * p.n_tiles || p.dbg_mode != 0) {
+      set_error("conv_gemm: the CTA-pair kernel takes whole tiles only");
+      return 1;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int& mc = max_clusters[dev & 63];
+    if (mc == 0) {
+      cfg.gridDim = dim3(num_sms & ~1);
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, conv_gemm_kernel<BN, EPI, BMN, CTAS>, &cfg) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        n = num_sms / 2;
+      }
+      mc = n;
+    }
+    const int pairs = num_tiles < mc ? num_tiles : mc;
+    cfg.gridDim = dim3(2 * pairs);
+    SL_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BN, EPI, BMN, CTAS>, p));
+    return 0;
+  }
   const int grid = num_tiles < num_sms ? num_tiles : num_sms;
   if (p.ksplit <= 1 && (p.full_tiles + (num_tiles - p.full_tiles) * p.tail_split < grid || p.tail_split < 1)) {
     set_error("conv_gemm: inconsistent tail split");
     return 1;
   }
-  SL_CUDA(launch_pdl(PDL_CONV, conv_gemm_kernel<BN, EPI, BMN>, dim3(grid), dim3(kThreads), C::SMEM_BYTES, stream, p));
+  SL_CUDA(launch_pdl(PDL_CONV, conv_gemm_kernel<BN, EPI, BMN, CTAS>, dim3(grid), dim3(kThreads), C::SMEM_BYTES, stream,
+                     p));
   return 0;
 }
 
@@ -603,25 +709,36 @@ int launch(const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
 
 int conv_gemm_launch(const ConvGemmParams& p, int block_n, int epi, bool b_mn_major, int num_sms,
                      cudaStream_t stream) {
+  if (p.ctas == 2) {
+    SL_REQUIRE(block_n == 256 && epi != EPI_SOFTMAX, "the CTA-pair kernel is built for 256-filter tiles");
+    SL_REQUIRE(!b_mn_major || p.b_grouped, "the CTA-pair kernel needs the grouped weight map");
+    if (epi == EPI_F32) {
+      SL_REQUIRE(b_mn_major, "split-K epilogue is built for the dgrad tiles");
+      return launch<256, EPI_F32, true, 2>(p, num_sms, stream);
+    }
+    return b_mn_major ? launch<256, EPI_PACKED, true, 2>(p, num_sms, stream)
+                      : launch<256, EPI_PACKED, false, 2>(p, num_sms, stream);
+  }
+  SL_REQUIRE(p.ctas == 1, "ctas must be 1 or 2");
   if (epi == EPI_SOFTMAX) {
     SL_REQUIRE(block_n == 64 && !b_mn_major, "softmax epilogue needs a 64-wide K-major tile");
-    return launch<64, EPI_SOFTMAX, false>(p, num_sms, stream);
+    return launch<64, EPI_SOFTMAX, false, 1>(p, num_sms, stream);
   }
   if (epi == EPI_F32) {
     SL_REQUIRE(b_mn_major && (block_n == 128 || block_n == 256), "split-K epilogue is built for the dgrad tiles");
-    return block_n == 256 ? launch<256, EPI_F32, true>(p, num_sms, stream)
-                          : launch<128, EPI_F32, true>(p, num_sms, stream);
+    return block_n == 256 ? launch<256, EPI_F32, true, 1>(p, num_sms, stream)
+                          : launch<128, EPI_F32, true, 1>(p, num_sms, stream);
   }
   switch (block_n) {
     case 64:
-      return b_mn_major ? launch<64, EPI_PACKED, true>(p, num_sms, stream)
-                        : launch<64, EPI_PACKED, false>(p, num_sms, stream);
+      return b_mn_major ? launch<64, EPI_PACKED, true, 1>(p, num_sms, stream)
+                        : launch<64, EPI_PACKED, false, 1>(p, num_sms, stream);
     case 128:
-      return b_mn_major ? launch<128, EPI_PACKED, true>(p, num_sms, stream)
-                        : launch<128, EPI_PACKED, false>(p, num_sms, stream);
+      return b_mn_major ? launch<128, EPI_PACKED, true, 1>(p, num_sms, stream)
+                        : launch<128, EPI_PACKED, false, 1>(p, num_sms, stream);
     case 256:
-      return b_mn_major ? launch<256, EPI_PACKED, true>(p, num_sms, stream)
-                        : launch<256, EPI_PACKED, false>(p, num_sms, stream);
+      return b_mn_major ? launch<256, EPI_PACKED, true, 1>(p, num_sms, stream)
+                        : launch<256, EPI_PACKED, false, 1>(p, num_sms, stream);
     default:
       set_error("conv_gemm: unsupported block_n");
       return 1;

@@ -19,6 +19,11 @@ struct ConvGemmParams {
   int T_out;
   int m_tiles_per_utt;
   int n_tiles;
+  // CTA pairs (cta_group::2): ctas = 2 runs the kernel as clusters of two CTAs that share one
+  // 256-frame x 256-filter tile; each CTA stages its 128 frames of A and 128 filters of B (tmB then
+  // has a box of BN / 2 filters) and the leader issues MMAs of M = 256 that read both halves
+  int ctas;     // 1 or 2
+  int m_units;  // ceil(B * m_tiles_per_utt / ctas): frame tiles per filter tile, in units of `ctas` tiles
   // tail splitting: the tiles of the last, partial wave of the persistent grid are cut into
   // tail_split (1, 2 or 4) narrower tiles so that the wave costs 1/tail_split of a tile time
   int full_tiles;  // tiles [0, full_tiles) are whole; the rest are split

@@ -381,7 +381,8 @@ static double lse(double a, double b) {
   const double m = std::max(a, b);
   return m + std::log(std::exp(a - m) + std::exp(b - m));
 }
-static bool test_ctc(int B, int T, int V, int L_lo, int L_hi, const char* name) {
+static bool test_ctc(int B, int T, int V, int L_lo, int L_hi, const char* name, float logit_scale = 2.0f,
+                     bool tight = false) {
   const int blank = V - 1;
   std::uniform_int_distribution<int> dl(L_lo, L_hi), dv(0, V - 2);
   std::vector<int> label_len(B), input_len(B);
@@ -399,10 +400,11 @@ static bool test_ctc(int B, int T, int V, int L_lo, int L_hi, const char* name) 
     }
     const int need = label_len[b] + rep;
     input_len[b] = std::min(T, std::max(need, T - static_cast<int>(rng() % (T / 3 + 1))));
+    if (tight) input_len[b] = std::min(T, need + static_cast<int>(rng() % 2));  // (almost) a single alignment
     if (need > T) printf("  (case %d infeasible: need %d > T %d)\n", b, need, T);
   }
   // logits -> probs (double), logp
-  auto z = randn(static_cast<size_t>(B) * T * V, 2.0f);
+  auto z = randn(static_cast<size_t>(B) * T * V, logit_scale);
   std::vector<double> p(z.size()), lp(z.size());
   std::vector<float> pf(z.size()), lpf(static_cast<size_t>(B) * T * 64, -INFINITY);
   for (size_t r = 0; r < z.size() / V; ++r) {
@@ -480,6 +482,20 @@ static bool test_ctc(int B, int T, int V, int L_lo, int L_hi, const char* name) 
   Dev<float> dzu(static_cast<size_t>(B) * T * V);
   SLCK(sl_unpack_activation(dzp.p, dzu.p, B, T, V, T, 64, SL_PREC_BF16X2, nullptr));
   SLCK(sl_sync_check());
+  {  // timing of the loss + gradient launch pair (CUDA events, 10 iterations after the run above)
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0));
+    for (int it = 0; it < 10; ++it)
+      SLCK(sl_ctc_loss(dlp.p, dp.p, dlab.p, dil.p, dll.p, dloss.p, dzp.p, nullptr, static_cast<float>(scale), B, T, V,
+                       L_max, blank, SL_PREC_BF16, ws.p, wsb, nullptr));
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    printf("  %-26s loss + gradient: %.4f ms per call (B=%d T=%d L_max=%d)\n", name, ms / 10, B, T, L_max);
+  }
   auto gl = dloss.down(), gdz = ddz.down(), gdzu = dzu.down();
   char label[128];
   bool ok = true;
@@ -746,6 +762,9 @@ int main(int argc, char** argv) {
       {"tail4_k3_250", 10, 2000, 250, 250, 3, 1, SL_ACT_RELU},
       {"tail2_k1_64_128", 10, 2000, 64, 128, 1, 1, SL_ACT_RELU},
       {"tail_k1_250_2000", 3, 1000, 250, 2000, 1, 1, SL_ACT_RELU},
+      // odd number of frame tiles: the last CTA pair has a tile-less CTA
+      {"pair_odd_k3_250", 1, 300, 250, 250, 3, 1, SL_ACT_RELU},
+      {"pair_odd_k20_250_500", 3, 300, 250, 500, 20, 1, SL_ACT_RELU},
   };
   for (const auto& cc : fwd_cases)
     for (int prec = 1; prec <= 2; ++prec) {
@@ -761,6 +780,8 @@ int main(int argc, char** argv) {
       {"tail4_k3_250", 10, 2000, 250, 250, 3, 1, SL_ACT_RELU},
       {"tail2_k1_128_64", 10, 2000, 128, 64, 1, 1, SL_ACT_RELU},
       {"splitk_k8_250_2000", 10, 2000, 250, 2000, 8, 1, SL_ACT_RELU},
+      {"pair_odd_k3_250", 1, 300, 250, 250, 3, 1, SL_ACT_RELU},
+      {"pair_odd_k20_250_500", 3, 300, 250, 500, 20, 1, SL_ACT_RELU},
   };
   for (const auto& cc : dg_cases)
     for (int prec = 1; prec <= 2; ++prec) {
@@ -784,6 +805,12 @@ int main(int argc, char** argv) {
   if (want("ctc_mid")) run("ctc_mid", test_ctc(6, 313, 29, 20, 150, "ctc_mid"));
   if (want("ctc_german")) run("ctc_german", test_ctc(3, 200, 33, 10, 60, "ctc_german"));
   if (want("ctc_long")) run("ctc_long", test_ctc(2, 1500, 29, 500, 700, "ctc_long"));
+  // near one-hot distributions (log-probs down to the 1e-8 floor) and (almost) unique alignments: the
+  // steepest lattice profiles the linear-domain kernel has to carry through its exponent blocks
+  if (want("ctc_peaky")) run("ctc_peaky", test_ctc(4, 300, 29, 40, 140, "ctc_peaky", 12.0f));
+  if (want("ctc_tight")) run("ctc_tight", test_ctc(4, 260, 29, 150, 160, "ctc_tight", 12.0f, true));
+  if (want("ctc_empty")) run("ctc_empty", test_ctc(3, 50, 29, 0, 1, "ctc_empty"));
+  if (want("ctc_bench")) run("ctc_bench", test_ctc(64, 626, 29, 150, 150, "ctc_bench"));
   printf("selftest finished: %d failure(s)\n", failures);
   return failures ? 1 : 0;
 }
