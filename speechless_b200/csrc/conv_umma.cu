@@ -32,8 +32,16 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // bf16 elements per smem row = 128 B = one swizzle span
 constexpr int UMMA_K = 16;
-constexpr int kThreads = 256;
-constexpr int kEpiThreads = 128;
+// warps 0-3: TMA producer, MMA issuer, TMEM allocator, idle; then the epilogue warps.  A lone warp
+// per scheduler issues one of its (mostly dependent) instructions every ~2.6 cycles (measured), so
+// the bias / ReLU / mask / pack epilogue runs on TWO warps per TMEM lane quadrant, which share the
+// 64-column chunks of a tile alternately; the softmax epilogue (one chunk per tile) keeps one.
+template <int EPI>
+struct Threads {
+  static constexpr int kEpiSets = EPI == EPI_SOFTMAX ? 1 : 2;
+  static constexpr int kEpiThreads = 128 * kEpiSets;
+  static constexpr int kThreads = 128 + kEpiThreads;
+};
 constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
 constexpr int STAGING_BYTES = BLOCK_M * 128;  // 128 rows x 128 B
 constexpr int WARP_STAGING_BYTES = 32 * 128;  // one epilogue warp's 32-row slab
@@ -137,9 +145,11 @@ __device__ __forceinline__ void arrive_leader(uint64_t* bar) {
 }
 
 template <int BN, int EPI, bool BMN, int CTAS>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(Threads<EPI>::kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   using C = Cfg<BN, CTAS>;
+  constexpr int kEpiSets = Threads<EPI>::kEpiSets;
+  constexpr int kEpiThreads = Threads<EPI>::kEpiThreads;
   const int rank = CTAS == 2 ? static_cast<int>(cluster_ctarank()) : 0;
   const int cta = CTAS == 2 ? static_cast<int>(blockIdx.x) / CTAS : static_cast<int>(blockIdx.x);  // work-item lane
   const int n_ctas = static_cast<int>(gridDim.x) / CTAS;
@@ -180,7 +190,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       mbar_init(&halo_full[a], 1);
       mbar_init(&halo_empty[a], 1);
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 4 * CTAS);  // the epilogue warps of every CTA of the pair
+      mbar_init(&tmem_empty[a], 4 * kEpiSets * CTAS);  // every epilogue warp of every CTA of the pair
     }
     fence_barrier_init();
   }
@@ -426,12 +436,15 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
-    const int ew = warp - 4;  // == warp % 4 : TMEM lane quadrant this warp may read
+    const int ew = warp & 3;          // TMEM lane quadrant this warp may read
+    const int set = (warp - 4) >> 2;  // which of the kEpiSets warps of the quadrant: takes chunks set, set + 2, ...
     const int row = ew * 32 + lane;
     const int et = threadIdx.x - 128;
     int it = 0;
-    uint32_t store_count = 0;
     int staged_n0 = -1;
+    // one 32-row x 128-byte staging slab per warp: by the time a warp has prepared its next chunk,
+    // the TMA store of the previous one has long finished reading the slab
+    uint8_t* const sbuf = staging + (warp - 4) * WARP_STAGING_BYTES;
     for (int tile = cta; tile < num_tiles; tile += n_ctas, ++it) {
       const WorkItem w = decode_item<BN, CTAS>(p, tile, rank);
       const int b = w.b, t0 = w.t0, n0 = w.n0;
@@ -458,7 +471,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             (static_cast<size_t>(b) * p.mask_T + (t * p.out_t_scale + p.out_t_off)) * p.mask_row_bytes + (n0 >> 3));
 #pragma unroll
         for (int c = 0; c < BN / 64; ++c)
-          if (c < n_chunks) mask_in[c] = __ldg(mp + c);
+          if (c < n_chunks && (c % kEpiSets) == set) mask_in[c] = __ldg(mp + c);
       }
 
       mbar_wait(&tmem_full[as], aphase);
@@ -470,12 +483,11 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         // split-K partial sums: fp32 accumulator -> per-warp swizzled slab -> TMA reduce-add
         const bool has_data = w.tap_end > w.tap_begin;
 #pragma unroll 1
-        for (int c = 0; c < (has_data ? w.width / 32 : 0); ++c) {
+        for (int c = set; c < (has_data ? w.width / 32 : 0); c += kEpiSets) {
           uint32_t r[32];
           tmem_ld_32x32(taddr + c * 32, r);
           tmem_ld_wait();
-          uint8_t* sbuf = staging + ew * (2 * WARP_STAGING_BYTES) + (store_count & 1) * WARP_STAGING_BYTES;
-          if (lane == 0) tma_wait_group_read<1>();
+          if (lane == 0) tma_wait_group_read<0>();
           __syncwarp();
           uint8_t* rowp = sbuf + lane * 128;
 #pragma unroll
@@ -489,20 +501,24 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             tma_reduce_add_3d(&p.tmY, sbuf, n0 + c * 32, t0 + ew * 32, b);
             tma_commit_group();
           }
-          ++store_count;
         }
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) arrive_leader<CTAS>(&tmem_empty[as]);
       } else if (EPI == EPI_PACKED) {
+        if (set >= n_chunks) {  // narrow tail tile: nothing for this warp, but the MMA warp counts every arrival
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) arrive_leader<CTAS>(&tmem_empty[as]);
+        }
 #pragma unroll 1
-        for (int c = 0; c < n_chunks; ++c) {
+        for (int c = set; c < n_chunks; c += kEpiSets) {
           uint32_t r0[32], r1[32];
           tmem_ld_32x32(taddr + c * 64, r0);
           tmem_ld_32x32(taddr + c * 64 + 32, r1);
           tmem_ld_wait();
-          if (c == n_chunks - 1) {
-            // accumulator fully drained: hand the TMEM stage back to the MMA warp
+          if (c + kEpiSets >= n_chunks) {
+            // this warp's share of the accumulator is drained: hand the TMEM stage back to the MMA warp
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) arrive_leader<CTAS>(&tmem_empty[as]);
@@ -510,8 +526,19 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           float v[64];
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            v[i] = __uint_as_float(r0[i]) + bias_s[c * 64 + i];
-            v[32 + i] = __uint_as_float(r1[i]) + bias_s[c * 64 + 32 + i];
+            v[i] = __uint_as_float(r0[i]);
+            v[32 + i] = __uint_as_float(r1[i]);
+          }
+          if (p.bias != nullptr) {  // (uniform) the input-gradient GEMMs have none
+            const float4* bs = reinterpret_cast<const float4*>(bias_s + c * 64);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float4 q = bs[i];
+              v[4 * i] += q.x;
+              v[4 * i + 1] += q.y;
+              v[4 * i + 2] += q.z;
+              v[4 * i + 3] += q.w;
+            }
           }
           if (p.relu) {
 #pragma unroll
@@ -544,21 +571,10 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
                                       (static_cast<size_t>(b) * p.T_out + t) * p.mask_row_bytes +
                                       ((n0 + c * 64) >> 3)) = mb;
           }
-          for (int plane = 0; plane < p.y_planes; ++plane) {
-            uint32_t packed[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              if (plane == 0) {
-                packed[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
-              } else {
-                packed[i] = pack_bf16x2(v[2 * i] - bf16_round(v[2 * i]),
-                                        v[2 * i + 1] - bf16_round(v[2 * i + 1]));
-              }
-            }
-            // Each epilogue warp owns a 32-row slab: it stages and TMA-stores it on its own, so
-            // the four warps never wait for each other (bulk async-groups are per thread).
-            uint8_t* sbuf = staging + ew * (2 * WARP_STAGING_BYTES) + (store_count & 1) * WARP_STAGING_BYTES;
-            if (lane == 0) tma_wait_group_read<1>();  // the store that last read sbuf is done
+          // Each epilogue warp owns a 32-row slab: it stages and TMA-stores it on its own, so the
+          // warps never wait for each other (bulk async-groups are per thread).
+          auto stage_and_store = [&](const uint32_t (&packed)[32], int col0) {
+            if (lane == 0) tma_wait_group_read<0>();  // the store that last read sbuf is done
             __syncwarp();
             uint8_t* rowp = sbuf + lane * 128;
 #pragma unroll
@@ -570,10 +586,22 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-              tma_store_3d(&p.tmY, sbuf, n0 + c * 64 + (plane ? p.y_lo_off : 0), t0 + ew * 32, b);
+              tma_store_3d(&p.tmY, sbuf, col0, t0 + ew * 32, b);
               tma_commit_group();
             }
-            ++store_count;
+          };
+          {
+            uint32_t packed[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) packed[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+            stage_and_store(packed, n0 + c * 64);
+          }
+          if (p.y_planes == 2) {  // (uniform) split-bf16 mode only: the residual plane x - bf16(x)
+            uint32_t packed[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              packed[i] = pack_bf16x2(v[2 * i] - bf16_round(v[2 * i]), v[2 * i + 1] - bf16_round(v[2 * i + 1]));
+            stage_and_store(packed, n0 + c * 64 + p.y_lo_off);
           }
         }
       } else {
@@ -670,7 +698,7 @@ int launch(const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
       return 1;
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(Threads<EPI>::kThreads);
     cfg.dynamicSmemBytes = C::SMEM_BYTES;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -700,7 +728,7 @@ int launch(const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
     set_error("conv_gemm: inconsistent tail split");
     return 1;
   }
-  SL_CUDA(launch_pdl(PDL_CONV, conv_gemm_kernel<BN, EPI, BMN, CTAS>, dim3(grid), dim3(kThreads), C::SMEM_BYTES, stream,
+  SL_CUDA(launch_pdl(PDL_CONV, conv_gemm_kernel<BN, EPI, BMN, CTAS>, dim3(grid), dim3(Threads<EPI>::kThreads), C::SMEM_BYTES, stream,
                      p));
   return 0;
 }

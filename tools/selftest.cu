@@ -630,7 +630,7 @@ struct PerfLayer {
   const char* name;
   int cin, cout, k, s;
 };
-static bool run_perf(int B, int T, int prec, int iters) {
+static bool run_perf(int B, int T, int prec, int iters, const char* only = nullptr) {
   const PerfLayer layers[] = {{"striding_conv", 128, 250, 48, 2}, {"inner_conv", 250, 250, 7, 1},
                               {"big_conv_1", 250, 2000, 32, 1},   {"big_conv_2", 2000, 2000, 1, 1},
                               {"output_conv", 2000, 29, 1, 1}};
@@ -666,6 +666,11 @@ static bool run_perf(int B, int T, int prec, int iters) {
     }
     const double flops = 2.0 * L.k * L.cin * L.cout * static_cast<double>(T_out) * B;
     const bool is_out = L.cout == 29;
+    const bool skip_timing = only != nullptr && std::string(L.name).find(only) == std::string::npos;
+    if (skip_timing) {  // shapes still have to chain
+      t_in = T_out;
+      continue;
+    }
     auto time_it = [&](const char* what, auto fn) -> bool {
       for (int i = 0; i < 2; ++i)
         if (fn() != 0) return false;
@@ -720,7 +725,7 @@ int main(int argc, char** argv) {
     const int B = argc > 2 ? atoi(argv[2]) : 64;
     const int T = argc > 3 ? atoi(argv[3]) : 1251;
     const int prec = argc > 4 ? atoi(argv[4]) : 1;
-    return run_perf(B, T, prec, 5) ? 0 : 1;
+    return run_perf(B, T, prec, 5, argc > 5 ? argv[5] : nullptr) ? 0 : 1;
   }
   const std::string filter = argc > 1 ? argv[1] : "";
   auto want = [&](const char* n) { return filter.empty() || std::string(n).find(filter) != std::string::npos; };
