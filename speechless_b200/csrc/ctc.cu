@@ -181,6 +181,263 @@ __global__ void ctc_alpha_beta_kernel(const float* __restrict__ logp,
 }
 
 // ---------------------------------------------------------------------------------------------
+// Halo-blocked variant (the default): K time steps between block barriers.
+//
+// The lattice column lives in REGISTERS: lane l of warp w holds the SPT consecutive states
+// base_w + l*SPT ..., where base_w = w*OWN - 2K and OWN = 32*SPT - 2K.  The first 2K slots of a
+// warp are a HALO that overlaps the last 2K owned states of warp w-1.  A state at step t depends
+// on itself and its two left neighbours at step t-1, so after k steps without any exchange the
+// slots >= 2k of a warp are still exact: K steps run with one warp shuffle per step and no
+// shared-memory round trip or barrier; then every warp publishes its owned states to a
+// double-buffered smem column, ONE barrier, and the halos are reloaded.  The redundant halo work
+// (2K of 32*SPT slots) buys a K-fold cut of the barrier + smem latency of the one-barrier-per-step
+// kernel above.  ncu on the first version of this kernel showed what bounds such a recurrence with
+// 1-2 warps per scheduler: not the SFU, but the NUMBER of dependent instructions per step (~2 cycles
+// of fixed-latency "wait" stall per instruction).  Hence the step is written for a minimal count:
+//  * "log 0" is the finite sentinel NEG = -1e30 (absorbing under +emission, 2^(NEG - m) = 0), so no
+//    NaN guard is needed for (-inf) - (-inf);
+//  * "state does not exist" and "skip transition not allowed" are additive biases (0 or NEG) folded
+//    into the emission / the s-2 term — no predicates, no selects;
+//  * SPT is even and base_w is even, so slot parity = state parity in walking order (S is odd, so
+//    this also holds for the reversed beta problem): even slots are blank states (two-term
+//    log-sum-exp: 1 ex2 + 1 lg2), odd slots label states (three terms: 2 ex2 + 1 lg2 — the largest
+//    term is 2^0 and is not exponentiated);
+//  * emission rows are read with immediate offsets from a per-block base pointer; full K-blocks run
+//    without per-step bounds checks; the direction is a template parameter of the walk.
+// An extra warp of the alpha CTA counting-sorts the label positions by symbol for the gradient
+// kernel (see ctc_grad_sorted_kernel) while the compute warps walk the lattice.
+constexpr float NEG = -1e30f;
+
+__device__ __forceinline__ void bar_sync_named(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+constexpr int SORT_EXTRA = 96;  // ints after the packed labels: seg[VP + 1] (+ padding)
+
+// Stable counting sort of the label positions of one utterance by symbol, by ONE warp.
+// packed[i] = symbol | slot << 8 (slot = position of label i in the symbol-sorted order),
+// seg[v] = first slot of symbol v, seg[VP] = L.  cnt: VP ints of scratch smem.
+__device__ __forceinline__ void sort_labels_by_symbol(const int32_t* __restrict__ lab, int L, int* __restrict__ packed,
+                                                      int* __restrict__ seg, int* cnt, int lane) {
+  cnt[lane] = 0;
+  cnt[lane + 32] = 0;
+  __syncwarp();
+  for (int i0 = 0; i0 < L; i0 += 32) {
+    const int i = i0 + lane;
+    const int v = i < L ? lab[i] : -1 - lane;  // (distinct dummies)
+    const unsigned same = __match_any_sync(0xffffffffu, v);
+    if (i < L) {
+      const int before = cnt[v];
+      packed[i] = v | ((before + __popc(same & ((1u << lane) - 1))) << 8);
+      __syncwarp(same);
+      if ((same >> lane) == 1u) cnt[v] = before + __popc(same);  // highest lane of the group
+    }
+    __syncwarp();
+  }
+  // exclusive prefix over the symbols (V <= 64: two per lane)
+  const int c0 = cnt[lane], c1 = cnt[lane + 32];
+  int inc0 = c0, inc1 = c1;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int u0 = __shfl_up_sync(0xffffffffu, inc0, o), u1 = __shfl_up_sync(0xffffffffu, inc1, o);
+    if (lane >= o) {
+      inc0 += u0;
+      inc1 += u1;
+    }
+  }
+  const int total0 = __shfl_sync(0xffffffffu, inc0, 31);
+  __syncwarp();
+  cnt[lane] = inc0 - c0;
+  cnt[lane + 32] = total0 + inc1 - c1;
+  seg[lane] = inc0 - c0;
+  seg[lane + 32] = total0 + inc1 - c1;
+  if (lane == 31) seg[VP] = total0 + inc1;
+  __syncwarp();
+  for (int i = lane; i < L; i += 32) {  // (each lane revisits the entries it wrote itself)
+    const int pk = packed[i];
+    packed[i] = (pk & 255) | (((pk >> 8) + cnt[pk & 255]) << 8);
+  }
+}
+
+template <int SPT, int K, int DIR>
+__device__ __forceinline__ void halo_walk(const float* lp_s, float* col, int col_stride, const float* lp_b, int P, int S,
+                                          int s0, int lane, int tid, int nthreads, const float (&skipb)[SPT],
+                                          const float (&onb)[SPT], const float* const (&em_ptr)[SPT], float* out,
+                                          ptrdiff_t out_step, unsigned st_mask) {
+  constexpr int HALO = 2 * K;
+  const bool owner = lane * SPT >= HALO;
+  auto issue_chunk = [&](int c) {
+    float* dst = const_cast<float*>(lp_s) + (c & 1) * CHUNK * VP;
+    for (int i = tid; i < CHUNK * (VP / 4); i += nthreads) {
+      const int r = i / (VP / 4), piece = i % (VP / 4);
+      const int tt = c * CHUNK + r;
+      if (tt < P) {
+        const int t = DIR ? (P - 1 - tt) : tt;
+        cp_async16(dst + r * VP + piece * 4, lp_b + static_cast<size_t>(t) * VP + piece * 4);
+      }
+    }
+    cp_async_commit();
+  };
+  issue_chunk(0);
+  issue_chunk(1);
+
+  float prev[SPT];
+  const float* ep[SPT];  // emission pointers of the current K-block's first row
+  // one step: prev -> prev; k = row within the block (an immediate offset in the unrolled full blocks)
+  auto step = [&](int k) {
+    const float left = __shfl_up_sync(0xffffffffu, prev[SPT - 1], 1);  // lane 0: own value, stays inside the halo
+    float cur[SPT];
+#pragma unroll
+    for (int i = 0; i < SPT; ++i) {
+      const float emb = fmaf(ep[i][k * VP], LOG2E, onb[i]);
+      const float a0 = prev[i];
+      const float a1 = i >= 1 ? prev[i - 1] : left;
+      float m, sum;
+      if (i & 1) {
+        const float a2 = (i >= 2 ? prev[i - 2] : left) + skipb[i];
+        const float hi = fmaxf(a0, a1), lo = fminf(a0, a1);
+        m = fmaxf(hi, a2);
+        const float md = fminf(hi, a2);  // {a0,a1,a2} \ {max} = {lo, md}
+        sum = (1.0f + ex2_approx(lo - m)) + ex2_approx(md - m);
+      } else {
+        m = fmaxf(a0, a1);
+        sum = 1.0f + ex2_approx(fminf(a0, a1) - m);
+      }
+      cur[i] = (m + emb) + lg2_approx(sum);
+    }
+    if (DIR == 0) {
+      if (st_mask) {
+        if constexpr (SPT == 2) {
+          *reinterpret_cast<float2*>(out) = make_float2(cur[0], cur[1]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < SPT; i += 4)
+            *reinterpret_cast<float4*>(out + i) = make_float4(cur[i], cur[i + 1], cur[i + 2], cur[i + 3]);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < SPT; ++i)
+        if ((st_mask >> i) & 1u) out[-i] = cur[i];
+    }
+    out += out_step;
+#pragma unroll
+    for (int i = 0; i < SPT; ++i) prev[i] = cur[i];
+  };
+
+  for (int t0 = 0; t0 < P; t0 += K) {
+    const int kb = t0 / K;
+    if ((t0 & (CHUNK - 1)) == 0) cp_async_wait<0>();  // the chunk issued one chunk ago has long landed
+    bar_sync_named(1, nthreads);  // owned states of block kb-1 published; chunk visible; ring slot free
+    if ((t0 & (CHUNK - 1)) == 0 && t0 > 0) issue_chunk(t0 / CHUNK + 1);
+    const float* pc = col + ((kb + 1) & 1) * col_stride + HALO + s0;
+#pragma unroll
+    for (int i = 0; i < SPT; ++i) prev[i] = pc[i];
+#pragma unroll
+    for (int i = 0; i < SPT; ++i) ep[i] = em_ptr[i] + (t0 & (2 * CHUNK - 1)) * VP;  // (a K-block never wraps the ring)
+    if (t0 + K <= P) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) step(k);
+    } else {
+      for (int k = 0; t0 + k < P; ++k) step(k);
+    }
+    if (owner) {
+      float* wc = col + (kb & 1) * col_stride + HALO + s0;
+#pragma unroll
+      for (int i = 0; i < SPT; ++i) wc[i] = prev[i];
+    }
+  }
+  cp_async_wait<0>();
+  bar_sync_named(1, nthreads);
+}
+
+template <int SPT, int K>
+__global__ void __launch_bounds__(1024)
+    ctc_lattice_halo_kernel(const float* __restrict__ logp, const int32_t* __restrict__ labels,
+                            const int32_t* __restrict__ input_len, const int32_t* __restrict__ label_len,
+                            float* __restrict__ loss, float* __restrict__ beta_loss,
+                            float* __restrict__ alpha, float* __restrict__ beta, int* __restrict__ sort_ws,
+                            int T, int L_max, int blank, int S_stride, int col_stride) {
+  static_assert(SPT % 2 == 0 && CHUNK % K == 0 && 2 * K < 32 * SPT, "slot parity / chunk alignment");
+  constexpr int HALO = 2 * K;
+  constexpr int OWN = 32 * SPT - HALO;
+  extern __shared__ uint8_t smem_raw[];
+  ptx::pdl_launch_dependents();
+  const int dir = blockIdx.x & 1;
+  const int b = blockIdx.x >> 1;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nthreads = blockDim.x - 32;  // compute threads; the last warp is the label sorter
+  const int L = label_len[b];
+  const int P = min(input_len[b], T);
+  const int S = 2 * L + 1;
+
+  float* lp_s = reinterpret_cast<float*>(smem_raw);  // ring of 2*CHUNK rows x VP
+  float* col = lp_s + 2 * CHUNK * VP;                // [2][col_stride], index = state + HALO
+
+  if (tid >= nthreads) {
+    // label sorter (does not take part in the walk's barriers); the labels are inputs of the step,
+    // not products of the kernel before, so it does not wait for it either
+    if (dir == 0) {
+      const int L_pad = (L_max + 31) & ~31;
+      int* packed = sort_ws + static_cast<size_t>(b) * (L_pad + SORT_EXTRA);
+      sort_labels_by_symbol(labels + static_cast<size_t>(b) * L_max, L, packed, packed + L_pad,
+                            reinterpret_cast<int*>(col + 2 * col_stride), lane);
+    }
+    return;
+  }
+
+  // virtual column of step -1: state 0 holds log 1, so the generic recurrence yields
+  // alpha_0(0) = em(0), alpha_0(1) = em(1), everything else "log 0"
+  for (int i = tid; i < 2 * col_stride; i += nthreads) col[i] = (i == col_stride + HALO) ? 0.0f : NEG;
+
+  const int s0 = warp * OWN - HALO + lane * SPT;  // even; negative inside warp 0's halo
+  float skipb[SPT], onb[SPT];
+  const float* em_ptr[SPT];
+  unsigned st_mask = 0;
+#pragma unroll
+  for (int i = 0; i < SPT; ++i) {
+    const int s = s0 + i;
+    const bool on = s >= 0 && s < S;
+    auto symbol = [&](int st) {  // extended label sequence in walking order (reversed for beta)
+      const int so = dir ? (S - 1 - st) : st;
+      return (so & 1) ? labels[static_cast<size_t>(b) * L_max + (so >> 1)] : blank;
+    };
+    const int e = (on && (i & 1)) ? symbol(s) : blank;
+    const bool skip = (on && (i & 1) && s >= 3) ? (e != symbol(s - 2)) : false;
+    skipb[i] = skip ? 0.0f : NEG;
+    onb[i] = on ? 0.0f : NEG;
+    em_ptr[i] = lp_s + e;
+    if (on && lane * SPT >= HALO) st_mask |= 1u << i;
+  }
+  ptx::pdl_wait();  // logp comes from the output_conv kernel right before
+
+  const float* lp_b = logp + static_cast<size_t>(b) * T * VP;
+  float* lat = (dir ? beta : alpha) + static_cast<size_t>(b) * T * S_stride;
+  if (dir == 0)
+    halo_walk<SPT, K, 0>(lp_s, col, col_stride, lp_b, P, S, s0, lane, tid, nthreads, skipb, onb, em_ptr, lat + s0,
+                         static_cast<ptrdiff_t>(S_stride), st_mask);
+  else
+    halo_walk<SPT, K, 1>(lp_s, col, col_stride, lp_b, P, S, s0, lane, tid, nthreads, skipb, onb, em_ptr,
+                         lat + static_cast<size_t>(P > 0 ? P - 1 : 0) * S_stride + (S - 1 - s0),
+                         -static_cast<ptrdiff_t>(S_stride), st_mask);
+
+  if (tid == 0) {
+    float l = INFINITY;
+    if (P > 0) {
+      const float* fc = col + (((P + K - 1) / K - 1) & 1) * col_stride + HALO;  // column of the last step
+      const float a = fc[S - 1];
+      const float c = S >= 2 ? fc[S - 2] : NEG;
+      const float m = fmaxf(a, c);
+      l = (m < -1e29f) ? INFINITY : -(m + log2f(exp2f(a - m) + exp2f(c - m))) * LN2;
+    }
+    if (dir == 0)
+      loss[b] = l;
+    else
+      beta_loss[b] = l;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Wavefront variant of the alpha/beta recurrence: no block-wide barrier inside the time loop.
 // (Opt-in experiment, SL_CTC_WAVE=1: correct, but slower than the barrier kernel — see the launcher.)
 //
@@ -496,6 +753,140 @@ __global__ void ctc_grad_kernel(const float* __restrict__ logp, const float* __r
   }
 }
 
+// Same gradient, without shared-memory atomics (the default).  The atomics of the kernel above
+// (one per label state and frame, ~2 cycles per lane on the SM's single atomic unit) cost more than
+// its HBM traffic.  Here each block first counting-sorts the label positions of its utterance by
+// symbol (stable, one warp, __match_any_sync per 32 labels): rank[i] = slot of label i in the
+// symbol-sorted order, seg[v] = first slot of symbol v.  Per frame a warp then writes the occupancy
+// term of every label state to its slot (plain conflict-light STS) and lane v adds up the
+// contiguous segment of symbol v in label order — deterministic, no atomics.
+__global__ void ctc_grad_sorted_kernel(const float* __restrict__ logp, const float* __restrict__ probs,
+                                       const int32_t* __restrict__ labels,
+                                       const int32_t* __restrict__ input_len,
+                                       const int32_t* __restrict__ label_len,
+                                       const float* __restrict__ loss, const float* __restrict__ alpha,
+                                       const float* __restrict__ beta, const int* __restrict__ sort_ws,
+                                       __nv_bfloat16* __restrict__ dz_packed, float* __restrict__ dz_f32,
+                                       float grad_scale, int T, int V, int L_max, int blank, int S_stride,
+                                       int planes, int frames_per_block) {
+  extern __shared__ uint8_t smem_raw[];
+  ptx::pdl_launch_dependents();
+  const int L_pad = (L_max + 31) & ~31;
+  int* packed = reinterpret_cast<int*>(smem_raw);  // [L_pad]  symbol | slot << 8
+  int* seg = packed + L_pad;                       // [SORT_EXTRA] first slot of each symbol
+  float* per_warp = reinterpret_cast<float*>(seg + SORT_EXTRA);  // [warps][VP + L_pad]
+  const int b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int L = label_len[b];
+  const int P = min(input_len[b], T);
+  const int S = 2 * L + 1;
+  const int t_begin = blockIdx.x * frames_per_block;
+  const int t_end = min(t_begin + frames_per_block, T);
+  ptx::pdl_wait();  // alpha / beta / loss / the sorted labels come from the lattice kernel right before
+  if (t_begin < P) {  // (block-uniform)
+    const int* src = sort_ws + static_cast<size_t>(b) * (L_pad + SORT_EXTRA);
+    for (int i = threadIdx.x; i < L; i += blockDim.x) packed[i] = src[i];
+    for (int i = threadIdx.x; i <= VP; i += blockDim.x) seg[i] = src[L_pad + i];
+    __syncthreads();
+  }
+  const float loss_b = loss[b];
+  const float loss2 = loss_b * LOG2E;
+  float* lp_row = per_warp + warp * (VP + L_pad);  // per-warp copy of the log-prob row (base 2)
+  float* xs = lp_row + VP;                         // [L_pad] occupancy terms in symbol-sorted order
+  const int row_elems = planes * 64;
+
+  for (int t = t_begin + warp; t < t_end; t += nwarps) {
+    const size_t ro = static_cast<size_t>(b) * T + t;
+    float dz[2] = {0.f, 0.f};  // symbols lane and lane + 32
+    if (t < P && isfinite(loss_b)) {
+      const float* lp_g = logp + ro * VP;
+      const float lp_mine[2] = {lp_g[lane], lp_g[lane + 32]};
+      float pv[2] = {0.f, 0.f};
+      if (lane < V) pv[0] = probs[ro * V + lane];
+      if (lane + 32 < V) pv[1] = probs[ro * V + lane + 32];
+      lp_row[lane] = lp_mine[0] * LOG2E;
+      lp_row[lane + 32] = lp_mine[1] * LOG2E;
+      __syncwarp();
+      const float4* a_row = reinterpret_cast<const float4*>(alpha + ro * S_stride);
+      const float4* b_row = reinterpret_cast<const float4*>(beta + ro * S_stride);
+      const float off_blank = loss2 - lp_row[blank];
+      float blank_acc = 0.f;
+      for (int base = 0; base < S; base += 512) {
+        // up to 4 passes of 128 states issued together (8 x 16-byte loads in flight per lane)
+        float4 av[4], bv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int s = base + j * 128 + lane * 4;
+          if (s < S) {
+            av[j] = __ldg(a_row + (s >> 2));
+            bv[j] = __ldg(b_row + (s >> 2));
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int s = base + j * 128 + lane * 4;
+          if (s < S) {
+            // s is a multiple of 4: states s, s+2 are blanks, s+1, s+3 carry labels s/2, s/2+1
+            // (one 8-byte read for both labels; past the last label it reads unused padding)
+            const int2 pk = *reinterpret_cast<const int2*>(packed + (s >> 1));
+            blank_acc += ex2_approx(av[j].x + bv[j].x + off_blank);
+            if (s + 1 < S) xs[pk.x >> 8] = ex2_approx(av[j].y + bv[j].y - lp_row[pk.x & 255] + loss2);
+            if (s + 2 < S) blank_acc += ex2_approx(av[j].z + bv[j].z + off_blank);
+            if (s + 3 < S) xs[pk.y >> 8] = ex2_approx(av[j].w + bv[j].w - lp_row[pk.y & 255] + loss2);
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) blank_acc += __shfl_xor_sync(0xffffffffu, blank_acc, o);
+      __syncwarp();
+      float dLdp[2] = {0.f, 0.f};
+      float dot = 0.f;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int v = lane + 32 * h;
+        if (v < V) {
+          float occ = blank_acc;
+          if (v != blank) {
+            const int k0 = seg[v], k1 = seg[v + 1];
+            float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+            int k = k0;
+            for (; k + 4 <= k1; k += 4) {
+              acc0 += xs[k];
+              acc1 += xs[k + 1];
+              acc2 += xs[k + 2];
+              acc3 += xs[k + 3];
+            }
+            for (; k < k1; ++k) acc0 += xs[k];
+            occ = (acc0 + acc1) + (acc2 + acc3);
+          }
+          const float g = expf(lp_mine[h]) - occ;
+          dLdp[h] = g / (pv[h] + 1e-8f);
+          dot += pv[h] * dLdp[h];
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) dz[h] = pv[h] * (dLdp[h] - dot) * grad_scale;
+      __syncwarp();
+    }
+    if (dz_f32 != nullptr) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+        if (lane + 32 * h < V) dz_f32[ro * V + lane + 32 * h] = dz[h];
+    }
+    if (dz_packed != nullptr) {
+      __nv_bfloat16* row = dz_packed + ro * row_elems;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const __nv_bfloat16 hi = __float2bfloat16_rn(dz[h]);
+        row[lane + 32 * h] = hi;
+        if (planes == 2) row[64 + lane + 32 * h] = __float2bfloat16_rn(dz[h] - __bfloat162float(hi));
+      }
+    }
+  }
+}
+
 // Greedy decode: one warp per utterance, 32 frames per iteration.  argmax (lowest index
 // wins ties), emit iff not blank and (merge_repeated ? differs from previous frame's
 // argmax : true); positions by ballot/popc prefix.
@@ -544,7 +935,10 @@ int ctc_s_stride(int L_max) { return ((2 * L_max + 1) + 31) & ~31; }
 
 size_t ctc_workspace_bytes(int B, int T, int L_max) {
   const size_t lat = static_cast<size_t>(B) * T * ctc_s_stride(L_max) * sizeof(float);
-  return 2 * lat + 256 + static_cast<size_t>(B) * sizeof(float);
+  // alpha | beta | beta_loss[B] (256-byte slot granularity) | per utterance: symbol-sorted label slots + segments
+  const size_t bl = (static_cast<size_t>(B) * sizeof(float) + 255) & ~static_cast<size_t>(255);
+  const size_t sort = static_cast<size_t>(B) * (((L_max + 31) & ~31) + SORT_EXTRA) * sizeof(int);
+  return 2 * lat + bl + sort + 256;
 }
 
 int ctc_loss_launch(const float* logp, const float* probs, const int32_t* labels,
@@ -561,27 +955,59 @@ int ctc_loss_launch(const float* logp, const float* probs, const int32_t* labels
   float* alpha = reinterpret_cast<float*>(workspace);
   float* beta = alpha + lat;
   float* beta_loss = beta + lat;
+  int* sort_ws = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(beta_loss) +
+                                        ((static_cast<size_t>(B) * sizeof(float) + 255) & ~static_cast<size_t>(255)));
 
   const int S_max = 2 * L_max + 1;
+  SL_REQUIRE(S_max <= 4096, "label too long (max 2047 characters)");
+  const char* legacy_env = std::getenv("SL_CTC_LEGACY");  // 1: one barrier per step, 2: wavefront (experiments)
+  const int legacy = legacy_env ? std::atoi(legacy_env) : 0;
+  if (legacy == 0) {
+    // halo-blocked kernel: (states per lane, steps per barrier); owned states per warp = 32*SPT - 2K
+    int spt = S_max <= 8 * 48 ? 2 : (S_max <= 31 * 112 ? 4 : 8);
+    int kk = 8;
+    if (const char* e = std::getenv("SL_CTC_SPT")) spt = std::atoi(e);  // tuning aids
+    if (const char* e = std::getenv("SL_CTC_K")) kk = std::atoi(e);
+    const int own = 32 * spt - 2 * kk;
+    SL_REQUIRE(own > 0, "SL_CTC_SPT / SL_CTC_K combination not built");
+    const int nw = (S_max + own - 1) / own;
+    SL_REQUIRE(nw <= 31, "SL_CTC_SPT too small for this label length");  // + the label-sorter warp
+    const int col_stride = ((nw * own + 2 * kk) + 3) & ~3;
+    const size_t smem = (2 * CHUNK * VP + 2 * col_stride + VP) * sizeof(float);
+    bool launched = false;
+#define SL_LAUNCH_HALO(SPT, KK)                                                                     \
+  if (!launched && spt == SPT && kk == KK) {                                                        \
+    if (smem > 48 * 1024)                                                                           \
+      SL_CUDA(cudaFuncSetAttribute(ctc_lattice_halo_kernel<SPT, KK>,                                \
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); \
+    SL_CUDA(launch_pdl(PDL_CTC, ctc_lattice_halo_kernel<SPT, KK>, dim3(2 * B), dim3((nw + 1) * 32), smem, stream, \
+                       logp, labels, input_len, label_len, loss, beta_loss, alpha, beta, sort_ws, T, L_max, blank, \
+                       S_stride, col_stride));                                                      \
+    launched = true;                                                                                \
+  }
+    SL_LAUNCH_HALO(2, 4)
+    SL_LAUNCH_HALO(2, 8)
+    SL_LAUNCH_HALO(2, 16)
+    SL_LAUNCH_HALO(4, 8)
+    SL_LAUNCH_HALO(4, 16)
+    SL_LAUNCH_HALO(8, 8)
+    SL_LAUNCH_HALO(8, 16)
+#undef SL_LAUNCH_HALO
+    SL_REQUIRE(launched, "SL_CTC_SPT / SL_CTC_K combination not built");
+    SL_CUDA(cudaGetLastError());
+  } else {
   // one state per thread while the lattice fits a CTA (measured: 0.149 / 0.166 / 0.176 ms for 1 / 2 / 4
   // states per thread at S = 301: more warps hide the dependent-instruction latency better)
   int spt = S_max <= 1024 ? 1 : 2;
   if (S_max > 2048) spt = 4;
-  if (const char* e = std::getenv("SL_CTC_SPT")) {  // tuning aid: states per thread (1, 2 or 4)
-    const int v = std::atoi(e);
-    if ((v == 1 || v == 2 || v == 4) && (S_max + v - 1) / v <= 1024) spt = v;
-  }
-  SL_REQUIRE(S_max <= 4096, "label too long (max 2047 characters)");
   int threads = ((S_max + spt - 1) / spt + 31) & ~31;
   if (threads < 64) threads = 64;
-  const char* wave_env = std::getenv("SL_CTC_WAVE");
   const int wspt = S_max <= 31 * 64 ? 2 : 4;  // wavefront kernel: 2 states per lane (4 beyond 1984 states)
   const int n_compute = (S_max + 32 * wspt - 1) / (32 * wspt);
   // Measured on B200 (B=64, P=625, S=301): the wavefront kernel needs 0.21 ms, the block-barrier
-  // kernel below 0.11 ms — a lone warp per scheduler executes its ~160 dependent instructions per
-  // step at ~4 cycles each, while the barrier version interleaves warps.  The wavefront variant
-  // therefore stays opt-in (SL_CTC_WAVE=1) as a documented experiment.
-  if (wave_env && std::atoi(wave_env) == 1 && n_compute <= 31) {  // + one loader warp <= 1024 threads
+  // kernel 0.11 ms — a lone warp per scheduler executes its ~160 dependent instructions per
+  // step at ~4 cycles each, while the barrier version interleaves warps.
+  if (legacy == 2 && n_compute <= 31) {  // + one loader warp <= 1024 threads
     const int wthreads = (n_compute + 1) * 32;
     const size_t wsmem = LP_RING * VP * sizeof(float) + static_cast<size_t>(n_compute) * EDGE_RING * sizeof(uint4) +
                          static_cast<size_t>(n_compute) * 32 * wspt * sizeof(float) + (n_compute + 1) * sizeof(int);
@@ -615,17 +1041,32 @@ int ctc_loss_launch(const float* logp, const float* probs, const int32_t* labels
 #undef SL_LAUNCH_AB
   SL_CUDA(cudaGetLastError());
   }
+  }
 
   if (dlogits_packed != nullptr || dlogits_f32 != nullptr) {
     SL_REQUIRE(probs != nullptr, "gradient needs the softmax probabilities");
-    const int frames_per_block = 16;  // 2 frames per warp: many short, independent chains in flight
+    int frames_per_block = 16;  // 2 frames per warp: many short, independent chains in flight
+    if (const char* e = std::getenv("SL_CTC_GRAD_FPB")) frames_per_block = std::max(1, std::atoi(e));  // tuning aid
     const int warps = 8;
     dim3 grid((T + frames_per_block - 1) / frames_per_block, B);
-    const size_t gsmem = ((L_max + 31) & ~31) * sizeof(int) + warps * 2 * VP * sizeof(float);
-    SL_CUDA(launch_pdl(PDL_CTC, ctc_grad_kernel, grid, dim3(warps * 32), gsmem, stream, logp, probs, labels, input_len,
-                       label_len, static_cast<const float*>(loss), static_cast<const float*>(alpha),
-                       static_cast<const float*>(beta), reinterpret_cast<__nv_bfloat16*>(dlogits_packed),
-                       dlogits_f32, grad_scale, T, V, L_max, blank, S_stride, planes, frames_per_block));
+    const int L_pad = (L_max + 31) & ~31;
+    if (legacy == 0) {
+      const size_t gsmem = (L_pad + SORT_EXTRA) * sizeof(int) + static_cast<size_t>(warps) * (VP + L_pad) * sizeof(float);
+      if (gsmem > 48 * 1024)
+        SL_CUDA(cudaFuncSetAttribute(ctc_grad_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(gsmem)));
+      SL_CUDA(launch_pdl(PDL_CTC, ctc_grad_sorted_kernel, grid, dim3(warps * 32), gsmem, stream, logp, probs, labels,
+                         input_len, label_len, static_cast<const float*>(loss), static_cast<const float*>(alpha),
+                         static_cast<const float*>(beta), static_cast<const int*>(sort_ws),
+                         reinterpret_cast<__nv_bfloat16*>(dlogits_packed), dlogits_f32, grad_scale, T, V, L_max, blank,
+                         S_stride, planes, frames_per_block));
+    } else {
+      const size_t gsmem = L_pad * sizeof(int) + warps * 2 * VP * sizeof(float);
+      SL_CUDA(launch_pdl(PDL_CTC, ctc_grad_kernel, grid, dim3(warps * 32), gsmem, stream, logp, probs, labels,
+                         input_len, label_len, static_cast<const float*>(loss), static_cast<const float*>(alpha),
+                         static_cast<const float*>(beta), reinterpret_cast<__nv_bfloat16*>(dlogits_packed),
+                         dlogits_f32, grad_scale, T, V, L_max, blank, S_stride, planes, frames_per_block));
+    }
   }
   return 0;
 }
