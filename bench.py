@@ -69,7 +69,15 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def mark(self):
+        """Start of the timed region: nvidia-smi takes ~0.2 s to produce its first line, so the sampler is
+        started before the warm-up and only the lines read from here on are counted."""
+        deadline = time.perf_counter() + 3.0
+        while self.proc is not None and not self.lines and time.perf_counter() < deadline:
+            time.sleep(0.02)  # (before the timed region starts)
+        self.t_mark = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
@@ -81,7 +89,10 @@ class ClockSampler:
             self.proc.kill()
         sm, sm_max, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
+        t_mark = getattr(self, "t_mark", 0.0)
+        for stamp, line in self.lines:
+            if stamp < t_mark:
+                continue
             parts = [p.strip() for p in line.split(",")]
             if len(parts) < 8:
                 continue
@@ -242,12 +253,14 @@ def run_ours(args):
     # ---- device-resident arm ----
     ws = tower.upload(host_x)
     tower.set_labels(ws, inputs[names.label_batch], inputs[names.prediction_lengths], inputs[names.label_lengths])
+    sampler = ClockSampler(dp.local_rank) if rank == 0 else None
     for _ in range(args.warmup):
         device_step(ws)
     torch.cuda.synchronize()
     dp.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(dp.local_rank) if rank == 0 else None
+    if sampler:
+        sampler.mark()
     launches_before = tower.launches
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     host_t0 = time.perf_counter()
@@ -389,7 +402,7 @@ def run_ours(args):
 def main():
     parser = argparse.ArgumentParser()
     parser.add_argument("--gpus", type=int, default=1)
-    parser.add_argument("--steps", type=int, default=20)
+    parser.add_argument("--steps", type=int, default=40)
     parser.add_argument("--warmup", type=int, default=5)
     parser.add_argument("--impl", default="ours", choices=["ours", "reference"])
     parser.add_argument("--workload", default="full", choices=sorted(WORKLOADS))
