@@ -55,20 +55,39 @@ inline int pdl_mask() {  // SL_PDL: bitmask of PdlClass values (tuning aid)
   }
   return v;
 }
+struct ClusterX {  // optional thread-block-cluster width of a launch (1 = no cluster attribute)
+  int x;
+};
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(int pdl_class, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
-                              cudaStream_t stream, Args&&... args) {
+inline cudaError_t launch_pdl_cluster(int pdl_class, ClusterX cluster, void (*kernel)(KArgs...), dim3 grid, dim3 block,
+                                      size_t smem, cudaStream_t stream, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (pdl_mask() & pdl_class) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (cluster.x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = static_cast<unsigned>(cluster.x);
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = (pdl_mask() & pdl_class) ? 1 : 0;
+  cfg.numAttrs = n;
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(int pdl_class, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t stream, Args&&... args) {
+  return launch_pdl_cluster(pdl_class, ClusterX{1}, kernel, grid, block, smem, stream, std::forward<Args>(args)...);
 }
 }  // namespace sl
 
@@ -260,6 +279,11 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
   return r;
 }
 __device__ __forceinline__ void cluster_sync_all() {

@@ -259,13 +259,22 @@ __device__ __forceinline__ void sort_labels_by_symbol(const int32_t* __restrict_
   }
 }
 
-template <int SPT, int K, int DIR>
-__device__ __forceinline__ void halo_walk(const float* lp_s, float* col, int col_stride, const float* lp_b, int P, int S,
-                                          int s0, int lane, int tid, int nthreads, const float (&skipb)[SPT],
+// push_rank >= 0 (cluster mode, last compute warp of a CTA): the lanes holding the warp's last 2K
+// owned states also store them into the halo slots of the next CTA of the cluster (DSMEM).
+template <int SPT, int K, int DIR, bool CL>
+__device__ __forceinline__ void halo_walk(const float* lp_s, float* col, int col_stride, const float* lp_b, int P,
+                                          int ls0, int lane, int tid, int nthreads, const float (&skipb)[SPT],
                                           const float (&onb)[SPT], const float* const (&em_ptr)[SPT], float* out,
-                                          ptrdiff_t out_step, unsigned st_mask) {
+                                          ptrdiff_t out_step, unsigned st_mask, int push_rank, int own_per_cta) {
   constexpr int HALO = 2 * K;
   const bool owner = lane * SPT >= HALO;
+  const bool pusher = CL && push_rank >= 0 && lane * SPT >= 32 * SPT - HALO;
+  auto barrier = [&]() {
+    if constexpr (CL)
+      ptx::cluster_sync_all();
+    else
+      bar_sync_named(1, nthreads);
+  };
   auto issue_chunk = [&](int c) {
     float* dst = const_cast<float*>(lp_s) + (c & 1) * CHUNK * VP;
     for (int i = tid; i < CHUNK * (VP / 4); i += nthreads) {
@@ -328,9 +337,9 @@ __device__ __forceinline__ void halo_walk(const float* lp_s, float* col, int col
   for (int t0 = 0; t0 < P; t0 += K) {
     const int kb = t0 / K;
     if ((t0 & (CHUNK - 1)) == 0) cp_async_wait<0>();  // the chunk issued one chunk ago has long landed
-    bar_sync_named(1, nthreads);  // owned states of block kb-1 published; chunk visible; ring slot free
+    barrier();  // owned states of block kb-1 published; chunk visible; ring slot free
     if ((t0 & (CHUNK - 1)) == 0 && t0 > 0) issue_chunk(t0 / CHUNK + 1);
-    const float* pc = col + ((kb + 1) & 1) * col_stride + HALO + s0;
+    const float* pc = col + ((kb + 1) & 1) * col_stride + HALO + ls0;
 #pragma unroll
     for (int i = 0; i < SPT; ++i) prev[i] = pc[i];
 #pragma unroll
@@ -342,16 +351,23 @@ __device__ __forceinline__ void halo_walk(const float* lp_s, float* col, int col
       for (int k = 0; t0 + k < P; ++k) step(k);
     }
     if (owner) {
-      float* wc = col + (kb & 1) * col_stride + HALO + s0;
+      float* wc = col + (kb & 1) * col_stride + HALO + ls0;
 #pragma unroll
       for (int i = 0; i < SPT; ++i) wc[i] = prev[i];
+      if (pusher) {
+        // same buffer, local index of the next CTA: its state base is own_per_cta further on
+        const uint32_t remote = ptx::mapa_u32(ptx::smem_u32(wc - own_per_cta), static_cast<uint32_t>(push_rank));
+#pragma unroll
+        for (int i = 0; i < SPT; ++i)
+          asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote + 4u * i), "f"(prev[i]) : "memory");
+      }
     }
   }
   cp_async_wait<0>();
-  bar_sync_named(1, nthreads);
+  barrier();
 }
 
-template <int SPT, int K>
+template <int SPT, int K, bool CL>
 __global__ void __launch_bounds__(1024)
     ctc_lattice_halo_kernel(const float* __restrict__ logp, const int32_t* __restrict__ labels,
                             const int32_t* __restrict__ input_len, const int32_t* __restrict__ label_len,
@@ -363,34 +379,45 @@ __global__ void __launch_bounds__(1024)
   constexpr int OWN = 32 * SPT - HALO;
   extern __shared__ uint8_t smem_raw[];
   ptx::pdl_launch_dependents();
-  const int dir = blockIdx.x & 1;
-  const int b = blockIdx.x >> 1;
+  // cluster mode: the CTAs of a cluster split the warps (= the state range) of one (utterance, direction)
+  const int crank = CL ? static_cast<int>(ptx::cluster_ctarank()) : 0;
+  const int csize = CL ? static_cast<int>(ptx::cluster_nctarank()) : 1;
+  const int unit = blockIdx.x / csize;
+  const int dir = unit & 1;
+  const int b = unit >> 1;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nthreads = blockDim.x - 32;  // compute threads; the last warp is the label sorter
+  const int own_per_cta = (nthreads >> 5) * OWN;
   const int L = label_len[b];
   const int P = min(input_len[b], T);
   const int S = 2 * L + 1;
 
   float* lp_s = reinterpret_cast<float*>(smem_raw);  // ring of 2*CHUNK rows x VP
-  float* col = lp_s + 2 * CHUNK * VP;                // [2][col_stride], index = state + HALO
+  float* col = lp_s + 2 * CHUNK * VP;                // [2][col_stride], index = state - crank*own_per_cta + HALO
 
   if (tid >= nthreads) {
-    // label sorter (does not take part in the walk's barriers); the labels are inputs of the step,
-    // not products of the kernel before, so it does not wait for it either
-    if (dir == 0) {
+    // label sorter (does not take part in the walk's CTA barriers); the labels are inputs of the
+    // step, not products of the kernel before, so it does not wait for it either
+    if (dir == 0 && crank == 0) {
       const int L_pad = (L_max + 31) & ~31;
       int* packed = sort_ws + static_cast<size_t>(b) * (L_pad + SORT_EXTRA);
       sort_labels_by_symbol(labels + static_cast<size_t>(b) * L_max, L, packed, packed + L_pad,
                             reinterpret_cast<int*>(col + 2 * col_stride), lane);
+    }
+    if constexpr (CL) {  // cluster barriers count every thread: one per K-block and the final one
+      for (int t0 = 0; t0 < P; t0 += K) ptx::cluster_sync_all();
+      ptx::cluster_sync_all();
     }
     return;
   }
 
   // virtual column of step -1: state 0 holds log 1, so the generic recurrence yields
   // alpha_0(0) = em(0), alpha_0(1) = em(1), everything else "log 0"
-  for (int i = tid; i < 2 * col_stride; i += nthreads) col[i] = (i == col_stride + HALO) ? 0.0f : NEG;
+  for (int i = tid; i < 2 * col_stride; i += nthreads)
+    col[i] = (i == col_stride + HALO && crank == 0) ? 0.0f : NEG;
 
-  const int s0 = warp * OWN - HALO + lane * SPT;  // even; negative inside warp 0's halo
+  const int ls0 = warp * OWN - HALO + lane * SPT;  // state index relative to this CTA's first owned state
+  const int s0 = crank * own_per_cta + ls0;        // even; negative inside the very first halo
   float skipb[SPT], onb[SPT];
   const float* em_ptr[SPT];
   unsigned st_mask = 0;
@@ -413,18 +440,20 @@ __global__ void __launch_bounds__(1024)
 
   const float* lp_b = logp + static_cast<size_t>(b) * T * VP;
   float* lat = (dir ? beta : alpha) + static_cast<size_t>(b) * T * S_stride;
+  const int push_rank = (CL && crank + 1 < csize && warp == (nthreads >> 5) - 1) ? crank + 1 : -1;
   if (dir == 0)
-    halo_walk<SPT, K, 0>(lp_s, col, col_stride, lp_b, P, S, s0, lane, tid, nthreads, skipb, onb, em_ptr, lat + s0,
-                         static_cast<ptrdiff_t>(S_stride), st_mask);
+    halo_walk<SPT, K, 0, CL>(lp_s, col, col_stride, lp_b, P, ls0, lane, tid, nthreads, skipb, onb, em_ptr, lat + s0,
+                             static_cast<ptrdiff_t>(S_stride), st_mask, push_rank, own_per_cta);
   else
-    halo_walk<SPT, K, 1>(lp_s, col, col_stride, lp_b, P, S, s0, lane, tid, nthreads, skipb, onb, em_ptr,
-                         lat + static_cast<size_t>(P > 0 ? P - 1 : 0) * S_stride + (S - 1 - s0),
-                         -static_cast<ptrdiff_t>(S_stride), st_mask);
+    halo_walk<SPT, K, 1, CL>(lp_s, col, col_stride, lp_b, P, ls0, lane, tid, nthreads, skipb, onb, em_ptr,
+                             lat + static_cast<size_t>(P > 0 ? P - 1 : 0) * S_stride + (S - 1 - s0),
+                             -static_cast<ptrdiff_t>(S_stride), st_mask, push_rank, own_per_cta);
 
-  if (tid == 0) {
+  // the CTA owning the last state reports the loss (state S-2 is its own or sits in its halo)
+  if (tid == 0 && (S - 1) / own_per_cta == crank) {
     float l = INFINITY;
     if (P > 0) {
-      const float* fc = col + (((P + K - 1) / K - 1) & 1) * col_stride + HALO;  // column of the last step
+      const float* fc = col + (((P + K - 1) / K - 1) & 1) * col_stride + HALO - crank * own_per_cta;
       const float a = fc[S - 1];
       const float c = S >= 2 ? fc[S - 2] : NEG;
       const float m = fmaxf(a, c);
@@ -964,25 +993,46 @@ int ctc_loss_launch(const float* logp, const float* probs, const int32_t* labels
   const int legacy = legacy_env ? std::atoi(legacy_env) : 0;
   if (legacy == 0) {
     // halo-blocked kernel: (states per lane, steps per barrier); owned states per warp = 32*SPT - 2K
-    int spt = S_max <= 8 * 48 ? 2 : (S_max <= 31 * 112 ? 4 : 8);
+    int spt = S_max <= 8 * 48 ? 2 : 4;
     int kk = 8;
-    if (const char* e = std::getenv("SL_CTC_SPT")) spt = std::atoi(e);  // tuning aids
+    const char* spt_env = std::getenv("SL_CTC_SPT");  // tuning aids
+    if (spt_env) spt = std::atoi(spt_env);
     if (const char* e = std::getenv("SL_CTC_K")) kk = std::atoi(e);
-    const int own = 32 * spt - 2 * kk;
-    SL_REQUIRE(own > 0, "SL_CTC_SPT / SL_CTC_K combination not built");
-    const int nw = (S_max + own - 1) / own;
-    SL_REQUIRE(nw <= 31, "SL_CTC_SPT too small for this label length");  // + the label-sorter warp
+    int own = 0, nw = 0, cluster = 1;
+    for (;;) {
+      own = 32 * spt - 2 * kk;
+      SL_REQUIRE(own > 0, "SL_CTC_SPT / SL_CTC_K combination not built");
+      const int nw_all = (S_max + own - 1) / own;
+      // few long utterances: split the warps of one lattice over a cluster of CTAs (halo exchange through
+      // DSMEM, cluster barrier per K-block) so that the whole GPU works on the recurrence
+      // (a cluster barrier costs ~1500 cycles against ~50 for a CTA barrier — measured — so clusters pay only
+      // for lattices of more than a few warps, and run with K = 32: 16 x 60 s, S = 1801 on one B200 took
+      // 1.32 ms without clusters, 0.77 / 0.58 / 0.48 ms with clusters of 4 and K = 8 / 16 / 32)
+      cluster = 1;
+      if (spt >= 4)
+        while (cluster < 8 && 2 * B * cluster * 2 <= 148 && nw_all >= 4 * cluster) cluster *= 2;
+      if (const char* e = std::getenv("SL_CTC_CLUSTER")) cluster = std::max(1, std::atoi(e));
+      if (cluster > 1 && kk == 8 && !std::getenv("SL_CTC_K")) {
+        kk = 32;
+        continue;
+      }
+      SL_REQUIRE(cluster == 1 || cluster == 2 || cluster == 4 || cluster == 8, "SL_CTC_CLUSTER must be 1, 2, 4 or 8");
+      nw = (nw_all + cluster - 1) / cluster;  // compute warps per CTA (+ the label-sorter warp <= 32)
+      if (nw <= 31 || spt_env || spt >= 8) break;
+      spt *= 2;
+    }
+    SL_REQUIRE(nw <= 31, "SL_CTC_SPT too small for this label length");
     const int col_stride = ((nw * own + 2 * kk) + 3) & ~3;
     const size_t smem = (2 * CHUNK * VP + 2 * col_stride + VP) * sizeof(float);
     bool launched = false;
 #define SL_LAUNCH_HALO(SPT, KK)                                                                     \
   if (!launched && spt == SPT && kk == KK) {                                                        \
+    auto kern = cluster > 1 ? ctc_lattice_halo_kernel<SPT, KK, true> : ctc_lattice_halo_kernel<SPT, KK, false>; \
     if (smem > 48 * 1024)                                                                           \
-      SL_CUDA(cudaFuncSetAttribute(ctc_lattice_halo_kernel<SPT, KK>,                                \
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); \
-    SL_CUDA(launch_pdl(PDL_CTC, ctc_lattice_halo_kernel<SPT, KK>, dim3(2 * B), dim3((nw + 1) * 32), smem, stream, \
-                       logp, labels, input_len, label_len, loss, beta_loss, alpha, beta, sort_ws, T, L_max, blank, \
-                       S_stride, col_stride));                                                      \
+      SL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); \
+    SL_CUDA(launch_pdl_cluster(PDL_CTC, ClusterX{cluster}, kern, dim3(2 * B * cluster), dim3((nw + 1) * 32), smem, \
+                               stream, logp, labels, input_len, label_len, loss, beta_loss, alpha, beta, sort_ws, T, \
+                               L_max, blank, S_stride, col_stride));                                \
     launched = true;                                                                                \
   }
     SL_LAUNCH_HALO(2, 4)
@@ -990,6 +1040,8 @@ int ctc_loss_launch(const float* logp, const float* probs, const int32_t* labels
     SL_LAUNCH_HALO(2, 16)
     SL_LAUNCH_HALO(4, 8)
     SL_LAUNCH_HALO(4, 16)
+    SL_LAUNCH_HALO(4, 32)
+    SL_LAUNCH_HALO(8, 32)
     SL_LAUNCH_HALO(8, 8)
     SL_LAUNCH_HALO(8, 16)
 #undef SL_LAUNCH_HALO
