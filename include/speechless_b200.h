@@ -169,6 +169,22 @@ int sl_ctc_greedy_decode(const float* probs, const int32_t* input_len,
                          int32_t* out, int32_t* out_len, int B, int T, int V,
                          int blank, int merge_repeated, void* stream);
 
+/* ---- beam-search decode (replaces tf.nn.ctc_beam_search_decoder, net.py:444-451, stock scorer) ---- */
+/* scores (B,T,V) fp32: softmax probabilities (inputs_are_probs = 1: log(p + 1e-8) is taken first, as
+ * net.py:430 does) or unnormalised log-scores; every frame is log-softmax-normalised like TF's
+ * CTCBeamSearchDecoder::Step.  Prefix beam search of width beam_width (1..128, beam_width * V <= 4096);
+ * the top_paths best prefixes of utterance b go to out[b, p, :] (int32, -1 padded to T), out_len[b, p],
+ * out_logp[b, p] (log P(prefix | x)), best first.  merge_repeated follows TF: it only drops, from the
+ * OUTPUT, a label equal to its predecessor ("A A _ A A" -> [0] with, [0, 0] without; reference
+ * test_ctc_decoders.py:38-39) — the reference calls it with merge_repeated = 0 (net.py:441-447).
+ * The KenLM scorer of the patched TensorFlow fork (net.py:420-422) is not part of this entry point. */
+size_t sl_ctc_beam_search_workspace_bytes(int B, int T, int beam_width);
+int sl_ctc_beam_search_decode(const float* scores, const int32_t* input_len, int32_t* out,
+                              int32_t* out_len, float* out_logp, int B, int T, int V, int blank,
+                              int beam_width, int top_paths, int merge_repeated,
+                              int inputs_are_probs, void* workspace, size_t workspace_bytes,
+                              void* stream);
+
 /* ---- audio front end (replaces the librosa pipeline of labeled_example.py:99-140) ---- */
 /* audio (B, audio_stride) fp32 raw samples (sample_counts[b] valid each) ->
  * out[b, t, m] for t < 1 + sample_counts[b]/hop: mel projection (mel_t = transposed Slaney

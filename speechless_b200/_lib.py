@@ -42,6 +42,9 @@ SIGNATURES = {
                             c_float, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "sl_ctc_greedy_decode": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                      c_void_p]),
+    "sl_ctc_beam_search_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "sl_ctc_beam_search_decode": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                          c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "sl_spectrogram": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                c_void_p]),
     "sl_z_normalize": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),

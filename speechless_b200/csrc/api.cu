@@ -43,6 +43,9 @@ int ctc_loss_launch(const float*, const float*, const int32_t*, const int32_t*, 
                     cudaStream_t);
 int ctc_greedy_launch(const float*, const int32_t*, int32_t*, int32_t*, int, int, int, int, int,
                       cudaStream_t);
+size_t beam_search_workspace_bytes(int B, int T, int beam_width);
+int beam_search_launch(const float*, const int32_t*, int32_t*, int32_t*, float*, int, int, int, int, int, int, int,
+                       int, void*, size_t, cudaStream_t);
 
 static int round64(int c) { return (c + 63) & ~63; }
 static int dbg_mode() {
@@ -617,6 +620,21 @@ int sl_ctc_greedy_decode(const float* probs, const int32_t* input_len, int32_t* 
   SL_REQUIRE(B > 0 && T > 0 && V > 0, "bad shape");
   return ctc_greedy_launch(probs, input_len, out, out_len, B, T, V, blank, merge_repeated,
                            static_cast<cudaStream_t>(stream));
+}
+
+size_t sl_ctc_beam_search_workspace_bytes(int B, int T, int beam_width) {
+  return beam_search_workspace_bytes(B, T, beam_width < 1 ? 1 : beam_width);
+}
+
+int sl_ctc_beam_search_decode(const float* scores, const int32_t* input_len, int32_t* out, int32_t* out_len,
+                              float* out_logp, int B, int T, int V, int blank, int beam_width, int top_paths,
+                              int merge_repeated, int inputs_are_probs, void* workspace, size_t workspace_bytes,
+                              void* stream) {
+  SL_REQUIRE(scores && input_len && out && out_len && out_logp && workspace, "null pointer");
+  SL_REQUIRE(B > 0 && T > 0 && V > 0, "bad shape");
+  return beam_search_launch(scores, input_len, out, out_len, out_logp, B, T, V, blank, beam_width, top_paths,
+                            merge_repeated, inputs_are_probs, workspace, workspace_bytes,
+                            static_cast<cudaStream_t>(stream));
 }
 
 int sl_adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1,

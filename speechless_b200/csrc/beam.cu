@@ -1,0 +1,354 @@
+// beam.cu — CTC prefix beam search, one CTA per utterance.
+//
+// Replaces tf.nn.ctc_beam_search_decoder as the reference calls it (net.py:444-451) with the STOCK
+// scorer; the KenLM scorer lives in a patched TensorFlow fork (net.py:420-422) that is not in the
+// reference tree.  Semantics restated from TensorFlow's ctc_beam_search.h (see
+// oracle/beam_search_oracle.py for the CPU restatement and its pinning):
+//   * the beam holds up to W label prefixes, each with log P(prefix, last frame blank) `pb`,
+//     log P(prefix, last frame = its last label) `pl` and their log-sum `tot`;
+//   * per frame every active prefix i is continued
+//       pl' = logaddexp(pl, parent active ? (label_i == label_parent ? pb_parent : tot_parent) : 0) + lp[label_i]
+//       pb' = tot + lp[blank],
+//     and spawns the children (i, c) that are not already in the beam with
+//       pl = lp[c] + (c == label_i ? pb_i : tot_i),  pb = 0;
+//     the W best of {continued prefixes} U {children} survive.  (TF's Step additionally wipes a prefix
+//     that is displaced before the child loop reaches its parent, which silently drops that prefix's
+//     own children for the frame; this order-dependent side effect is NOT reproduced — see
+//     `tf_deactivation` in oracle/beam_search_oracle.py.  It cannot occur for beam_width = 1.)
+//   * merge_repeated only post-processes the output (a label equal to its successor's is dropped),
+//     which is what makes "A A _ A A" decode to [0] / [0, 0] (reference test_ctc_decoders.py:38-39).
+//
+// Data layout: the beam lives in shared memory (two generations of W slots); the W*V candidate scores
+// of a frame stay in registers (4 per thread) as order-preserving integers, the score of the W-th best
+// is found by a bit-wise binary search (33 block-wide counts; a full bitonic sort of 4096 64-bit keys
+// in shared memory was measured at 58 us per frame, this is ~10x less), the <= W survivors are ranked
+// by counting; prefixes are nodes (parent, label) of a tree in global
+// memory (a fresh node id = 1 + frame*W + slot, so no allocator is needed), walked back once at the
+// end.  A prefix keeps its node when it drops out of the beam and comes back later — TF keeps the
+// BeamEntry object in its tree, and its surviving children still point at it — so (parent node, label)
+// -> node is kept in an open-addressing hash table in global memory, and parent slots are re-derived
+// from node ids every frame.
+#include "common.cuh"
+
+namespace sl {
+
+namespace {
+
+constexpr int BS_THREADS = 1024;
+constexpr int BS_MAX_W = 128;
+constexpr int BS_MAX_CAND = 4096;  // beam_width * V candidates per frame
+constexpr int BS_VP = 64;
+
+__device__ __forceinline__ uint32_t float_to_ordered(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ordered_to_float(uint32_t o) {
+  return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+__device__ __forceinline__ float logaddexp(float a, float b) {
+  const float m = fmaxf(a, b);
+  if (m == -INFINITY) return -INFINITY;
+  return m + log1pf(expf(fminf(a, b) - m));
+}
+
+struct BeamGen {  // one generation of the beam (slots sorted best first)
+  int node[BS_MAX_W];
+  int label[BS_MAX_W];
+  int pslot[BS_MAX_W];  // slot of the parent prefix in the same generation, -1 = not in the beam
+  float pb[BS_MAX_W];
+  float pl[BS_MAX_W];
+  float tot[BS_MAX_W];
+};
+
+struct BeamSmem {
+  BeamGen gen[2];
+  float pbn[BS_MAX_W], pln[BS_MAX_W], totn[BS_MAX_W];  // continued prefixes of the current frame
+  unsigned long long child_active[BS_MAX_W];           // bit c: child (slot, c) is already in the beam
+  unsigned long long selected[BS_MAX_W];               // keys of the survivors of a frame, unordered
+  int parent_node[BS_MAX_W];                           // node id of the parent of next-generation slot r
+  float lp[BS_VP];
+  int counter[3];  // rotating block-wide counters of the selection
+  int n_selected;
+  int n_active;
+};
+
+constexpr int BS_CPT = BS_MAX_CAND / BS_THREADS;  // candidates per thread, kept in registers
+constexpr uint32_t ORD_NEG_INF = 0x007fffffu;     // float_to_ordered(-inf); 0 marks "no candidate"
+
+// Block-wide sum of a small per-thread count.  `it` is a per-thread copy of a block-uniform call
+// counter: call n uses counter n % 3 and clears counter (n + 1) % 3, whose last readers (call n - 2)
+// are all past the barrier of call n - 1.
+__device__ __forceinline__ int block_sum(BeamSmem& sm, int c, int& it) {
+  const int slot = it % 3;
+  if (threadIdx.x == 0) sm.counter[(it + 1) % 3] = 0;
+  c = __reduce_add_sync(0xffffffffu, c);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(&sm.counter[slot], c);
+  __syncthreads();
+  ++it;
+  return sm.counter[slot];
+}
+
+__global__ void __launch_bounds__(BS_THREADS)
+    ctc_beam_search_kernel(const float* __restrict__ scores, const int32_t* __restrict__ input_len,
+                           int32_t* __restrict__ out, int32_t* __restrict__ out_len, float* __restrict__ out_logp,
+                           int2* __restrict__ nodes_all, unsigned long long* __restrict__ hash_all, int hash_cap,
+                           int T, int V, int blank, int W, int top_paths, int merge_repeated, int inputs_are_probs) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  BeamSmem& sm = *reinterpret_cast<BeamSmem*>(smem_raw);
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int P = min(input_len[b], T);
+  int2* nodes = nodes_all + static_cast<size_t>(b) * (static_cast<size_t>(T) * W + 1);  // (parent node, label)
+  unsigned long long* hash = hash_all + static_cast<size_t>(b) * hash_cap;  // zeroed by the launcher
+  const float* sc = scores + static_cast<size_t>(b) * T * V;
+
+  if (tid == 0) {
+    nodes[0] = make_int2(-1, -1);  // root: the empty prefix, P = 1 with "last frame blank"
+    BeamGen& g = sm.gen[0];
+    g.node[0] = 0;
+    g.label[0] = -1;
+    g.pslot[0] = -1;
+    g.pb[0] = 0.f;
+    g.pl[0] = -INFINITY;
+    g.tot[0] = 0.f;
+    sm.n_active = 1;
+    sm.counter[0] = sm.counter[1] = sm.counter[2] = 0;
+  }
+  // the frame's scores are fetched one frame ahead (warp 0, two symbols per lane)
+  auto fetch = [&](int t, float& x0, float& x1) {
+    x0 = x1 = -INFINITY;
+    if (tid < 32 && t < P) {
+      const float* row = sc + static_cast<size_t>(t) * V;
+      if (tid < V) x0 = row[tid];
+      if (tid + 32 < V) x1 = row[tid + 32];
+    }
+  };
+  float x0, x1;
+  fetch(0, x0, x1);
+  __syncthreads();
+
+  int cur = 0, it = 0;
+  const int n_cand = W * V;
+  for (int t = 0; t < P; ++t) {
+    BeamGen& g = sm.gen[cur];
+    BeamGen& nx = sm.gen[cur ^ 1];
+    const int n = sm.n_active;
+    // 1. log-softmax of the frame (TF normalises every frame; the reference feeds log(p + 1e-8))
+    if (tid < 32) {
+      float y0 = x0, y1 = x1;
+      if (inputs_are_probs) {
+        y0 = tid < V ? logf(x0 + 1e-8f) : -INFINITY;
+        y1 = tid + 32 < V ? logf(x1 + 1e-8f) : -INFINITY;
+      }
+      float m = fmaxf(y0, y1);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      float s = (tid < V ? expf(y0 - m) : 0.f) + (tid + 32 < V ? expf(y1 - m) : 0.f);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float norm = m + logf(s);
+      sm.lp[tid] = y0 - norm;
+      sm.lp[tid + 32] = y1 - norm;
+    }
+    fetch(t + 1, x0, x1);
+    if (tid < W) sm.child_active[tid] = 0ull;
+    if (tid == 0) sm.n_selected = 0;
+    __syncthreads();
+    // 2. continue the active prefixes; mark which children are already in the beam
+    if (tid < n) {
+      const int lab = g.label[tid];
+      float pl = -INFINITY;
+      if (lab >= 0) {
+        const int ps = g.pslot[tid];
+        const float previous = ps >= 0 ? (lab == g.label[ps] ? g.pb[ps] : g.tot[ps]) : -INFINITY;
+        pl = logaddexp(g.pl[tid], previous) + sm.lp[lab];
+        if (ps >= 0) atomicOr(&sm.child_active[ps], 1ull << lab);
+      }
+      const float pb = g.tot[tid] + sm.lp[blank];
+      sm.pbn[tid] = pb;
+      sm.pln[tid] = pl;
+      sm.totn[tid] = logaddexp(pb, pl);
+    }
+    __syncthreads();
+    // 3. candidates (slot i, symbol c), BS_CPT per thread in registers; c == blank stands for
+    //    "prefix i continued".  Order-preserving integer image of the score; 0 = no candidate.
+    uint32_t kv[BS_CPT];
+#pragma unroll
+    for (int q = 0; q < BS_CPT; ++q) {
+      const int idx = tid + q * BS_THREADS;
+      kv[q] = 0u;
+      if (idx < n_cand) {
+        const int i = idx / V, c = idx - i * V;
+        if (i < n) {
+          float key = -INFINITY;
+          if (c == blank)
+            key = sm.totn[i];
+          else if (!((sm.child_active[i] >> c) & 1ull))
+            key = sm.lp[c] + (c == g.label[i] ? g.pb[i] : g.tot[i]);
+          kv[q] = float_to_ordered(key);
+        }
+      }
+    }
+    // 4. the W best: binary search, bit by bit, for the score of the W-th best candidate (one block-wide
+    //    count per bit); ties at that score go to the lower candidate index
+    auto count_if = [&](auto pred) {
+      int c = 0;
+#pragma unroll
+      for (int q = 0; q < BS_CPT; ++q) c += pred(kv[q], tid + q * BS_THREADS) ? 1 : 0;
+      return block_sum(sm, c, it);
+    };
+    const int n_finite = count_if([](uint32_t k, int) { return k > ORD_NEG_INF; });
+    const int n_next = min(W, n_finite);
+    uint32_t thr = 0u;
+    for (int bit = 31; bit >= 0; --bit) {
+      const uint32_t cand = thr | (1u << bit);
+      if (count_if([cand](uint32_t k, int) { return k >= cand; }) >= n_next) thr = cand;
+    }
+    const int n_greater = count_if([thr](uint32_t k, int) { return k > thr; });
+    const int n_ties = count_if([thr](uint32_t k, int) { return k == thr; });
+    int idx_limit = BS_MAX_CAND;  // ties with candidate index <= idx_limit are taken
+    if (n_greater + n_ties > n_next) {
+      const int need = n_next - n_greater;
+      int lo = 0;
+      for (int bit = 11; bit >= 0; --bit) {
+        const int cand = lo | (1 << bit);
+        if (count_if([thr, cand](uint32_t k, int idx) { return k == thr && idx < cand; }) < need) lo = cand;
+      }
+      idx_limit = lo;
+    }
+#pragma unroll
+    for (int q = 0; q < BS_CPT; ++q) {
+      const int idx = tid + q * BS_THREADS;
+      if (kv[q] > thr || (kv[q] == thr && kv[q] > ORD_NEG_INF && idx <= idx_limit)) {
+        const int pos = atomicAdd(&sm.n_selected, 1);
+        sm.selected[pos] = (static_cast<unsigned long long>(kv[q]) << 32) |
+                           static_cast<unsigned long long>(0xffffffffu - static_cast<uint32_t>(idx));
+      }
+    }
+    __syncthreads();
+    // 5. survivor r takes the slot given by its rank (keys are unique: score, then lower index first)
+    if (tid < n_next) {
+      const unsigned long long key = sm.selected[tid];
+      int slot = 0;
+      for (int s2 = 0; s2 < n_next; ++s2) slot += sm.selected[s2] > key ? 1 : 0;
+      const float f = ordered_to_float(static_cast<uint32_t>(key >> 32));
+      const int idx = static_cast<int>(0xffffffffu - static_cast<uint32_t>(key & 0xffffffffull));
+      const int i = idx / V, c = idx - i * V;
+      if (c == blank) {
+        const int node = g.node[i];
+        nx.node[slot] = node;
+        nx.label[slot] = g.label[i];
+        nx.pb[slot] = sm.pbn[i];
+        nx.pl[slot] = sm.pln[i];
+        nx.tot[slot] = sm.totn[i];
+        sm.parent_node[slot] = nodes[node].x;
+      } else {
+        // the prefix (node of i) + c: reuse its node if it has been in the beam before
+        const int pn = g.node[i];
+        const unsigned long long tag = (static_cast<unsigned long long>(pn) * BS_VP + c + 1ull) << 32;
+        int id = 1 + t * W + slot;
+        unsigned h = (static_cast<unsigned>(pn) * 2654435761u + static_cast<unsigned>(c) * 40503u) & (hash_cap - 1);
+        for (;;) {
+          const unsigned long long seen = atomicCAS(&hash[h], 0ull, tag | static_cast<unsigned>(id));
+          if (seen == 0ull) {
+            nodes[id] = make_int2(pn, c);
+            break;
+          }
+          if ((seen >> 32) == (tag >> 32)) {
+            id = static_cast<int>(seen & 0xffffffffull);
+            break;
+          }
+          h = (h + 1) & (hash_cap - 1);
+        }
+        nx.node[slot] = id;
+        nx.label[slot] = c;
+        nx.pb[slot] = -INFINITY;
+        nx.pl[slot] = f;
+        nx.tot[slot] = f;
+        sm.parent_node[slot] = pn;
+      }
+    }
+    __syncthreads();
+    if (tid < n_next) {
+      const int pn = sm.parent_node[tid];
+      int ps = -1;
+      for (int s2 = 0; s2 < n_next; ++s2)
+        if (nx.node[s2] == pn) ps = s2;
+      nx.pslot[tid] = ps;
+    }
+    if (tid == 0) sm.n_active = n_next;
+    __syncthreads();
+    cur ^= 1;
+  }
+
+  // output: walk the best prefixes back to the root (TF LabelSeq: with merge_repeated a label equal
+  // to the label of the node visited just before it, i.e. its successor, is dropped)
+  const BeamGen& g = sm.gen[cur];
+  const int n = sm.n_active;
+  if (tid < top_paths) {
+    int32_t* o = out + (static_cast<size_t>(b) * top_paths + tid) * T;
+    int len = 0;
+    if (tid < n) {
+      int prev = -1;
+      for (int node = g.node[tid]; node > 0; node = nodes[node].x) {
+        const int lab = nodes[node].y;
+        if (!merge_repeated || lab != prev) ++len;
+        prev = lab;
+      }
+      int pos = len;
+      prev = -1;
+      for (int node = g.node[tid]; node > 0; node = nodes[node].x) {
+        const int lab = nodes[node].y;
+        if (!merge_repeated || lab != prev) o[--pos] = lab;
+        prev = lab;
+      }
+    }
+    for (int i = len; i < T; ++i) o[i] = -1;
+    out_len[b * top_paths + tid] = tid < n ? len : 0;
+    out_logp[b * top_paths + tid] = tid < n ? g.tot[tid] : -INFINITY;
+  }
+}
+
+}  // namespace
+
+static int beam_hash_capacity(int T, int beam_width) {
+  size_t cap = 64;
+  while (cap < 2 * (static_cast<size_t>(T) * beam_width + 1)) cap <<= 1;
+  return static_cast<int>(cap);
+}
+static size_t beam_nodes_bytes(int B, int T, int beam_width) {
+  const size_t n = static_cast<size_t>(B) * (static_cast<size_t>(T) * beam_width + 1) * sizeof(int2);
+  return (n + 255) & ~static_cast<size_t>(255);
+}
+size_t beam_search_workspace_bytes(int B, int T, int beam_width) {
+  return beam_nodes_bytes(B, T, beam_width) +
+         static_cast<size_t>(B) * beam_hash_capacity(T, beam_width) * sizeof(unsigned long long);
+}
+
+int beam_search_launch(const float* scores, const int32_t* input_len, int32_t* out, int32_t* out_len, float* out_logp,
+                       int B, int T, int V, int blank, int beam_width, int top_paths, int merge_repeated,
+                       int inputs_are_probs, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  SL_REQUIRE(V >= 2 && V <= BS_VP, "beam search supports 2..64 symbols (incl. blank)");
+  SL_REQUIRE(blank >= 0 && blank < V, "blank out of range");
+  SL_REQUIRE(beam_width >= 1 && beam_width <= BS_MAX_W, "beam_width must be 1..128");
+  SL_REQUIRE(beam_width * V <= BS_MAX_CAND, "beam_width * symbols must not exceed 4096");
+  SL_REQUIRE(top_paths >= 1 && top_paths <= beam_width, "top_paths must be 1..beam_width");
+  SL_REQUIRE(workspace_bytes >= beam_search_workspace_bytes(B, T, beam_width), "beam search workspace too small");
+  SL_REQUIRE(static_cast<size_t>(T) * beam_width < (1u << 24), "too many frames x beam entries");
+  const size_t smem = sizeof(BeamSmem);
+  SL_CUDA(cudaFuncSetAttribute(ctc_beam_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               static_cast<int>(smem)));
+  const int hash_cap = beam_hash_capacity(T, beam_width);
+  unsigned long long* hash = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(workspace) +
+                                                                   beam_nodes_bytes(B, T, beam_width));
+  SL_CUDA(cudaMemsetAsync(hash, 0, static_cast<size_t>(B) * hash_cap * sizeof(unsigned long long), stream));
+  ctc_beam_search_kernel<<<B, BS_THREADS, smem, stream>>>(scores, input_len, out, out_len, out_logp,
+                                                          reinterpret_cast<int2*>(workspace), hash, hash_cap, T, V,
+                                                          blank, beam_width, top_paths, merge_repeated,
+                                                          inputs_are_probs);
+  SL_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace sl

@@ -227,13 +227,18 @@ class Wav2Letter:
                  out_filter_count: int = 2000,
                  compute_dtype: str = "bf16x2",
                  device=None,
-                 seed: Optional[int] = None):
+                 seed: Optional[int] = None,
+                 decoder_beam_width: int = 100,
+                 decoder_top_paths: int = 32):
         if frozen_layer_count > 0 and load_model_from_directory is None:
             raise ValueError("Layers cannot be frozen if model is trained from scratch.")
         if compute_dtype not in ("bf16", "bf16x2"):
             raise ValueError("compute_dtype must be 'bf16' or 'bf16x2'")
 
         self.kenlm_directory = kenlm_directory
+        self.rescorer = None
+        self.decoder_beam_width = decoder_beam_width
+        self.decoder_top_paths = min(decoder_top_paths, decoder_beam_width)
         self.grapheme_encoding = AsgGraphemeEncoding(allowed_characters=allowed_characters) \
             if use_asg else CtcGraphemeEncoding(allowed_characters=allowed_characters)
         self.asg_transition_probabilities = asg_transition_probabilities
@@ -261,8 +266,18 @@ class Wav2Letter:
             if allowed_characters != expected_characters:
                 raise ValueError("Allowed characters {} differ from those expected by kenlm decoder: {}".
                                  format(allowed_characters, expected_characters))
-            raise NotImplementedError("KenLM beam-search decoding needs the reference's patched TensorFlow "
-                                      "(net.py:420-422) and is not built (SURVEY.md §8f-4).")
+            # The reference hands the directory to a patched TensorFlow whose beam search scores words with
+            # KenLM (net.py:420-422,444-451).  Here: device beam search (stock scorer) + n-best re-scoring
+            # with a word n-gram model in ARPA text format, same three weights (language_model.py).
+            from speechless_b200.language_model import ArpaLanguageModel, NBestRescorer, find_arpa_file
+            arpa_file = find_arpa_file(self.kenlm_directory)
+            if arpa_file is None:
+                raise NotImplementedError(
+                    "No *.arpa file in {}: KenLM's binary format needs the KenLM library of the reference's patched "
+                    "TensorFlow (net.py:420-422), which is not available; export the model as ARPA text.".format(
+                        self.kenlm_directory))
+            self.rescorer = NBestRescorer(ArpaLanguageModel.read(arpa_file), kenlm_weight=.8, word_count_weight=0,
+                                          valid_word_count_weight=2.3)
 
         if load_model_from_directory is not None:
             self.load_weights(
@@ -419,10 +434,40 @@ class Wav2Letter:
         tower.set_labels(ws, input_by_name[names.label_batch], input_by_name[names.prediction_lengths],
                          input_by_name[names.label_lengths])
         loss = tower.ctc(ws, want_grad=False)
+        if self.kenlm_directory is not None:
+            return self._beam_search_with_language_model(ws), loss.cpu().numpy().reshape(-1, 1)
         decoded, decoded_lengths = tower.greedy_decode(ws, merge_repeated=True)
         decoded = decoded.cpu().numpy()
         width = max(int(decoded_lengths.max().item()), 1)
         return decoded[:, :width], loss.cpu().numpy().reshape(-1, 1)
+
+    def beam_search_batch(self, ws, beam_width: Optional[int] = None, top_paths: int = 1,
+                          merge_repeated: bool = False) -> List[List[Tuple[List[int], float]]]:
+        """Device prefix beam search over a forwarded workspace: per utterance the `top_paths` best
+        (grapheme indices, log-probability) pairs, best first (tf.nn.ctc_beam_search_decoder semantics; the
+        reference calls it with merge_repeated=False, net.py:441-447)."""
+        decoded, lengths, log_probabilities = self.tower.beam_search_decode(
+            ws, beam_width=beam_width or self.decoder_beam_width, top_paths=top_paths, merge_repeated=merge_repeated)
+        decoded, lengths, log_probabilities = decoded.cpu().numpy(), lengths.cpu().numpy(), log_probabilities.cpu().numpy()
+        return [[(decoded[b, p, :lengths[b, p]].tolist(), float(log_probabilities[b, p]))
+                 for p in range(decoded.shape[1]) if numpy.isfinite(log_probabilities[b, p])]
+                for b in range(decoded.shape[0])]
+
+    def _beam_search_with_language_model(self, ws) -> ndarray:
+        """Dense (B, max length) grapheme matrix, -1 padded like the greedy path: the hypothesis of the
+        device beam search that the language model re-scores best."""
+        n_best = self.beam_search_batch(ws, top_paths=self.decoder_top_paths, merge_repeated=False)
+        winners = []
+        for hypotheses in n_best:
+            texts = [(self.grapheme_encoding.decode_graphemes(graphemes, merge_repeated=False), log_probability)
+                     for graphemes, log_probability in hypotheses]
+            best_text, _ = self.rescorer.best(texts)
+            winners.append(next(graphemes for (graphemes, _), (text, _) in zip(hypotheses, texts) if text == best_text))
+        width = max(max((len(w) for w in winners), default=0), 1)
+        dense = -numpy.ones((len(winners), width), dtype=numpy.int32)
+        for row, winner in enumerate(winners):
+            dense[row, :len(winner)] = winner
+        return dense
 
     def test_and_predict_batch(self, labeled_spectrogram_batch: List[LabeledSpectrogram]) -> ExpectationsVsPredictions:
         input_by_name, dummy_labels = self._inputs_for_loss_net(labeled_spectrogram_batch)

@@ -1,0 +1,192 @@
+"""CTC prefix beam search: the CPU oracle against the reference's own vectors and brute force, the
+word n-gram re-scorer, and (gpu) the CUDA kernel against the oracle through the C-ABI."""
+import numpy as np
+import pytest
+
+from oracle import beam_search_oracle as bso
+
+# reference speechless/test/test_ctc_decoders.py:22-24: "A A blank A A", V = 2, blank = 1
+AA_BLANK_AA = np.array([[1.0, 0.0], [1.0, 0.0], [0.0, 1.0], [1.0, 0.0], [1.0, 0.0]], dtype=np.float32)
+
+
+def test_oracle_reproduces_the_reference_beam_search_rows():
+    # test_ctc_decoders.py:38-39: beam_width=1 -> [0] with merge_repeated, [0, 0] without
+    (merged, _), = bso.beam_search_decode(AA_BLANK_AA, beam_width=1, merge_repeated=True)
+    (unmerged, _), = bso.beam_search_decode(AA_BLANK_AA, beam_width=1, merge_repeated=False)
+    assert merged == [0]
+    assert unmerged == [0, 0]
+
+
+def test_wide_beam_is_exact_against_path_enumeration():
+    rng = np.random.default_rng(0)
+    for _ in range(40):
+        T, V = int(rng.integers(1, 7)), int(rng.integers(2, 5))
+        scores = rng.normal(size=(T, V)) * 2
+        totals = bso.brute_force_labelings(scores)
+        best = max(totals, key=totals.get)
+        ranked = bso.beam_search_decode(scores, beam_width=10000, top_paths=3, merge_repeated=False)
+        assert tuple(ranked[0][0]) == best
+        assert ranked[0][1] == pytest.approx(totals[best], abs=1e-9)
+        for labels, log_probability in ranked:  # every reported hypothesis carries its exact total
+            assert log_probability == pytest.approx(totals[tuple(labels)], abs=1e-9)
+
+
+def test_tf_deactivation_only_matters_for_narrow_beams():
+    """The order-independent rule the kernel implements equals TF's for beam_width = 1 and for beams
+    that never overflow; in between it may keep hypotheses TF drops (never a worse best path)."""
+    rng = np.random.default_rng(3)
+    differing = 0
+    for _ in range(60):
+        T, V, W = int(rng.integers(4, 30)), int(rng.integers(2, 7)), int(rng.integers(2, 7))
+        scores = rng.normal(size=(T, V)) * rng.uniform(0.5, 4)
+        for width in (1, W, 100000):
+            if width == 100000:
+                scores = scores[:6, :4]  # (every prefix stays in the beam: keep the tree small)
+            tf_like = bso.beam_search_decode(scores, beam_width=width, merge_repeated=False)
+            plain = bso.beam_search_decode(scores, beam_width=width, merge_repeated=False, tf_deactivation=False)
+            if width == W:
+                differing += tf_like[0][0] != plain[0][0]
+                continue
+            assert tf_like[0][0] == plain[0][0] and tf_like[0][1] == pytest.approx(plain[0][1], abs=1e-9)
+    assert differing < 30  # (informative: a minority of the narrow-beam cases)
+
+
+def test_beam_width_one_differs_from_greedy_as_the_reference_documents():
+    # greedy (merge_repeated=True) gives [0, 0] on the same input: test_ctc_decoders.py:40
+    from oracle import keras_tf_oracle as oracle
+    probabilities = np.exp(bso.log_softmax(AA_BLANK_AA.astype(np.float64)))[None]
+    dense, lengths = oracle.greedy_decode(probabilities, [5])
+    assert dense[0, :lengths[0]].tolist() == [0, 0]
+
+
+ARPA = """\\data\\
+ngram 1=6
+ngram 2=3
+
+\\1-grams:
+-1.0\t<unk>\t0.0
+-99\t<s>\t-0.5
+-1.2\t</s>\t0.0
+-0.7\tthe\t-0.3
+-0.9\tcat\t-0.2
+-1.5\tthe cat is not a word\t0.0
+
+\\2-grams:
+-0.2\t<s> the\t0.0
+-0.3\tthe cat\t0.0
+-0.4\tcat </s>\t0.0
+
+\\end\\
+"""
+
+
+def test_arpa_back_off_and_rescoring(tmp_path):
+    from speechless_b200.language_model import ArpaLanguageModel, NBestRescorer, find_arpa_file, LN10
+    (tmp_path / "tiny.arpa").write_text(ARPA.replace("-1.5\tthe cat is not a word\t0.0\n", "-1.5\tdog\t0.0\n"), encoding="utf8")
+    lm = ArpaLanguageModel.read(find_arpa_file(tmp_path))
+    assert lm.order == 2
+    # seen bigrams: direct look-up; unseen: back-off weight of the history + unigram
+    assert lm.log10_probability("cat", ["<s>", "the"]) == pytest.approx(-0.3)
+    assert lm.log10_probability("the", ["cat"]) == pytest.approx(-0.2 + -0.7)
+    assert lm.log10_probability("zebra", ["the"]) == pytest.approx(-0.3 + -1.0)  # -> <unk>
+    assert lm.log10_sentence(["the", "cat"]) == pytest.approx(-0.2 - 0.3 - 0.4)
+    rescorer = NBestRescorer(lm)  # reference weights .8 / 0 / 2.3 (net.py:448-451)
+    expected = -5.0 + .8 * LN10 * (-0.9) + 2.3 * 2
+    assert rescorer.score("the cat", -5.0) == pytest.approx(expected)
+    # the language model overrules a slightly better acoustic score of a non-word
+    assert rescorer.best([("the cxt", -4.0), ("the cat", -5.0)])[0] == "the cat"
+
+
+def _random_case(rng, B, T, V, peaky):
+    logits = rng.normal(size=(B, T, V)) * peaky
+    probabilities = np.exp(bso.log_softmax(logits)).astype(np.float32)
+    lengths = rng.integers(max(1, T // 2), T + 1, size=B).astype(np.int32)
+    lengths[0] = T
+    return probabilities, lengths
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,T,V,beam_width,top_paths,merge,peaky", [
+    (1, 5, 2, 1, 1, True, 1.0),
+    (3, 40, 5, 1, 1, False, 2.0),
+    (4, 60, 6, 4, 3, False, 2.0),      # narrow beam: prefixes drop out and come back
+    (4, 60, 6, 4, 3, True, 3.0),
+    (3, 120, 29, 16, 4, False, 3.0),
+    (2, 200, 29, 100, 8, False, 4.0),  # TF's default width, the English alphabet
+    (2, 90, 33, 100, 2, False, 4.0),   # German alphabet
+])
+def test_cuda_beam_search_matches_the_oracle(B, T, V, beam_width, top_paths, merge, peaky):
+    import torch
+    from speechless_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(B * 1000 + T + V + beam_width)
+    probabilities, lengths = _random_case(rng, B, T, V, peaky)
+    if T == 5:  # the reference's own vector
+        probabilities = np.exp(bso.log_softmax(AA_BLANK_AA.astype(np.float64)))[None].astype(np.float32)
+        lengths = np.array([5], dtype=np.int32)
+    device = torch.device("cuda:0")
+    p = torch.from_numpy(probabilities).to(device)
+    n = torch.from_numpy(lengths).to(device)
+    out = torch.empty((B, top_paths, T), dtype=torch.int32, device=device)
+    out_len = torch.empty((B, top_paths), dtype=torch.int32, device=device)
+    out_logp = torch.empty((B, top_paths), dtype=torch.float32, device=device)
+    ws = torch.empty(lib.sl_ctc_beam_search_workspace_bytes(B, T, beam_width), dtype=torch.uint8, device=device)
+    _lib.check(lib.sl_ctc_beam_search_decode(_lib.ptr(p), _lib.ptr(n), _lib.ptr(out), _lib.ptr(out_len),
+                                             _lib.ptr(out_logp), B, T, V, V - 1, beam_width, top_paths,
+                                             1 if merge else 0, 1, _lib.ptr(ws), ws.numel(), None))
+    torch.cuda.synchronize()
+    out, out_len, out_logp = out.cpu().numpy(), out_len.cpu().numpy(), out_logp.cpu().numpy()
+    for b in range(B):
+        scores = np.log(probabilities[b, :lengths[b]].astype(np.float64) + 1e-8)  # net.py:430
+        # (the kernel implements the order-independent selection rule: see `tf_deactivation` in the oracle)
+        want = bso.beam_search_decode(scores, beam_width=beam_width, top_paths=top_paths, merge_repeated=merge,
+                                      tf_deactivation=False)
+        for path, (labels, log_probability) in enumerate(want):
+            got = out[b, path, :out_len[b, path]].tolist()
+            # fp32 on the device vs fp64 in the oracle: hypotheses closer than 1e-3 nats may swap ranks
+            if got != labels:
+                alternatives = [lp for lab, lp in want if lab == got]
+                assert alternatives and abs(alternatives[0] - log_probability) < 1e-3, (b, path, got, labels)
+            else:
+                assert out_logp[b, path] == pytest.approx(log_probability, rel=1e-4, abs=1e-3)
+            assert (out[b, path, out_len[b, path]:] == -1).all()
+
+
+@pytest.mark.gpu
+def test_wav2letter_decodes_with_beam_search_and_language_model(tmp_path):
+    from speechless_b200 import english_frequent_characters
+    from speechless_b200.net import Wav2Letter
+    from speechless_b200.labeled_example import LabeledSpectrogram
+
+    class Example(LabeledSpectrogram):
+        def __init__(self, id, label, spectrogram):
+            self.id, self.label, self._s = id, label, spectrogram
+
+        def z_normalized_transposed_spectrogram(self):
+            return self._s
+
+    (tmp_path / "vocabulary").write_text("".join(english_frequent_characters).upper(), encoding="utf8")
+    with pytest.raises(NotImplementedError):  # a KenLM binary alone cannot be read
+        Wav2Letter(128, english_frequent_characters, kenlm_directory=tmp_path, main_filter_count=64,
+                   out_filter_count=64, device="cuda:0", seed=3)
+    (tmp_path / "tiny.arpa").write_text(ARPA.replace("-1.5\tthe cat is not a word\t0.0\n", "-1.5\tdog\t0.0\n"), encoding="utf8")
+    net = Wav2Letter(128, english_frequent_characters, kenlm_directory=tmp_path, main_filter_count=64,
+                     out_filter_count=64, device="cuda:0", seed=3, decoder_beam_width=16, decoder_top_paths=8)
+    greedy = Wav2Letter(128, english_frequent_characters, main_filter_count=64, out_filter_count=64,
+                        device="cuda:0", seed=3)
+    rng = np.random.default_rng(1)
+    batch = [Example("a", "the cat", rng.standard_normal((120, 128))), Example("b", "dog", rng.standard_normal((90, 128)))]
+    with_lm = net.test_and_predict_batch(batch)
+    without = greedy.test_and_predict_batch(batch)
+    # same weights (same seed) -> same losses; predictions are strings over the alphabet
+    assert [r.loss for r in with_lm.results] == pytest.approx([r.loss for r in without.results], rel=1e-5)
+    assert all(set(r.predicted) <= set(english_frequent_characters) for r in with_lm.results)
+    # the winner is one of the n-best hypotheses of the plain device beam search
+    tower = net.tower
+    ws = tower.upload(net._input_batch_and_prediction_lengths([e.z_normalized_transposed_spectrogram() for e in batch])[0])
+    tower.forward(ws)
+    tower.set_prediction_lengths(ws, [60, 45])
+    n_best = net.beam_search_batch(ws, top_paths=8)
+    for result, hypotheses in zip(with_lm.results, n_best):
+        texts = [net.grapheme_encoding.decode_graphemes(g, merge_repeated=False) for g, _ in hypotheses]
+        assert result.predicted in texts
