@@ -68,7 +68,7 @@ struct BeamSmem {
   unsigned long long selected[BS_MAX_W];               // keys of the survivors of a frame, unordered
   int parent_node[BS_MAX_W];                           // node id of the parent of next-generation slot r
   float lp[BS_VP];
-  int counter[3];  // rotating block-wide counters of the selection
+  int partial[2][32];  // per-warp partial counts of the selection (BS_THREADS / 32 warps)
   int n_selected;
   int n_active;
 };
@@ -76,17 +76,16 @@ struct BeamSmem {
 constexpr int BS_CPT = BS_MAX_CAND / BS_THREADS;  // candidates per thread, kept in registers
 constexpr uint32_t ORD_NEG_INF = 0x007fffffu;     // float_to_ordered(-inf); 0 marks "no candidate"
 
-// Block-wide sum of a small per-thread count.  `it` is a per-thread copy of a block-uniform call
-// counter: call n uses counter n % 3 and clears counter (n + 1) % 3, whose last readers (call n - 2)
-// are all past the barrier of call n - 1.
+// Block-wide sum of a small per-thread count, without atomics: warp sums go to one of two slot rows
+// (`it` is a per-thread copy of a block-uniform call counter; call n uses row n & 1, whose readers of
+// call n - 2 are all past the barrier of call n - 1), one barrier, every warp adds up the 32 slots.
 __device__ __forceinline__ int block_sum(BeamSmem& sm, int c, int& it) {
-  const int slot = it % 3;
-  if (threadIdx.x == 0) sm.counter[(it + 1) % 3] = 0;
+  int* part = sm.partial[it & 1];
   c = __reduce_add_sync(0xffffffffu, c);
-  if ((threadIdx.x & 31) == 0 && c) atomicAdd(&sm.counter[slot], c);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = c;
   __syncthreads();
   ++it;
-  return sm.counter[slot];
+  return __reduce_add_sync(0xffffffffu, part[threadIdx.x & 31]);
 }
 
 __global__ void __launch_bounds__(BS_THREADS)
@@ -113,7 +112,6 @@ __global__ void __launch_bounds__(BS_THREADS)
     g.pl[0] = -INFINITY;
     g.tot[0] = 0.f;
     sm.n_active = 1;
-    sm.counter[0] = sm.counter[1] = sm.counter[2] = 0;
   }
   // the frame's scores are fetched one frame ahead (warp 0, two symbols per lane)
   auto fetch = [&](int t, float& x0, float& x1) {
