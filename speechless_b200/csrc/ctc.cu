@@ -4,17 +4,20 @@
 // grapheme_enconding.py:125-126) and tf.nn.ctc_greedy_decoder (net.py:453-454).
 // Semantics restated in SURVEY.md Appendix A.2 / A.3.
 //
-// Three phases per batch:
-//   1. ctc_alpha_beta_kernel — the sequential part.  One CTA per (utterance, direction):
-//      the alpha CTA walks t = 0..P-1, the beta CTA walks t = P-1..0 concurrently on
-//      another SM (2B CTAs).  States live one-or-more per thread, the previous column in
-//      a double-buffered smem row, log-prob rows are prefetched 32 frames at a time with
-//      cp.async, and every column is streamed to HBM (fire-and-forget stores).
-//   2. ctc_grad_kernel — the bandwidth part, parallel over every (utterance, frame):
-//      one warp per frame folds alpha+beta over the states of each symbol and chains the
-//      gradient through log(p+1e-8) and the softmax to the pre-softmax logits, writing
-//      the packed bf16 tile the output_conv wgrad/dgrad kernels consume.
-//   3. (host) nothing: the loss per utterance is written by the alpha CTA.
+// Two launches per batch:
+//   1. ctc_lattice_halo_kernel — the sequential part.  One CTA (or a cluster of CTAs, for few long
+//      utterances) per (utterance, direction): the alpha walk runs t = 0..P-1, the beta walk
+//      t = P-1..0 concurrently on other SMs.  The lattice column lives in registers; K time steps run
+//      between barriers thanks to a 2K-state halo per warp; log-prob rows are prefetched 32 frames at a
+//      time with cp.async; every column is streamed to HBM.  An extra warp of the alpha CTA sorts the
+//      label positions by symbol for phase 2.  The loss per utterance is written by the alpha walk.
+//   2. ctc_grad_sorted_kernel — the bandwidth part, parallel over every (utterance, frame): one warp
+//      per frame folds alpha+beta over the states of each symbol (sorted slots, no atomics) and chains
+//      the gradient through log(p+1e-8) and the softmax to the pre-softmax logits, writing the packed
+//      bf16 tile the output_conv wgrad/dgrad kernels consume.
+// The first-generation kernels (one barrier per step: ctc_alpha_beta_kernel; warp wavefront:
+// ctc_alpha_beta_wave_kernel; smem-atomics gradient: ctc_grad_kernel) are kept behind SL_CTC_LEGACY
+// for A/B measurements.
 #include <cstdlib>
 
 #include "common.cuh"
