@@ -7,8 +7,13 @@
 // (B, T_max, 128) fp32, zero beyond each utterance's frame count, is exactly the zero-padded
 // `input_batch` of net.py:583-585, so it feeds the tower without leaving HBM.
 //
-// One CTA (256 threads) per frame: windowed 512-point FFT in shared memory (9 radix-2 stages, one
-// butterfly per thread per stage), power/dB, then 128 threads each take one mel bin.
+// One CTA (256 threads) per FR consecutive frames of one utterance.  Per CTA, once: the audio span of
+// its frames (coalesced, reflect-padded) -> smem; the Hann window and the FFT twiddles -> smem; the
+// band [first, last] of non-zero weights of every mel filter (the Slaney filters are triangles a few
+// bins wide: ~5 % of the dense 257 x 128 matrix) -> smem.  Per frame: windowed 512-point FFT in shared
+// memory (9 radix-2 stages, one butterfly per thread per stage) of TWO real frames packed as one complex
+// signal, power/dB of both, then 2 x 128 threads each take one mel bin of one frame over its band only.  (The first version did all of the set-up per frame and the
+// dense projection: 1.11 ms for 64 x 1251 frames; see profiles/README.md for this one.)
 #include "common.cuh"
 
 namespace sl {
@@ -19,64 +24,110 @@ constexpr int N_FFT = 512;
 constexpr int HOP = 128;
 constexpr int N_BINS = N_FFT / 2 + 1;  // 257
 constexpr int N_MEL = 128;
+constexpr int FR = 16;                 // frames per CTA
+constexpr int SPAN = (FR - 1) * HOP + N_FFT;
+constexpr int MAX_BAND = 40;           // widest supported mel filter, in FFT bins (dense fallback beyond)
 
 __global__ void __launch_bounds__(256) spectrogram_kernel(const float* __restrict__ audio,
                                                            const int32_t* __restrict__ sample_counts,
                                                            const float* __restrict__ mel_t,  // (257, 128)
                                                            float* __restrict__ out,          // (B, T_max, 128)
                                                            int audio_stride, int T_max) {
+  __shared__ float span[SPAN];
+  __shared__ float window[N_FFT];
   __shared__ float2 x[N_FFT];
   __shared__ float2 tw[N_FFT / 2];
-  __shared__ float level[N_BINS + 3];
+  __shared__ float level[2][N_BINS + 3];
+  __shared__ float band_w[N_MEL][MAX_BAND + 1];  // (+1: conflict-free column walks)
+  __shared__ int band_first[N_MEL], band_len[N_MEL];
   const int b = blockIdx.y;
-  const int t = blockIdx.x;
+  const int t_begin = blockIdx.x * FR;
   const int n_samples = sample_counts[b];
   const int frames = 1 + n_samples / HOP;  // librosa center=True
-  if (t >= frames) return;
+  if (t_begin >= frames) return;
+  const int t_end = min(t_begin + FR, frames);
   const int tid = threadIdx.x;
   const float* y = audio + static_cast<size_t>(b) * audio_stride;
 
-  // twiddles e^{-2 pi i k / 512} and the windowed, reflect-padded frame in bit-reversed order
+  // ---- per-CTA set-up ----
   {
     float s, c;
-    sincospif(-2.0f * tid / N_FFT, &s, &c);
+    sincospif(-2.0f * tid / N_FFT, &s, &c);  // twiddles e^{-2 pi i k / 512}
     tw[tid] = make_float2(c, s);
   }
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int n = tid + h * 256;
-    int i = t * HOP + n - N_FFT / 2;  // index into the un-padded signal
-    if (i < 0) i = -i;                // numpy 'reflect': no edge repeat
+  for (int n = tid; n < N_FFT; n += 256) window[n] = 0.5f - 0.5f * cospif(2.0f * n / N_FFT);  // periodic Hann
+  for (int j = tid; j < SPAN; j += 256) {
+    int i = t_begin * HOP + j - N_FFT / 2;  // index into the un-padded signal
+    if (i < 0) i = -i;                      // numpy 'reflect': no edge repeat
     if (i >= n_samples) i = 2 * (n_samples - 1) - i;
-    i = i < 0 ? 0 : i;                // (signals shorter than the half window)
-    const float w = 0.5f - 0.5f * cospif(2.0f * n / N_FFT);  // periodic Hann
-    x[__brev(static_cast<unsigned>(n)) >> (32 - 9)] = make_float2(w * y[i], 0.f);
+    i = i < 0 ? 0 : i;                      // (signals shorter than the half window)
+    span[j] = y[i];
   }
-  __syncthreads();
-#pragma unroll
-  for (int stage = 0; stage < 9; ++stage) {
-    const int half = 1 << stage;
-    const int j = tid & (half - 1);
-    const int base = ((tid >> stage) << (stage + 1)) + j;
-    const float2 w = tw[j << (8 - stage)];
-    const float2 a = x[base], bb = x[base + half];
-    const float2 wb = make_float2(w.x * bb.x - w.y * bb.y, w.x * bb.y + w.y * bb.x);
-    x[base] = make_float2(a.x + wb.x, a.y + wb.y);
-    x[base + half] = make_float2(a.x - wb.x, a.y - wb.y);
-    __syncthreads();
-  }
-  // power level in dB, floored at -150 (0 -> -150): labeled_example.py:153-160
-  for (int k = tid; k < N_BINS; k += 256) {
-    const float p = x[k].x * x[k].x + x[k].y * x[k].y;
-    float l = -150.f;
-    if (p > 0.f) l = fmaxf(10.f * log10f(p), -150.f);
-    level[k] = l;
-  }
-  __syncthreads();
   if (tid < N_MEL) {
-    float acc = 0.f;
-    for (int k = 0; k < N_BINS; ++k) acc = fmaf(mel_t[k * N_MEL + tid], level[k], acc);
-    out[(static_cast<size_t>(b) * T_max + t) * N_MEL + tid] = acc;
+    // band of non-zero weights of mel filter `tid` (coalesced column walk, L2 resident)
+    int first = N_BINS, last = -1;
+    for (int k = 0; k < N_BINS; ++k)
+      if (mel_t[k * N_MEL + tid] != 0.f) {
+        first = min(first, k);
+        last = k;
+      }
+    const int len = last >= first ? last - first + 1 : 0;
+    band_first[tid] = first;
+    band_len[tid] = len;  // > MAX_BAND: dense fallback below
+    if (len <= MAX_BAND)
+      for (int j = 0; j < len; ++j) band_w[tid][j] = mel_t[(first + j) * N_MEL + tid];
+  }
+  __syncthreads();
+
+  // Two REAL frames per complex FFT: z = f_t + i f_{t+1}  =>  F_t[k] = (Z[k] + conj(Z[N-k])) / 2,
+  // F_{t+1}[k] = (Z[k] - conj(Z[N-k])) / (2i).  An odd last frame is paired with zeros.
+  for (int t = t_begin; t < t_end; t += 2) {
+    const float* frame = span + (t - t_begin) * HOP;
+    const bool pair = t + 1 < t_end;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int n = tid + h * 256;
+      const float w = window[n];
+      x[__brev(static_cast<unsigned>(n)) >> (32 - 9)] = make_float2(w * frame[n], pair ? w * frame[n + HOP] : 0.f);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int stage = 0; stage < 9; ++stage) {
+      const int half = 1 << stage;
+      const int j = tid & (half - 1);
+      const int base = ((tid >> stage) << (stage + 1)) + j;
+      const float2 w = tw[j << (8 - stage)];
+      const float2 a = x[base], bb = x[base + half];
+      const float2 wb = make_float2(w.x * bb.x - w.y * bb.y, w.x * bb.y + w.y * bb.x);
+      x[base] = make_float2(a.x + wb.x, a.y + wb.y);
+      x[base + half] = make_float2(a.x - wb.x, a.y - wb.y);
+      __syncthreads();
+    }
+    // power level in dB, floored at -150 (0 -> -150): labeled_example.py:153-160
+    for (int k = tid; k < N_BINS; k += 256) {
+      const float2 z = x[k], zc = x[(N_FFT - k) & (N_FFT - 1)];
+      const float ar = 0.5f * (z.x + zc.x), ai = 0.5f * (z.y - zc.y);  // F_t[k]
+      const float br = 0.5f * (z.y + zc.y), bi = 0.5f * (zc.x - z.x);  // F_{t+1}[k]
+      const float p0 = ar * ar + ai * ai, p1 = br * br + bi * bi;
+      level[0][k] = p0 > 0.f ? fmaxf(10.f * log10f(p0), -150.f) : -150.f;
+      level[1][k] = p1 > 0.f ? fmaxf(10.f * log10f(p1), -150.f) : -150.f;
+    }
+    __syncthreads();
+    {
+      const int which = tid >> 7, m = tid & (N_MEL - 1);  // threads 0..127: frame t, 128..255: frame t + 1
+      if (which == 0 || pair) {
+        const float* lv = level[which];
+        const int first = band_first[m], len = band_len[m];
+        float acc = 0.f;
+        if (len <= MAX_BAND) {
+          for (int j = 0; j < len; ++j) acc = fmaf(band_w[m][j], lv[first + j], acc);
+        } else {
+          for (int k = 0; k < N_BINS; ++k) acc = fmaf(mel_t[k * N_MEL + m], lv[k], acc);
+        }
+        out[(static_cast<size_t>(b) * T_max + t + which) * N_MEL + m] = acc;
+      }
+    }
+    // (the next pair's writes to x / level happen behind its own barriers)
   }
 }
 
@@ -130,7 +181,7 @@ __global__ void normalize_kernel(float* __restrict__ x, const int32_t* __restric
 
 int spectrogram_launch(const float* audio, const int32_t* sample_counts, const float* mel_t, float* out, int B,
                        int audio_stride, int T_max, cudaStream_t s) {
-  dim3 grid(T_max, B);
+  dim3 grid((T_max + FR - 1) / FR, B);
   spectrogram_kernel<<<grid, 256, 0, s>>>(audio, sample_counts, mel_t, out, audio_stride, T_max);
   SL_CUDA(cudaGetLastError());
   return 0;

@@ -28,16 +28,24 @@ def run():
     check(lib.sl_z_normalize(ptr(out), ptr(frame_counts), ptr(moments), B, frames, N_MELS, None))
 
 
-for _ in range(3):
-    run()
-torch.cuda.synchronize()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-for _ in range(20):
-    run()
-e1.record()
-torch.cuda.synchronize()
-ms = e0.elapsed_time(e1) / 20
+def timed(fn, n=20):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+ms_spec = timed(lambda: check(lib.sl_spectrogram(ptr(audio), ptr(sample_counts), ptr(front.mel_t), ptr(out), B, samples,
+                                                 frames, N_FFT, HOP_LENGTH, N_MELS, None)))
+ms_norm = timed(lambda: check(lib.sl_z_normalize(ptr(out), ptr(frame_counts), ptr(moments), B, frames, N_MELS, None)))
+print("  sl_spectrogram %.3f ms, sl_z_normalize %.3f ms" % (ms_spec, ms_norm))
+ms = timed(run)
 total = B * frames
 bytes_moved = audio.numel() * 4 + 3 * out.numel() * 4  # audio read, spectrogram write + read + write (z-norm)
 print("front end: %.3f ms per batch of %d x %d frames = %.1f M frames/s; %.1f MB -> %.0f GB/s" % (
