@@ -227,7 +227,9 @@ __device__ __forceinline__ void sort_labels_by_symbol(const int32_t* __restrict_
   __syncwarp();
   for (int i0 = 0; i0 < L; i0 += 32) {
     const int i = i0 + lane;
-    const int v = i < L ? lab[i] : -1 - lane;  // (distinct dummies)
+    // (distinct dummies past the end; symbols are clamped into the table: the host rejects labels outside
+    // [0, V - 2] before the launch, this only keeps a bad direct caller inside shared memory)
+    const int v = i < L ? min(max(lab[i], 0), VP - 1) : -1 - lane;
     const unsigned same = __match_any_sync(0xffffffffu, v);
     if (i < L) {
       const int before = cnt[v];
