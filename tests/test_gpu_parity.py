@@ -239,6 +239,38 @@ def test_ctc_long_form_states_per_thread_paths(env):
     assert rel_err(dz, dwant) < 3e-2
 
 
+@pytest.mark.parametrize("spt,k,cluster,legacy", [
+    (2, 4, 1, 0), (2, 8, 1, 0), (2, 16, 1, 0), (4, 8, 1, 0), (4, 16, 1, 0), (4, 32, 1, 0), (8, 8, 1, 0),
+    (8, 16, 1, 0), (8, 32, 1, 0),
+    (2, 8, 2, 0), (4, 16, 2, 0), (4, 32, 4, 0), (8, 32, 8, 0), (2, 4, 8, 0),  # cluster-split lattices (DSMEM halo)
+    (0, 0, 1, 1), (0, 0, 1, 2),  # first-generation kernels kept for A/B runs
+])
+def test_ctc_every_lattice_configuration(env, monkeypatch, spt, k, cluster, legacy):
+    """Every (states per lane, steps per barrier, cluster width) instantiation of the lattice kernel the
+    launcher can pick or be told to use (SL_CTC_* tuning variables) against the oracle, ragged batch."""
+    if legacy:
+        monkeypatch.setenv("SL_CTC_LEGACY", str(legacy))
+    else:
+        monkeypatch.setenv("SL_CTC_SPT", str(spt))
+        monkeypatch.setenv("SL_CTC_K", str(k))
+        monkeypatch.setenv("SL_CTC_CLUSTER", str(cluster))
+    rng = np.random.default_rng(100 * spt + k + cluster)
+    B, T, V = 4, 330, 29
+    probs = env.oracle.softmax(rng.standard_normal((B, T, V)) * 3).astype(np.float32)
+    ll = np.array([160, 3, 97, 0])
+    labels = -np.ones((B, 160), dtype=np.int32)
+    for b in range(B):
+        lab = rng.integers(0, V - 1, size=ll[b])
+        lab[2::7] = lab[1:-1:7][:len(lab[2::7])]  # adjacent repeats
+        labels[b, :ll[b]] = lab
+    pred = np.array([330, 17, 209, 64])
+    loss, dz, beta_loss, _ = _ctc_via_abi(env, probs, labels, pred, ll, scale=0.25)
+    want, dwant = env.oracle.ctc_batch_cost_with_logit_grad(probs, labels, pred, ll)
+    assert np.abs(loss / want - 1).max() < 1e-4
+    assert np.abs(beta_loss / want - 1).max() < 1e-4
+    assert rel_err(dz, dwant / 4) < 3e-3
+
+
 # ------------------------------------------------------------------ greedy decode (integer work: bit exact)
 def test_greedy_decode_reference_vector_on_gpu(env):
     torch, lib, check, ptr = env.torch, env.lib, env._lib.check, env._lib.ptr
