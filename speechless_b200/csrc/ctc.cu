@@ -1102,7 +1102,8 @@ int ctc_loss_launch(const float* logp, const float* probs, const int32_t* labels
 
   if (dlogits_packed != nullptr || dlogits_f32 != nullptr) {
     SL_REQUIRE(probs != nullptr, "gradient needs the softmax probabilities");
-    int frames_per_block = 16;  // 2 frames per warp: many short, independent chains in flight
+    int frames_per_block = 32;  // 4 frames per warp (measured at the bench shape: 8 / 16 / 32 / 64 frames per block
+                                // -> 0.1022 / 0.0994 / 0.0976 / 0.0976 ms for loss + gradient)
     if (const char* e = std::getenv("SL_CTC_GRAD_FPB")) frames_per_block = std::max(1, std::atoi(e));  // tuning aid
     const int warps = 8;
     dim3 grid((T + frames_per_block - 1) / frames_per_block, B);
