@@ -375,7 +375,7 @@ static int plan_dgrad_ksplit(int B, int T, int cin_pad, int cout_pad, int k) {
   if (ksteps < 256) return 1;
   int best = 1;
   double best_cost = static_cast<double>((tiles + sms - 1) / sms);
-  for (int ks = 2; ks <= 8 && ks <= k / 4; ks *= 2) {
+  for (int ks = 2; ks <= 8 && ks <= (cout_pad / 64) / 4; ks *= 2) {  // (the split runs over 64-channel chunks)
     // each split item also pays a fixed epilogue + pipeline ramp (~3 % of a 1024-step tile)
     const double cost = static_cast<double>((tiles * ks + sms - 1) / sms) / ks * (1.0 + 0.01 * ks);
     if (cost < best_cost * 0.95) {

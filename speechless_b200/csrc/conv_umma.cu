@@ -68,7 +68,7 @@ struct Cfg {
 // Work item of the persistent loop: an output tile, or one of the tail_split narrow slices of a
 // tile of the last partial wave.
 struct WorkItem {
-  int b, t0, n0, width, tap_begin, tap_end;
+  int b, t0, n0, width, chunk_begin, chunk_end;  // [chunk_begin, chunk_end): 64-channel chunks of the contraction
 };
 // `rank`: this CTA's rank in its pair (0 without pairs); a pair works on the frame tiles
 // 2 * unit and 2 * unit + 1 of one filter tile.  The odd tile out (if any) gets b = p.B: its loads
@@ -76,15 +76,19 @@ struct WorkItem {
 template <int BN, int CTAS>
 __device__ __forceinline__ WorkItem decode_item(const ConvGemmParams& p, int item, int rank) {
   int tile = item, sub = 0, width = BN;
-  int tap_begin = 0, tap_end = p.taps;
+  int chunk_begin = 0, chunk_end = p.chunks;
   if (p.ksplit > 1) {
-    // split-major order: CTAs running together share a tap range (the same weights in L2)
+    // Split K over CHANNEL chunks (all taps each), not over tap ranges: a tap-range item still needs
+    // the activation rows of (almost) the whole tile for every channel, so ksplit tap-range items read
+    // the A operand ksplit times (ncu on the big_conv_1 input gradient: 900 MB of DRAM reads for a 164 MB
+    // tensor); channel ranges partition both operands.  Split-major order: CTAs running together share a
+    // chunk range (the same weight slices in L2).
     const int total = p.m_units * p.n_tiles;
     const int split = item / total;
     tile = item - split * total;
-    const int per = (p.taps + p.ksplit - 1) / p.ksplit;
-    tap_begin = split * per;
-    tap_end = tap_begin + per < p.taps ? tap_begin + per : p.taps;
+    const int per = (p.chunks + p.ksplit - 1) / p.ksplit;
+    chunk_begin = split * per < p.chunks ? split * per : p.chunks;
+    chunk_end = chunk_begin + per < p.chunks ? chunk_begin + per : p.chunks;
   } else if (item >= p.full_tiles) {
     const int r = item - p.full_tiles;
     tile = p.full_tiles + r / p.tail_split;
@@ -105,8 +109,8 @@ __device__ __forceinline__ WorkItem decode_item(const ConvGemmParams& p, int ite
   }
   w.n0 = n_tile * BN + sub * width;
   w.width = width;
-  w.tap_begin = tap_begin;
-  w.tap_end = tap_end;
+  w.chunk_begin = chunk_begin;
+  w.chunk_end = chunk_end;
   return w;
 }
 
@@ -235,7 +239,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           // chunk-major: one halo tile per (chunk, term), then one B tile per tap
           uint8_t* b_ring = smem + 2 * C::HALO_BYTES;
           const uint32_t b_tx = (w.width / CTAS) * (BLOCK_K * 2);
-          for (int chunk = 0; chunk < p.chunks; ++chunk) {
+          for (int chunk = w.chunk_begin; chunk < w.chunk_end; ++chunk) {
             for (int term = 0; term < p.terms; ++term) {
               const int a_c = chunk * BLOCK_K + (term == 2 ? p.a_lo_off : 0);
               const int b_c = chunk * BLOCK_K + (term == 1 ? p.b_lo_off : 0);
@@ -246,7 +250,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
                 hbuf = 0;
                 hphase ^= 1;
               }
-              for (int tap = w.tap_begin; tap < w.tap_end; ++tap) {
+              for (int tap = 0; tap < p.taps; ++tap) {
                 const int wtap = p.w_tap0 + tap * p.w_tap_step;
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 uint8_t* b_s = b_ring + stage * C::B_BYTES;
@@ -265,7 +269,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           }
           continue;
         }
-        for (int tap = w.tap_begin; tap < w.tap_end; ++tap) {
+        for (int tap = 0; tap < p.taps; ++tap) {
           const int jp = tap - p.pad_l;  // signed frame offset of this tap
           int q, par;
           if (p.stride == 1) {
@@ -276,7 +280,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             par = jp - q * p.stride;
           }
           const int wtap = p.w_tap0 + tap * p.w_tap_step;
-          for (int chunk = 0; chunk < p.chunks; ++chunk) {
+          for (int chunk = w.chunk_begin; chunk < w.chunk_end; ++chunk) {
             for (int term = 0; term < p.terms; ++term) {
               const int a_c = chunk * BLOCK_K + (term == 2 ? p.a_lo_off : 0);
               const int b_c = chunk * BLOCK_K + (term == 1 ? p.b_lo_off : 0);
@@ -348,7 +352,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     uint32_t hphase = 0;
     for (int tile = cta; tile < num_tiles; tile += n_ctas, ++it) {
       const WorkItem w = decode_item<BN, CTAS>(p, tile, rank);
-      const int ksteps = (w.tap_end - w.tap_begin) * p.chunks * p.terms;
+      const int ksteps = p.taps * (w.chunk_end - w.chunk_begin) * p.terms;
       const uint32_t idesc = make_idesc_bf16(BLOCK_M * CTAS, w.width, 0, BMN ? 1 : 0);
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
@@ -357,9 +361,10 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * BN);
       if (p.halo) {
         const uint32_t b_ring = smem_u32(smem + 2 * C::HALO_BYTES);
-        const int ntaps = w.tap_end - w.tap_begin;
+        const int ntaps = p.taps;
+        const int n_ct = (w.chunk_end - w.chunk_begin) * p.terms;
         uint32_t first = 1;
-        for (int ct = 0; ct < p.chunks * p.terms; ++ct) {
+        for (int ct = 0; ct < n_ct; ++ct) {
           mbar_wait(&halo_full[hbuf], hphase);
           const uint32_t halo_addr = smem_u32(smem + hbuf * C::HALO_BYTES);
           for (int ti = 0; ti < ntaps; ++ti) {
@@ -367,7 +372,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             tcgen05_fence_after();
             if (lane == 0) {
               // tap j reads halo rows [j, j + 128): start address advanced by j rows of 128 B
-              const uint32_t a_addr = halo_addr + static_cast<uint32_t>(w.tap_begin + ti) * 128u;
+              const uint32_t a_addr = halo_addr + static_cast<uint32_t>(ti) * 128u;
               const uint32_t b_addr = b_ring + stage * C::B_BYTES;
 #pragma unroll
               for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
@@ -383,7 +388,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
               }
               commit<CTAS>(&empty_bar[stage]);
               if (ti == ntaps - 1) commit<CTAS>(&halo_empty[hbuf]);
-              if (ti == ntaps - 1 && ct == p.chunks * p.terms - 1) commit<CTAS>(&tmem_full[as]);
+              if (ti == ntaps - 1 && ct == n_ct - 1) commit<CTAS>(&tmem_full[as]);
             }
             __syncwarp();
             if (++stage == C::kStagesB) {
@@ -481,7 +486,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
 
       if (EPI == EPI_F32) {
         // split-K partial sums: fp32 accumulator -> per-warp swizzled slab -> TMA reduce-add
-        const bool has_data = w.tap_end > w.tap_begin;
+        const bool has_data = w.chunk_end > w.chunk_begin;
 #pragma unroll 1
         for (int c = set; c < (has_data ? w.width / 32 : 0); c += kEpiSets) {
           uint32_t r[32];

@@ -29,7 +29,8 @@ struct ConvGemmParams {
   int full_tiles;  // tiles [0, full_tiles) are whole; the rest are split
   int tail_split;
   // split K (EPI_F32 only): every tile is computed by ksplit work items, each over a contiguous
-  // range of filter taps, whose fp32 partial sums meet in HBM through TMA reduce-add
+  // range of 64-channel chunks of the contraction (all taps), whose fp32 partial sums meet in HBM
+  // through TMA reduce-add
   int ksplit;
   // halo mode (stride 1, taps > 1): the A operand of tap j is the same smem tile shifted by j
   // rows, so one halo tile of 128 + taps - 1 frames is loaded per 64-channel chunk and every tap's
