@@ -13,7 +13,7 @@
 // bins wide: ~5 % of the dense 257 x 128 matrix) -> smem.  Per frame: windowed 512-point FFT in shared
 // memory (9 radix-2 stages, one butterfly per thread per stage) of TWO real frames packed as one complex
 // signal, power/dB of both, then 2 x 128 threads each take one mel bin of one frame over its band only.  (The first version did all of the set-up per frame and the
-// dense projection: 1.11 ms for 64 x 1251 frames; see profiles/README.md for this one.)
+// dense projection: 1.07 ms for 64 x 1251 frames; this one: 0.26 ms)
 #include "common.cuh"
 
 namespace sl {
@@ -35,8 +35,12 @@ __global__ void __launch_bounds__(256) spectrogram_kernel(const float* __restric
                                                            int audio_stride, int T_max) {
   __shared__ float span[SPAN];
   __shared__ float window[N_FFT];
-  __shared__ float2 x[N_FFT];
-  __shared__ float2 tw[N_FFT / 2];
+  // x is indexed through PX(i) = i + i / 32: one pad slot per 32 elements makes the bit-reversed scatter of
+  // the windowed frame conflict free (without it the 32 lanes of a store hit one bank: ncu counted 58 % of
+  // all shared-memory wavefronts of the first version as bank conflicts); tw holds the twiddles of every
+  // stage contiguously (stage s, butterfly j at 2^s - 1 + j) instead of one strided table
+  __shared__ float2 x[N_FFT + N_FFT / 32];
+  __shared__ float2 tw[N_FFT];
   __shared__ float level[2][N_BINS + 3];
   __shared__ float band_w[N_MEL][MAX_BAND + 1];  // (+1: conflict-free column walks)
   __shared__ int band_first[N_MEL], band_len[N_MEL];
@@ -50,10 +54,13 @@ __global__ void __launch_bounds__(256) spectrogram_kernel(const float* __restric
   const float* y = audio + static_cast<size_t>(b) * audio_stride;
 
   // ---- per-CTA set-up ----
-  {
+  auto PX = [](int i) { return i + (i >> 5); };
+  for (int idx = tid; idx < N_FFT - 1; idx += 256) {
+    const int stage = 31 - __clz(idx + 1);  // entries 2^s - 1 .. 2^(s+1) - 2 belong to stage s
+    const int j = idx + 1 - (1 << stage);
     float s, c;
-    sincospif(-2.0f * tid / N_FFT, &s, &c);  // twiddles e^{-2 pi i k / 512}
-    tw[tid] = make_float2(c, s);
+    sincospif(-2.0f * (j << (8 - stage)) / N_FFT, &s, &c);  // e^{-2 pi i j 2^(8-s) / 512}
+    tw[idx] = make_float2(c, s);
   }
   for (int n = tid; n < N_FFT; n += 256) window[n] = 0.5f - 0.5f * cospif(2.0f * n / N_FFT);  // periodic Hann
   for (int j = tid; j < SPAN; j += 256) {
@@ -63,19 +70,38 @@ __global__ void __launch_bounds__(256) spectrogram_kernel(const float* __restric
     i = i < 0 ? 0 : i;                      // (signals shorter than the half window)
     span[j] = y[i];
   }
+  // band of non-zero weights of every mel filter: all 256 threads walk the (257, 128) matrix once
+  // (two threads per filter, every other row each; coalesced, L2 resident, independent loads — a
+  // single thread per filter walking its column with a dependent branch per row cost more than the
+  // FFTs of the CTA's 16 frames)
   if (tid < N_MEL) {
-    // band of non-zero weights of mel filter `tid` (coalesced column walk, L2 resident)
+    band_first[tid] = N_BINS;
+    band_len[tid] = -1;  // (holds the last non-zero row until the second barrier)
+  }
+  __syncthreads();
+  {
+    const int m = tid & (N_MEL - 1);
     int first = N_BINS, last = -1;
-    for (int k = 0; k < N_BINS; ++k)
-      if (mel_t[k * N_MEL + tid] != 0.f) {
+#pragma unroll 8
+    for (int k = tid >> 7; k < N_BINS; k += 2) {
+      const float w = __ldg(mel_t + k * N_MEL + m);
+      if (w != 0.f) {
         first = min(first, k);
-        last = k;
+        last = max(last, k);
       }
+    }
+    if (last >= 0) {
+      atomicMin(&band_first[m], first);
+      atomicMax(&band_len[m], last);
+    }
+  }
+  __syncthreads();
+  if (tid < N_MEL) {
+    const int first = band_first[tid], last = band_len[tid];
     const int len = last >= first ? last - first + 1 : 0;
-    band_first[tid] = first;
     band_len[tid] = len;  // > MAX_BAND: dense fallback below
     if (len <= MAX_BAND)
-      for (int j = 0; j < len; ++j) band_w[tid][j] = mel_t[(first + j) * N_MEL + tid];
+      for (int j = 0; j < len; ++j) band_w[tid][j] = __ldg(mel_t + (first + j) * N_MEL + tid);
   }
   __syncthreads();
 
@@ -88,7 +114,8 @@ __global__ void __launch_bounds__(256) spectrogram_kernel(const float* __restric
     for (int h = 0; h < 2; ++h) {
       const int n = tid + h * 256;
       const float w = window[n];
-      x[__brev(static_cast<unsigned>(n)) >> (32 - 9)] = make_float2(w * frame[n], pair ? w * frame[n + HOP] : 0.f);
+      x[PX(static_cast<int>(__brev(static_cast<unsigned>(n)) >> (32 - 9)))] =
+          make_float2(w * frame[n], pair ? w * frame[n + HOP] : 0.f);
     }
     __syncthreads();
 #pragma unroll
@@ -96,16 +123,17 @@ __global__ void __launch_bounds__(256) spectrogram_kernel(const float* __restric
       const int half = 1 << stage;
       const int j = tid & (half - 1);
       const int base = ((tid >> stage) << (stage + 1)) + j;
-      const float2 w = tw[j << (8 - stage)];
-      const float2 a = x[base], bb = x[base + half];
+      const float2 w = tw[half - 1 + j];
+      const int ia = PX(base), ib = PX(base + half);
+      const float2 a = x[ia], bb = x[ib];
       const float2 wb = make_float2(w.x * bb.x - w.y * bb.y, w.x * bb.y + w.y * bb.x);
-      x[base] = make_float2(a.x + wb.x, a.y + wb.y);
-      x[base + half] = make_float2(a.x - wb.x, a.y - wb.y);
+      x[ia] = make_float2(a.x + wb.x, a.y + wb.y);
+      x[ib] = make_float2(a.x - wb.x, a.y - wb.y);
       __syncthreads();
     }
     // power level in dB, floored at -150 (0 -> -150): labeled_example.py:153-160
     for (int k = tid; k < N_BINS; k += 256) {
-      const float2 z = x[k], zc = x[(N_FFT - k) & (N_FFT - 1)];
+      const float2 z = x[PX(k)], zc = x[PX((N_FFT - k) & (N_FFT - 1))];
       const float ar = 0.5f * (z.x + zc.x), ai = 0.5f * (z.y - zc.y);  // F_t[k]
       const float br = 0.5f * (z.y + zc.y), bi = 0.5f * (zc.x - z.x);  // F_{t+1}[k]
       const float p0 = ar * ar + ai * ai, p1 = br * br + bi * bi;
