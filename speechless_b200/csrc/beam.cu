@@ -34,7 +34,7 @@ namespace sl {
 
 namespace {
 
-constexpr int BS_THREADS = 1024;
+constexpr int BS_THREADS = 1024;  // (256 threads x 16 candidates each measured slower: 8.2 vs 7.2 ms at width 100)
 constexpr int BS_MAX_W = 128;
 constexpr int BS_MAX_CAND = 4096;  // beam_width * V candidates per frame
 constexpr int BS_VP = 64;
@@ -85,7 +85,8 @@ __device__ __forceinline__ int block_sum(BeamSmem& sm, int c, int& it) {
   if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = c;
   __syncthreads();
   ++it;
-  return __reduce_add_sync(0xffffffffu, part[threadIdx.x & 31]);
+  const int lane = threadIdx.x & 31;
+  return __reduce_add_sync(0xffffffffu, lane < BS_THREADS / 32 ? part[lane] : 0);
 }
 
 __global__ void __launch_bounds__(BS_THREADS)
@@ -199,14 +200,23 @@ __global__ void __launch_bounds__(BS_THREADS)
     const int n_finite = count_if([](uint32_t k, int) { return k > ORD_NEG_INF; });
     const int n_next = min(W, n_finite);
     uint32_t thr = 0u;
-    for (int bit = 31; bit >= 0; --bit) {
+    bool exact = false;  // some prefix of the threshold already separates exactly n_next candidates
+    for (int bit = 31; bit >= 0 && !exact; --bit) {
       const uint32_t cand = thr | (1u << bit);
-      if (count_if([cand](uint32_t k, int) { return k >= cand; }) >= n_next) thr = cand;
+      const int c = count_if([cand](uint32_t k, int) { return k >= cand; });
+      if (c >= n_next) thr = cand;
+      exact = c == n_next;
     }
-    const int n_greater = count_if([thr](uint32_t k, int) { return k > thr; });
-    const int n_ties = count_if([thr](uint32_t k, int) { return k == thr; });
     int idx_limit = BS_MAX_CAND;  // ties with candidate index <= idx_limit are taken
-    if (n_greater + n_ties > n_next) {
+    int n_greater = 0, n_ties = 0;
+    if (exact) {
+      thr -= 1u;        // "k >= thr" as "k > thr - 1" (thr > 0: it is at least the image of a finite score)
+      idx_limit = -1;   // ...and nothing that merely equals thr - 1
+    } else {
+      n_greater = count_if([thr](uint32_t k, int) { return k > thr; });
+      n_ties = count_if([thr](uint32_t k, int) { return k == thr; });
+    }
+    if (!exact && n_greater + n_ties > n_next) {
       const int need = n_next - n_greater;
       int lo = 0;
       for (int bit = 11; bit >= 0; --bit) {
