@@ -537,6 +537,12 @@ int sl_conv1d_wgrad(const void* x_packed, const void* dy_packed, float* dw, floa
   const int bn = cin_pad >= 256 ? 256 : cin_pad;
   SL_REQUIRE(cin_pad % bn == 0 && (bn == 64 || bn == 128 || bn == 256), "unsupported channel count");
   p.grouped = grouped_tma();
+  // 128 input channels (striding_conv on 128 mel bins): pair adjacent taps into N = 256 tiles
+  const char* pair_env = std::getenv("SL_WGRAD_TAP_PAIR");  // tuning aid: 0 disables
+  const bool tap_pair = bn == 128 && k >= 2 && p.grouped && !(pair_env && std::atoi(pair_env) == 0);
+  p.tap_step = tap_pair ? 2 : 1;
+  p.tap_units = tap_pair ? (k + 1) / 2 : k;
+  const int bn_tile = tap_pair ? 256 : bn;  // columns of the accumulator tile
   int rc = p.grouped ? make_act_group_map(&p.tmDY, dy_packed, planes * cout_pad, 1, T_out, B, 64, 2, false)
                      : make_act_map3(&p.tmDY, dy_packed, planes * cout_pad, T_out, B, 64);
   if (rc) return rc;
@@ -569,13 +575,13 @@ int sl_conv1d_wgrad(const void* x_packed, const void* dy_packed, float* dw, floa
     if (rc) return rc;
   }
   // K split: minimise  waves x (pipeline steps per unit + epilogue)  over the split count
-  const int base_units = k * p.m_tiles * p.n_tiles;
+  const int base_units = p.tap_units * p.m_tiles * p.n_tiles;
   const int k_total = B * p.tchunks;
   int ksplit = 1;
   {
     const int sms = num_sms();
-    const double step_cycles = 512.0 * bn / 256.0 * p.terms;  // 4 MMAs of 128 x bn x 16 per stage
-    const double epilogue_cycles = 1500.0 * bn / 32.0 / 8.0 + 2000.0;
+    const double step_cycles = 512.0 * bn_tile / 256.0 * p.terms;  // 4 MMAs of 128 x bn x 16 per stage
+    const double epilogue_cycles = 1500.0 * bn_tile / 32.0 / 8.0 + 2000.0;
     double best = 1e300;
     for (int ks = 1; ks <= k_total && ks <= 256; ++ks) {
       const int per = (k_total + ks - 1) / ks;
@@ -596,7 +602,7 @@ int sl_conv1d_wgrad(const void* x_packed, const void* dy_packed, float* dw, floa
   p.db = db;
   p.n_filters = Cout;
   if (db != nullptr && !accumulate) SL_CUDA(cudaMemsetAsync(db, 0, static_cast<size_t>(Cout) * sizeof(float), s));
-  return wgrad_launch(p, bn, num_sms(), s);
+  return wgrad_launch(p, bn_tile, num_sms(), s);
 }
 
 size_t sl_ctc_workspace_bytes(int B, int T, int L_max) {

@@ -109,6 +109,12 @@ struct WgradParams {
   int use_atomics;  // 1: TMA reduce-add into dw (split K / accumulate), 0: plain TMA store
   int dbg_mode;     // bring-up only (env SL_DBG_MODE)
   int grouped;      // tmDY rank 4 {64, T_out, C/64, B} / tmX rank 5 {64, S, T/S, C/64, B}: one TMA per operand
+  // tap pairing (cin_pad == 128, grouped maps only): a 256-column tile holds the 128 input channels of
+  // TWO adjacent taps — the X box of tap j and the one of tap j + 1 — so the MMAs run at N = 256 (an
+  // N = 128 MMA occupies the tensor pipe as long as an N = 256 one) and the dY tiles are staged once
+  // per tap pair.  tap_step = 2, tap_units = ceil(taps / 2); otherwise tap_step = 1, tap_units = taps.
+  int tap_step;
+  int tap_units;
 };
 
 int wgrad_launch(const WgradParams& p, int block_n, int num_sms, cudaStream_t stream);

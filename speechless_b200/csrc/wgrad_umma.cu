@@ -97,14 +97,14 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
 
   // unit -> (tap fastest, then m_tile, n_tile, split): CTAs running together work on the
   // same K range, i.e. read the same dY / X slabs from L2, and reduce into different dW tiles.
-  const int num_units = p.taps * p.m_tiles * p.n_tiles * p.ksplit;
+  const int num_units = p.tap_units * p.m_tiles * p.n_tiles * p.ksplit;
   const int k_total = p.B * p.tchunks;  // (utterance, frame chunk) pairs
   const int k_per = (k_total + p.ksplit - 1) / p.ksplit;
 
   auto decode = [&](int unit, int& tap, int& mt, int& nt, int& k_begin, int& k_end) {
     int u = unit;
-    tap = u % p.taps;
-    u /= p.taps;
+    tap = (u % p.tap_units) * p.tap_step;  // first tap of the unit (tap pairing: taps tap, tap + 1)
+    u /= p.tap_units;
     mt = u % p.m_tiles;
     u /= p.m_tiles;
     nt = u % p.n_tiles;
@@ -130,6 +130,19 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
         } else {
           q = jp >= 0 ? jp / p.stride : -((-jp + p.stride - 1) / p.stride);
           par = jp - q * p.stride;
+        }
+        // tap pairing: frame shift / parity of the second tap (a tap past the filter reads zeros
+        // through an out-of-range channel-group coordinate)
+        int q2 = 0, par2 = 0;
+        const bool second_valid = p.tap_step == 2 && tap + 1 < p.taps;
+        if (p.tap_step == 2) {
+          const int jp2 = jp + 1;
+          if (p.stride == 1) {
+            q2 = jp2;
+          } else {
+            q2 = jp2 >= 0 ? jp2 / p.stride : -((-jp2 + p.stride - 1) / p.stride);
+            par2 = jp2 - q2 * p.stride;
+          }
         }
         const int co0 = mt * BLOCK_M;
         const int ci0 = nt * BN;
@@ -158,7 +171,15 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
               // the tensor read as zeros; for output_conv (64 filters) the second group of the
               // 128-row tile is zero or the lo plane, and those rows are clipped at the store.
               tma_load_4d(&p.tmDY, &full_bar[stage], a_s, 0, tr, (co0 + dy_off) >> 6, b);
-              tma_load_5d(&p.tmX, &full_bar[stage], b_s, 0, par, tr + q, (ci0 + x_off) >> 6, b);
+              if (p.tap_step == 2) {
+                // two boxes of 2 channel groups each: columns [0, 128) = tap, [128, 256) = tap + 1
+                const int g = x_off >> 6;
+                tma_load_5d(&p.tmX, &full_bar[stage], b_s, 0, par, tr + q, g, b);
+                tma_load_5d(&p.tmX, &full_bar[stage], b_s + 2 * BOX_BYTES, 0, par2, tr + q2,
+                            second_valid ? g : (1 << 20), b);
+              } else {
+                tma_load_5d(&p.tmX, &full_bar[stage], b_s, 0, par, tr + q, (ci0 + x_off) >> 6, b);
+              }
             } else {
 #pragma unroll
               for (int i = 0; i < 2; ++i) {
@@ -229,8 +250,8 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
       decode(unit, tap, mt, nt, k_begin, k_end);
       // All taps x channel tiles of one (filter tile, K split) stream the same dY tiles, so the
       // column-sum work is dealt round-robin: this unit sums every `slices`-th frame chunk.
-      const int slices = p.taps * p.n_tiles;
-      const int my_slice = tap * p.n_tiles + nt;
+      const int slices = p.tap_units * p.n_tiles;
+      const int my_slice = (tap / p.tap_step) * p.n_tiles + nt;
       const int ksteps = (k_end - k_begin) * p.terms;
       float acc[4] = {0.f, 0.f, 0.f, 0.f};
       int term = 0;
@@ -309,10 +330,15 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
           __syncwarp();
           if (lane == 0) {
             // rows beyond cout_pad (output_conv: 64 of 128) are clipped by the tensor map
-            if (p.use_atomics)
-              tma_reduce_add_3d(&p.tmDW, sbuf, nt * BN + c * 32, mt * BLOCK_M + ew * 32, tap);
-            else
-              tma_store_3d(&p.tmDW, sbuf, nt * BN + c * 32, mt * BLOCK_M + ew * 32, tap);
+            // tap pairing: columns [128, 256) of the tile are the second tap's 128 input channels
+            const int col = p.tap_step == 2 ? (c & 3) * 32 : nt * BN + c * 32;
+            const int tap_c = p.tap_step == 2 ? tap + (c >> 2) : tap;
+            if (tap_c < p.taps) {
+              if (p.use_atomics)
+                tma_reduce_add_3d(&p.tmDW, sbuf, col, mt * BLOCK_M + ew * 32, tap_c);
+              else
+                tma_store_3d(&p.tmDW, sbuf, col, mt * BLOCK_M + ew * 32, tap_c);
+            }
             tma_commit_group();
           }
           ++store_count;
@@ -345,7 +371,7 @@ int launch(const WgradParams& p, int num_sms, cudaStream_t stream) {
                                  C::SMEM_BYTES));
     configured |= 1ull << (dev & 63);
   }
-  const int num_units = p.taps * p.m_tiles * p.n_tiles * p.ksplit;
+  const int num_units = p.tap_units * p.m_tiles * p.n_tiles * p.ksplit;
   const int grid = num_units < num_sms ? num_units : num_sms;
   SL_CUDA(launch_pdl(PDL_WGRAD, wgrad_kernel<BN>, dim3(grid), dim3(kThreads), C::SMEM_BYTES, stream, p));
   return 0;

@@ -809,6 +809,10 @@ int main(int argc, char** argv) {
       {"big1_k32_250_2000", 1, 150, 250, 2000, 32, 1, 0},
       {"big2_k1_2000_2000", 1, 200, 2000, 2000, 1, 1, 0},
       {"out_k1_2000_29", 2, 151, 2000, 29, 1, 1, 0},
+      // 128 input channels: adjacent taps are paired into N = 256 tiles (odd tap counts leave a half-empty pair)
+      {"pair_k5_128x250", 2, 300, 128, 250, 5, 1, 0},
+      {"pair_k7_s2_128x64", 3, 301, 128, 64, 7, 2, 0},
+      {"pair_k2_128x128", 2, 200, 128, 128, 2, 1, 0},
   };
   for (const auto& cc : wg_cases)
     for (int prec = 1; prec <= 2; ++prec) {
