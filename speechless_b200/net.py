@@ -453,6 +453,19 @@ class Wav2Letter:
                  for p in range(decoded.shape[1]) if numpy.isfinite(log_probabilities[b, p])]
                 for b in range(decoded.shape[0])]
 
+    def predict_batch_with_beam_search(self, spectrograms: List[ndarray], beam_width: Optional[int] = None,
+                                       top_paths: int = 1) -> List[List[Tuple[str, float]]]:
+        """Beam-search counterpart of `predict_batch_greedily`: per utterance the `top_paths` best
+        (text, log-probability) hypotheses of the device prefix beam search (no language model)."""
+        input_batch, prediction_lengths = self._input_batch_and_prediction_lengths(spectrograms)
+        tower = self.tower
+        ws = tower.upload(input_batch)
+        tower.forward(ws)
+        tower.set_prediction_lengths(ws, prediction_lengths)
+        return [[(self.grapheme_encoding.decode_graphemes(graphemes, merge_repeated=False), log_probability)
+                 for graphemes, log_probability in hypotheses]
+                for hypotheses in self.beam_search_batch(ws, beam_width=beam_width, top_paths=top_paths)]
+
     def _beam_search_with_language_model(self, ws) -> ndarray:
         """Dense (B, max length) grapheme matrix, -1 padded like the greedy path: the hypothesis of the
         device beam search that the language model re-scores best."""

@@ -190,3 +190,12 @@ def test_wav2letter_decodes_with_beam_search_and_language_model(tmp_path):
     for result, hypotheses in zip(with_lm.results, n_best):
         texts = [net.grapheme_encoding.decode_graphemes(g, merge_repeated=False) for g, _ in hypotheses]
         assert result.predicted in texts
+    # the public beam-search call: best hypothesis first, log-probabilities descending; with width 1 on
+    # these near-uniform outputs it still returns exactly one hypothesis per utterance
+    spectrograms = [e.z_normalized_transposed_spectrogram() for e in batch]
+    ranked = greedy.predict_batch_with_beam_search(spectrograms, beam_width=16, top_paths=4)
+    assert len(ranked) == 2 and all(len(h) == 4 for h in ranked)
+    for hypotheses in ranked:
+        scores = [score for _, score in hypotheses]
+        assert scores == sorted(scores, reverse=True)
+    assert [len(h) for h in greedy.predict_batch_with_beam_search(spectrograms, beam_width=1)] == [1, 1]
