@@ -87,7 +87,7 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-        sm, sm_max, reasons = [], None, set()
+        sm, sm_max, reasons, power = [], None, set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         t_mark = getattr(self, "t_mark", 0.0)
         for stamp, line in self.lines:
@@ -101,12 +101,17 @@ class ClockSampler:
                 sm_max = float(parts[2])
             except ValueError:
                 continue
+            try:
+                power.append(float(parts[3]))
+            except ValueError:
+                pass
             for name, value in zip(names, parts[4:8]):
                 if value.lower().startswith("active"):
                     reasons.add(name)
         sm.sort()
+        power.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": sm_max, "samples": len(sm),
-                "reasons": sorted(reasons)}
+                "reasons": sorted(reasons), "power_w": power[len(power) // 2] if power else None}
 
 
 def measured_peaks():
