@@ -198,16 +198,6 @@ static int make_weight_group_map(CUtensorMap* m, const void* base, int k_total, 
 
 using namespace sl;
 
-// 16-channel MMA steps the last 64-channel chunk of a contraction over `real` channels needs: the padding
-// channels are zero, so their MMAs are skipped (2000 channels: 31 chunks + 16 channels -> 1 step of 4)
-static int last_chunk_ummas(int real, int padded) {
-  if (const char* e = std::getenv("SL_FULL_K"))  // tuning aid: 1 = issue the MMAs of the padding channels too
-    if (std::atoi(e) == 1) return 4;
-  const int in_last = real - (padded - 64);
-  const int n = (in_last + 15) / 16;
-  return n < 1 ? 1 : (n > 4 ? 4 : n);
-}
-
 extern "C" {
 
 int sl_version(void) { return 100; }
@@ -335,7 +325,6 @@ int sl_conv1d_fwd(const void* x_packed, const void* w_fwd, const float* bias, vo
   }
   p.taps = k;
   p.chunks = cin_pad / 64;
-  p.last_chunk_ummas = last_chunk_ummas(Cin, cin_pad);
   p.terms = planes == 2 ? 3 : 1;
   p.a_lo_off = cin_pad;
   p.b_lo_off = cin_pad;
@@ -406,7 +395,7 @@ size_t sl_conv1d_dgrad_workspace_bytes(int B, int T, int Cin, int Cout, int k) {
 // one launch of the input-gradient GEMM: the output rows u = out_scale_t * v + out_off (v = 0..rows-1)
 // of dX, filter taps w_tap0, w_tap0 + w_step, ... (n_taps of them), dY frames shifted by i - a_pad
 static int dgrad_launch_rows(const void* dy_packed, const void* w_fwd, const void* relu_mask, void* dx_packed, int B,
-                             int T, int T_dy, int cin_pad, int cout_pad, int Cin, int Cout, int k, int planes, float out_scale,
+                             int T, int T_dy, int cin_pad, int cout_pad, int Cin, int k, int planes, float out_scale,
                              int rows, int row_step, int row_off, int n_taps, int w_tap0, int w_step, int a_pad,
                              void* workspace, size_t workspace_bytes, bool allow_ksplit, cudaStream_t s) {
   ConvGemmParams p;
@@ -445,7 +434,6 @@ static int dgrad_launch_rows(const void* dy_packed, const void* w_fwd, const voi
   }
   p.taps = n_taps;
   p.chunks = cout_pad / 64;
-  p.last_chunk_ummas = last_chunk_ummas(Cout, cout_pad);
   p.terms = planes == 2 ? 3 : 1;
   p.a_lo_off = cout_pad;
   p.b_lo_off = cin_pad;
@@ -503,7 +491,7 @@ int sl_conv1d_dgrad(const void* dy_packed, const void* w_fwd, const void* relu_m
   same_padding(T, k, stride, &T_out, &pad_l);
   if (stride == 1) {
     // dX[u] = sum_j dY[u + pad_l - j] W[j]  (SURVEY.md A.1): taps walked backwards
-    return dgrad_launch_rows(dy_packed, w_fwd, relu_mask, dx_packed, B, T, T_out, cin_pad, cout_pad, Cin, Cout, k, planes,
+    return dgrad_launch_rows(dy_packed, w_fwd, relu_mask, dx_packed, B, T, T_out, cin_pad, cout_pad, Cin, k, planes,
                              out_scale, T, 1, 0, k, k - 1, -1, k - 1 - pad_l, workspace, workspace_bytes, true, s);
   }
   // stride 2: y[v'] = sum_j x[2 v' + j - pad_l] W[j], so the rows u = 2 v + r of dX only see the taps
@@ -523,7 +511,7 @@ int sl_conv1d_dgrad(const void* dy_packed, const void* w_fwd, const void* relu_m
     }
     const int n_taps = jmax / 2 + 1;
     const int c_r = (r + pad_l - jmax) / 2;  // exact: the numerator is even
-    const int rc = dgrad_launch_rows(dy_packed, w_fwd, relu_mask, dx_packed, B, T, T_out, cin_pad, cout_pad, Cin, Cout, k,
+    const int rc = dgrad_launch_rows(dy_packed, w_fwd, relu_mask, dx_packed, B, T, T_out, cin_pad, cout_pad, Cin, k,
                                      planes, out_scale, rows, 2, r, n_taps, jmax, -2, -c_r, nullptr, 0, false, s);
     if (rc) return rc;
   }

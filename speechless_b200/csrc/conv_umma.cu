@@ -367,8 +367,6 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         for (int ct = 0; ct < n_ct; ++ct) {
           mbar_wait(&halo_full[hbuf], hphase);
           const uint32_t halo_addr = smem_u32(smem + hbuf * C::HALO_BYTES);
-          // the zero padding channels of the last chunk need no MMAs
-          const int n_umma = (w.chunk_begin + ct / p.terms == p.chunks - 1) ? p.last_chunk_ummas : BLOCK_K / UMMA_K;
           for (int ti = 0; ti < ntaps; ++ti) {
             mbar_wait(&full_bar[stage], phase);
             tcgen05_fence_after();
@@ -378,7 +376,6 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
               const uint32_t b_addr = b_ring + stage * C::B_BYTES;
 #pragma unroll
               for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                if (k >= n_umma) break;
                 const uint32_t aa = a_addr + k * UMMA_K * 2;
                 const uint64_t da = make_smem_desc_sw128_off(aa, 16, 1024, p.halo_base_mode ? (aa >> 7) & 7u : 0u);
                 const uint64_t db = BMN ? make_smem_desc_sw128(b_addr + k * 2048, BLOCK_K * 128, 1024)
@@ -410,19 +407,14 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         }
         continue;
       }
-      const int item_chunks = w.chunk_end - w.chunk_begin;
       for (int ks = 0; ks < ksteps; ++ks) {
         mbar_wait(&full_bar[stage], phase);
         tcgen05_fence_after();
-        // producer order: tap, chunk, term — the zero padding channels of the last chunk need no MMAs
-        const int chunk = w.chunk_begin + (ks / p.terms) % item_chunks;
-        const int n_umma = chunk == p.chunks - 1 ? p.last_chunk_ummas : BLOCK_K / UMMA_K;
         if (lane == 0) {
           const uint32_t a_addr = smem_u32(smem + stage * C::STAGE_BYTES);
           const uint32_t b_addr = a_addr + A_BYTES;
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            if (k >= n_umma) break;
             const uint64_t da = make_smem_desc_sw128(a_addr + k * UMMA_K * 2, 16, 1024);
             // MN-major B: 16 contraction rows = two 8-row swizzle atoms (2048 B); 64-channel
             // groups are BLOCK_K * 128 B apart (leading byte offset)

@@ -40,7 +40,6 @@ struct ConvGemmParams {
   int halo_base_mode;  // bring-up: 0 = descriptor base_offset 0, 1 = (start address >> 7) & 7
   int taps;
   int chunks;  // 64-channel chunks of the contraction dimension
-  int last_chunk_ummas;  // 16-channel MMA steps of the last chunk that touch real channels (1..4)
   int terms;   // 1 = bf16, 3 = split bf16 (hi*hi + hi*lo + lo*hi)
   int a_lo_off;
   int b_lo_off;
