@@ -97,6 +97,23 @@ def test_arpa_back_off_and_rescoring(tmp_path):
     assert rescorer.best([("the cxt", -4.0), ("the cat", -5.0)])[0] == "the cat"
 
 
+def test_arpa_reader_accepts_space_separated_files_and_rejects_garbage(tmp_path):
+    from speechless_b200.language_model import ArpaLanguageModel, find_arpa_file
+    spaced = ARPA.replace("-1.5\tthe cat is not a word\t0.0\n", "").replace("\t", " ")
+    (tmp_path / "spaced.arpa").write_text(spaced, encoding="utf8")
+    lm = ArpaLanguageModel.read(tmp_path / "spaced.arpa")
+    assert lm.knows("cat") and not lm.knows("dog")
+    assert lm.log10_probability("cat", ["the"]) == pytest.approx(-0.3)
+    (tmp_path / "bad.arpa").write_text("\\data\\\n\n\\1-grams:\nnot-a-number\n\\end\\\n", encoding="utf8")
+    with pytest.raises(ValueError):
+        ArpaLanguageModel.read(tmp_path / "bad.arpa")
+    (tmp_path / "empty.arpa").write_text("\\data\\\n\\end\\\n", encoding="utf8")
+    with pytest.raises(ValueError):
+        ArpaLanguageModel.read(tmp_path / "empty.arpa")
+    assert find_arpa_file(tmp_path).name == "bad.arpa"  # (first in sorted order)
+    assert find_arpa_file(tmp_path / "nowhere") is None
+
+
 def _random_case(rng, B, T, V, peaky):
     logits = rng.normal(size=(B, T, V)) * peaky
     probabilities = np.exp(bso.log_softmax(logits)).astype(np.float32)
