@@ -31,6 +31,27 @@ def test_wide_beam_is_exact_against_path_enumeration():
             assert log_probability == pytest.approx(totals[tuple(labels)], abs=1e-9)
 
 
+def test_beam_hypothesis_scores_are_bounded_by_the_ctc_forward_likelihood():
+    """Two oracles against each other: the score a beam search reports for a labeling is the mass of the
+    alignments it kept, so it can never exceed log p(labeling | x) of the CTC forward algorithm
+    (keras_tf_oracle.ctc_alpha_beta) and equals it when no relevant prefix was ever pruned."""
+    from oracle import keras_tf_oracle as oracle
+    rng = np.random.default_rng(11)
+    equal = 0
+    for _ in range(25):
+        T, V = int(rng.integers(5, 40)), int(rng.integers(3, 8))
+        scores = rng.normal(size=(T, V)) * rng.uniform(1, 4)
+        lp = bso.log_softmax(scores)
+        for width in (2, 8, 64):
+            for tf_like in (True, False):
+                for labels, log_probability in bso.beam_search_decode(scores, beam_width=width, top_paths=3,
+                                                                     merge_repeated=False, tf_deactivation=tf_like):
+                    exact = oracle.ctc_alpha_beta(lp, labels, V - 1)[2] if labels else float(lp[:, V - 1].sum())
+                    assert log_probability <= exact + 1e-9
+                    equal += abs(log_probability - exact) < 1e-9
+    assert equal > 0  # (some hypotheses keep all of their alignments even in narrow beams)
+
+
 def test_tf_deactivation_only_matters_for_narrow_beams():
     """The order-independent rule the kernel implements equals TF's for beam_width = 1 and for beams
     that never overflow; in between it may keep hypotheses TF drops (never a worse best path)."""
