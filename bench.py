@@ -357,6 +357,9 @@ def run_ours(args):
         "traffic": ncu_traffic(top["kernel"], args.workload, dtype),
         "algorithmic_flops": flops.get((top_kind, top_name)),
         "peak_source": "{} ({})".format("bf16_tflops_sustained of MEASURED_PEAKS.json", peaks["source"]),
+        # for orientation: the burst figure (a kernel timed alone) and the fraction against it
+        "peak_burst": peaks["bf16_tflops"],
+        "frac_burst": round(top["tflops"] / peaks["bf16_tflops"], 4) if "tflops" in top else None,
         "mma_terms_per_product": terms,
         "timing": "CUDA-event pair around each launch, {} instrumented steps right after the timed region "
                   "({:.3f} ms/step instrumented vs {:.3f} uninstrumented)".format(args.steps, ms_instrumented, ms_device),
