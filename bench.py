@@ -415,7 +415,7 @@ def main():
     parser.add_argument("--impl", default="ours", choices=["ours", "reference"])
     parser.add_argument("--workload", default="full", choices=sorted(WORKLOADS))
     parser.add_argument("--batch-per-gpu", type=int, default=None)
-    parser.add_argument("--dtype", default=None, choices=["bf16", "bf16x2"])
+    parser.add_argument("--dtype", default=None, choices=["bf16", "bf16x2", "fp16"])
     parser.add_argument("--no-cpu-baseline", action="store_true")
     parser.add_argument("--overlap-backward", type=int, default=0, help="run wgrad on a side stream (experiment)")
     parser.add_argument("--e2e-mode", default="fit", choices=["fit", "step"],

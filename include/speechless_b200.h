@@ -16,9 +16,9 @@
  *    nothing throws or aborts across the ABI;
  *  - activations are channels-last (B, T, C) like Keras' Conv1D
  *    (net.py:304-305).  The tensor-core kernels read/write the *packed* form:
- *    bf16, channels zero-padded to a multiple of 64, optionally followed by a
- *    second "lo" plane (x - bf16(x)) in the same row for the split-bf16
- *    (fp32-parity) mode: row = [hi(C_pad) | lo(C_pad)].
+ *    16-bit elements (bf16, or fp16 in SL_PREC_FP16), channels zero-padded to a
+ *    multiple of 64, optionally followed by a second "lo" plane (x - bf16(x)) in
+ *    the same row for the split-bf16 (fp32-parity) mode: row = [hi(C_pad) | lo(C_pad)].
  */
 #ifndef SPEECHLESS_B200_H
 #define SPEECHLESS_B200_H
@@ -35,9 +35,13 @@ extern "C" {
 #define SL_ERR_CUDA 2      /* CUDA runtime / driver error                 */
 #define SL_ERR_INFEASIBLE 3 /* CTC label not alignable in the given frames */
 
-/* precision of the packed bf16 tensors */
-#define SL_PREC_BF16 1    /* one bf16 plane, fp32 accumulate                 */
-#define SL_PREC_BF16X2 2  /* hi+lo bf16 planes, 3-term product (~fp32 parity) */
+/* precision of the packed 16-bit tensors (every tensor of one call chain uses the same one) */
+#define SL_PREC_BF16 1    /* one bf16 plane, fp32 accumulate: 8 mantissa bits, fp32 range         */
+#define SL_PREC_BF16X2 2  /* hi+lo bf16 planes, 3-term product (~fp32 parity), 3 MMAs per product  */
+#define SL_PREC_FP16 3    /* one fp16 plane, fp32 accumulate: 11 mantissa bits at the cost of the
+                             bf16 mode (logits <= 1e-3 rel at reference widths); gradients need a
+                             power-of-two loss scale: pass it in sl_ctc_loss' grad_scale and its
+                             inverse in sl_conv1d_wgrad's out_scale                                 */
 
 /* epilogue / activation selector of sl_conv1d_fwd (net.py:298,304-305,328-330) */
 #define SL_ACT_NONE 0
@@ -125,11 +129,12 @@ size_t sl_conv1d_dgrad_workspace_bytes(int B, int T, int Cin, int Cout, int k);
 
 /* dW (k,cout_pad,cin_pad) fp32 += sum_{b,t} x[b,t*s+j-pad_l,ci]*dy[b,t,co];
  * db (Cout) fp32 = sum_{b,t} dy.  dW/db are overwritten (accumulate=0) or
- * accumulated into (accumulate=1). */
+ * accumulated into (accumulate=1).  out_scale multiplies both sums on their way
+ * out (1 unless dy carries a loss scale, SL_PREC_FP16). */
 int sl_conv1d_wgrad(const void* x_packed, const void* dy_packed, float* dw,
                     float* db, int B, int T_in, int T_in_alloc, int Cin,
                     int Cout, int k, int stride, int prec, int accumulate,
-                    void* stream);
+                    float out_scale, void* stream);
 
 /* master-weight layout helpers: Keras (k,Cin,Cout) fp32 <-> internal (k,cout_pad,cin_pad) fp32 */
 int sl_weights_keras_to_internal(const float* w_keras, float* w_int, int k,
@@ -216,6 +221,29 @@ int sl_adam_step_fused(float* p, const float* g, float* m, float* v, size_t n,
                        void* const* w_fwd_host, const int* cin_pad_host, int n_layers,
                        int prec, float lr, float beta1, float beta2, float eps, int t,
                        void* stream);
+
+/* ---- data-parallel exchange step (the reference is single-process, so this replaces
+ * nothing in it: it is the collective the mean-over-batch objective of net.py:389 needs once the
+ * minibatch is sharded by utterance) ---- */
+#define SL_COMM_ID_BYTES 128
+/* rank 0: writes SL_COMM_ID_BYTES bytes of rendezvous id into id_out (HOST memory); the caller hands
+ * them to every rank (any side channel). */
+int sl_comm_unique_id(void* id_out_host);
+/* every rank, on its own GPU (cudaSetDevice first): joins the communicator of `nranks` processes.
+ * max_ctas > 0 bounds the CTAs the collective kernels may occupy (they run next to persistent
+ * one-CTA-per-SM tensor-core kernels); 0 = NCCL's default.  *comm_out is an opaque handle. */
+int sl_comm_init_rank(void** comm_out, const void* id_host, int nranks, int rank, int max_ctas);
+int sl_comm_size(void* comm);
+/* in-place SUM all-reduce of count floats at buf (device), stream ordered */
+int sl_allreduce_sum(void* comm, float* buf, size_t count, void* stream);
+int sl_comm_destroy(void* comm);
+int sl_comm_nccl_version(void);
+
+/* Upper bound on the CTAs of the persistent Conv1D kernels launched from now on by this process
+ * (0 = every SM of the device).  The data-parallel engine lowers it while a gradient bucket's
+ * all-reduce is in flight so that the collective's CTAs find free SMs instead of delaying the last
+ * CTAs of a 148-CTA grid. */
+int sl_set_sm_limit(int max_ctas);
 
 #ifdef __cplusplus
 }

@@ -78,10 +78,21 @@ def conv1d_same_backward(x: np.ndarray, w: np.ndarray, dy: np.ndarray, stride: i
     dw = np.zeros_like(w)
     for j in range(k):
         sl = slice(j, j + (t_out - 1) * stride + 1, stride)
-        dw[j] = np.einsum("bti,bto->io", xp[:, sl], dy)
+        dw[j] = np.tensordot(xp[:, sl], dy, axes=([0, 1], [0, 1]))  # sum_{b,t} x[b,t,i] dy[b,t,o]
         dxp[:, sl] += dy @ w[j].T
     db = dy.sum(axis=(0, 1))
     return dxp[:, pad_l:pad_l + T], dw, db
+
+
+def conv1d_same_backward_input(w: np.ndarray, dy: np.ndarray, T: int, stride: int = 1) -> np.ndarray:
+    """Only the input gradient of conv1d_same (for large shapes where dW is not wanted)."""
+    B = dy.shape[0]
+    k, Cin, _ = w.shape
+    t_out, pad_l, pad_r = same_padding(T, k, stride)
+    dxp = np.zeros((B, T + pad_l + pad_r, Cin), dtype=dy.dtype)
+    for j in range(k):
+        dxp[:, j:j + (t_out - 1) * stride + 1:stride] += dy @ w[j].T
+    return dxp[:, pad_l:pad_l + T]
 
 
 def softmax(z: np.ndarray) -> np.ndarray:
@@ -150,8 +161,11 @@ class Wav2LetterOracle:
         return a
 
     def loss_and_gradients(self, x, labels: np.ndarray, prediction_lengths, label_lengths, dropout_masks=None,
-                           dropout_scale: float = 1.0):
-        """Mean-over-batch CTC objective (net.py:389) and its gradient wrt every kernel / bias."""
+                           dropout_scale: float = 1.0, relu_masks=None):
+        """Mean-over-batch CTC objective (net.py:389) and its gradient wrt every kernel / bias.
+        `relu_masks` (optional, {layer index: bool (B, T', Cout)}) replaces the oracle's own ReLU sign
+        pattern: the gradient is discontinuous where a pre-activation crosses zero, so a reduced-precision
+        forward pass that flips a few near-zero units is compared "given the sign pattern it saw"."""
         probs, logits, inputs = self.forward(x, keep=True, dropout_masks=dropout_masks, dropout_scale=dropout_scale)
         B = probs.shape[0]
         losses, dlogits = ctc_batch_cost_with_logit_grad(probs, labels, prediction_lengths, label_lengths)
@@ -161,7 +175,10 @@ class Wav2LetterOracle:
             _, _, _, _, stride, act = self.specs[i]
             if act == "relu":
                 # d is the gradient wrt this layer's post-activation output
-                z_pos = conv1d_same(inputs[i], self.weights[i], self.biases[i], stride) > 0
+                if relu_masks is not None and relu_masks.get(i) is not None:
+                    z_pos = relu_masks[i]
+                else:
+                    z_pos = conv1d_same(inputs[i], self.weights[i], self.biases[i], stride) > 0
                 d = d * z_pos
             dx, dws[i], dbs[i] = conv1d_same_backward(inputs[i], self.weights[i], d, stride)
             if dropout_masks is not None and dropout_masks.get(i) is not None:

@@ -10,6 +10,8 @@ from pathlib import Path
 
 PREC_BF16 = 1
 PREC_BF16X2 = 2
+PREC_FP16 = 3
+PRECISIONS = {"bf16": PREC_BF16, "bf16x2": PREC_BF16X2, "fp16": PREC_FP16}
 ACT_NONE, ACT_RELU, ACT_SOFTMAX = 0, 1, 2
 
 _LIB_NAME = "libspeechless_b200.so"
@@ -33,7 +35,7 @@ SIGNATURES = {
                                ctypes.c_uint64, c_void_p]),
     "sl_conv1d_dgrad_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "sl_conv1d_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
-                                c_int, c_int, c_int, c_void_p]),
+                                c_int, c_int, c_int, c_float, c_void_p]),
     "sl_weights_keras_to_internal": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "sl_weights_internal_to_keras": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "sl_pack_weights_internal": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
@@ -52,7 +54,15 @@ SIGNATURES = {
                              c_int, c_void_p]),
     "sl_adam_step_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_int, c_int, c_float, c_float, c_float, c_float, c_int, c_void_p]),
+    "sl_comm_unique_id": (c_int, [c_void_p]),
+    "sl_comm_init_rank": (c_int, [ctypes.POINTER(c_void_p), c_void_p, c_int, c_int, c_int]),
+    "sl_comm_size": (c_int, [c_void_p]),
+    "sl_allreduce_sum": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "sl_comm_destroy": (c_int, [c_void_p]),
+    "sl_comm_nccl_version": (c_int, []),
+    "sl_set_sm_limit": (c_int, [c_int]),
 }
+COMM_ID_BYTES = 128
 
 
 def library_path() -> Path:

@@ -52,15 +52,17 @@ static int dbg_mode() {
   const char* e = std::getenv("SL_DBG_MODE");  // measurement aid for kernel bring-up; results are garbage
   return e ? std::atoi(e) : 0;
 }
-static int planes_of(int prec) { return prec == SL_PREC_BF16X2 ? 2 : 1; }
+static int planes_of(int prec) { return prec_planes(prec); }
+static bool valid_prec(int prec) { return prec == SL_PREC_BF16 || prec == SL_PREC_BF16X2 || prec == SL_PREC_FP16; }
 
+static int g_sm_limit = 0;  // sl_set_sm_limit: CTAs the persistent conv grids may use (0 = all SMs)
 static int num_sms() {
   static int cached[64] = {0};
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 148;
   int& n = cached[dev & 63];
   if (n == 0 && (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)) n = 148;
-  return n;
+  return (g_sm_limit > 0 && g_sm_limit < n) ? g_sm_limit : n;
 }
 
 // TF "SAME" padding
@@ -209,6 +211,12 @@ int sl_last_error(char* buf, size_t n) {
   return SL_OK;
 }
 
+int sl_set_sm_limit(int max_ctas) {
+  SL_REQUIRE(max_ctas >= 0, "limit must be >= 0");
+  g_sm_limit = max_ctas;
+  return SL_OK;
+}
+
 int sl_sync_check(void) {
   SL_CUDA(cudaDeviceSynchronize());
   SL_CUDA(cudaGetLastError());
@@ -220,7 +228,8 @@ int sl_pack_activation(const float* x, void* x_packed, int B, int T, int C, int 
   SL_REQUIRE(x && x_packed, "null pointer");
   SL_REQUIRE(B > 0 && T > 0 && C > 0 && T_alloc >= T, "bad shape");
   SL_REQUIRE(c_pad % 64 == 0 && c_pad >= C, "c_pad must be a multiple of 64 and >= C");
-  return pack_activation_launch(x, x_packed, B, T, C, T_alloc, c_pad, planes_of(prec),
+  SL_REQUIRE(valid_prec(prec), "bad precision");
+  return pack_activation_launch(x, x_packed, B, T, C, T_alloc, c_pad, prec,
                                 static_cast<cudaStream_t>(stream));
 }
 
@@ -232,7 +241,8 @@ int sl_window_activation(const float* x, void* x_windowed, int B, int T, int C, 
   SL_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "dropout rate must be in [0, 1)");
   int T_out, pad_l;
   same_padding(T, k, stride, &T_out, &pad_l);
-  return window_activation_launch(x, x_windowed, B, T, C, k, stride, T_out, pad_l, c_pad, planes_of(prec), drop_p,
+  SL_REQUIRE(valid_prec(prec), "bad precision");
+  return window_activation_launch(x, x_windowed, B, T, C, k, stride, T_out, pad_l, c_pad, prec, drop_p,
                                   seed, static_cast<cudaStream_t>(stream));
 }
 
@@ -240,7 +250,8 @@ int sl_unpack_activation(const void* x_packed, float* x, int B, int T, int C, in
                          int prec, void* stream) {
   SL_REQUIRE(x && x_packed, "null pointer");
   SL_REQUIRE(B > 0 && T > 0 && C > 0 && T_alloc >= T && c_pad >= C, "bad shape");
-  return unpack_activation_launch(x_packed, x, B, T, C, T_alloc, c_pad, planes_of(prec),
+  SL_REQUIRE(valid_prec(prec), "bad precision");
+  return unpack_activation_launch(x_packed, x, B, T, C, T_alloc, c_pad, prec,
                                   static_cast<cudaStream_t>(stream));
 }
 
@@ -262,7 +273,8 @@ int sl_pack_weights_internal(const float* w_int, void* w_fwd, int k, int cin_pad
                              void* stream) {
   SL_REQUIRE(w_int && w_fwd, "null pointer");
   SL_REQUIRE(cin_pad % 64 == 0 && cout_pad % 64 == 0 && k > 0, "bad shape");
-  return pack_weights_internal_launch(w_int, w_fwd, k, cin_pad, cout_pad, planes_of(prec),
+  SL_REQUIRE(valid_prec(prec), "bad precision");
+  return pack_weights_internal_launch(w_int, w_fwd, k, cin_pad, cout_pad, prec,
                                       static_cast<cudaStream_t>(stream));
 }
 
@@ -270,12 +282,13 @@ int sl_pack_weights(const float* w_keras, void* w_fwd, int k, int Cin, int Cout,
                     int prec, void* stream) {
   // convenience path (tests, weight loading): via a temporary internal master copy
   SL_REQUIRE(w_keras && w_fwd, "null pointer");
+  SL_REQUIRE(valid_prec(prec), "bad precision");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   float* tmp = nullptr;
   const size_t bytes = static_cast<size_t>(k) * cin_pad * cout_pad * sizeof(float);
   SL_CUDA(cudaMallocAsync(&tmp, bytes, s));
   int rc = keras_to_internal_launch(w_keras, tmp, k, Cin, Cout, cin_pad, cout_pad, s);
-  if (rc == 0) rc = pack_weights_internal_launch(tmp, w_fwd, k, cin_pad, cout_pad, planes_of(prec), s);
+  if (rc == 0) rc = pack_weights_internal_launch(tmp, w_fwd, k, cin_pad, cout_pad, prec, s);
   cudaFreeAsync(tmp, s);
   return rc;
 }
@@ -288,7 +301,7 @@ int sl_conv1d_fwd(const void* x_packed, const void* w_fwd, const float* bias, vo
   SL_REQUIRE(B > 0 && T_in > 0 && Cin > 0 && Cout > 0 && k > 0, "bad shape");
   SL_REQUIRE(stride == 1 || stride == 2, "stride must be 1 or 2");
   SL_REQUIRE(T_in_alloc >= T_in && T_in_alloc % stride == 0, "T_in_alloc must cover T_in and divide by stride");
-  SL_REQUIRE(prec == SL_PREC_BF16 || prec == SL_PREC_BF16X2, "bad precision");
+  SL_REQUIRE(valid_prec(prec), "bad precision");
   const int planes = planes_of(prec);
   const int cin_pad = round64(Cin), cout_pad = round64(Cout);
   int T_out, pad_l;
@@ -326,6 +339,7 @@ int sl_conv1d_fwd(const void* x_packed, const void* w_fwd, const float* bias, vo
   p.taps = k;
   p.chunks = cin_pad / 64;
   p.terms = planes == 2 ? 3 : 1;
+  p.fp16 = prec_fp16(prec);
   p.a_lo_off = cin_pad;
   p.b_lo_off = cin_pad;
   p.stride = stride;
@@ -395,11 +409,12 @@ size_t sl_conv1d_dgrad_workspace_bytes(int B, int T, int Cin, int Cout, int k) {
 // one launch of the input-gradient GEMM: the output rows u = out_scale_t * v + out_off (v = 0..rows-1)
 // of dX, filter taps w_tap0, w_tap0 + w_step, ... (n_taps of them), dY frames shifted by i - a_pad
 static int dgrad_launch_rows(const void* dy_packed, const void* w_fwd, const void* relu_mask, void* dx_packed, int B,
-                             int T, int T_dy, int cin_pad, int cout_pad, int Cin, int k, int planes, float out_scale,
+                             int T, int T_dy, int cin_pad, int cout_pad, int Cin, int k, int prec, float out_scale,
                              int rows, int row_step, int row_off, int n_taps, int w_tap0, int w_step, int a_pad,
                              void* workspace, size_t workspace_bytes, bool allow_ksplit, cudaStream_t s) {
   ConvGemmParams p;
   std::memset(&p, 0, sizeof(p));
+  const int planes = planes_of(prec);
   const int bn = cin_pad >= 256 ? 256 : cin_pad;
   SL_REQUIRE(cin_pad % bn == 0 && (bn == 64 || bn == 128 || bn == 256), "unsupported channel count");
   int rc = make_act_load_map(&p.tmA, dy_packed, planes * cout_pad, 1, T_dy, B, 128);
@@ -435,6 +450,7 @@ static int dgrad_launch_rows(const void* dy_packed, const void* w_fwd, const voi
   p.taps = n_taps;
   p.chunks = cout_pad / 64;
   p.terms = planes == 2 ? 3 : 1;
+  p.fp16 = prec_fp16(prec);
   p.a_lo_off = cout_pad;
   p.b_lo_off = cin_pad;
   p.stride = 1;
@@ -472,7 +488,7 @@ static int dgrad_launch_rows(const void* dy_packed, const void* w_fwd, const voi
     rc = conv_gemm_launch(p, bn, EPI_F32, true, num_sms(), s);
     if (rc) return rc;
     return dgrad_finalize_launch(static_cast<const float*>(workspace), relu_mask, dx_packed,
-                                 static_cast<size_t>(B) * T, cin_pad, planes, out_scale, s);
+                                 static_cast<size_t>(B) * T, cin_pad, prec, out_scale, s);
   }
   return conv_gemm_launch(p, bn, EPI_PACKED, true, num_sms(), s);
 }
@@ -483,7 +499,7 @@ int sl_conv1d_dgrad(const void* dy_packed, const void* w_fwd, const void* relu_m
   SL_REQUIRE(dy_packed && w_fwd && dx_packed, "null pointer");
   SL_REQUIRE(B > 0 && T > 0 && Cin > 0 && Cout > 0 && k > 0, "bad shape");
   SL_REQUIRE(stride == 1 || stride == 2, "stride must be 1 or 2");
-  SL_REQUIRE(prec == SL_PREC_BF16 || prec == SL_PREC_BF16X2, "bad precision");
+  SL_REQUIRE(valid_prec(prec), "bad precision");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int planes = planes_of(prec);
   const int cin_pad = round64(Cin), cout_pad = round64(Cout);
@@ -491,7 +507,7 @@ int sl_conv1d_dgrad(const void* dy_packed, const void* w_fwd, const void* relu_m
   same_padding(T, k, stride, &T_out, &pad_l);
   if (stride == 1) {
     // dX[u] = sum_j dY[u + pad_l - j] W[j]  (SURVEY.md A.1): taps walked backwards
-    return dgrad_launch_rows(dy_packed, w_fwd, relu_mask, dx_packed, B, T, T_out, cin_pad, cout_pad, Cin, k, planes,
+    return dgrad_launch_rows(dy_packed, w_fwd, relu_mask, dx_packed, B, T, T_out, cin_pad, cout_pad, Cin, k, prec,
                              out_scale, T, 1, 0, k, k - 1, -1, k - 1 - pad_l, workspace, workspace_bytes, true, s);
   }
   // stride 2: y[v'] = sum_j x[2 v' + j - pad_l] W[j], so the rows u = 2 v + r of dX only see the taps
@@ -512,7 +528,7 @@ int sl_conv1d_dgrad(const void* dy_packed, const void* w_fwd, const void* relu_m
     const int n_taps = jmax / 2 + 1;
     const int c_r = (r + pad_l - jmax) / 2;  // exact: the numerator is even
     const int rc = dgrad_launch_rows(dy_packed, w_fwd, relu_mask, dx_packed, B, T, T_out, cin_pad, cout_pad, Cin, k,
-                                     planes, out_scale, rows, 2, r, n_taps, jmax, -2, -c_r, nullptr, 0, false, s);
+                                     prec, out_scale, rows, 2, r, n_taps, jmax, -2, -c_r, nullptr, 0, false, s);
     if (rc) return rc;
   }
   return 0;
@@ -520,12 +536,12 @@ int sl_conv1d_dgrad(const void* dy_packed, const void* w_fwd, const void* relu_m
 
 int sl_conv1d_wgrad(const void* x_packed, const void* dy_packed, float* dw, float* db, int B, int T_in,
                     int T_in_alloc, int Cin, int Cout, int k, int stride, int prec, int accumulate,
-                    void* stream) {
+                    float out_scale, void* stream) {
   SL_REQUIRE(x_packed && dy_packed && dw, "null pointer");
   SL_REQUIRE(B > 0 && T_in > 0 && Cin > 0 && Cout > 0 && k > 0, "bad shape");
   SL_REQUIRE(stride == 1 || stride == 2, "stride must be 1 or 2");
   SL_REQUIRE(T_in_alloc >= T_in && T_in_alloc % stride == 0, "T_in_alloc must cover T_in and divide by stride");
-  SL_REQUIRE(prec == SL_PREC_BF16 || prec == SL_PREC_BF16X2, "bad precision");
+  SL_REQUIRE(valid_prec(prec), "bad precision");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int planes = planes_of(prec);
   const int cin_pad = round64(Cin), cout_pad = round64(Cout);
@@ -557,6 +573,8 @@ int sl_conv1d_wgrad(const void* x_packed, const void* dy_packed, float* dw, floa
   p.n_tiles = cin_pad / bn;
   p.tchunks = (T_out + 63) / 64;
   p.terms = planes == 2 ? 3 : 1;
+  p.fp16 = prec_fp16(prec);
+  p.out_scale = out_scale;
   p.dy_lo_off = cout_pad;
   p.x_lo_off = cin_pad;
   p.stride = stride;
@@ -594,6 +612,10 @@ int sl_conv1d_wgrad(const void* x_packed, const void* dy_packed, float* dw, floa
       }
     }
   }
+  if (const char* e = std::getenv("SL_WGRAD_KSPLIT")) {  // tuning / test aid: force the K split
+    const int forced = std::atoi(e);
+    if (forced >= 1 && forced <= k_total && ((k_total + forced - 1) / forced) * (forced - 1) < k_total) ksplit = forced;
+  }
   p.ksplit = ksplit;
   p.use_atomics = (ksplit > 1 || accumulate) ? 1 : 0;
   const size_t dw_bytes = static_cast<size_t>(k) * cout_pad * cin_pad * sizeof(float);
@@ -616,7 +638,7 @@ int sl_ctc_loss(const float* logp, const float* probs, const int32_t* labels, co
   SL_REQUIRE(logp && labels && input_len && label_len && loss && workspace, "null pointer");
   SL_REQUIRE(B > 0 && T > 0, "bad shape");
   return ctc_loss_launch(logp, probs, labels, input_len, label_len, loss, dlogits_packed, dlogits_f32,
-                         grad_scale, B, T, V, L_max, blank, planes_of(prec), workspace, workspace_bytes,
+                         grad_scale, B, T, V, L_max, blank, prec, workspace, workspace_bytes,
                          static_cast<cudaStream_t>(stream));
 }
 
@@ -677,7 +699,8 @@ int sl_dropout_fwd(const void* x_packed, void* y_packed, const void* relu_mask_i
   SL_REQUIRE(x_packed && y_packed && mask_out, "null pointer");
   SL_REQUIRE(B > 0 && T > 0 && C > 0 && T_alloc >= T, "bad shape");
   SL_REQUIRE(p >= 0.0f && p < 1.0f, "dropout rate must be in [0, 1)");
-  return dropout_launch(x_packed, y_packed, relu_mask_in, mask_out, B, T, T_alloc, round64(C), planes_of(prec), p,
+  SL_REQUIRE(valid_prec(prec), "bad precision");
+  return dropout_launch(x_packed, y_packed, relu_mask_in, mask_out, B, T, T_alloc, round64(C), prec, p,
                         seed, static_cast<cudaStream_t>(stream));
 }
 
@@ -697,7 +720,7 @@ int sl_adam_step_fused(float* p, const float* g, float* m, float* v, size_t n, c
                "bad layer placement");
   if (n == 0) return SL_OK;
   return adam_fused_launch(p, g, m, v, n, w_begin_host, w_end_host, w_fwd_host, cin_pad_host, n_layers,
-                           planes_of(prec), lr, beta1, beta2, eps, t, static_cast<cudaStream_t>(stream));
+                           prec, lr, beta1, beta2, eps, t, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

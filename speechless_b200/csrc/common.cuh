@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
@@ -409,25 +410,58 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128_off(uint32_t smem_addr,
   return make_smem_desc_sw128(smem_addr, lbo_bytes, sbo_bytes) | (static_cast<uint64_t>(base_offset & 7u) << 49);
 }
 
-// instruction descriptor, kind::f16: bf16 x bf16 -> fp32
-//   [4,6) c_format=1(F32) [7,10) a_format=1(BF16) [10,13) b_format=1(BF16)
+// instruction descriptor, kind::f16: (bf16 x bf16 | fp16 x fp16) -> fp32
+//   [4,6) c_format=1(F32) [7,10) a_format (0 = F16, 1 = BF16) [10,13) b_format (same)
 //   [15] a_major (0=K,1=MN) [16] b_major [17,23) N>>3 [24,29) M>>4
+__host__ __device__ constexpr uint32_t make_idesc_16(int M, int N, int a_mn_major, int b_mn_major,
+                                                     int fp16) {
+  return (1u << 4) | ((fp16 ? 0u : 1u) << 7) | ((fp16 ? 0u : 1u) << 10) |
+         (static_cast<uint32_t>(a_mn_major) << 15) | (static_cast<uint32_t>(b_mn_major) << 16) |
+         (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_major,
                                                        int b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
-         (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
-         (static_cast<uint32_t>(M >> 4) << 24);
+  return make_idesc_16(M, N, a_mn_major, b_mn_major, 0);
 }
 
 }  // namespace ptx
 
-// ---- bf16 helpers ----
+// ---- precision selector of the packed 16-bit tensors (SL_PREC_* of the C-ABI) ----
+//   1 = one bf16 plane, 2 = hi + lo bf16 planes (3-term products), 3 = one fp16 plane
+__host__ __device__ constexpr int prec_planes(int prec) { return prec == 2 ? 2 : 1; }
+__host__ __device__ constexpr int prec_fp16(int prec) { return prec == 3 ? 1 : 0; }
+
+// ---- 16-bit helpers ----
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo_elem, hi_elem);
   return *reinterpret_cast<uint32_t*>(&v);
 }
 __device__ __forceinline__ float bf16_round(float x) {
   return __bfloat162float(__float2bfloat16_rn(x));
+}
+__device__ __forceinline__ uint32_t pack_fp16x2(float lo_elem, float hi_elem) {
+  __half2 v = __floats2half2_rn(lo_elem, hi_elem);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+// two packed 16-bit values -> fp32, in either format (`fp16` is warp-uniform everywhere it is used)
+__device__ __forceinline__ uint32_t pack_16x2(float lo_elem, float hi_elem, int fp16) {
+  return fp16 ? pack_fp16x2(lo_elem, hi_elem) : pack_bf16x2(lo_elem, hi_elem);
+}
+__device__ __forceinline__ float2 unpack_16x2(uint32_t w, int fp16) {
+  if (fp16) return __half22float2(*reinterpret_cast<const __half2*>(&w));
+  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+__device__ __forceinline__ uint16_t pack_16(float x, int fp16) {
+  if (fp16) {
+    const __half h = __float2half_rn(x);
+    return *reinterpret_cast<const uint16_t*>(&h);
+  }
+  const __nv_bfloat16 h = __float2bfloat16_rn(x);
+  return *reinterpret_cast<const uint16_t*>(&h);
+}
+__device__ __forceinline__ float unpack_16(uint16_t w, int fp16) {
+  if (fp16) return __half2float(*reinterpret_cast<const __half*>(&w));
+  return __uint_as_float(static_cast<uint32_t>(w) << 16);
 }
 
 }  // namespace sl

@@ -353,7 +353,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     for (int tile = cta; tile < num_tiles; tile += n_ctas, ++it) {
       const WorkItem w = decode_item<BN, CTAS>(p, tile, rank);
       const int ksteps = p.taps * (w.chunk_end - w.chunk_begin) * p.terms;
-      const uint32_t idesc = make_idesc_bf16(BLOCK_M * CTAS, w.width, 0, BMN ? 1 : 0);
+      const uint32_t idesc = make_idesc_16(BLOCK_M * CTAS, w.width, 0, BMN ? 1 : 0, p.fp16);
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(&tmem_empty[as], aphase ^ 1);
@@ -597,8 +597,13 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           };
           {
             uint32_t packed[32];
+            if (p.fp16) {  // (uniform)
 #pragma unroll
-            for (int i = 0; i < 32; ++i) packed[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+              for (int i = 0; i < 32; ++i) packed[i] = pack_fp16x2(v[2 * i], v[2 * i + 1]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) packed[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+            }
             stage_and_store(packed, n0 + c * 64);
           }
           if (p.y_planes == 2) {  // (uniform) split-bf16 mode only: the residual plane x - bf16(x)

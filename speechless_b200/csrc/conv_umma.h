@@ -40,7 +40,8 @@ struct ConvGemmParams {
   int halo_base_mode;  // bring-up: 0 = descriptor base_offset 0, 1 = (start address >> 7) & 7
   int taps;
   int chunks;  // 64-channel chunks of the contraction dimension
-  int terms;   // 1 = bf16, 3 = split bf16 (hi*hi + hi*lo + lo*hi)
+  int terms;   // 1 = one plane (bf16 or fp16), 3 = split bf16 (hi*hi + hi*lo + lo*hi)
+  int fp16;    // operands and packed output are fp16 instead of bf16 (SL_PREC_FP16)
   int a_lo_off;
   int b_lo_off;
   int stride;
@@ -99,6 +100,8 @@ struct WgradParams {
   int halo_base_mode;  // bring-up: 0 = descriptor base_offset 0, 1 = (start address >> 7) & 7
   int tchunks;  // ceil(T_out / 64)
   int terms;
+  int fp16;         // operands are fp16 instead of bf16 (SL_PREC_FP16)
+  float out_scale;  // multiplies dW and db on their way out (1 / loss scale of the fp16 mode)
   int dy_lo_off;
   int x_lo_off;
   int stride;

@@ -675,7 +675,8 @@ __global__ void ctc_grad_kernel(const float* __restrict__ logp, const float* __r
                                 const float* __restrict__ loss, const float* __restrict__ alpha,
                                 const float* __restrict__ beta, __nv_bfloat16* __restrict__ dz_packed,
                                 float* __restrict__ dz_f32, float grad_scale, int T, int V,
-                                int L_max, int blank, int S_stride, int planes, int frames_per_block) {
+                                int L_max, int blank, int S_stride, int planes, int fp16,
+                                int frames_per_block) {
   extern __shared__ uint8_t smem_raw[];
   ptx::pdl_launch_dependents();
   ptx::pdl_wait();  // alpha / beta / loss come from the lattice kernel right before
@@ -779,6 +780,10 @@ __global__ void ctc_grad_kernel(const float* __restrict__ logp, const float* __r
       __nv_bfloat16* row = dz_packed + ro * row_elems;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
+        if (fp16) {  // (uniform)
+          reinterpret_cast<uint16_t*>(row)[lane + 32 * h] = pack_16(dz[h], 1);
+          continue;
+        }
         const __nv_bfloat16 hi = __float2bfloat16_rn(dz[h]);
         row[lane + 32 * h] = hi;
         if (planes == 2) row[64 + lane + 32 * h] = __float2bfloat16_rn(dz[h] - __bfloat162float(hi));
@@ -802,7 +807,7 @@ __global__ void ctc_grad_sorted_kernel(const float* __restrict__ logp, const flo
                                        const float* __restrict__ beta, const int* __restrict__ sort_ws,
                                        __nv_bfloat16* __restrict__ dz_packed, float* __restrict__ dz_f32,
                                        float grad_scale, int T, int V, int L_max, int blank, int S_stride,
-                                       int planes, int frames_per_block) {
+                                       int planes, int fp16, int frames_per_block) {
   extern __shared__ uint8_t smem_raw[];
   ptx::pdl_launch_dependents();
   const int L_pad = (L_max + 31) & ~31;
@@ -913,6 +918,10 @@ __global__ void ctc_grad_sorted_kernel(const float* __restrict__ logp, const flo
       __nv_bfloat16* row = dz_packed + ro * row_elems;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
+        if (fp16) {  // (uniform)
+          reinterpret_cast<uint16_t*>(row)[lane + 32 * h] = pack_16(dz[h], 1);
+          continue;
+        }
         const __nv_bfloat16 hi = __float2bfloat16_rn(dz[h]);
         row[lane + 32 * h] = hi;
         if (planes == 2) row[64 + lane + 32 * h] = __float2bfloat16_rn(dz[h] - __bfloat162float(hi));
@@ -978,8 +987,9 @@ size_t ctc_workspace_bytes(int B, int T, int L_max) {
 int ctc_loss_launch(const float* logp, const float* probs, const int32_t* labels,
                     const int32_t* input_len, const int32_t* label_len, float* loss,
                     void* dlogits_packed, float* dlogits_f32, float grad_scale, int B, int T, int V,
-                    int L_max, int blank, int planes, void* workspace, size_t workspace_bytes,
+                    int L_max, int blank, int prec, void* workspace, size_t workspace_bytes,
                     cudaStream_t stream) {
+  const int planes = prec_planes(prec), fp16 = prec_fp16(prec);
   SL_REQUIRE(V <= VP && V >= 2, "CTC kernels support 2..64 symbols (incl. blank)");
   SL_REQUIRE(blank >= 0 && blank < V, "blank out of range");
   SL_REQUIRE(L_max >= 1, "L_max must be >= 1 (pad empty label batches to width 1)");
@@ -1117,13 +1127,13 @@ int ctc_loss_launch(const float* logp, const float* probs, const int32_t* labels
                          input_len, label_len, static_cast<const float*>(loss), static_cast<const float*>(alpha),
                          static_cast<const float*>(beta), static_cast<const int*>(sort_ws),
                          reinterpret_cast<__nv_bfloat16*>(dlogits_packed), dlogits_f32, grad_scale, T, V, L_max, blank,
-                         S_stride, planes, frames_per_block));
+                         S_stride, planes, fp16, frames_per_block));
     } else {
       const size_t gsmem = L_pad * sizeof(int) + warps * 2 * VP * sizeof(float);
       SL_CUDA(launch_pdl(PDL_CTC, ctc_grad_kernel, grid, dim3(warps * 32), gsmem, stream, logp, probs, labels,
                          input_len, label_len, static_cast<const float*>(loss), static_cast<const float*>(alpha),
                          static_cast<const float*>(beta), reinterpret_cast<__nv_bfloat16*>(dlogits_packed),
-                         dlogits_f32, grad_scale, T, V, L_max, blank, S_stride, planes, frames_per_block));
+                         dlogits_f32, grad_scale, T, V, L_max, blank, S_stride, planes, fp16, frames_per_block));
     }
   }
   return 0;

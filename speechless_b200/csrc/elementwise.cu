@@ -1,5 +1,5 @@
 // elementwise.cu — HBM-bound helper kernels: packing between the Keras-facing fp32 tensors
-// and the packed bf16 form, bias gradient, Keras-2 Adam.
+// and the packed 16-bit form (bf16, split bf16 or fp16), dropout, Keras-2 Adam.
 #include "common.cuh"
 
 namespace sl {
@@ -11,7 +11,7 @@ namespace {
 // (The first version took a pair of channels per thread with 64-bit divisions: 27 us for the 41 MB
 // input batch of the bench shape, 1.5 TB/s.)
 __global__ void pack_activation_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y,
-                                       int B, int T, int C, int T_alloc, int c_pad, int planes) {
+                                       int B, int T, int C, int T_alloc, int c_pad, int planes, int fp16) {
   ptx::pdl_launch_dependents();
   ptx::pdl_wait();
   const unsigned groups = static_cast<unsigned>(c_pad) / 8u;
@@ -49,6 +49,12 @@ __global__ void pack_activation_kernel(const float* __restrict__ x, __nv_bfloat1
     }
     __nv_bfloat16* dst = y + row * (static_cast<size_t>(planes) * c_pad) + c;
     uint32_t hi[4], lo[4];
+    if (fp16) {  // (uniform) one fp16 plane
+#pragma unroll
+      for (int e = 0; e < 4; ++e) hi[e] = pack_fp16x2(v[2 * e], v[2 * e + 1]);
+      *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      continue;
+    }
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
@@ -63,7 +69,7 @@ __global__ void pack_activation_kernel(const float* __restrict__ x, __nv_bfloat1
 }
 
 __global__ void unpack_activation_kernel(const __nv_bfloat16* __restrict__ y, float* __restrict__ x,
-                                         int B, int T, int C, int T_alloc, int c_pad, int planes) {
+                                         int B, int T, int C, int T_alloc, int c_pad, int planes, int fp16) {
   const size_t total = static_cast<size_t>(B) * T * C;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -73,7 +79,7 @@ __global__ void unpack_activation_kernel(const __nv_bfloat16* __restrict__ y, fl
     const int b = static_cast<int>(bt / T);
     const __nv_bfloat16* src =
         y + (static_cast<size_t>(b) * T_alloc + t) * (static_cast<size_t>(planes) * c_pad);
-    float v = __bfloat162float(src[c]);
+    float v = unpack_16(reinterpret_cast<const uint16_t*>(src)[c], fp16);
     if (planes == 2) v += __bfloat162float(src[c_pad + c]);
     x[i] = v;
   }
@@ -108,7 +114,7 @@ __global__ void internal_to_keras_kernel(const float* __restrict__ wi, float* __
 
 // internal fp32 (k,cout_pad,cin_pad) -> w_fwd bf16 (k,cout_pad,planes*cin_pad): same order
 __global__ void pack_w_fwd_kernel(const float* __restrict__ wi, __nv_bfloat16* __restrict__ wf,
-                                  size_t rows, int cin_pad, int planes) {
+                                  size_t rows, int cin_pad, int planes, int fp16) {
   const size_t pairs = cin_pad / 2;
   const size_t total = rows * pairs;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -117,62 +123,15 @@ __global__ void pack_w_fwd_kernel(const float* __restrict__ wi, __nv_bfloat16* _
     const int c = static_cast<int>(i - row * pairs) * 2;
     const float2 v = *reinterpret_cast<const float2*>(wi + row * cin_pad + c);
     __nv_bfloat16* dst = wf + row * (static_cast<size_t>(planes) * cin_pad);
+    if (fp16) {  // (uniform)
+      *reinterpret_cast<uint32_t*>(dst + c) = pack_fp16x2(v.x, v.y);
+      continue;
+    }
     const __nv_bfloat162 hi = __floats2bfloat162_rn(v.x, v.y);
     *reinterpret_cast<__nv_bfloat162*>(dst + c) = hi;
     if (planes == 2)
       *reinterpret_cast<__nv_bfloat162*>(dst + cin_pad + c) =
           __floats2bfloat162_rn(v.x - __bfloat162float(hi.x), v.y - __bfloat162float(hi.y));
-  }
-}
-
-// db[c] += sum over rows of dy (hi + lo planes).  256 threads; each thread owns one 16-byte
-// vector (8 channels) of the packed row and walks rows with 4 loads in flight; row lanes are
-// folded through smem and one thread per channel group issues the atomics.
-__global__ void bias_grad_kernel(const __nv_bfloat16* __restrict__ dy, float* __restrict__ db,
-                                 size_t rows, int c_pad, int planes, int C) {
-  __shared__ float red[256 * 8];
-  const int vpr = planes * c_pad / 8;              // 16-byte vectors per row
-  const int tpr = vpr < 256 ? vpr : 256;           // threads across one row
-  const int rpp = 256 / tpr;                       // rows per pass of the block
-  const int lane_col = threadIdx.x % tpr, lane_row = threadIdx.x / tpr;
-  const uint4* base = reinterpret_cast<const uint4*>(dy);
-  for (int cg = lane_col; cg < vpr; cg += tpr) {
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    const size_t stride = static_cast<size_t>(gridDim.x) * rpp;
-    // (widths that do not divide 256 leave the last threads without a row lane)
-    size_t r = lane_row < rpp ? static_cast<size_t>(blockIdx.x) * rpp + lane_row : rows;
-    auto add = [&](const uint4& q) {
-      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        acc[2 * e] += __uint_as_float(w[e] << 16);
-        acc[2 * e + 1] += __uint_as_float(w[e] & 0xffff0000u);
-      }
-    };
-    for (; r + 3 * stride < rows; r += 4 * stride) {
-      const uint4 q0 = __ldg(base + r * vpr + cg);
-      const uint4 q1 = __ldg(base + (r + stride) * vpr + cg);
-      const uint4 q2 = __ldg(base + (r + 2 * stride) * vpr + cg);
-      const uint4 q3 = __ldg(base + (r + 3 * stride) * vpr + cg);
-      add(q0);
-      add(q1);
-      add(q2);
-      add(q3);
-    }
-    for (; r < rows; r += stride) add(__ldg(base + r * vpr + cg));
-    __syncthreads();
-#pragma unroll
-    for (int e = 0; e < 8; ++e) red[threadIdx.x * 8 + e] = acc[e];
-    __syncthreads();
-    if (lane_row == 0) {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        float s = 0.f;
-        for (int rr = 0; rr < rpp; ++rr) s += red[(rr * tpr + lane_col) * 8 + e];
-        const int channel = (cg * 8 + e) % c_pad;  // hi and lo planes fold onto the same channel
-        if (channel < C) atomicAdd(db + channel, s);
-      }
-    }
   }
 }
 
@@ -186,6 +145,7 @@ struct AdamLayers {
   AdamLayer layer[16];
   int count;
   int planes;
+  int fp16;
 };
 
 // Keras-2 Adam over the whole flat buffer, fused with the refresh of the bf16
@@ -220,6 +180,10 @@ __global__ void adam_fused_kernel(float* __restrict__ p, const float* __restrict
           const unsigned long long row = local / cin_pad;
           const int c = static_cast<int>(local - row * cin_pad);
           __nv_bfloat16* dst = L.layer[l].w_fwd + row * (static_cast<size_t>(L.planes) * cin_pad) + c;
+          if (L.fp16) {  // (uniform)
+            *reinterpret_cast<uint2*>(dst) = make_uint2(pack_fp16x2(pp.x, pp.y), pack_fp16x2(pp.z, pp.w));
+            break;
+          }
           const __nv_bfloat162 h0 = __floats2bfloat162_rn(pp.x, pp.y), h1 = __floats2bfloat162_rn(pp.z, pp.w);
           uint2 hv;
           hv.x = *reinterpret_cast<const uint32_t*>(&h0);
@@ -277,7 +241,7 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 // One thread per 8 channels: two float4 loads, one mask byte, one (or two) 16-byte stores.
 __global__ void dgrad_finalize_kernel(const float* __restrict__ acc, const uint8_t* __restrict__ mask,
                                       __nv_bfloat16* __restrict__ dx, size_t rows, int c_pad, int planes,
-                                      float out_scale) {
+                                      int fp16, float out_scale) {
   ptx::pdl_launch_dependents();
   ptx::pdl_wait();
   const int groups = c_pad / 8;
@@ -299,7 +263,7 @@ __global__ void dgrad_finalize_kernel(const float* __restrict__ acc, const uint8
     uint32_t hi[4], lo[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      hi[e] = pack_bf16x2(v[2 * e], v[2 * e + 1]);
+      hi[e] = pack_16x2(v[2 * e], v[2 * e + 1], fp16);
       lo[e] = pack_bf16x2(v[2 * e] - bf16_round(v[2 * e]), v[2 * e + 1] - bf16_round(v[2 * e + 1]));
     }
     __nv_bfloat16* dst = dx + row * (static_cast<size_t>(planes) * c_pad) + g * 8;
@@ -322,8 +286,8 @@ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
 }
 __global__ void dropout_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                const uint8_t* __restrict__ relu_mask_in, uint8_t* __restrict__ mask_out, int B,
-                               int T, int T_alloc, int c_pad, int planes, unsigned threshold16, float scale,
-                               unsigned long long seed) {
+                               int T, int T_alloc, int c_pad, int planes, int fp16, unsigned threshold16,
+                               float scale, unsigned long long seed) {
   ptx::pdl_launch_dependents();
   ptx::pdl_wait();
   const int groups = c_pad / 8;
@@ -354,11 +318,12 @@ __global__ void dropout_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat1
     uint32_t ho[4], lo[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      float v0 = __uint_as_float(hw[e] << 16) + __uint_as_float(lw[e] << 16);
-      float v1 = __uint_as_float(hw[e] & 0xffff0000u) + __uint_as_float(lw[e] & 0xffff0000u);
+      const float2 hv = unpack_16x2(hw[e], fp16);
+      float v0 = hv.x + __uint_as_float(lw[e] << 16);
+      float v1 = hv.y + __uint_as_float(lw[e] & 0xffff0000u);
       v0 = ((keep >> (2 * e)) & 1u) ? v0 * scale : 0.f;
       v1 = ((keep >> (2 * e + 1)) & 1u) ? v1 * scale : 0.f;
-      ho[e] = pack_bf16x2(v0, v1);
+      ho[e] = pack_16x2(v0, v1, fp16);
       lo[e] = pack_bf16x2(v0 - bf16_round(v0), v1 - bf16_round(v1));
     }
     *reinterpret_cast<uint4*>(y + base) = make_uint4(ho[0], ho[1], ho[2], ho[3]);
@@ -379,7 +344,7 @@ __global__ void dropout_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat1
 // *source* sample, so a dropped sample is dropped in every window that contains it.
 __global__ void window_activation_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int B,
                                          int T, int C, int k, int stride, int T_out, int pad_l, int c_pad,
-                                         int planes, unsigned threshold16, float scale,
+                                         int planes, int fp16, unsigned threshold16, float scale,
                                          unsigned long long seed) {
   ptx::pdl_launch_dependents();
   ptx::pdl_wait();
@@ -405,6 +370,10 @@ __global__ void window_activation_kernel(const float* __restrict__ x, __nv_bfloa
       }
     }
     __nv_bfloat16* dst = y + row * (static_cast<size_t>(planes) * c_pad) + col;
+    if (fp16) {  // (uniform)
+      *reinterpret_cast<uint16_t*>(dst) = pack_16(v, 1);
+      continue;
+    }
     const __nv_bfloat16 hi = __float2bfloat16_rn(v);
     dst[0] = hi;
     if (planes == 2) dst[c_pad] = __float2bfloat16_rn(v - __bfloat162float(hi));
@@ -420,17 +389,19 @@ inline int grid_for(size_t total, int block) {
 }  // namespace
 
 int pack_activation_launch(const float* x, void* y, int B, int T, int C, int T_alloc, int c_pad,
-                           int planes, cudaStream_t s) {
+                           int prec, cudaStream_t s) {
+  const int planes = prec_planes(prec);
   const size_t total = static_cast<size_t>(B) * T_alloc * (c_pad / 8);
   SL_CUDA(launch_pdl(PDL_ELEMENTWISE, pack_activation_kernel, dim3(grid_for(total, 256)), dim3(256), 0, s, x,
-                     reinterpret_cast<__nv_bfloat16*>(y), B, T, C, T_alloc, c_pad, planes));
+                     reinterpret_cast<__nv_bfloat16*>(y), B, T, C, T_alloc, c_pad, planes, prec_fp16(prec)));
   return 0;
 }
 int unpack_activation_launch(const void* y, float* x, int B, int T, int C, int T_alloc, int c_pad,
-                             int planes, cudaStream_t s) {
+                             int prec, cudaStream_t s) {
+  const int planes = prec_planes(prec);
   const size_t total = static_cast<size_t>(B) * T * C;
   unpack_activation_kernel<<<grid_for(total, 256), 256, 0, s>>>(
-      reinterpret_cast<const __nv_bfloat16*>(y), x, B, T, C, T_alloc, c_pad, planes);
+      reinterpret_cast<const __nv_bfloat16*>(y), x, B, T, C, T_alloc, c_pad, planes, prec_fp16(prec));
   SL_CUDA(cudaGetLastError());
   return 0;
 }
@@ -449,59 +420,53 @@ int internal_to_keras_launch(const float* wi, float* wk, int k, int Cin, int Cou
   return 0;
 }
 int pack_weights_internal_launch(const float* wi, void* wf, int k, int cin_pad, int cout_pad,
-                                 int planes, cudaStream_t s) {
+                                 int prec, cudaStream_t s) {
+  const int planes = prec_planes(prec);
   const size_t rows = static_cast<size_t>(k) * cout_pad;
   pack_w_fwd_kernel<<<grid_for(rows * (cin_pad / 2), 256), 256, 0, s>>>(
-      wi, reinterpret_cast<__nv_bfloat16*>(wf), rows, cin_pad, planes);
+      wi, reinterpret_cast<__nv_bfloat16*>(wf), rows, cin_pad, planes, prec_fp16(prec));
   SL_CUDA(cudaGetLastError());
   return 0;
 }
-int dgrad_finalize_launch(const float* acc, const void* mask, void* dx, size_t rows, int c_pad, int planes,
+int dgrad_finalize_launch(const float* acc, const void* mask, void* dx, size_t rows, int c_pad, int prec,
                           float out_scale, cudaStream_t s) {
+  const int planes = prec_planes(prec);
   SL_CUDA(launch_pdl(PDL_ELEMENTWISE, dgrad_finalize_kernel, dim3(grid_for(rows * (c_pad / 8), 256)), dim3(256), 0, s, acc,
                      reinterpret_cast<const uint8_t*>(mask), reinterpret_cast<__nv_bfloat16*>(dx), rows, c_pad,
-                     planes, out_scale));
+                     planes, prec_fp16(prec), out_scale));
   return 0;
 }
 int dropout_launch(const void* x, void* y, const void* relu_mask_in, void* mask_out, int B, int T, int T_alloc,
-                   int c_pad, int planes, float p, unsigned long long seed, cudaStream_t s) {
+                   int c_pad, int prec, float p, unsigned long long seed, cudaStream_t s) {
+  const int planes = prec_planes(prec);
   const unsigned threshold16 = static_cast<unsigned>(p * 65536.0f + 0.5f);
   const size_t rows = static_cast<size_t>(B) * T_alloc;
   dropout_kernel<<<grid_for(rows * (c_pad / 8), 256), 256, 0, s>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y),
       reinterpret_cast<const uint8_t*>(relu_mask_in), reinterpret_cast<uint8_t*>(mask_out), B, T, T_alloc, c_pad,
-      planes, threshold16, 1.0f / (1.0f - static_cast<float>(threshold16) / 65536.0f), seed);
+      planes, prec_fp16(prec), threshold16, 1.0f / (1.0f - static_cast<float>(threshold16) / 65536.0f), seed);
   SL_CUDA(cudaGetLastError());
   return 0;
 }
 int window_activation_launch(const float* x, void* y, int B, int T, int C, int k, int stride, int T_out, int pad_l,
-                             int c_pad, int planes, float p, unsigned long long seed, cudaStream_t s) {
+                             int c_pad, int prec, float p, unsigned long long seed, cudaStream_t s) {
+  const int planes = prec_planes(prec);
   const unsigned threshold16 = p > 0.f ? static_cast<unsigned>(p * 65536.0f + 0.5f) : 0u;
   const size_t total = static_cast<size_t>(B) * T_out * c_pad;
   window_activation_kernel<<<grid_for(total, 256), 256, 0, s>>>(
-      x, reinterpret_cast<__nv_bfloat16*>(y), B, T, C, k, stride, T_out, pad_l, c_pad, planes, threshold16,
+      x, reinterpret_cast<__nv_bfloat16*>(y), B, T, C, k, stride, T_out, pad_l, c_pad, planes, prec_fp16(prec),
+      threshold16,
       1.0f / (1.0f - static_cast<float>(threshold16) / 65536.0f), seed);
-  SL_CUDA(cudaGetLastError());
-  return 0;
-}
-int bias_grad_launch(const void* dy, float* db, size_t rows, int c_pad, int planes, int C,
-                     cudaStream_t s) {
-  const int vpr = planes * c_pad / 8;
-  const int rpp = vpr < 256 ? 256 / vpr : 1;
-  size_t blocks = (rows + static_cast<size_t>(rpp) * 8 - 1) / (static_cast<size_t>(rpp) * 8);
-  if (blocks > 148 * 4) blocks = 148 * 4;
-  if (blocks < 1) blocks = 1;
-  bias_grad_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(
-      reinterpret_cast<const __nv_bfloat16*>(dy), db, rows, c_pad, planes, C);
   SL_CUDA(cudaGetLastError());
   return 0;
 }
 int adam_fused_launch(float* p, const float* g, float* m, float* v, size_t n, const size_t* begins,
                       const size_t* ends, void* const* w_fwd, const int* cin_pads, int n_layers,
-                      int planes, float lr, float b1, float b2, float eps, int t, cudaStream_t s) {
+                      int prec, float lr, float b1, float b2, float eps, int t, cudaStream_t s) {
   AdamLayers L;
   L.count = n_layers;
-  L.planes = planes;
+  L.planes = prec_planes(prec);
+  L.fp16 = prec_fp16(prec);
   for (int i = 0; i < n_layers; ++i) {
     L.layer[i].begin = begins[i];
     L.layer[i].end = ends[i];

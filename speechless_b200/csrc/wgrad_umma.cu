@@ -202,7 +202,7 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
       }
     }
   } else if (warp == 1) {
-    constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BN, 1, 1);
+    const uint32_t idesc = make_idesc_16(BLOCK_M, BN, 1, 1, p.fp16);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
@@ -265,10 +265,11 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
           for (int r = 0; r < KT; ++r) {
             const int phys = (sub >> 1) ^ (r & 7);  // SWIZZLE_128B: 16-byte chunk index ^= row % 8
             const uint2 q = *reinterpret_cast<const uint2*>(a_s + r * 128 + phys * 16 + (sub & 1) * 8);
-            acc[0] += __uint_as_float(q.x << 16);
-            acc[1] += __uint_as_float(q.x & 0xffff0000u);
-            acc[2] += __uint_as_float(q.y << 16);
-            acc[3] += __uint_as_float(q.y & 0xffff0000u);
+            const float2 f0 = unpack_16x2(q.x, p.fp16), f1 = unpack_16x2(q.y, p.fp16);
+            acc[0] += f0.x;
+            acc[1] += f0.y;
+            acc[2] += f1.x;
+            acc[3] += f1.y;
           }
         }
         __syncwarp();
@@ -286,7 +287,7 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
         const int co = mt * BLOCK_M + grp * 64 + sub * 4;
 #pragma unroll
         for (int e = 0; e < 4; ++e)
-          if (co + e < p.n_filters) atomicAdd(p.db + co + e, acc[e]);
+          if (co + e < p.n_filters) atomicAdd(p.db + co + e, acc[e] * p.out_scale);
       }
     }
   } else if (warp >= 4) {
@@ -321,6 +322,10 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
           if (lane == 0) tma_wait_group_read<1>();
           __syncwarp();
           uint8_t* rowp = sbuf + lane * 128;
+          if (p.out_scale != 1.0f) {  // (uniform) undo the loss scale of the fp16 mode: exact, a power of two
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * p.out_scale);
+          }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int phys = j ^ (lane & 7);

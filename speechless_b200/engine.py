@@ -14,6 +14,8 @@ HBM layout
   act[l]    (B, T', planes*cout_pad)       bf16   post-ReLU output of layer l (kept for backward)
   probs (B,T',V) fp32, logp (B,T',64) fp32, CTC lattices alpha/beta (B,T',S_pad) fp32.
 """
+import math
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -21,7 +23,7 @@ import numpy as np
 import torch
 
 from speechless_b200 import _lib
-from speechless_b200._lib import ACT_NONE, ACT_RELU, ACT_SOFTMAX, PREC_BF16, PREC_BF16X2, check, ptr
+from speechless_b200._lib import ACT_NONE, ACT_RELU, ACT_SOFTMAX, PREC_BF16, PREC_BF16X2, PREC_FP16, check, ptr
 
 
 def round_up(value: int, multiple: int) -> int:
@@ -122,7 +124,7 @@ class _Workspace:
         self.host_slots = [self.x_host, None]
         self.slot_copied = [None, None]   # event on the copy stream: slot holds the new batch
         self.slot_consumed = [None, None]  # event on the compute stream: pack kernel has read the slot
-        self.x_packed = torch.zeros((B, self.T_alloc, planes * first.cin_pad), dtype=torch.bfloat16, device=dev)
+        self.x_packed = torch.zeros((B, self.T_alloc, planes * first.cin_pad), dtype=tower.storage_dtype, device=dev)
         self.t_out: List[int] = []
         self.acts: List[torch.Tensor] = []
         t = T
@@ -137,7 +139,7 @@ class _Workspace:
         for index, (layer, t_out) in enumerate(zip(tower.layers[:-1], self.t_out[:-1])):
             alloc = round_up(t_out, tower.layers[index + 1].gemm_stride)
             self.t_alloc_out.append(alloc)
-            self.acts.append(torch.zeros((B, alloc, planes * layer.cout_pad), dtype=torch.bfloat16, device=dev))
+            self.acts.append(torch.zeros((B, alloc, planes * layer.cout_pad), dtype=tower.storage_dtype, device=dev))
             self.masks.append(torch.empty((B, t_out, layer.cout_pad // 8), dtype=torch.uint8, device=dev))
         V = tower.layers[-1].cout
         self.probs = torch.empty((B, self.Tp, V), dtype=torch.float32, device=dev)
@@ -160,15 +162,16 @@ class _Workspace:
         self.layer_inputs: List[Optional[torch.Tensor]] = [None] * len(tower.layers)
         self.dropout_seeds: Dict[int, int] = {}
         self.input_dropped = False  # raw-wave input: dropout was applied while packing
+        self.loss_scale = 1.0  # power of two the packed gradients of the last ctc() call carry (fp16 mode)
 
     def ensure_backward(self, tower: "ConvTower"):
         if self.dz_packed is None:
             dev, planes = tower.device, tower.planes
-            self.dz_packed = torch.empty((self.B, self.Tp, planes * 64), dtype=torch.bfloat16, device=dev)
+            self.dz_packed = torch.empty((self.B, self.Tp, planes * 64), dtype=tower.storage_dtype, device=dev)
             widest = max(layer.cout_pad for layer in tower.layers[:-1])
             rows = max(self.t_out)
             for i in range(2):
-                self.dact[i] = torch.empty((self.B, rows, planes * widest), dtype=torch.bfloat16, device=dev)
+                self.dact[i] = torch.empty((self.B, rows, planes * widest), dtype=tower.storage_dtype, device=dev)
 
 
 class ConvTower:
@@ -176,7 +179,8 @@ class ConvTower:
 
     def __init__(self, layers: List[LayerSpec], device: torch.device, precision: int = PREC_BF16X2,
                  frozen_layer_count: int = 0, dropout: Optional[float] = None,
-                 dropout_layers: Sequence[int] = (), dropout_seed: int = 0):
+                 dropout_layers: Sequence[int] = (), dropout_seed: int = 0,
+                 loss_scale_target: Optional[float] = None):
         if not torch.cuda.is_available():
             raise RuntimeError("speechless_b200 needs a CUDA device (B200); there is no CPU fallback.")
         self.lib = _lib.load()
@@ -184,6 +188,16 @@ class ConvTower:
         self.device = device
         self.precision = precision
         self.planes = 2 if precision == PREC_BF16X2 else 1
+        # fp16 operands: 11 mantissa bits at the bf16 cost, but 5 exponent bits.  Activations of a
+        # z-normalised input stay far inside the range; the back-propagated gradients (<= 1/B at the
+        # logits) would sink into the subnormals, so they carry a power-of-two LOSS SCALE: the CTC
+        # kernel emits dlogits * S with S chosen so that |dlogits * S| <= loss_scale_target, every
+        # input gradient inherits the factor, and the weight-gradient epilogue multiplies by 1/S
+        # (exact).  bf16 modes have the fp32 range and run with S = 1.
+        self.storage_dtype = torch.float16 if precision == PREC_FP16 else torch.bfloat16
+        if loss_scale_target is None:
+            loss_scale_target = float(os.environ.get("SL_LOSS_SCALE_TARGET", "256")) if precision == PREC_FP16 else 0.0
+        self.loss_scale_target = loss_scale_target
         self.frozen_layer_count = frozen_layer_count
         # inverted dropout in front of the listed conv layers, training phase only (net.py:301-303);
         # the kernel quantises p to 16 bits, the scale below matches it exactly
@@ -209,7 +223,7 @@ class ConvTower:
             self.grads: Optional[torch.Tensor] = None
             self.adam_m: Optional[torch.Tensor] = None
             self.adam_v: Optional[torch.Tensor] = None
-            self.w_fwd = [torch.zeros((l.gemm_kernel, l.cout_pad, self.planes * l.cin_pad), dtype=torch.bfloat16,
+            self.w_fwd = [torch.zeros((l.gemm_kernel, l.cout_pad, self.planes * l.cin_pad), dtype=self.storage_dtype,
                                       device=device) for l in layers]
         self._workspaces: Dict[Tuple[int, int], _Workspace] = {}
         self._current: Optional[_Workspace] = None
@@ -492,8 +506,12 @@ class ConvTower:
             ws.input_len.copy_(torch.from_numpy(pl))
 
     def ctc(self, ws: _Workspace, want_grad: bool, grad_scale: float = 1.0, want_f32_grad: bool = False) -> torch.Tensor:
-        """Per-utterance loss (device, (B,)); optionally d(grad_scale*sum loss)/d logits as packed bf16."""
+        """Per-utterance loss (device, (B,)); optionally d(grad_scale*sum loss)/d logits as the packed
+        16-bit tile (times `ws.loss_scale` in the fp16 mode, see __init__)."""
         V = self.layers[-1].cout
+        # |dlogits| <= grad_scale (softmax minus posterior): largest power of two S with grad_scale*S <= target
+        ws.loss_scale = 2.0 ** math.floor(math.log2(self.loss_scale_target / grad_scale)) \
+            if (want_grad and self.loss_scale_target > 0 and grad_scale > 0) else 1.0
         with torch.cuda.device(self.device):
             if want_grad:
                 ws.ensure_backward(self)
@@ -502,9 +520,11 @@ class ConvTower:
             self._timed("ctc", "ctc_loss", lambda: self.lib.sl_ctc_loss(
                 ptr(ws.logp), ptr(ws.probs), ptr(ws.labels), ptr(ws.input_len), ptr(ws.label_len), ptr(ws.loss),
                 ptr(ws.dz_packed) if want_grad else None,
-                ptr(ws.dz_f32) if (want_grad and want_f32_grad) else None, float(grad_scale), ws.B, ws.Tp, V,
-                ws.labels.shape[1], V - 1, self.precision, ptr(ws.ctc_ws), ws.ctc_ws.numel(), self.stream))
+                ptr(ws.dz_f32) if (want_grad and want_f32_grad) else None, float(grad_scale * ws.loss_scale), ws.B,
+                ws.Tp, V, ws.labels.shape[1], V - 1, self.precision, ptr(ws.ctc_ws), ws.ctc_ws.numel(), self.stream))
             self.launches += 2 if want_grad else 1
+            if want_grad and want_f32_grad and ws.loss_scale != 1.0:
+                ws.dz_f32.mul_(1.0 / ws.loss_scale)  # (parity tests only) report the unscaled gradient
         return ws.loss
 
     def greedy_decode(self, ws: _Workspace, merge_repeated: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -596,7 +616,7 @@ class ConvTower:
                 launch_wgrad = lambda: self._timed("wgrad", layer.name, lambda: self.lib.sl_conv1d_wgrad(
                     ptr(x), ptr(dy), ptr(self._w(self.grads, layer)), ptr(self._b(self.grads, layer)), ws.B, t_in,
                     t_alloc, layer.gemm_cin, layer.cout, layer.gemm_kernel, layer.gemm_stride, self.precision, 1,
-                    self.stream))
+                    1.0 / ws.loss_scale, self.stream))
                 previous_wgrad_done = wgrad_done
                 if side is None:
                     launch_wgrad()

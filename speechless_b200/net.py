@@ -35,7 +35,7 @@ from typing import Callable, Dict, Iterable, List, Optional, Tuple
 import numpy
 from numpy import ndarray, zeros, array, reshape, concatenate
 
-from speechless_b200._lib import PREC_BF16, PREC_BF16X2
+from speechless_b200._lib import PRECISIONS
 from speechless_b200.grapheme_enconding import CtcGraphemeEncoding, AsgGraphemeEncoding
 from speechless_b200.labeled_example import LabeledSpectrogram
 from speechless_b200.results import (ExpectationVsPrediction, ExpectationsVsPredictions,
@@ -235,8 +235,8 @@ class Wav2Letter:
                  decoder_top_paths: int = 32):
         if frozen_layer_count > 0 and load_model_from_directory is None:
             raise ValueError("Layers cannot be frozen if model is trained from scratch.")
-        if compute_dtype not in ("bf16", "bf16x2"):
-            raise ValueError("compute_dtype must be 'bf16' or 'bf16x2'")
+        if compute_dtype not in PRECISIONS:
+            raise ValueError("compute_dtype must be one of {}".format(sorted(PRECISIONS)))
 
         self.kenlm_directory = kenlm_directory
         self.rescorer = None
@@ -315,7 +315,7 @@ class Wav2Letter:
             if combined_index < self.frozen_layer_count:
                 frozen_convs += 1
             combined_index += 1
-        self.tower = ConvTower(layers, device, PREC_BF16X2 if self.compute_dtype == "bf16x2" else PREC_BF16,
+        self.tower = ConvTower(layers, device, PRECISIONS[self.compute_dtype],
                                frozen_layer_count=frozen_convs, dropout=self.dropout, dropout_layers=dropout_layers,
                                dropout_seed=self.seed if self.seed is not None else 0)
         self.tower.init_glorot(self.seed)

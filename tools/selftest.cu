@@ -357,7 +357,7 @@ static bool run_wgrad(const ConvCase& cc, int prec) {
   Dev<float> dwi(static_cast<size_t>(k) * cop * cip), dwk(static_cast<size_t>(k) * Cin * Cout), db(Cout);
   SLCK(sl_pack_activation(dx.p, xp.p, B, T, Cin, T_alloc, cip, prec, nullptr));
   SLCK(sl_pack_activation(ddy.p, dyp.p, B, T_out, Cout, T_out, cop, prec, nullptr));
-  SLCK(sl_conv1d_wgrad(xp.p, dyp.p, dwi.p, db.p, B, T, T_alloc, Cin, Cout, k, s, prec, 0, nullptr));
+  SLCK(sl_conv1d_wgrad(xp.p, dyp.p, dwi.p, db.p, B, T, T_alloc, Cin, Cout, k, s, prec, 0, 1.0f, nullptr));
   SLCK(sl_weights_internal_to_keras(dwi.p, dwk.p, k, Cin, Cout, cip, cop, nullptr));
   SLCK(sl_sync_check());
   std::vector<double> rdw, rdb;
@@ -715,7 +715,7 @@ static bool run_perf(int B, int T, int prec, int iters, const char* only = nullp
                                dgws.n > 1 ? dgws.p : nullptr, dgws.n > 1 ? dgws.n : 0, nullptr);
       });
     ok &= time_it("wgrad", [&] {
-      return sl_conv1d_wgrad(xp.p, yp.p, dw.p, db.p, B, t_in, T_alloc, L.cin, L.cout, L.k, L.s, prec, 1, nullptr);
+      return sl_conv1d_wgrad(xp.p, yp.p, dw.p, db.p, B, t_in, T_alloc, L.cin, L.cout, L.k, L.s, prec, 1, 1.0f, nullptr);
     });
     if (!ok) {
       char buf[1024];
