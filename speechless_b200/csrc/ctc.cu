@@ -211,6 +211,24 @@ __global__ void ctc_alpha_beta_kernel(const float* __restrict__ logp,
 // kernel (see ctc_grad_sorted_kernel) while the compute warps walk the lattice.
 constexpr float NEG = -1e30f;
 
+// progress flags between the lattice walkers and the gradient CTAs of one launch
+__device__ __forceinline__ void st_release_cta_shared(int* p, int v) {
+  asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(ptx::smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_cta_shared(const int* p) {
+  int v;
+  asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"(ptx::smem_u32(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_gpu(int* p, int v) {
+  asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 __device__ __forceinline__ void bar_sync_named(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -270,7 +288,8 @@ template <int SPT, int K, int DIR, bool CL>
 __device__ __forceinline__ void halo_walk(const float* lp_s, float* col, int col_stride, const float* lp_b, int P,
                                           int ls0, int lane, int tid, int nthreads, const float (&skipb)[SPT],
                                           const float (&onb)[SPT], const float* const (&em_ptr)[SPT], float* out,
-                                          ptrdiff_t out_step, unsigned st_mask, int push_rank, int own_per_cta) {
+                                          ptrdiff_t out_step, unsigned st_mask, int push_rank, int own_per_cta,
+                                          int* smem_progress) {
   constexpr int HALO = 2 * K;
   const bool owner = lane * SPT >= HALO;
   const bool pusher = CL && push_rank >= 0 && lane * SPT >= 32 * SPT - HALO;
@@ -343,6 +362,8 @@ __device__ __forceinline__ void halo_walk(const float* lp_s, float* col, int col
     const int kb = t0 / K;
     if ((t0 & (CHUNK - 1)) == 0) cp_async_wait<0>();  // the chunk issued one chunk ago has long landed
     barrier();  // owned states of block kb-1 published; chunk visible; ring slot free
+    // every lattice row of the steps < t0 has been stored by its thread: tell the publisher warp
+    if (!CL && smem_progress != nullptr && tid == 0 && t0 > 0) st_release_cta_shared(smem_progress, t0);
     if ((t0 & (CHUNK - 1)) == 0 && t0 > 0) issue_chunk(t0 / CHUNK + 1);
     const float* pc = col + ((kb + 1) & 1) * col_stride + HALO + ls0;
 #pragma unroll
@@ -370,7 +391,24 @@ __device__ __forceinline__ void halo_walk(const float* lp_s, float* col, int col
   }
   cp_async_wait<0>();
   barrier();
+  if (!CL && smem_progress != nullptr && tid == 0) st_release_cta_shared(smem_progress, P);
 }
+
+// One (utterance, direction) of the lattice phase, run by a whole CTA (or by a cluster of CTAs, CL).
+// progress != nullptr (fused loss + gradient launch): the spare warp also PUBLISHES how many time steps of
+// this walk are complete in global memory — progress[2 b + dir] — for the gradient CTAs of the same launch.
+// The walking warps never wait for the publication: walker thread 0 drops the step count into shared memory
+// after each K-block barrier (st.release.cta), the publisher warp picks it up (ld.acquire.cta), issues the
+// device-scope fence that makes the rows stored before that barrier visible, and stores the flag.
+template <int SPT, int K, bool CL>
+__device__ __forceinline__ void lattice_cta_body(uint8_t* smem_raw, int unit, const float* __restrict__ logp,
+                                                 const int32_t* __restrict__ labels,
+                                                 const int32_t* __restrict__ input_len,
+                                                 const int32_t* __restrict__ label_len, float* __restrict__ loss,
+                                                 float* __restrict__ beta_loss, float* __restrict__ alpha,
+                                                 float* __restrict__ beta, int* __restrict__ sort_ws, int T,
+                                                 int L_max, int blank, int S_stride, int col_stride,
+                                                 int* __restrict__ progress);
 
 template <int SPT, int K, bool CL>
 __global__ void __launch_bounds__(1024)
@@ -379,15 +417,28 @@ __global__ void __launch_bounds__(1024)
                             float* __restrict__ loss, float* __restrict__ beta_loss,
                             float* __restrict__ alpha, float* __restrict__ beta, int* __restrict__ sort_ws,
                             int T, int L_max, int blank, int S_stride, int col_stride) {
+  extern __shared__ uint8_t smem_raw[];
+  ptx::pdl_launch_dependents();
+  const int csize = CL ? static_cast<int>(ptx::cluster_nctarank()) : 1;
+  lattice_cta_body<SPT, K, CL>(smem_raw, static_cast<int>(blockIdx.x) / csize, logp, labels, input_len, label_len, loss,
+                               beta_loss, alpha, beta, sort_ws, T, L_max, blank, S_stride, col_stride, nullptr);
+}
+
+template <int SPT, int K, bool CL>
+__device__ __forceinline__ void lattice_cta_body(uint8_t* smem_raw, int unit, const float* __restrict__ logp,
+                                                 const int32_t* __restrict__ labels,
+                                                 const int32_t* __restrict__ input_len,
+                                                 const int32_t* __restrict__ label_len, float* __restrict__ loss,
+                                                 float* __restrict__ beta_loss, float* __restrict__ alpha,
+                                                 float* __restrict__ beta, int* __restrict__ sort_ws, int T,
+                                                 int L_max, int blank, int S_stride, int col_stride,
+                                                 int* __restrict__ progress) {
   static_assert(SPT % 2 == 0 && CHUNK % K == 0 && 2 * K < 32 * SPT, "slot parity / chunk alignment");
   constexpr int HALO = 2 * K;
   constexpr int OWN = 32 * SPT - HALO;
-  extern __shared__ uint8_t smem_raw[];
-  ptx::pdl_launch_dependents();
   // cluster mode: the CTAs of a cluster split the warps (= the state range) of one (utterance, direction)
   const int crank = CL ? static_cast<int>(ptx::cluster_ctarank()) : 0;
   const int csize = CL ? static_cast<int>(ptx::cluster_nctarank()) : 1;
-  const int unit = blockIdx.x / csize;
   const int dir = unit & 1;
   const int b = unit >> 1;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -399,6 +450,12 @@ __global__ void __launch_bounds__(1024)
 
   float* lp_s = reinterpret_cast<float*>(smem_raw);  // ring of 2*CHUNK rows x VP
   float* col = lp_s + 2 * CHUNK * VP;                // [2][col_stride], index = state - crank*own_per_cta + HALO
+  int* sort_scratch = reinterpret_cast<int*>(col + 2 * col_stride);  // [VP]
+  int* smem_progress = progress != nullptr ? sort_scratch + VP : nullptr;  // steps of this walk stored so far
+  if (progress != nullptr) {
+    if (tid == 0) *smem_progress = 0;
+    __syncthreads();
+  }
 
   if (tid >= nthreads) {
     // label sorter (does not take part in the walk's CTA barriers); the labels are inputs of the
@@ -406,12 +463,35 @@ __global__ void __launch_bounds__(1024)
     if (dir == 0 && crank == 0) {
       const int L_pad = (L_max + 31) & ~31;
       int* packed = sort_ws + static_cast<size_t>(b) * (L_pad + SORT_EXTRA);
-      sort_labels_by_symbol(labels + static_cast<size_t>(b) * L_max, L, packed, packed + L_pad,
-                            reinterpret_cast<int*>(col + 2 * col_stride), lane);
+      sort_labels_by_symbol(labels + static_cast<size_t>(b) * L_max, L, packed, packed + L_pad, sort_scratch, lane);
     }
+    // ... and publisher of the walk's progress (the sorted labels above are covered by the first fence)
+    auto publish = [&](int done) {
+      __threadfence();
+      if (lane == 0) st_relaxed_gpu(progress + unit, done);
+    };
     if constexpr (CL) {  // cluster barriers count every thread: one per K-block and the final one
-      for (int t0 = 0; t0 < P; t0 += K) ptx::cluster_sync_all();
+      for (int t0 = 0; t0 < P; t0 += K) {
+        ptx::cluster_sync_all();  // every CTA of the cluster has stored the rows of the steps < t0
+        if (progress != nullptr && crank == 0 && t0 > 0) publish(t0);
+      }
       ptx::cluster_sync_all();
+      if (progress != nullptr && crank == 0) publish(P);
+    } else if (progress != nullptr) {
+      int published = 0;
+      unsigned spins = 0;
+      while (published < P) {
+        const int done = ld_acquire_cta_shared(smem_progress);
+        if (done > published) {
+          publish(done);
+          published = done;
+          spins = 0;
+        } else {
+          __nanosleep(100);
+          if (++spins > (1u << 24)) __trap();  // a protocol bug must fail, not hang
+        }
+      }
+      if (P <= 0) publish(0);
     }
     return;
   }
@@ -448,11 +528,11 @@ __global__ void __launch_bounds__(1024)
   const int push_rank = (CL && crank + 1 < csize && warp == (nthreads >> 5) - 1) ? crank + 1 : -1;
   if (dir == 0)
     halo_walk<SPT, K, 0, CL>(lp_s, col, col_stride, lp_b, P, ls0, lane, tid, nthreads, skipb, onb, em_ptr, lat + s0,
-                             static_cast<ptrdiff_t>(S_stride), st_mask, push_rank, own_per_cta);
+                             static_cast<ptrdiff_t>(S_stride), st_mask, push_rank, own_per_cta, smem_progress);
   else
     halo_walk<SPT, K, 1, CL>(lp_s, col, col_stride, lp_b, P, ls0, lane, tid, nthreads, skipb, onb, em_ptr,
                              lat + static_cast<size_t>(P > 0 ? P - 1 : 0) * S_stride + (S - 1 - s0),
-                             -static_cast<ptrdiff_t>(S_stride), st_mask, push_rank, own_per_cta);
+                             -static_cast<ptrdiff_t>(S_stride), st_mask, push_rank, own_per_cta, smem_progress);
 
   // the CTA owning the last state reports the loss (state S-2 is its own or sits in its halo)
   if (tid == 0 && (S - 1) / own_per_cta == crank) {
@@ -794,42 +874,47 @@ __global__ void ctc_grad_kernel(const float* __restrict__ logp, const float* __r
 
 // Same gradient, without shared-memory atomics (the default).  The atomics of the kernel above
 // (one per label state and frame, ~2 cycles per lane on the SM's single atomic unit) cost more than
-// its HBM traffic.  Here each block first counting-sorts the label positions of its utterance by
-// symbol (stable, one warp, __match_any_sync per 32 labels): rank[i] = slot of label i in the
+// its HBM traffic.  Here the label positions of the utterance are counting-sorted by symbol once (by the
+// spare warp of the alpha walker, see sort_labels_by_symbol): rank[i] = slot of label i in the
 // symbol-sorted order, seg[v] = first slot of symbol v.  Per frame a warp then writes the occupancy
 // term of every label state to its slot (plain conflict-light STS) and lane v adds up the
 // contiguous segment of symbol v in label order — deterministic, no atomics.
-__global__ void ctc_grad_sorted_kernel(const float* __restrict__ logp, const float* __restrict__ probs,
-                                       const int32_t* __restrict__ labels,
-                                       const int32_t* __restrict__ input_len,
-                                       const int32_t* __restrict__ label_len,
-                                       const float* __restrict__ loss, const float* __restrict__ alpha,
-                                       const float* __restrict__ beta, const int* __restrict__ sort_ws,
-                                       __nv_bfloat16* __restrict__ dz_packed, float* __restrict__ dz_f32,
-                                       float grad_scale, int T, int V, int L_max, int blank, int S_stride,
-                                       int planes, int fp16, int frames_per_block) {
-  extern __shared__ uint8_t smem_raw[];
-  ptx::pdl_launch_dependents();
+//
+// grad_item: the frames [t_begin, t_end) of utterance b, one warp per frame, by every warp of the CTA.
+// Normalisation of the occupancies  occ_t(v) = sum_{s: e[s]=v} alpha_t(s) beta_t(s) / (y_t(v) Z):
+//   loss != nullptr  Z = exp(-loss[b]) from the finished alpha walk (two-launch path);
+//   loss == nullptr  (fused launch: the walks are still running) every frame is normalised by its own
+//                    sum over all states — mathematically the same Z for every t — with the exponent
+//                    offset taken from a max pass over the warp's first frame of the item (the per-frame
+//                    maxima of one utterance differ by at most log2 S).
+template <int NP>  // passes of 128 states whose loads are issued together (registers against memory-level parallelism)
+__device__ __forceinline__ void grad_item(uint8_t* smem_raw, int b, int t_begin, int t_end, bool reload_labels,
+                                          const float* __restrict__ logp, const float* __restrict__ probs,
+                                          const int32_t* __restrict__ input_len,
+                                          const int32_t* __restrict__ label_len, const float* __restrict__ loss,
+                                          const float* __restrict__ alpha, const float* __restrict__ beta,
+                                          const int* __restrict__ sort_ws, __nv_bfloat16* __restrict__ dz_packed,
+                                          float* __restrict__ dz_f32, float grad_scale, int T, int V, int L_max,
+                                          int blank, int S_stride, int planes, int fp16) {
   const int L_pad = (L_max + 31) & ~31;
   int* packed = reinterpret_cast<int*>(smem_raw);  // [L_pad]  symbol | slot << 8
   int* seg = packed + L_pad;                       // [SORT_EXTRA] first slot of each symbol
   float* per_warp = reinterpret_cast<float*>(seg + SORT_EXTRA);  // [warps][VP + L_pad]
-  const int b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int L = label_len[b];
   const int P = min(input_len[b], T);
   const int S = 2 * L + 1;
-  const int t_begin = blockIdx.x * frames_per_block;
-  const int t_end = min(t_begin + frames_per_block, T);
-  ptx::pdl_wait();  // alpha / beta / loss / the sorted labels come from the lattice kernel right before
-  if (t_begin < P) {  // (block-uniform)
+  if (t_begin < P && reload_labels) {  // (block-uniform)
     const int* src = sort_ws + static_cast<size_t>(b) * (L_pad + SORT_EXTRA);
-    for (int i = threadIdx.x; i < L; i += blockDim.x) packed[i] = src[i];
-    for (int i = threadIdx.x; i <= VP; i += blockDim.x) seg[i] = src[L_pad + i];
+    for (int i = threadIdx.x; i < L; i += blockDim.x) packed[i] = __ldcg(src + i);
+    for (int i = threadIdx.x; i <= VP; i += blockDim.x) seg[i] = __ldcg(src + L_pad + i);
     __syncthreads();
   }
-  const float loss_b = loss[b];
-  const float loss2 = loss_b * LOG2E;
+  const bool self_normalised = loss == nullptr;
+  const float loss_b = self_normalised ? 0.f : loss[b];
+  bool feasible = self_normalised ? true : isfinite(loss_b);
+  float offset2 = self_normalised ? 0.f : loss_b * LOG2E;  // added to every base-2 exponent
+  bool have_offset = !self_normalised;
   float* lp_row = per_warp + warp * (VP + L_pad);  // per-warp copy of the log-prob row (base 2)
   float* xs = lp_row + VP;                         // [L_pad] occupancy terms in symbol-sorted order
   const int row_elems = planes * 64;
@@ -837,7 +922,7 @@ __global__ void ctc_grad_sorted_kernel(const float* __restrict__ logp, const flo
   for (int t = t_begin + warp; t < t_end; t += nwarps) {
     const size_t ro = static_cast<size_t>(b) * T + t;
     float dz[2] = {0.f, 0.f};  // symbols lane and lane + 32
-    if (t < P && isfinite(loss_b)) {
+    if (t < P && feasible) {
       const float* lp_g = logp + ro * VP;
       const float lp_mine[2] = {lp_g[lane], lp_g[lane + 32]};
       float pv[2] = {0.f, 0.f};
@@ -846,45 +931,63 @@ __global__ void ctc_grad_sorted_kernel(const float* __restrict__ logp, const flo
       lp_row[lane] = lp_mine[0] * LOG2E;
       lp_row[lane + 32] = lp_mine[1] * LOG2E;
       __syncwarp();
+      // (the lattices were written during this launch in the fused path: L2-coherent loads, not the
+      // read-only path)
       const float4* a_row = reinterpret_cast<const float4*>(alpha + ro * S_stride);
       const float4* b_row = reinterpret_cast<const float4*>(beta + ro * S_stride);
-      const float off_blank = loss2 - lp_row[blank];
-      float blank_acc = 0.f;
-      for (int base = 0; base < S; base += 512) {
-        // up to 4 passes of 128 states issued together (8 x 16-byte loads in flight per lane)
-        float4 av[4], bv[4];
+      if (!have_offset) {
+        // max over the states of alpha + beta - lp: the exponent offset of this warp's frames
+        float m = NEG;
+        for (int s = lane * 4; s < S; s += 128) {
+          const float4 av = __ldcg(a_row + (s >> 2)), bv = __ldcg(b_row + (s >> 2));
+          const int2 pk = *reinterpret_cast<const int2*>(packed + (s >> 1));
+          m = fmaxf(m, av.x + bv.x - lp_row[blank]);
+          if (s + 1 < S) m = fmaxf(m, av.y + bv.y - lp_row[pk.x & 255]);
+          if (s + 2 < S) m = fmaxf(m, av.z + bv.z - lp_row[blank]);
+          if (s + 3 < S) m = fmaxf(m, av.w + bv.w - lp_row[pk.y & 255]);
+        }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        offset2 = -m;
+        have_offset = true;
+        feasible = m > -1e29f;  // no alignment at all: zero gradient (the walk reports an infinite loss)
+      }
+      const float off_blank = offset2 - lp_row[blank];
+      float blank_acc = 0.f;
+      for (int base = 0; base < S; base += 128 * NP) {
+        // up to NP passes of 128 states issued together (2 NP x 16-byte loads in flight per lane)
+        float4 av[NP], bv[NP];
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
           const int s = base + j * 128 + lane * 4;
           if (s < S) {
-            av[j] = __ldg(a_row + (s >> 2));
-            bv[j] = __ldg(b_row + (s >> 2));
+            av[j] = __ldcg(a_row + (s >> 2));
+            bv[j] = __ldcg(b_row + (s >> 2));
           }
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < NP; ++j) {
           const int s = base + j * 128 + lane * 4;
           if (s < S) {
             // s is a multiple of 4: states s, s+2 are blanks, s+1, s+3 carry labels s/2, s/2+1
             // (one 8-byte read for both labels; past the last label it reads unused padding)
             const int2 pk = *reinterpret_cast<const int2*>(packed + (s >> 1));
             blank_acc += ex2_approx(av[j].x + bv[j].x + off_blank);
-            if (s + 1 < S) xs[pk.x >> 8] = ex2_approx(av[j].y + bv[j].y - lp_row[pk.x & 255] + loss2);
+            if (s + 1 < S) xs[pk.x >> 8] = ex2_approx(av[j].y + bv[j].y - lp_row[pk.x & 255] + offset2);
             if (s + 2 < S) blank_acc += ex2_approx(av[j].z + bv[j].z + off_blank);
-            if (s + 3 < S) xs[pk.y >> 8] = ex2_approx(av[j].w + bv[j].w - lp_row[pk.y & 255] + loss2);
+            if (s + 3 < S) xs[pk.y >> 8] = ex2_approx(av[j].w + bv[j].w - lp_row[pk.y & 255] + offset2);
           }
         }
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) blank_acc += __shfl_xor_sync(0xffffffffu, blank_acc, o);
       __syncwarp();
-      float dLdp[2] = {0.f, 0.f};
-      float dot = 0.f;
+      float occ[2] = {0.f, 0.f};
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int v = lane + 32 * h;
         if (v < V) {
-          float occ = blank_acc;
+          occ[h] = blank_acc;
           if (v != blank) {
             const int k0 = seg[v], k1 = seg[v + 1];
             float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
@@ -896,9 +999,25 @@ __global__ void ctc_grad_sorted_kernel(const float* __restrict__ logp, const flo
               acc3 += xs[k + 3];
             }
             for (; k < k1; ++k) acc0 += xs[k];
-            occ = (acc0 + acc1) + (acc2 + acc3);
+            occ[h] = (acc0 + acc1) + (acc2 + acc3);
           }
-          const float g = expf(lp_mine[h]) - occ;
+        }
+      }
+      if (self_normalised) {
+        float total = occ[0] + occ[1];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+        const float inv = feasible && total > 0.f ? 1.0f / total : 0.f;
+        occ[0] *= inv;
+        occ[1] *= inv;
+      }
+      float dLdp[2] = {0.f, 0.f};
+      float dot = 0.f;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int v = lane + 32 * h;
+        if (v < V) {
+          const float g = expf(lp_mine[h]) - occ[h];
           dLdp[h] = g / (pv[h] + 1e-8f);
           dot += pv[h] * dLdp[h];
         }
@@ -906,7 +1025,7 @@ __global__ void ctc_grad_sorted_kernel(const float* __restrict__ logp, const flo
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
 #pragma unroll
-      for (int h = 0; h < 2; ++h) dz[h] = pv[h] * (dLdp[h] - dot) * grad_scale;
+      for (int h = 0; h < 2; ++h) dz[h] = feasible ? pv[h] * (dLdp[h] - dot) * grad_scale : 0.f;
       __syncwarp();
     }
     if (dz_f32 != nullptr) {
@@ -927,6 +1046,96 @@ __global__ void ctc_grad_sorted_kernel(const float* __restrict__ logp, const flo
         if (planes == 2) row[64 + lane + 32 * h] = __float2bfloat16_rn(dz[h] - __bfloat162float(hi));
       }
     }
+  }
+}
+
+__global__ void ctc_grad_sorted_kernel(const float* __restrict__ logp, const float* __restrict__ probs,
+                                       const int32_t* __restrict__ labels,
+                                       const int32_t* __restrict__ input_len,
+                                       const int32_t* __restrict__ label_len,
+                                       const float* __restrict__ loss, const float* __restrict__ alpha,
+                                       const float* __restrict__ beta, const int* __restrict__ sort_ws,
+                                       __nv_bfloat16* __restrict__ dz_packed, float* __restrict__ dz_f32,
+                                       float grad_scale, int T, int V, int L_max, int blank, int S_stride,
+                                       int planes, int fp16, int frames_per_block) {
+  extern __shared__ uint8_t smem_raw[];
+  ptx::pdl_launch_dependents();
+  const int t_begin = blockIdx.x * frames_per_block;
+  const int t_end = min(t_begin + frames_per_block, T);
+  ptx::pdl_wait();  // alpha / beta / loss / the sorted labels come from the lattice kernel right before
+  grad_item<4>(smem_raw, blockIdx.y, t_begin, t_end, true, logp, probs, input_len, label_len, loss, alpha, beta, sort_ws,
+            dz_packed, dz_f32, grad_scale, T, V, L_max, blank, S_stride, planes, fp16);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused launch: lattices AND gradient in one grid.  CTAs [0, n_walk) are the lattice walkers above; the
+// remaining CTAs are persistent GRADIENT CTAs.  The gradient of frame t needs alpha_t (ready once the
+// alpha walk has passed t) and beta_t (ready once the beta walk, coming from the other end, has passed
+// t): the frames in the middle of an utterance become available when both walks are half way, the
+// outermost ones when they finish.  The gradient CTAs therefore process (utterance, frame chunk) items
+// from the middle outwards, waiting on the walkers' progress flags (ld.acquire.gpu), and the whole
+// bandwidth-bound gradient phase runs underneath the second half of the latency-bound walks — on the
+// SMs' idle issue slots and against lattice rows that are still in L2 — instead of as a second launch
+// after them.  Walkers never wait for gradient CTAs, and every CTA of the grid is co-resident (the
+// launcher sizes the grid with the occupancy API), so the waits cannot deadlock; they are bounded anyway.
+template <int SPT, int K, bool CL>
+__global__ void __launch_bounds__(1024)
+    ctc_fused_kernel(const float* __restrict__ logp, const float* __restrict__ probs,
+                     const int32_t* __restrict__ labels, const int32_t* __restrict__ input_len,
+                     const int32_t* __restrict__ label_len, float* __restrict__ loss,
+                     float* __restrict__ beta_loss, float* __restrict__ alpha, float* __restrict__ beta,
+                     int* __restrict__ sort_ws, int* __restrict__ progress, __nv_bfloat16* __restrict__ dz_packed,
+                     float* __restrict__ dz_f32, float grad_scale, int B, int T, int V, int L_max, int blank,
+                     int S_stride, int col_stride, int planes, int fp16, int n_walk, int frames_per_item) {
+  extern __shared__ uint8_t smem_raw[];
+  ptx::pdl_launch_dependents();
+  if (static_cast<int>(blockIdx.x) < n_walk) {
+    const int csize = CL ? static_cast<int>(ptx::cluster_nctarank()) : 1;
+    lattice_cta_body<SPT, K, CL>(smem_raw, static_cast<int>(blockIdx.x) / csize, logp, labels, input_len, label_len,
+                                 loss, beta_loss, alpha, beta, sort_ws, T, L_max, blank, S_stride, col_stride,
+                                 progress);
+    return;
+  }
+  ptx::pdl_wait();  // logp / probs come from the output_conv kernel right before
+  const int g = static_cast<int>(blockIdx.x) - n_walk, G = static_cast<int>(gridDim.x) - n_walk;
+  const int n_chunks = (T + frames_per_item - 1) / frames_per_item;
+  const int items = B * n_chunks;
+  int loaded_b = -1;
+  for (int item = g; item < items; item += G) {
+    const int b = item % B, j = item / B;
+    const int P = min(input_len[b], T);
+    // j-th chunk of the utterance in order of availability: the middle one, then alternately one
+    // further down / up, then what is left of the longer side
+    const int c_mid = min((P / 2) / frames_per_item, n_chunks - 1);
+    const int down = c_mid, up = n_chunks - 1 - c_mid;
+    const int both = min(down, up);
+    int c;
+    if (j == 0) {
+      c = c_mid;
+    } else if (j <= 2 * both) {
+      const int q = (j + 1) >> 1;
+      c = (j & 1) ? c_mid - q : c_mid + q;
+    } else {
+      const int r = j - 2 * both;
+      c = down > up ? c_mid - both - r : c_mid + both + r;
+    }
+    const int t_begin = c * frames_per_item;
+    const int t_end = min(t_begin + frames_per_item, T);
+    if (threadIdx.x == 0 && t_begin < P) {
+      const int need_a = min(t_end, P), need_b = P - t_begin;
+      unsigned spins = 0;
+      while (ld_acquire_gpu(progress + 2 * b) < need_a || ld_acquire_gpu(progress + 2 * b + 1) < need_b) {
+        __nanosleep(200);
+        if (++spins > (1u << 24)) {
+          printf("speechless_b200: CTC gradient CTA timed out waiting for the lattice walk (utterance %d)\n", b);
+          __trap();
+        }
+      }
+    }
+    __syncthreads();  // flags seen (the acquire orders every thread's loads behind it); smem of the last item is free
+    grad_item<2>(smem_raw, b, t_begin, t_end, b != loaded_b, logp, probs, input_len, label_len, nullptr, alpha, beta,
+              sort_ws, dz_packed, dz_f32, grad_scale, T, V, L_max, blank, S_stride, planes, fp16);
+    if (t_begin < P) loaded_b = b;
   }
 }
 
@@ -981,7 +1190,9 @@ size_t ctc_workspace_bytes(int B, int T, int L_max) {
   // alpha | beta | beta_loss[B] (256-byte slot granularity) | per utterance: symbol-sorted label slots + segments
   const size_t bl = (static_cast<size_t>(B) * sizeof(float) + 255) & ~static_cast<size_t>(255);
   const size_t sort = static_cast<size_t>(B) * (((L_max + 31) & ~31) + SORT_EXTRA) * sizeof(int);
-  return 2 * lat + bl + sort + 256;
+  // ... | progress flags of the fused launch: steps completed per (utterance, direction)
+  const size_t flags = (static_cast<size_t>(2 * B) * sizeof(int) + 255) & ~static_cast<size_t>(255);
+  return 2 * lat + bl + sort + flags + 512;
 }
 
 int ctc_loss_launch(const float* logp, const float* probs, const int32_t* labels,
@@ -1001,6 +1212,11 @@ int ctc_loss_launch(const float* logp, const float* probs, const int32_t* labels
   float* beta_loss = beta + lat;
   int* sort_ws = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(beta_loss) +
                                         ((static_cast<size_t>(B) * sizeof(float) + 255) & ~static_cast<size_t>(255)));
+  const size_t sort_bytes = static_cast<size_t>(B) * (((L_max + 31) & ~31) + SORT_EXTRA) * sizeof(int);
+  int* progress = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(sort_ws) + ((sort_bytes + 255) & ~static_cast<size_t>(255)));
+  const bool want_grad = dlogits_packed != nullptr || dlogits_f32 != nullptr;
+  if (want_grad) SL_REQUIRE(probs != nullptr, "gradient needs the softmax probabilities");
+  bool grad_done = false;
 
   const int S_max = 2 * L_max + 1;
   SL_REQUIRE(S_max <= 4096, "label too long (max 2047 characters)");
@@ -1038,8 +1254,79 @@ int ctc_loss_launch(const float* logp, const float* probs, const int32_t* labels
     }
     SL_REQUIRE(nw <= 31, "SL_CTC_SPT too small for this label length");
     const int col_stride = ((nw * own + 2 * kk) + 3) & ~3;
-    const size_t smem = (2 * CHUNK * VP + 2 * col_stride + VP) * sizeof(float);
+    const size_t smem = (2 * CHUNK * VP + 2 * col_stride + VP + 8) * sizeof(float);
     bool launched = false;
+    // Fused launch (default when a gradient is wanted): gradient CTAs ride along with the walkers
+    // (ctc_fused_kernel).  SL_CTC_FUSED=0 selects the two-launch path; SL_CTC_GRAD_CTAS bounds their number.
+    const char* fused_env = std::getenv("SL_CTC_FUSED");
+    if (want_grad && !(fused_env && std::atoi(fused_env) == 0)) {
+      const int threads = (nw + 1) * 32;
+      const int nwarps = nw + 1;
+      const int L_pad = (L_max + 31) & ~31;
+      const size_t gsmem = (L_pad + SORT_EXTRA) * sizeof(int) + static_cast<size_t>(nwarps) * (VP + L_pad) * sizeof(float);
+      const size_t fsmem = smem > gsmem ? smem : gsmem;
+      const int n_walk = 2 * B * cluster;
+      int frames_per_item = 2 * nwarps;
+      if (const char* e = std::getenv("SL_CTC_GRAD_FPI")) frames_per_item = std::max(1, std::atoi(e));  // tuning aid
+      const int items = B * ((T + frames_per_item - 1) / frames_per_item);
+      int dev = 0, sms = 148;
+      SL_CUDA(cudaGetDevice(&dev));
+      SL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      int want_ctas = 2 * sms;
+      if (const char* e = std::getenv("SL_CTC_GRAD_CTAS")) want_ctas = std::max(1, std::atoi(e));
+#define SL_LAUNCH_FUSED(SPT, KK)                                                                    \
+  if (!launched && spt == SPT && kk == KK) {                                                        \
+    auto kern = cluster > 1 ? ctc_fused_kernel<SPT, KK, true> : ctc_fused_kernel<SPT, KK, false>;   \
+    if (fsmem > 48 * 1024)                                                                          \
+      SL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(fsmem))); \
+    /* every CTA of the grid must be co-resident: the gradient CTAs wait for the walkers */        \
+    int capacity = 0;                                                                               \
+    if (cluster > 1) {                                                                              \
+      cudaLaunchConfig_t cfg = {};                                                                  \
+      cfg.gridDim = dim3(sms / cluster * cluster);                                                  \
+      cfg.blockDim = dim3(threads);                                                                 \
+      cfg.dynamicSmemBytes = fsmem;                                                                 \
+      cudaLaunchAttribute attr[1];                                                                  \
+      attr[0].id = cudaLaunchAttributeClusterDimension;                                             \
+      attr[0].val.clusterDim.x = static_cast<unsigned>(cluster);                                    \
+      attr[0].val.clusterDim.y = 1;                                                                 \
+      attr[0].val.clusterDim.z = 1;                                                                 \
+      cfg.attrs = attr;                                                                             \
+      cfg.numAttrs = 1;                                                                             \
+      int clusters = 0;                                                                             \
+      if (cudaOccupancyMaxActiveClusters(&clusters, kern, &cfg) != cudaSuccess) {                   \
+        cudaGetLastError();                                                                         \
+        clusters = 0;                                                                               \
+      }                                                                                             \
+      capacity = clusters * cluster;                                                                \
+    } else {                                                                                        \
+      int per_sm = 0;                                                                               \
+      SL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, fsmem));        \
+      capacity = per_sm * sms;                                                                      \
+    }                                                                                               \
+    int n_grad = std::min(std::min(want_ctas, items), capacity - n_walk);                          \
+    n_grad = n_grad / cluster * cluster;                                                            \
+    if (n_grad >= cluster && n_grad >= 8) {                                                         \
+      SL_CUDA(cudaMemsetAsync(progress, 0, static_cast<size_t>(2 * B) * sizeof(int), stream));      \
+      SL_CUDA(launch_pdl_cluster(PDL_CTC, ClusterX{cluster}, kern, dim3(n_walk + n_grad), dim3(threads), fsmem, stream, \
+                                 logp, probs, labels, input_len, label_len, loss, beta_loss, alpha, beta, sort_ws,  \
+                                 progress, reinterpret_cast<__nv_bfloat16*>(dlogits_packed), dlogits_f32, grad_scale, \
+                                 B, T, V, L_max, blank, S_stride, col_stride, planes, fp16, n_walk, frames_per_item)); \
+      launched = true;                                                                              \
+      grad_done = true;                                                                             \
+    }                                                                                               \
+  }
+      SL_LAUNCH_FUSED(2, 4)
+      SL_LAUNCH_FUSED(2, 8)
+      SL_LAUNCH_FUSED(2, 16)
+      SL_LAUNCH_FUSED(4, 8)
+      SL_LAUNCH_FUSED(4, 16)
+      SL_LAUNCH_FUSED(4, 32)
+      SL_LAUNCH_FUSED(8, 32)
+      SL_LAUNCH_FUSED(8, 8)
+      SL_LAUNCH_FUSED(8, 16)
+#undef SL_LAUNCH_FUSED
+    }
 #define SL_LAUNCH_HALO(SPT, KK)                                                                     \
   if (!launched && spt == SPT && kk == KK) {                                                        \
     auto kern = cluster > 1 ? ctc_lattice_halo_kernel<SPT, KK, true> : ctc_lattice_halo_kernel<SPT, KK, false>; \
@@ -1110,8 +1397,7 @@ int ctc_loss_launch(const float* logp, const float* probs, const int32_t* labels
   }
   }
 
-  if (dlogits_packed != nullptr || dlogits_f32 != nullptr) {
-    SL_REQUIRE(probs != nullptr, "gradient needs the softmax probabilities");
+  if (want_grad && !grad_done) {
     int frames_per_block = 32;  // 4 frames per warp (measured at the bench shape: 8 / 16 / 32 / 64 frames per block
                                 // -> 0.1022 / 0.0994 / 0.0976 / 0.0976 ms for loss + gradient)
     if (const char* e = std::getenv("SL_CTC_GRAD_FPB")) frames_per_block = std::max(1, std::atoi(e));  // tuning aid

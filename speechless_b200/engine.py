@@ -235,6 +235,11 @@ class ConvTower:
         self._adam_tables = None
         self._copy_stream = None
         self._side_stream = None
+        self._update_stream = None
+        self._sm_limit_until = 0  # launch count at which sl_set_sm_limit is lifted again
+        # bucketed all-reduce + Adam on an update stream, overlapped with backward (backward_and_update)
+        self.pipeline_update = os.environ.get("SL_PIPELINE_UPDATE", "1") != "0"
+        self.sm_count = torch.cuda.get_device_properties(device).multi_processor_count
 
     # ------------------------------------------------------------------ helpers
     @property
@@ -312,6 +317,16 @@ class ConvTower:
                                                         layer.gemm_kernel, layer.cin_pad, layer.cout_pad,
                                                         self.precision, self.stream))
                 self.launches += 1
+
+    def broadcast_parameters(self, src: int = 0) -> None:
+        """Data parallelism: every replica starts from rank `src`'s fp32 master weights (plumbing over
+        torch.distributed; the 16-bit operands are re-derived locally)."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()):
+            return
+        with torch.cuda.device(self.device):
+            dist.broadcast(self.params, src=src)
+            self.repack()
 
     # ------------------------------------------------------------------ forward
     def workspace(self, B: int, T: int) -> _Workspace:
@@ -582,12 +597,15 @@ class ConvTower:
             end_layer = start_layer
         return buckets
 
-    def backward(self, ws: Optional[_Workspace] = None, on_bucket_ready=None) -> None:
+    def backward(self, ws: Optional[_Workspace] = None, on_bucket_ready=None, on_bucket_consumed=None) -> None:
         """Fill self.grads from ws.dz_packed (set by ctc(want_grad=True)).
 
         `on_bucket_ready(begin, end)` is called (on the launching stream) as soon as the weight
         gradients of a bucket of `grad_buckets()` have been enqueued, so the data-parallel
         all-reduce of the big top layers overlaps the backward pass of the layers below.
+        `on_bucket_consumed(begin, end)` follows once the input gradient of the bucket's lowest
+        layer — the last reader of the bucket's 16-bit weights — has been enqueued too: from that
+        point of the stream on, the bucket's parameters may be updated.
 
         The chain dY_l -> dgrad_l -> dY_{l-1} runs on the current stream; with
         `overlap_backward` the weight gradients (which only consume dY_l and the saved
@@ -607,7 +625,8 @@ class ConvTower:
             dy = ws.dz_packed
             flip = 0
             wgrad_done = None  # event: the wgrad that still reads the buffer the next dgrad overwrites
-            bucket_starts = {b[0]: (b[1], b[2]) for b in self.grad_buckets()} if on_bucket_ready else {}
+            bucket_starts = {b[0]: (b[1], b[2]) for b in self.grad_buckets()} \
+                if (on_bucket_ready or on_bucket_consumed) else {}
             for index in range(len(self.layers) - 1, first - 1, -1):
                 layer = self.layers[index]
                 x = ws.layer_inputs[index]  # the tensor the forward conv actually read (dropped or not)
@@ -618,6 +637,7 @@ class ConvTower:
                     t_alloc, layer.gemm_cin, layer.cout, layer.gemm_kernel, layer.gemm_stride, self.precision, 1,
                     1.0 / ws.loss_scale, self.stream))
                 previous_wgrad_done = wgrad_done
+                self._lift_sm_limit()
                 if side is None:
                     launch_wgrad()
                 else:
@@ -626,10 +646,12 @@ class ConvTower:
                         launch_wgrad()
                         wgrad_done = side.record_event()
                 self.launches += 1
-                if index in bucket_starts:
+                if index in bucket_starts and on_bucket_ready is not None:
                     if side is not None:
                         main.wait_stream(side)
                     on_bucket_ready(*bucket_starts[index])
+                if index in bucket_starts and on_bucket_consumed is not None and index == first:
+                    on_bucket_consumed(*bucket_starts[index])  # the lowest trainable layer has no input gradient
                 if index > first:
                     below = self.layers[index - 1]
                     dx = ws.dact[flip].view(-1)[:ws.B * t_in * self.planes * below.cout_pad].view(
@@ -646,11 +668,14 @@ class ConvTower:
                     if need and (ws.dgrad_ws is None or ws.dgrad_ws.numel() < need):
                         ws.dgrad_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
                     scratch = ws.dgrad_ws if need else None
+                    self._lift_sm_limit()
                     self._timed("dgrad", layer.name, lambda: self.lib.sl_conv1d_dgrad(
                         ptr(dy), ptr(self.w_fwd[index]), ptr(mask), ptr(dx), ws.B, t_in, layer.gemm_cin, layer.cout,
                         layer.gemm_kernel, layer.gemm_stride, self.precision, out_scale, ptr(scratch), need,
                         self.stream))
                     self.launches += 2 if (need or layer.gemm_stride == 2) else 1
+                    if index in bucket_starts and on_bucket_consumed is not None:
+                        on_bucket_consumed(*bucket_starts[index])
                     dy = dx
                     flip ^= 1
             if side is not None:
@@ -674,6 +699,87 @@ class ConvTower:
                 targets, cin_pads, len(self.layers), self.precision, lr, beta_1, beta_2, epsilon, iteration,
                 self.stream))
             self.launches += 1
+
+    def adam_step_range(self, begin: int, end: int, lr: float, beta_1: float, beta_2: float, epsilon: float,
+                        iteration: int, stream: Optional[int] = None) -> None:
+        """The same fused update on floats [begin, end) of the flat buffer only (a bucket of
+        `grad_buckets()`: whole layers), on `stream`."""
+        import ctypes
+        inside = [(i, l) for i, l in enumerate(self.layers) if begin <= l.w_offset and l.w_offset + l.w_size <= end]
+        n = len(inside)
+        begins = (ctypes.c_size_t * max(n, 1))(*[l.w_offset - begin for _, l in inside])
+        ends = (ctypes.c_size_t * max(n, 1))(*[l.w_offset + l.w_size - begin for _, l in inside])
+        targets = (ctypes.c_void_p * max(n, 1))(*[self.w_fwd[i].data_ptr() for i, _ in inside])
+        cin_pads = (ctypes.c_int * max(n, 1))(*[l.cin_pad for _, l in inside])
+        offset = 4 * begin
+        with torch.cuda.device(self.device):
+            self._timed("adam", "adam", lambda: self.lib.sl_adam_step_fused(
+                self.params.data_ptr() + offset, self.grads.data_ptr() + offset, self.adam_m.data_ptr() + offset,
+                self.adam_v.data_ptr() + offset, end - begin, begins, ends, targets, cin_pads, n, self.precision, lr,
+                beta_1, beta_2, epsilon, iteration, self.stream if stream is None else stream))
+            self.launches += 1
+
+    def backward_and_update(self, ws: Optional[_Workspace], loss: torch.Tensor, optimizer, data_parallel=None
+                            ) -> torch.Tensor:
+        """Backward pass, the data-parallel exchange step and the Keras-2 Adam update, pipelined by
+        gradient bucket: as soon as the weight gradients of a bucket exist, an UPDATE
+        STREAM all-reduces them over NVLink (few CTAs: `DataParallel.max_ctas`) and applies Adam to that
+        bucket, while the compute stream carries on with the input / weight gradients of the layers
+        below.  Only the last, small bucket's all-reduce + update are exposed.  Without data parallelism
+        the same pipeline hides the optimizer step behind the backward pass.
+
+        While a bucket's all-reduce is in flight the persistent Conv1D grids of the next
+        `data_parallel.limited_launches` launches are sized to 148 - max_ctas CTAs
+        (`sl_set_sm_limit`), so the collective finds free SMs instead of delaying the tail of a
+        148-CTA grid.  `optimizer.iterations` must already count this step.  Returns the (global)
+        sum of the per-utterance losses as a device scalar."""
+        ws = ws or self._current
+        dp = data_parallel if (data_parallel is not None and data_parallel.active) else None
+        hyper = (optimizer.lr, optimizer.beta_1, optimizer.beta_2, optimizer.epsilon, optimizer.iterations)
+        self.ensure_training_state()
+        with torch.cuda.device(self.device):
+            main = torch.cuda.current_stream(self.device)
+            loss_sum = loss.sum()
+            if self.profile is not None or not self.pipeline_update:
+                # measurement / A-B mode: everything in order on the compute stream
+                self.backward(ws, on_bucket_ready=(lambda b, e: dp.allreduce_range(self.grads, b, e)) if dp else None)
+                if dp:
+                    dp.allreduce_scalar(loss_sum)
+                for _, begin, end in self.grad_buckets():
+                    self.adam_step_range(begin, end, *hyper)
+                return loss_sum
+            if self._update_stream is None:
+                self._update_stream = torch.cuda.Stream(device=self.device)
+            update = self._update_stream
+            update.wait_stream(main)  # (the previous step's update has long been joined; orders the zero fill)
+
+            def ready(begin, end):
+                if dp is None:
+                    return
+                update.wait_event(main.record_event())
+                dp.allreduce_range(self.grads, begin, end, stream=update)
+                if dp.max_ctas > 0 and dp.limited_launches > 0:
+                    check(self.lib.sl_set_sm_limit(max(1, self.sm_count - dp.max_ctas)))
+                    self._sm_limit_until = self.launches + dp.limited_launches
+
+            def consumed(begin, end):
+                update.wait_event(main.record_event())
+                self.adam_step_range(begin, end, *hyper, stream=update.cuda_stream)
+
+            try:
+                self.backward(ws, on_bucket_ready=ready, on_bucket_consumed=consumed)
+            finally:
+                self._lift_sm_limit(force=True)
+            if dp:
+                dp.allreduce_scalar(loss_sum, stream=update, after=main)
+            main.wait_stream(update)
+        return loss_sum
+
+    def _lift_sm_limit(self, force: bool = False) -> None:
+        """Back to full-width persistent grids once the launches that overlap an all-reduce are out."""
+        if self._sm_limit_until and (force or self.launches >= self._sm_limit_until):
+            check(self.lib.sl_set_sm_limit(0))
+            self._sm_limit_until = 0
 
     def sync(self) -> None:
         torch.cuda.current_stream(self.device).synchronize()

@@ -138,15 +138,22 @@ class PredictiveNet:
                 group.create_dataset(names[1], data=arrays["{}/bias".format(layer.name)])
 
     def load_weights(self, path) -> None:
+        """The exact file given wins; `weights-epochN.npz` next to it is the fallback when the `.h5` does not
+        exist or cannot be read for lack of h5py (this image has none, so the `.h5` branch is unreachable
+        here: DESIGN.md §7)."""
         npz = self._npz_path(path)
-        if npz.exists():
+        try:
+            import h5py
+        except ImportError:
+            h5py = None
+        exact = Path(str(path))
+        use_npz = npz.exists() and (exact == npz or not exact.exists() or h5py is None)
+        if use_npz:
             with numpy.load(str(npz)) as arrays:
                 for layer in self.conv_layers:
                     layer.set_weights([arrays["{}/kernel".format(layer.name)], arrays["{}/bias".format(layer.name)]])
             return
-        try:
-            import h5py
-        except ImportError:
+        if h5py is None:
             raise IOError("{} not found and h5py is unavailable to read {}".format(npz, path))
         with h5py.File(str(path), "r") as f:
             root = f["model_weights"] if "model_weights" in f else f
@@ -232,7 +239,8 @@ class Wav2Letter:
                  device=None,
                  seed: Optional[int] = None,
                  decoder_beam_width: int = 100,
-                 decoder_top_paths: int = 32):
+                 decoder_top_paths: int = 32,
+                 data_parallel=None):
         if frozen_layer_count > 0 and load_model_from_directory is None:
             raise ValueError("Layers cannot be frozen if model is trained from scratch.")
         if compute_dtype not in PRECISIONS:
@@ -259,6 +267,12 @@ class Wav2Letter:
         self.out_filter_count = out_filter_count
         self.compute_dtype = compute_dtype
         self.seed = seed
+        # One process per GPU: `data_parallel` (speechless_b200.distributed.DataParallel) makes
+        # `train` shard every batch by utterance and `test_and_predict_batches` shard by batch; the device
+        # defaults to the rank's own GPU and rank 0's initial weights are broadcast to every replica.
+        self.data_parallel = data_parallel if (data_parallel is not None and data_parallel.active) else None
+        if device is None and self.data_parallel is not None:
+            device = "cuda:{}".format(self.data_parallel.local_rank)
         self._device = device
         self.predictive_net = self.create_predictive_net()
         self.prediction_phase_flag = 0.
@@ -286,6 +300,8 @@ class Wav2Letter:
             self.load_weights(
                 allowed_characters_for_loaded_model, load_epoch, load_model_from_directory,
                 loaded_first_layers_count=frozen_layer_count if reinitialize_trainable_loaded_layers else None)
+        if self.data_parallel is not None:
+            self.tower.broadcast_parameters()
 
     # ------------------------------------------------------------------ construction
     def create_predictive_net(self) -> PredictiveNet:
@@ -475,6 +491,9 @@ class Wav2Letter:
         n_best = self.beam_search_batch(ws, top_paths=self.decoder_top_paths, merge_repeated=False)
         winners = []
         for hypotheses in n_best:
+            if not hypotheses:  # no finite hypothesis (e.g. NaN probabilities): empty transcription, not a crash
+                winners.append([])
+                continue
             texts = [(self.grapheme_encoding.decode_graphemes(graphemes, merge_repeated=False), log_probability)
                      for graphemes, log_probability in hypotheses]
             best_text, _ = self.rescorer.best(texts)
@@ -516,10 +535,20 @@ class Wav2Letter:
         log(str(result) + " (batch {})".format(index))
         return result
 
-    def test_and_predict_batches(self, labeled_spectrogram_batches: Iterable[
-        List[LabeledSpectrogram]]) -> ExpectationsVsPredictionsInBatches:
-        return ExpectationsVsPredictionsInBatches([self.test_and_predict_batch_with_log(index, batch)
-                                                   for index, batch in enumerate(labeled_spectrogram_batches)])
+    def test_and_predict_batches(self, labeled_spectrogram_batches: Iterable[List[LabeledSpectrogram]],
+                                 data_parallel=None) -> ExpectationsVsPredictionsInBatches:
+        """Under data parallelism the batches are dealt round-robin to the ranks (evaluation needs no
+        collective on the data path); the per-batch results are gathered on the host and every
+        rank returns the complete, ordered result."""
+        data_parallel = data_parallel or self.data_parallel
+        if data_parallel is None or not data_parallel.active:
+            return ExpectationsVsPredictionsInBatches([self.test_and_predict_batch_with_log(index, batch)
+                                                       for index, batch in enumerate(labeled_spectrogram_batches)])
+        mine = [(index, self.test_and_predict_batch_with_log(index, batch))
+                for index, batch in enumerate(labeled_spectrogram_batches)
+                if index % data_parallel.world_size == data_parallel.rank]
+        everyone = [pair for pairs in data_parallel.gather_objects(mine) for pair in pairs]
+        return ExpectationsVsPredictionsInBatches([result for _, result in sorted(everyone, key=lambda p: p[0])])
 
     def test_and_predict_batches_with_log(
             self, corpus_name: str, batches: Iterable[List[LabeledSpectrogram]]) -> ExpectationsVsPredictionsInBatches:
@@ -539,9 +568,13 @@ class Wav2Letter:
                        allreduce: Optional[Callable] = None, data_parallel=None) -> float:
         """One optimisation step on this GPU's shard: forward, CTC loss + gradient, backward,
         (gradient all-reduce), Keras-2 Adam.  Objective = mean over the *global* batch (net.py:389).
-        Returns the batch-mean loss (the global one when an all-reduce hook is given).  `data_parallel` (a
-        `speechless_b200.distributed.DataParallel`) overlaps the bucketed all-reduce with backward;
-        `allreduce(grads, loss_sum)` is the plain, non-overlapped hook."""
+        Returns the batch-mean loss — the GLOBAL one whenever gradients are all-reduced.  `data_parallel` (a
+        `speechless_b200.distributed.DataParallel`, default: the one given to the constructor) pipelines the
+        bucketed all-reduce and the per-bucket Adam update with backward (`ConvTower.backward_and_update`);
+        `allreduce(grads, loss_sum)` is the plain, non-overlapped hook.  Under data parallelism the caller
+        passes this rank's shard, padded to the GLOBAL longest utterance when the single-process result is to
+        be reproduced exactly (padding is unmasked, net.py:578-587; `train` does this), and
+        `global_batch_size` (or the key of that name in `input_by_name`)."""
         if self.use_asg:
             raise NotImplementedError("ASG is not yet implemented.")
         names = Wav2Letter.InputNames
@@ -550,21 +583,18 @@ class Wav2Letter:
         tower.forward(ws, training=True)  # learning phase 1: dropout active (net.py:597-606)
         tower.set_labels(ws, input_by_name[names.label_batch], input_by_name[names.prediction_lengths],
                          input_by_name[names.label_lengths])
-        batch_size = global_batch_size if global_batch_size is not None else ws.B
+        batch_size = input_by_name.get("global_batch_size", global_batch_size if global_batch_size is not None else ws.B)
         loss = tower.ctc(ws, want_grad=True, grad_scale=1.0 / batch_size)
-        if data_parallel is not None and data_parallel.active:
-            tower.backward(ws, on_bucket_ready=lambda begin, end: data_parallel.allreduce_bucket_async(
-                tower.grads, begin, end))
-            loss_sum = loss.sum()
-            data_parallel.finish(loss_sum)
-        else:
+        self.optimizer.iterations += 1
+        if allreduce is not None:
             tower.backward(ws)
             loss_sum = loss.sum()
-            if allreduce is not None:
-                allreduce(tower.grads, loss_sum)
-        self.optimizer.iterations += 1
-        tower.adam_step(self.optimizer.lr, self.optimizer.beta_1, self.optimizer.beta_2, self.optimizer.epsilon,
-                        self.optimizer.iterations)
+            allreduce(tower.grads, loss_sum)
+            tower.adam_step(self.optimizer.lr, self.optimizer.beta_1, self.optimizer.beta_2, self.optimizer.epsilon,
+                            self.optimizer.iterations)
+        else:
+            loss_sum = tower.backward_and_update(ws, loss, self.optimizer,
+                                                 data_parallel=data_parallel or self.data_parallel)
         return float(loss_sum.item()) / batch_size
 
     def fit_batches(self, input_batches: Iterable[Dict[str, ndarray]], global_batch_size: Optional[int] = None,
@@ -572,13 +602,14 @@ class Wav2Letter:
         """Train on consecutive batches (the dictionaries `_inputs_for_loss_net` builds), pipelined:
         the host->device copy of batch i+1 runs on a copy stream while batch i computes, and the
         per-step loss is read back asynchronously — one host synchronisation at the end.  Returns
-        each step's (shard contribution to the) batch-mean loss.  Same arithmetic as calling
-        `train_on_batch` per batch."""
+        each step's batch-mean loss (the global mean under data parallelism: the loss sums are all-reduced
+        with the gradients).  Same arithmetic as calling `train_on_batch` per batch."""
         import torch
         if self.use_asg:
             raise NotImplementedError("ASG is not yet implemented.")
         names = Wav2Letter.InputNames
         tower = self.tower
+        data_parallel = data_parallel or self.data_parallel
         iterator = iter(input_batches)
         current = next(iterator, None)
         if current is None:
@@ -594,19 +625,10 @@ class Wav2Letter:
             tower.forward(ws, training=True)
             tower.set_labels(ws, current[names.label_batch], current[names.prediction_lengths],
                              current[names.label_lengths])
-            batch_size = global_batch_size if global_batch_size is not None else ws.B
+            batch_size = current.get("global_batch_size", global_batch_size if global_batch_size is not None else ws.B)
             loss = tower.ctc(ws, want_grad=True, grad_scale=1.0 / batch_size)
-            if data_parallel is not None and data_parallel.active:
-                tower.backward(ws, on_bucket_ready=lambda begin, end: data_parallel.allreduce_bucket_async(
-                    tower.grads, begin, end))
-                loss_sum = loss.sum()
-                data_parallel.finish(loss_sum)
-            else:
-                tower.backward(ws)
-                loss_sum = loss.sum()
             self.optimizer.iterations += 1
-            tower.adam_step(self.optimizer.lr, self.optimizer.beta_1, self.optimizer.beta_2,
-                            self.optimizer.epsilon, self.optimizer.iterations)
+            loss_sum = tower.backward_and_update(ws, loss, self.optimizer, data_parallel=data_parallel)
             if len(device_losses) % 64 == 0:  # pinned allocations are slow: one per 64 steps
                 host_block = torch.empty((64,), dtype=torch.float32, pin_memory=True)
             host_loss = host_block[len(device_losses) % 64]
@@ -624,22 +646,38 @@ class Wav2Letter:
               net_directory: Path,
               batches_per_epoch: int,
               *,
-              epochs: int = 100000000):
+              epochs: int = 100000000,
+              data_parallel=None):
         """Same schedule as the reference's `fit_generator` call (net.py:550-556): log the preview
         batch, then epochs of `batches_per_epoch` steps starting at `load_epoch`, calling the
         callbacks of `create_callbacks` at every epoch end.  `epochs` (keyword-only, default as in
-        the reference) bounds the run for tests; a finite batch iterable ends training quietly."""
-        print_preview_batch = lambda: log(self.test_and_predict_batch(preview_labeled_spectrogram_batch))
+        the reference) bounds the run for tests; a finite batch iterable ends training quietly.
+
+        `data_parallel` (default: the constructor's): every rank is handed the SAME batch iterable — what the
+        reference's single process would consume — trains on its contiguous share of each batch, padded to the
+        batch's longest utterance, and the gradients of the global-mean objective are all-reduced, so N GPUs
+        take exactly the single-GPU optimisation steps.  Rank 0 alone logs and writes checkpoints."""
+        data_parallel = data_parallel or self.data_parallel
+        if data_parallel is not None and not data_parallel.active:
+            data_parallel = None
+        leader = data_parallel is None or data_parallel.rank == 0
+
+        def print_preview_batch():
+            result = self.test_and_predict_batch(preview_labeled_spectrogram_batch)
+            if leader:
+                log(result)
+
         print_preview_batch()
         callbacks = self.create_callbacks(callback=print_preview_batch,
-                                          tensor_board_log_directory=tensor_board_log_directory,
-                                          net_directory=net_directory)
+                                          tensor_board_log_directory=tensor_board_log_directory if leader else None,
+                                          net_directory=net_directory, save=leader)
         initial_epoch = self.load_epoch if (self.load_epoch is not None) else 0
-        batches = _Prefetcher(self._loss_inputs_generator(labeled_spectrogram_batches))
+        batches = _Prefetcher(self._loss_inputs_generator(labeled_spectrogram_batches, data_parallel))
         try:
             for epoch in range(initial_epoch, epochs):
                 started = time.time()
-                losses = self.fit_batches(inputs for inputs, _dummy in itertools.islice(batches, batches_per_epoch))
+                losses = self.fit_batches((inputs for inputs, _dummy in itertools.islice(batches, batches_per_epoch)),
+                                          data_parallel=data_parallel)
                 if len(losses) < batches_per_epoch:
                     return  # the batch iterable is exhausted
                 logs = {"loss": sum(losses) / len(losses), "seconds": time.time() - started}
@@ -653,7 +691,7 @@ class Wav2Letter:
         return "weights-epoch{}.h5".format(epoch)
 
     def create_callbacks(self, callback: Callable[[], None], tensor_board_log_directory: Path, net_directory: Path,
-                         callback_step: int = 1, save_step: int = 1) -> List[Callable]:
+                         callback_step: int = 1, save_step: int = 1, save: bool = True) -> List[Callable]:
         """Epoch-end hooks with the reference's semantics (net.py:562-576): run `callback` every
         `callback_step` epochs, save `weights-epoch{N}` every `save_step` epochs for N > 0.  The
         TensorBoard callback becomes a JSON-lines scalar log in `tensor_board_log_directory`."""
@@ -661,7 +699,7 @@ class Wav2Letter:
         def custom_callback(epoch: int, logs=()):
             if epoch % callback_step == 0:
                 callback()
-            if epoch % save_step == 0 and epoch > 0:
+            if save and epoch % save_step == 0 and epoch > 0:
                 mkdir(net_directory)
                 self.predictive_net.save_weights(str(Path(net_directory) / self.model_file_name(epoch)))
 
@@ -675,10 +713,20 @@ class Wav2Letter:
         return [scalar_log, custom_callback]
 
     # ------------------------------------------------------------------ batching (net.py:500-511, 578-607)
-    def _loss_inputs_generator(self, labeled_spectrogram_batches: Iterable[List[LabeledSpectrogram]]) -> Iterable[
-        Tuple[Dict, ndarray]]:
+    def _loss_inputs_generator(self, labeled_spectrogram_batches: Iterable[List[LabeledSpectrogram]],
+                               data_parallel=None) -> Iterable[Tuple[Dict, ndarray]]:
         for labeled_spectrogram_batch in labeled_spectrogram_batches:
-            yield self._inputs_for_loss_net(labeled_spectrogram_batch)
+            if data_parallel is None:
+                yield self._inputs_for_loss_net(labeled_spectrogram_batch)
+                continue
+            # this rank's contiguous share, padded to the longest utterance of the WHOLE batch: the unmasked
+            # zero padding (net.py:578-587) bleeds into the last valid frames, so only the global pad length
+            # reproduces the single-process step; labels are padded per shard (the -1 padding is never read)
+            shard = data_parallel.shard(labeled_spectrogram_batch)
+            longest = max(x.z_normalized_transposed_spectrogram().shape[0] for x in labeled_spectrogram_batch)
+            inputs = self._input_dictionary_for_loss_net(shard, pad_to_length=longest)
+            inputs["global_batch_size"] = len(labeled_spectrogram_batch)
+            yield inputs, zeros((len(shard),))
 
     def _inputs_for_loss_net(self, labeled_spectrogram_batch: List[LabeledSpectrogram]) -> Tuple[
         Dict[str, ndarray], ndarray]:
@@ -688,14 +736,16 @@ class Wav2Letter:
             labeled_spectrogram_batch=labeled_spectrogram_batch)
         return training_input_dictionary, dummy_labels_for_dummy_loss_function
 
-    def _input_batch_and_prediction_lengths(self, spectrograms: List[ndarray]) -> Tuple[ndarray, List[int]]:
+    def _input_batch_and_prediction_lengths(self, spectrograms: List[ndarray],
+                                            pad_to_length: Optional[int] = None) -> Tuple[ndarray, List[int]]:
         """Zero-pad to the longest utterance; prediction length = T // ratio (floor, net.py:582)
         although the tower emits ceil(T / ratio) frames.  Padded frames are NOT masked."""
         batch_size = len(spectrograms)
         input_size_per_time_step = spectrograms[0].shape[1]
         input_lengths = [spectrogram.shape[0] for spectrogram in spectrograms]
         prediction_lengths = [s // self.input_to_prediction_length_ratio for s in input_lengths]
-        input_batch = zeros((batch_size, max(input_lengths), input_size_per_time_step), dtype=numpy.float32)
+        padded_length = max(input_lengths) if pad_to_length is None else max(pad_to_length, max(input_lengths))
+        input_batch = zeros((batch_size, padded_length, input_size_per_time_step), dtype=numpy.float32)
         for index, spectrogram in enumerate(spectrograms):
             input_batch[index, :spectrogram.shape[0], :spectrogram.shape[1]] = spectrogram
         return input_batch, prediction_lengths
@@ -703,10 +753,11 @@ class Wav2Letter:
     def _prediction_length_batch(self, prediction_lengths: List[int], batch_size: int) -> ndarray:
         return reshape(array(prediction_lengths), (batch_size, 1))
 
-    def _input_dictionary_for_loss_net(self, labeled_spectrogram_batch: List[LabeledSpectrogram]) -> Dict[str, ndarray]:
+    def _input_dictionary_for_loss_net(self, labeled_spectrogram_batch: List[LabeledSpectrogram],
+                                       pad_to_length: Optional[int] = None) -> Dict[str, ndarray]:
         spectrograms = [x.z_normalized_transposed_spectrogram() for x in labeled_spectrogram_batch]
         labels = [x.label for x in labeled_spectrogram_batch]
-        input_batch, prediction_lengths = self._input_batch_and_prediction_lengths(spectrograms)
+        input_batch, prediction_lengths = self._input_batch_and_prediction_lengths(spectrograms, pad_to_length)
         label_lengths = reshape(array([len(label) for label in labels]), (len(labeled_spectrogram_batch), 1))
         return {
             Wav2Letter.InputNames.input_batch: input_batch,

@@ -201,7 +201,11 @@ def test_ctc_tensorflow_known_answers_on_gpu(env):
     assert rel_err(dz, dwant) < 1e-4
 
 
-def test_ctc_loss_and_gradient_parity_ragged(env):
+@pytest.mark.parametrize("fused", [1, 0])
+def test_ctc_loss_and_gradient_parity_ragged(env, monkeypatch, fused):
+    """fused = 1: gradient CTAs ride along with the lattice walkers in one launch (progress flags, every frame
+    normalised by its own likelihood); fused = 0: lattice launch, then gradient launch normalised by the loss."""
+    monkeypatch.setenv("SL_CTC_FUSED", str(fused))
     rng = np.random.default_rng(17)
     B, T, V = 7, 313, 29
     probs = env.oracle.softmax(rng.standard_normal((B, T, V)) * 2).astype(np.float32)
@@ -226,8 +230,10 @@ def test_ctc_loss_and_gradient_parity_ragged(env):
     assert np.abs(unpacked - dz).max() < 1e-6
 
 
-def test_ctc_long_form_states_per_thread_paths(env):
-    """60 s shape class: S = 2L+1 > 1024 states -> 2 states per thread."""
+@pytest.mark.parametrize("fused", [1, 0])
+def test_ctc_long_form_states_per_thread_paths(env, monkeypatch, fused):
+    """60 s shape class: S = 2L+1 > 1024 states -> 4 states per lane, cluster-split lattices."""
+    monkeypatch.setenv("SL_CTC_FUSED", str(fused))
     rng = np.random.default_rng(3)
     B, T, V, L = 2, 1900, 29, 700
     probs = env.oracle.softmax(rng.standard_normal((B, T, V))).astype(np.float32)
@@ -237,6 +243,27 @@ def test_ctc_long_form_states_per_thread_paths(env):
     assert np.abs(loss / want - 1).max() < 1e-4
     assert np.abs(beta_loss / want - 1).max() < 1e-4
     assert rel_err(dz, dwant) < 3e-2
+
+
+@pytest.mark.parametrize("fused", [1, 0])
+def test_ctc_unalignable_label_through_the_abi(env, monkeypatch, fused):
+    """A direct C-ABI caller may pass a label that does not fit its frames (the Python host rejects it before
+    the launch like TF does): infinite loss, zero gradient for that utterance, the others unaffected."""
+    monkeypatch.setenv("SL_CTC_FUSED", str(fused))
+    rng = np.random.default_rng(5)
+    B, T, V = 3, 40, 29
+    probs = env.oracle.softmax(rng.standard_normal((B, T, V))).astype(np.float32)
+    labels = -np.ones((B, 12), dtype=np.int32)
+    labels[0, :4] = [1, 2, 3, 4]
+    labels[1, :3] = [7, 7, 7]       # needs 5 frames
+    labels[2, :12] = rng.integers(0, V - 1, size=12)
+    pred, ll = np.array([40, 4, 33]), np.array([4, 3, 12])
+    loss, dz, _, _ = _ctc_via_abi(env, probs, labels, pred, ll)
+    assert np.isinf(loss[1]) and np.abs(dz[1]).max() == 0
+    keep = [0, 2]
+    want, dwant = env.oracle.ctc_batch_cost_with_logit_grad(probs[keep], labels[keep], pred[keep], ll[keep])
+    assert np.abs(loss[keep] / want - 1).max() < 1e-4
+    assert rel_err(dz[keep], dwant) < 3e-3
 
 
 @pytest.mark.parametrize("spt,k,cluster,legacy", [
@@ -264,11 +291,13 @@ def test_ctc_every_lattice_configuration(env, monkeypatch, spt, k, cluster, lega
         lab[2::7] = lab[1:-1:7][:len(lab[2::7])]  # adjacent repeats
         labels[b, :ll[b]] = lab
     pred = np.array([330, 17, 209, 64])
-    loss, dz, beta_loss, _ = _ctc_via_abi(env, probs, labels, pred, ll, scale=0.25)
     want, dwant = env.oracle.ctc_batch_cost_with_logit_grad(probs, labels, pred, ll)
-    assert np.abs(loss / want - 1).max() < 1e-4
-    assert np.abs(beta_loss / want - 1).max() < 1e-4
-    assert rel_err(dz, dwant / 4) < 3e-3
+    for fused in ((1, 0) if not legacy else (0,)):
+        monkeypatch.setenv("SL_CTC_FUSED", str(fused))
+        loss, dz, beta_loss, _ = _ctc_via_abi(env, probs, labels, pred, ll, scale=0.25)
+        assert np.abs(loss / want - 1).max() < 1e-4
+        assert np.abs(beta_loss / want - 1).max() < 1e-4
+        assert rel_err(dz, dwant / 4) < 3e-3
 
 
 # ------------------------------------------------------------------ greedy decode (integer work: bit exact)
@@ -533,7 +562,10 @@ def test_fit_batches_pipeline_equals_stepwise(env):
     assert np.abs(np.array(b) / np.array(a) - 1).max() < 1e-5
     for la, lb in zip(stepwise.predictive_net.layers, pipelined.predictive_net.layers):
         for u, v in zip(la.get_weights(), lb.get_weights()):
-            assert np.abs(u - v).max() < 2e-4  # 5 Adam steps of 1e-4; reduction order differs
+            # 5 Adam steps of 1e-4: the TMA reduce-add order of the K-split weight gradients differs from run to
+            # run, and Adam turns a noise-floor gradient of either sign into a full +-1e-4 step
+            assert np.abs(u - v).max() < 6e-4
+            assert np.linalg.norm(u - v) < 0.05 * np.sqrt(u.size) * 5e-4
     assert pipelined.fit_batches(iter([])) == []
 
 

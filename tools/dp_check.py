@@ -1,13 +1,22 @@
 #!/usr/bin/env python
-"""Data-parallel equivalence check (run under torchrun, one rank per GPU):
-the SUM all-reduce of per-shard gradients of the GLOBAL mean CTC objective must equal the
-single-GPU gradient of the full batch, and replicas must stay identical after Adam steps.
+"""Data-parallel equivalence check (run under torchrun, one rank per GPU): N GPUs must take exactly the
+optimisation steps one GPU takes on the full batch.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
         --master-port 29511 tools/dp_check.py
+
+Three arms against a single-GPU model trained on the full (ragged) batches:
+  hook      `train_on_batch(allreduce=dp.allreduce)`: whole-buffer all-reduce after backward
+  pipelined `train_on_batch(data_parallel=dp)`: per-bucket all-reduce + Adam on the update stream,
+            persistent grids narrowed while a bucket is in flight (`ConvTower.backward_and_update`)
+  surface   `Wav2Letter(..., data_parallel=dp).train(...)` + sharded `test_and_predict_batches` — the
+            reference's public calls (net.py:521-556); every rank is handed the same batch iterable
+Every shard is padded to the global longest utterance (padding is unmasked).
+Prints one JSON line (rank 0) and exits non-zero on mismatch.
 """
 import json
 import sys
+import tempfile
 from pathlib import Path
 
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
@@ -27,51 +36,72 @@ def main():
     torch.cuda.set_device(dp.local_rank)
     device = torch.device("cuda", dp.local_rank)
     global_batch = 4 * dp.world_size
-    examples = synthetic_batch(global_batch, [300 - 7 * i for i in range(global_batch)], alphabet, seed=5,
-                               label_length=20)
+    steps = 3
+    batches = [synthetic_batch(global_batch, [300 - 7 * i - 3 * s for i in range(global_batch)], alphabet, seed=5 + s,
+                               label_length=20) for s in range(steps)]
     kwargs = dict(main_filter_count=128, out_filter_count=256, seed=3, device=device, compute_dtype="bf16x2")
     names = Wav2Letter.InputNames
 
-    def step_inputs(net, batch, pad_to):
-        inputs, _ = net._inputs_for_loss_net(batch)
-        x = inputs[names.input_batch]
-        if x.shape[1] < pad_to:  # every shard is padded to the GLOBAL max T
-            padded = np.zeros((x.shape[0], pad_to, x.shape[2]), dtype=x.dtype)
-            padded[:, :x.shape[1]] = x
-            inputs[names.input_batch] = padded
-        return inputs
+    def shard_inputs(net, batch):
+        longest = max(e.z_normalized_transposed_spectrogram().shape[0] for e in batch)
+        return net._input_dictionary_for_loss_net(dp.shard(batch), pad_to_length=longest)
 
-    max_t = max(e.z_normalized_transposed_spectrogram().shape[0] for e in examples)
-    # --- data parallel: each rank trains on its shard
-    net = Wav2Letter(128, alphabet, **kwargs)
-    shard = dp.shard(examples)
-    losses = []
-    for _ in range(3):
-        losses.append(net.train_on_batch(step_inputs(net, shard, max_t), global_batch_size=global_batch,
-                                         allreduce=dp.allreduce))
-    grads_dp = net.tower.grads.clone()
-    params_dp = net.tower.params.clone()
-    loss_dp = torch.tensor(losses, device=device, dtype=torch.float64)  # already the global batch mean
-
-    # --- replicas identical?
-    reference = params_dp.clone()
-    dist.broadcast(reference, src=0)
-    replicas_identical = bool(torch.equal(reference, params_dp))
-
-    # --- single GPU on the full batch (every rank computes it; compare on each)
+    # --- single GPU on the full batches (every rank computes it; compare on each)
     single = Wav2Letter(128, alphabet, **kwargs)
-    single_losses = [single.train_on_batch(step_inputs(single, examples, max_t)) for _ in range(3)]
-    grads_single = single.tower.grads
+    single_losses = [single.train_on_batch(single._inputs_for_loss_net(batch)[0]) for batch in batches]
+    grads_single = single.tower.grads.clone()
+    params_single = single.tower.params.clone()
     scale = float(grads_single.abs().max())
-    grad_err = float((grads_dp - grads_single).abs().max()) / scale
-    param_err = float((params_dp - single.tower.params).abs().max())
-    loss_err = float(np.abs(loss_dp.cpu().numpy() / np.array(single_losses) - 1).max())
-    ok = replicas_identical and grad_err < 2e-3 and loss_err < 1e-5 and param_err < 5e-4
-    gathered = [None] * dp.world_size
-    dist.all_gather_object(gathered, dict(rank=dp.rank, ok=ok, replicas_identical=replicas_identical,
-                                          grad_rel_err=grad_err, loss_rel_err=loss_err, param_abs_err=param_err))
+
+    report = {}
+    ok = True
+    for arm in ("hook", "pipelined"):
+        net = Wav2Letter(128, alphabet, **kwargs)
+        losses = []
+        for batch in batches:
+            inputs = shard_inputs(net, batch)
+            if arm == "hook":
+                losses.append(net.train_on_batch(inputs, global_batch_size=global_batch, allreduce=dp.allreduce))
+            else:
+                losses.append(net.train_on_batch(inputs, global_batch_size=global_batch, data_parallel=dp))
+        torch.cuda.synchronize()
+        reference = net.tower.params.clone()
+        dist.broadcast(reference, src=0)
+        entry = dict(
+            replicas_identical=bool(torch.equal(reference, net.tower.params)),
+            grad_rel_err=float((net.tower.grads - grads_single).abs().max()) / scale,
+            param_abs_err=float((net.tower.params - params_single).abs().max()),
+            loss_rel_err=float(np.abs(np.array(losses) / np.array(single_losses) - 1).max()))
+        entry["ok"] = entry["replicas_identical"] and entry["grad_rel_err"] < 2e-3 and entry["loss_rel_err"] < 1e-5 \
+            and entry["param_abs_err"] < 5e-4
+        ok = ok and entry["ok"]
+        report[arm] = entry
+
+    # --- the public surface: train() + sharded evaluation
+    with tempfile.TemporaryDirectory() as tmp:
+        surface = Wav2Letter(128, alphabet, data_parallel=dp, **{k: v for k, v in kwargs.items() if k != "device"})
+        surface.train(iter(batches), preview_labeled_spectrogram_batch=batches[0][:2], tensor_board_log_directory=None,
+                      net_directory=Path(tmp) / "nets", batches_per_epoch=steps, epochs=1)
+        evaluation = surface.test_and_predict_batches(batches)
+    torch.cuda.synchronize()
+    want = single.test_and_predict_batches(batches)
+    got_losses = np.array([r.loss for b in evaluation.result_batches for r in b.results])
+    want_losses = np.array([r.loss for b in want.result_batches for r in b.results])
+    entry = dict(param_abs_err=float((surface.tower.params - params_single).abs().max()),
+                 evaluation_count=int(len(got_losses)),
+                 evaluation_loss_rel_err=float(np.abs(got_losses / want_losses - 1).max()),
+                 predictions_equal=[r.predicted for b in evaluation.result_batches for r in b.results] ==
+                                   [r.predicted for b in want.result_batches for r in b.results],
+                 own_communicator=dp.owns_communicator, comm_max_ctas=dp.max_ctas)
+    entry["ok"] = entry["param_abs_err"] < 5e-4 and entry["evaluation_loss_rel_err"] < 1e-3 and \
+        entry["evaluation_count"] == steps * global_batch
+    ok = ok and entry["ok"]
+    report["surface"] = entry
+
+    gathered = dp.gather_objects(dict(rank=dp.rank, ok=ok, **report))
     if dp.rank == 0:
         print(json.dumps({"world_size": dp.world_size, "ok": all(g["ok"] for g in gathered), "ranks": gathered}))
+    dp.close()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
 
