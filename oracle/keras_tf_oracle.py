@@ -25,11 +25,14 @@ Pinning status
 * CTC loss: pinned to TensorFlow's own known-answer vectors (ctc_loss_op_test.py
   `testBasic`: -log p = 3.34211 / 5.42262) plus brute-force path enumeration; gradients
   against finite differences and torch autograd.
-* Conv1D tower numerics and the Adam trajectory: **parity unpinned** against Keras/TF
-  itself (no reference test holds a numeric vector for them, and Keras/TF cannot run
-  here).  They are cross-validated against independent implementations
-  (torch.nn.functional.conv1d with explicit asymmetric padding, torch autograd, a
-  hand-stepped Adam) in tests/test_oracle_crosscheck.py.
+* Conv1D forward / input gradient / filter gradient (SAME padding incl. the asymmetric stride-2 case)
+  and the Adam update: PINNED to TensorFlow's published known answers — the literal expected vectors of
+  `conv_ops_test.py::Conv2DTest` (testConv2D1x1Filter, 1x2Filter, 2x2Filter, 2x2FilterStride2[Same],
+  2x2Depth{1,3}ValidBackprop{Input,Filter}) and `adam_test.py::adam_update_numpy`, typed into
+  tests/test_oracle_published_vectors.py (Keras' Conv1D is TF's conv2d on a height-1 image).  The
+  composition of the pieces into the 11-layer tower has no published vector; it is cross-validated
+  against independent implementations (torch.nn.functional.conv1d with explicit asymmetric padding,
+  torch autograd, a hand-stepped Adam) in tests/test_oracle_crosscheck.py.
 """
 from itertools import groupby, product
 from typing import List, Optional, Sequence, Tuple

@@ -12,10 +12,13 @@ unpinned — `requirements.txt:2`; not installable offline):
                                                     (area) normalisation, fmin 0, fmax sr/2
     note: the mel projection is applied to the dB values, as the reference does.
 
-Pinning: **parity unpinned** against librosa itself (the reference's only test of this piece,
-`test_labeled_example.py:14-21`, needs librosa and downloaded audio).  Cross-validated in
-tests/test_spectrogram_oracle.py against independent implementations available offline:
-`torch.stft` and `transformers.audio_utils.mel_filter_bank(norm="slaney", mel_scale="slaney")`.
+Pinning: the mel scale and filterbank are PINNED to librosa's documented values (docstring examples of
+`hz_to_mel`, `mel_to_hz`, `mel_frequencies(n_mels=40)` — all 40 frequencies — and
+`filters.mel(sr=22050, n_fft=2048)`; tests/test_oracle_published_vectors.py).  The whole pipeline against
+librosa itself stays unpinned: the reference's only test of it (`test_labeled_example.py:14-21`) needs
+librosa and downloaded audio.  Cross-validated in tests/test_spectrogram_oracle.py against independent
+implementations available offline: `torch.stft` and
+`transformers.audio_utils.mel_filter_bank(norm="slaney", mel_scale="slaney")`.
 """
 import numpy as np
 

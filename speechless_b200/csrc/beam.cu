@@ -11,10 +11,11 @@
 //       pb' = tot + lp[blank],
 //     and spawns the children (i, c) that are not already in the beam with
 //       pl = lp[c] + (c == label_i ? pb_i : tot_i),  pb = 0;
-//     the W best of {continued prefixes} U {children} survive.  (TF's Step additionally wipes a prefix
+//     the W best of {continued prefixes} U {children} survive.  TF's Step additionally wipes a prefix
 //     that is displaced before the child loop reaches its parent, which silently drops that prefix's
-//     own children for the frame; this order-dependent side effect is NOT reproduced — see
-//     `tf_deactivation` in oracle/beam_search_oracle.py.  It cannot occur for beam_width = 1.)
+//     own children for the frame (`tf_deactivation` in oracle/beam_search_oracle.py; it cannot occur for
+//     beam_width = 1).  The default mode reproduces this order-dependent behaviour literally
+//     (tf_exact_child_loop); SL_BEAM_ORDER_INDEPENDENT=1 selects the parallel "W best of the union" rule.
 //   * merge_repeated only post-processes the output (a label equal to its successor's is dropped),
 //     which is what makes "A A _ A A" decode to [0] / [0, 0] (reference test_ctc_decoders.py:38-39).
 //
@@ -28,6 +29,8 @@
 // BeamEntry object in its tree, and its surviving children still point at it — so (parent node, label)
 // -> node is kept in an open-addressing hash table in global memory, and parent slots are re-derived
 // from node ids every frame.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace sl {
@@ -71,6 +74,12 @@ struct BeamSmem {
   int partial[2][32];  // per-warp partial counts of the selection (BS_THREADS / 32 warps)
   int n_selected;
   int n_active;
+  // TF-exact mode (sequential child loop of TensorFlow's CTCBeamSearchDecoder::Step, run by warp 0)
+  float leaf_score[BS_MAX_W];            // the `leaves_` TopN of the frame being built
+  int leaf_idx[BS_MAX_W];                // candidate index slot * V + symbol (symbol == blank: prefix `slot` continued)
+  unsigned char child_slot[BS_MAX_W][BS_VP];  // slot of the beam entry that is child (slot, symbol), valid where child_active
+  unsigned char displaced[BS_MAX_W];     // beam entry popped from `leaves_` during this frame's child loop
+  unsigned char wiped[BS_MAX_W];         // ... and then "deactivated" through its parent: it proposes no children
 };
 
 constexpr int BS_CPT = BS_MAX_CAND / BS_THREADS;  // candidates per thread, kept in registers
@@ -89,11 +98,135 @@ __device__ __forceinline__ int block_sum(BeamSmem& sm, int c, int& it) {
   return __reduce_add_sync(0xffffffffu, lane < BS_THREADS / 32 ? part[lane] : 0);
 }
 
+// TensorFlow's CTCBeamSearchDecoder::Step, child loop included, restated literally (ctc_beam_search.h; CPU
+// restatement with the derivation: oracle/beam_search_oracle.py, tf_deactivation = True).  `leaves_` starts as the
+// continued prefixes of the beam.  Then, for every beam entry b in order of its previous total (= slot order)
+// whose previous total still beats the bottom of `leaves_` (and has not been wiped), and every label c in
+// order: the child (b, c) is skipped if it is in `leaves_`; otherwise it is scored afresh
+// (lp[c] + previous mass of b) and, if it beats the bottom, replaces it.  The order-dependent part: a beam
+// entry X that has been replaced ("displaced") before the loop reaches its parent is re-scored as if new when
+// the parent gets to it, cannot beat the bottom that displaced it, and has its previous probabilities wiped —
+// so X proposes no children in this frame.  Inherently sequential (each insertion moves the bottom), but
+// cheap: one warp, `leaves_` in shared memory, per beam entry one ballot of the labels whose score beats the
+// bottom (it only rises) and a visit of those few.  Returns the number of leaves; their keys go to
+// sm.selected in the format of the parallel selection.  All threads call it (barriers inside).
+__device__ __noinline__ int tf_exact_child_loop(BeamSmem& sm, const BeamGen& g, int n, int V, int blank, int W) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (tid < n) {
+    sm.leaf_score[tid] = sm.totn[tid];
+    sm.leaf_idx[tid] = tid * V + blank;
+  }
+  __syncthreads();
+  if (tid < 32) {
+    int count = n;  // (continued prefixes of probability zero stay, as in TF, and are dropped at the end)
+    float bottom = INFINITY;
+    int bottom_pos = -1;
+    auto find_bottom = [&]() {
+      float m = INFINITY;
+      int pos = -1;
+      for (int k = lane; k < count; k += 32) {
+        const float v = sm.leaf_score[k];
+        if (v < m || pos < 0) {
+          m = v;
+          pos = k;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float om = __shfl_xor_sync(0xffffffffu, m, o);
+        const int op = __shfl_xor_sync(0xffffffffu, pos, o);
+        if (op >= 0 && (pos < 0 || om < m || (om == m && op > pos))) {
+          m = om;
+          pos = op;
+        }
+      }
+      bottom = m;
+      bottom_pos = pos;
+    };
+    find_bottom();
+    for (int i = 0; i < n; ++i) {
+      const float old_total = g.tot[i];
+      // is_candidate(b.old): not wiped, finite, and (beam not full or better than the bottom)
+      if (sm.wiped[i] || !(old_total > -INFINITY) || !(count < W || old_total > bottom)) continue;
+      const int lab_i = g.label[i];
+      const unsigned long long in_beam = sm.child_active[i];
+      // per lane: labels lane and lane + 32
+      float sc[2];
+      unsigned visit[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = lane + 32 * h;
+        sc[h] = -INFINITY;
+        bool v = false;
+        if (c < V && c != blank) {
+          sc[h] = sm.lp[c] + (c == lab_i ? g.pb[i] : g.tot[i]);
+          const bool beam_child = (in_beam >> c) & 1ull;
+          // worth a visit: a new candidate that may beat the bottom, or a beam entry that may have been displaced
+          v = beam_child || (sc[h] > -INFINITY && (count < W || sc[h] > bottom));
+        }
+        visit[h] = __ballot_sync(0xffffffffu, v);
+      }
+      for (int h = 0; h < 2; ++h) {
+        unsigned todo = visit[h];
+        while (todo) {
+          const int l = __ffs(todo) - 1;
+          todo &= todo - 1;
+          const int c = l + 32 * h;
+          const float score = __shfl_sync(0xffffffffu, sc[h], l);
+          const bool beam_child = (in_beam >> c) & 1ull;
+          const int j = beam_child ? sm.child_slot[i][c] : -1;
+          if (beam_child && !sm.displaced[j]) continue;  // active: already among the leaves
+          const bool candidate = score > -INFINITY && (count < W || score > bottom);
+          if (!candidate) {
+            if (beam_child && lane == 0) sm.wiped[j] = 1;  // "deactivate child"
+            __syncwarp();
+            continue;
+          }
+          int pos = count;
+          if (count == W) {
+            pos = bottom_pos;
+            const int gone = sm.leaf_idx[pos];
+            const int gi = gone / V;
+            if (gone - gi * V == blank && lane == 0) sm.displaced[gi] = 1;  // a continued beam entry leaves
+          } else {
+            ++count;
+          }
+          __syncwarp();
+          if (lane == 0) {
+            sm.leaf_score[pos] = score;
+            sm.leaf_idx[pos] = i * V + c;
+            if (beam_child) sm.displaced[j] = 0;  // it is back among the leaves (as a fresh entry)
+          }
+          __syncwarp();
+          find_bottom();
+        }
+      }
+    }
+    // keys of the surviving finite leaves, in the format of the parallel selection
+    int kept = 0;
+    for (int k0 = 0; k0 < count; k0 += 32) {
+      const int k = k0 + lane;
+      const bool ok = k < count && sm.leaf_score[k] > -INFINITY;
+      const unsigned m = __ballot_sync(0xffffffffu, ok);
+      if (ok) {
+        const int at = kept + __popc(m & ((1u << lane) - 1));
+        sm.selected[at] = (static_cast<unsigned long long>(float_to_ordered(sm.leaf_score[k])) << 32) |
+                          static_cast<unsigned long long>(0xffffffffu - static_cast<uint32_t>(sm.leaf_idx[k]));
+      }
+      kept += __popc(m);
+    }
+    if (lane == 0) sm.n_selected = kept;
+  }
+  __syncthreads();
+  return sm.n_selected;
+}
+
 __global__ void __launch_bounds__(BS_THREADS)
     ctc_beam_search_kernel(const float* __restrict__ scores, const int32_t* __restrict__ input_len,
                            int32_t* __restrict__ out, int32_t* __restrict__ out_len, float* __restrict__ out_logp,
                            int2* __restrict__ nodes_all, unsigned long long* __restrict__ hash_all, int hash_cap,
-                           int T, int V, int blank, int W, int top_paths, int merge_repeated, int inputs_are_probs) {
+                           int T, int V, int blank, int W, int top_paths, int merge_repeated, int inputs_are_probs,
+                           int tf_exact) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   BeamSmem& sm = *reinterpret_cast<BeamSmem*>(smem_raw);
   const int b = blockIdx.x;
@@ -151,7 +284,11 @@ __global__ void __launch_bounds__(BS_THREADS)
       sm.lp[tid + 32] = y1 - norm;
     }
     fetch(t + 1, x0, x1);
-    if (tid < W) sm.child_active[tid] = 0ull;
+    if (tid < W) {
+      sm.child_active[tid] = 0ull;
+      sm.displaced[tid] = 0;
+      sm.wiped[tid] = 0;
+    }
     if (tid == 0) sm.n_selected = 0;
     __syncthreads();
     // 2. continue the active prefixes; mark which children are already in the beam
@@ -162,7 +299,10 @@ __global__ void __launch_bounds__(BS_THREADS)
         const int ps = g.pslot[tid];
         const float previous = ps >= 0 ? (lab == g.label[ps] ? g.pb[ps] : g.tot[ps]) : -INFINITY;
         pl = logaddexp(g.pl[tid], previous) + sm.lp[lab];
-        if (ps >= 0) atomicOr(&sm.child_active[ps], 1ull << lab);
+        if (ps >= 0) {
+          atomicOr(&sm.child_active[ps], 1ull << lab);
+          sm.child_slot[ps][lab] = static_cast<unsigned char>(tid);
+        }
       }
       const float pb = g.tot[tid] + sm.lp[blank];
       sm.pbn[tid] = pb;
@@ -170,71 +310,76 @@ __global__ void __launch_bounds__(BS_THREADS)
       sm.totn[tid] = logaddexp(pb, pl);
     }
     __syncthreads();
-    // 3. candidates (slot i, symbol c), BS_CPT per thread in registers; c == blank stands for
-    //    "prefix i continued".  Order-preserving integer image of the score; 0 = no candidate.
-    uint32_t kv[BS_CPT];
+    int n_next;
+    if (tf_exact) {
+      n_next = tf_exact_child_loop(sm, g, n, V, blank, W);  // fills sm.selected[0 .. n_next)
+    } else {
+      // 3. candidates (slot i, symbol c), BS_CPT per thread in registers; c == blank stands for
+      //    "prefix i continued".  Order-preserving integer image of the score; 0 = no candidate.
+      uint32_t kv[BS_CPT];
 #pragma unroll
-    for (int q = 0; q < BS_CPT; ++q) {
-      const int idx = tid + q * BS_THREADS;
-      kv[q] = 0u;
-      if (idx < n_cand) {
-        const int i = idx / V, c = idx - i * V;
-        if (i < n) {
-          float key = -INFINITY;
-          if (c == blank)
-            key = sm.totn[i];
-          else if (!((sm.child_active[i] >> c) & 1ull))
-            key = sm.lp[c] + (c == g.label[i] ? g.pb[i] : g.tot[i]);
-          kv[q] = float_to_ordered(key);
+      for (int q = 0; q < BS_CPT; ++q) {
+        const int idx = tid + q * BS_THREADS;
+        kv[q] = 0u;
+        if (idx < n_cand) {
+          const int i = idx / V, c = idx - i * V;
+          if (i < n) {
+            float key = -INFINITY;
+            if (c == blank)
+              key = sm.totn[i];
+            else if (!((sm.child_active[i] >> c) & 1ull))
+              key = sm.lp[c] + (c == g.label[i] ? g.pb[i] : g.tot[i]);
+            kv[q] = float_to_ordered(key);
+          }
         }
       }
-    }
-    // 4. the W best: binary search, bit by bit, for the score of the W-th best candidate (one block-wide
-    //    count per bit); ties at that score go to the lower candidate index
-    auto count_if = [&](auto pred) {
-      int c = 0;
+      // 4. the W best: binary search, bit by bit, for the score of the W-th best candidate (one block-wide
+      //    count per bit); ties at that score go to the lower candidate index
+      auto count_if = [&](auto pred) {
+        int c = 0;
 #pragma unroll
-      for (int q = 0; q < BS_CPT; ++q) c += pred(kv[q], tid + q * BS_THREADS) ? 1 : 0;
-      return block_sum(sm, c, it);
-    };
-    const int n_finite = count_if([](uint32_t k, int) { return k > ORD_NEG_INF; });
-    const int n_next = min(W, n_finite);
-    uint32_t thr = 0u;
-    bool exact = false;  // some prefix of the threshold already separates exactly n_next candidates
-    for (int bit = 31; bit >= 0 && !exact; --bit) {
-      const uint32_t cand = thr | (1u << bit);
-      const int c = count_if([cand](uint32_t k, int) { return k >= cand; });
-      if (c >= n_next) thr = cand;
-      exact = c == n_next;
-    }
-    int idx_limit = BS_MAX_CAND;  // ties with candidate index <= idx_limit are taken
-    int n_greater = 0, n_ties = 0;
-    if (exact) {
-      thr -= 1u;        // "k >= thr" as "k > thr - 1" (thr > 0: it is at least the image of a finite score)
-      idx_limit = -1;   // ...and nothing that merely equals thr - 1
-    } else {
-      n_greater = count_if([thr](uint32_t k, int) { return k > thr; });
-      n_ties = count_if([thr](uint32_t k, int) { return k == thr; });
-    }
-    if (!exact && n_greater + n_ties > n_next) {
-      const int need = n_next - n_greater;
-      int lo = 0;
-      for (int bit = 11; bit >= 0; --bit) {
-        const int cand = lo | (1 << bit);
-        if (count_if([thr, cand](uint32_t k, int idx) { return k == thr && idx < cand; }) < need) lo = cand;
+        for (int q = 0; q < BS_CPT; ++q) c += pred(kv[q], tid + q * BS_THREADS) ? 1 : 0;
+        return block_sum(sm, c, it);
+      };
+      const int n_finite = count_if([](uint32_t k, int) { return k > ORD_NEG_INF; });
+      n_next = min(W, n_finite);
+      uint32_t thr = 0u;
+      bool exact = false;  // some prefix of the threshold already separates exactly n_next candidates
+      for (int bit = 31; bit >= 0 && !exact; --bit) {
+        const uint32_t cand = thr | (1u << bit);
+        const int c = count_if([cand](uint32_t k, int) { return k >= cand; });
+        if (c >= n_next) thr = cand;
+        exact = c == n_next;
       }
-      idx_limit = lo;
-    }
+      int idx_limit = BS_MAX_CAND;  // ties with candidate index <= idx_limit are taken
+      int n_greater = 0, n_ties = 0;
+      if (exact) {
+        thr -= 1u;        // "k >= thr" as "k > thr - 1" (thr > 0: it is at least the image of a finite score)
+        idx_limit = -1;   // ...and nothing that merely equals thr - 1
+      } else {
+        n_greater = count_if([thr](uint32_t k, int) { return k > thr; });
+        n_ties = count_if([thr](uint32_t k, int) { return k == thr; });
+      }
+      if (!exact && n_greater + n_ties > n_next) {
+        const int need = n_next - n_greater;
+        int lo = 0;
+        for (int bit = 11; bit >= 0; --bit) {
+          const int cand = lo | (1 << bit);
+          if (count_if([thr, cand](uint32_t k, int idx) { return k == thr && idx < cand; }) < need) lo = cand;
+        }
+        idx_limit = lo;
+      }
 #pragma unroll
-    for (int q = 0; q < BS_CPT; ++q) {
-      const int idx = tid + q * BS_THREADS;
-      if (kv[q] > thr || (kv[q] == thr && kv[q] > ORD_NEG_INF && idx <= idx_limit)) {
-        const int pos = atomicAdd(&sm.n_selected, 1);
-        sm.selected[pos] = (static_cast<unsigned long long>(kv[q]) << 32) |
-                           static_cast<unsigned long long>(0xffffffffu - static_cast<uint32_t>(idx));
+      for (int q = 0; q < BS_CPT; ++q) {
+        const int idx = tid + q * BS_THREADS;
+        if (kv[q] > thr || (kv[q] == thr && kv[q] > ORD_NEG_INF && idx <= idx_limit)) {
+          const int pos = atomicAdd(&sm.n_selected, 1);
+          sm.selected[pos] = (static_cast<unsigned long long>(kv[q]) << 32) |
+                             static_cast<unsigned long long>(0xffffffffu - static_cast<uint32_t>(idx));
+        }
       }
+      __syncthreads();
     }
-    __syncthreads();
     // 5. survivor r takes the slot given by its rank (keys are unique: score, then lower index first)
     if (tid < n_next) {
       const unsigned long long key = sm.selected[tid];
@@ -351,10 +496,12 @@ int beam_search_launch(const float* scores, const int32_t* input_len, int32_t* o
   unsigned long long* hash = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(workspace) +
                                                                    beam_nodes_bytes(B, T, beam_width));
   SL_CUDA(cudaMemsetAsync(hash, 0, static_cast<size_t>(B) * hash_cap * sizeof(unsigned long long), stream));
+  const char* oi = std::getenv("SL_BEAM_ORDER_INDEPENDENT");  // 1: parallel selection rule (A/B, see the header comment)
+  const int tf_exact = (oi && std::atoi(oi) != 0) ? 0 : 1;
   ctc_beam_search_kernel<<<B, BS_THREADS, smem, stream>>>(scores, input_len, out, out_len, out_logp,
                                                           reinterpret_cast<int2*>(workspace), hash, hash_cap, T, V,
                                                           blank, beam_width, top_paths, merge_repeated,
-                                                          inputs_are_probs);
+                                                          inputs_are_probs, tf_exact);
   SL_CUDA(cudaGetLastError());
   return 0;
 }

@@ -18,6 +18,7 @@
 // The first-generation kernels (one barrier per step: ctc_alpha_beta_kernel; warp wavefront:
 // ctc_alpha_beta_wave_kernel; smem-atomics gradient: ctc_grad_kernel) are kept behind SL_CTC_LEGACY
 // for A/B measurements.
+#include <cstdio>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -31,6 +32,12 @@ constexpr int VP = 64;     // padded symbol row of the logp tensor (V <= 64)
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(ptx::smem_u32(smem_dst)),
+               "l"(gmem_src)
+               : "memory");
+}
+// L2-only variant: for rows written by other CTAs of the same launch
+__device__ __forceinline__ void cp_async16_cg(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ptx::smem_u32(smem_dst)),
                "l"(gmem_src)
                : "memory");
 }
@@ -210,6 +217,8 @@ __global__ void ctc_alpha_beta_kernel(const float* __restrict__ logp,
 // An extra warp of the alpha CTA counting-sorts the label positions by symbol for the gradient
 // kernel (see ctc_grad_sorted_kernel) while the compute warps walk the lattice.
 constexpr float NEG = -1e30f;
+constexpr int FLAG_STRIDE = 32;  // ints: every progress flag has a 128-byte line of its own
+constexpr int ROLE_COUNTERS = 32 + 256;  // ints behind the flags: role counters of the fused launch (+ one per SM)
 
 // progress flags between the lattice walkers and the gradient CTAs of one launch
 __device__ __forceinline__ void st_release_cta_shared(int* p, int v) {
@@ -289,7 +298,7 @@ __device__ __forceinline__ void halo_walk(const float* lp_s, float* col, int col
                                           int ls0, int lane, int tid, int nthreads, const float (&skipb)[SPT],
                                           const float (&onb)[SPT], const float* const (&em_ptr)[SPT], float* out,
                                           ptrdiff_t out_step, unsigned st_mask, int push_rank, int own_per_cta,
-                                          int* smem_progress) {
+                                          int* smem_progress, int dbg = 0) {
   constexpr int HALO = 2 * K;
   const bool owner = lane * SPT >= HALO;
   const bool pusher = CL && push_rank >= 0 && lane * SPT >= 32 * SPT - HALO;
@@ -363,7 +372,12 @@ __device__ __forceinline__ void halo_walk(const float* lp_s, float* col, int col
     if ((t0 & (CHUNK - 1)) == 0) cp_async_wait<0>();  // the chunk issued one chunk ago has long landed
     barrier();  // owned states of block kb-1 published; chunk visible; ring slot free
     // every lattice row of the steps < t0 has been stored by its thread: tell the publisher warp
-    if (!CL && smem_progress != nullptr && tid == 0 && t0 > 0) st_release_cta_shared(smem_progress, t0);
+    if (!CL && smem_progress != nullptr && tid == 0 && t0 > 0) {
+      if (dbg == 6)
+        *reinterpret_cast<volatile int*>(smem_progress) = t0;
+      else
+        st_release_cta_shared(smem_progress, t0);
+    }
     if ((t0 & (CHUNK - 1)) == 0 && t0 > 0) issue_chunk(t0 / CHUNK + 1);
     const float* pc = col + ((kb + 1) & 1) * col_stride + HALO + ls0;
 #pragma unroll
@@ -408,7 +422,7 @@ __device__ __forceinline__ void lattice_cta_body(uint8_t* smem_raw, int unit, co
                                                  float* __restrict__ beta_loss, float* __restrict__ alpha,
                                                  float* __restrict__ beta, int* __restrict__ sort_ws, int T,
                                                  int L_max, int blank, int S_stride, int col_stride,
-                                                 int* __restrict__ progress);
+                                                 int* __restrict__ progress, int dbg = 0);
 
 template <int SPT, int K, bool CL>
 __global__ void __launch_bounds__(1024)
@@ -432,7 +446,7 @@ __device__ __forceinline__ void lattice_cta_body(uint8_t* smem_raw, int unit, co
                                                  float* __restrict__ beta_loss, float* __restrict__ alpha,
                                                  float* __restrict__ beta, int* __restrict__ sort_ws, int T,
                                                  int L_max, int blank, int S_stride, int col_stride,
-                                                 int* __restrict__ progress) {
+                                                 int* __restrict__ progress, int dbg) {
   static_assert(SPT % 2 == 0 && CHUNK % K == 0 && 2 * K < 32 * SPT, "slot parity / chunk alignment");
   constexpr int HALO = 2 * K;
   constexpr int OWN = 32 * SPT - HALO;
@@ -467,8 +481,9 @@ __device__ __forceinline__ void lattice_cta_body(uint8_t* smem_raw, int unit, co
     }
     // ... and publisher of the walk's progress (the sorted labels above are covered by the first fence)
     auto publish = [&](int done) {
+      if (dbg == 5) return;  // measurement aid: poll only
       __threadfence();
-      if (lane == 0) st_relaxed_gpu(progress + unit, done);
+      if (lane == 0) st_relaxed_gpu(progress + unit * FLAG_STRIDE, done);
     };
     if constexpr (CL) {  // cluster barriers count every thread: one per K-block and the final one
       for (int t0 = 0; t0 < P; t0 += K) {
@@ -528,11 +543,11 @@ __device__ __forceinline__ void lattice_cta_body(uint8_t* smem_raw, int unit, co
   const int push_rank = (CL && crank + 1 < csize && warp == (nthreads >> 5) - 1) ? crank + 1 : -1;
   if (dir == 0)
     halo_walk<SPT, K, 0, CL>(lp_s, col, col_stride, lp_b, P, ls0, lane, tid, nthreads, skipb, onb, em_ptr, lat + s0,
-                             static_cast<ptrdiff_t>(S_stride), st_mask, push_rank, own_per_cta, smem_progress);
+                             static_cast<ptrdiff_t>(S_stride), st_mask, push_rank, own_per_cta, smem_progress, dbg);
   else
     halo_walk<SPT, K, 1, CL>(lp_s, col, col_stride, lp_b, P, ls0, lane, tid, nthreads, skipb, onb, em_ptr,
                              lat + static_cast<size_t>(P > 0 ? P - 1 : 0) * S_stride + (S - 1 - s0),
-                             -static_cast<ptrdiff_t>(S_stride), st_mask, push_rank, own_per_cta, smem_progress);
+                             -static_cast<ptrdiff_t>(S_stride), st_mask, push_rank, own_per_cta, smem_progress, dbg);
 
   // the CTA owning the last state reports the loss (state S-2 is its own or sits in its halo)
   if (tid == 0 && (S - 1) / own_per_cta == crank) {
@@ -879,176 +894,206 @@ __global__ void ctc_grad_kernel(const float* __restrict__ logp, const float* __r
 // symbol-sorted order, seg[v] = first slot of symbol v.  Per frame a warp then writes the occupancy
 // term of every label state to its slot (plain conflict-light STS) and lane v adds up the
 // contiguous segment of symbol v in label order — deterministic, no atomics.
-//
-// grad_item: the frames [t_begin, t_end) of utterance b, one warp per frame, by every warp of the CTA.
-// Normalisation of the occupancies  occ_t(v) = sum_{s: e[s]=v} alpha_t(s) beta_t(s) / (y_t(v) Z):
-//   loss != nullptr  Z = exp(-loss[b]) from the finished alpha walk (two-launch path);
-//   loss == nullptr  (fused launch: the walks are still running) every frame is normalised by its own
-//                    sum over all states — mathematically the same Z for every t — with the exponent
-//                    offset taken from a max pass over the warp's first frame of the item (the per-frame
-//                    maxima of one utterance differ by at most log2 S).
-template <int NP>  // passes of 128 states whose loads are issued together (registers against memory-level parallelism)
-__device__ __forceinline__ void grad_item(uint8_t* smem_raw, int b, int t_begin, int t_end, bool reload_labels,
-                                          const float* __restrict__ logp, const float* __restrict__ probs,
-                                          const int32_t* __restrict__ input_len,
-                                          const int32_t* __restrict__ label_len, const float* __restrict__ loss,
-                                          const float* __restrict__ alpha, const float* __restrict__ beta,
-                                          const int* __restrict__ sort_ws, __nv_bfloat16* __restrict__ dz_packed,
-                                          float* __restrict__ dz_f32, float grad_scale, int T, int V, int L_max,
-                                          int blank, int S_stride, int planes, int fp16) {
-  const int L_pad = (L_max + 31) & ~31;
-  int* packed = reinterpret_cast<int*>(smem_raw);  // [L_pad]  symbol | slot << 8
-  int* seg = packed + L_pad;                       // [SORT_EXTRA] first slot of each symbol
-  float* per_warp = reinterpret_cast<float*>(seg + SORT_EXTRA);  // [warps][VP + L_pad]
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  const int L = label_len[b];
-  const int P = min(input_len[b], T);
-  const int S = 2 * L + 1;
-  if (t_begin < P && reload_labels) {  // (block-uniform)
-    const int* src = sort_ws + static_cast<size_t>(b) * (L_pad + SORT_EXTRA);
-    for (int i = threadIdx.x; i < L; i += blockDim.x) packed[i] = __ldcg(src + i);
-    for (int i = threadIdx.x; i <= VP; i += blockDim.x) seg[i] = __ldcg(src + L_pad + i);
-    __syncthreads();
-  }
-  const bool self_normalised = loss == nullptr;
-  const float loss_b = self_normalised ? 0.f : loss[b];
-  bool feasible = self_normalised ? true : isfinite(loss_b);
-  float offset2 = self_normalised ? 0.f : loss_b * LOG2E;  // added to every base-2 exponent
-  bool have_offset = !self_normalised;
-  float* lp_row = per_warp + warp * (VP + L_pad);  // per-warp copy of the log-prob row (base 2)
-  float* xs = lp_row + VP;                         // [L_pad] occupancy terms in symbol-sorted order
-  const int row_elems = planes * 64;
+struct GradCtx {
+  const float* logp;
+  const float* probs;
+  __nv_bfloat16* dz_packed;
+  float* dz_f32;
+  float grad_scale;
+  int T, V, blank, planes, fp16;
+  const int* packed;  // smem [L_pad]: symbol | slot << 8 of every label position
+  const int* seg;     // smem [VP + 1]: first slot of each symbol
+};
 
-  for (int t = t_begin + warp; t < t_end; t += nwarps) {
-    const size_t ro = static_cast<size_t>(b) * T + t;
-    float dz[2] = {0.f, 0.f};  // symbols lane and lane + 32
-    if (t < P && feasible) {
-      const float* lp_g = logp + ro * VP;
-      const float lp_mine[2] = {lp_g[lane], lp_g[lane + 32]};
-      float pv[2] = {0.f, 0.f};
-      if (lane < V) pv[0] = probs[ro * V + lane];
-      if (lane + 32 < V) pv[1] = probs[ro * V + lane + 32];
-      lp_row[lane] = lp_mine[0] * LOG2E;
-      lp_row[lane + 32] = lp_mine[1] * LOG2E;
-      __syncwarp();
-      // (the lattices were written during this launch in the fused path: L2-coherent loads, not the
-      // read-only path)
-      const float4* a_row = reinterpret_cast<const float4*>(alpha + ro * S_stride);
-      const float4* b_row = reinterpret_cast<const float4*>(beta + ro * S_stride);
-      if (!have_offset) {
-        // max over the states of alpha + beta - lp: the exponent offset of this warp's frames
-        float m = NEG;
-        for (int s = lane * 4; s < S; s += 128) {
-          const float4 av = __ldcg(a_row + (s >> 2)), bv = __ldcg(b_row + (s >> 2));
+// Normalisation of the occupancies  occ_t(v) = sum_{s: e[s]=v} alpha_t(s) beta_t(s) / (y_t(v) Z):
+//   self_normalised = false  Z = exp(-loss[b]) from the finished alpha walk (two-launch path): offset2 = loss * log2 e;
+//   self_normalised = true   (fused launch: the walks are still running) every frame is normalised by its own
+//                            sum over all states — mathematically the same Z for every t — with the exponent
+//                            offset taken from a max pass over the warp's first frame (the per-frame maxima of
+//                            one utterance differ by at most log2 S).
+struct GradNorm {
+  bool self_normalised;
+  bool have_offset;
+  bool feasible;
+  float offset2;  // added to every base-2 exponent
+};
+
+// The gradient row of ONE frame by ONE warp.  a_row / b_row: the frame's alpha / beta rows (base-2 logs), in
+// global memory (L2-coherent loads: the fused launch reads rows written during the same launch) or already
+// staged in shared memory (SMEM_ROWS).  lp_row [VP], xs [L_pad]: this warp's scratch.
+// this lane's two symbols (lane, lane + 32) of a frame's log-probability and probability rows
+struct FrameRows {
+  float lp[2];
+  float pv[2];
+};
+__device__ __forceinline__ FrameRows load_frame_rows(const GradCtx& c, int b, int t, int lane) {
+  const size_t ro = static_cast<size_t>(b) * c.T + t;
+  FrameRows r;
+  r.lp[0] = c.logp[ro * VP + lane];
+  r.lp[1] = c.logp[ro * VP + lane + 32];
+  r.pv[0] = lane < c.V ? c.probs[ro * c.V + lane] : 0.f;
+  r.pv[1] = lane + 32 < c.V ? c.probs[ro * c.V + lane + 32] : 0.f;
+  return r;
+}
+
+template <int NP, bool SMEM_ROWS>  // NP: passes of 128 states whose loads are issued together
+__device__ __forceinline__ void grad_frame(const GradCtx& c, int b, int t, int S, bool in_range, const FrameRows& fr,
+                                           const float4* a_row, const float4* b_row, float* lp_row, float* xs,
+                                           GradNorm& nrm, int lane) {
+  const size_t ro = static_cast<size_t>(b) * c.T + t;
+  const int V = c.V, blank = c.blank;
+  const int* packed = c.packed;
+  float dz[2] = {0.f, 0.f};  // symbols lane and lane + 32
+  if (in_range && nrm.feasible) {
+    const float lp_mine[2] = {fr.lp[0], fr.lp[1]};
+    const float pv[2] = {fr.pv[0], fr.pv[1]};
+    lp_row[lane] = lp_mine[0] * LOG2E;
+    lp_row[lane + 32] = lp_mine[1] * LOG2E;
+    __syncwarp();
+    auto row4 = [](const float4* p) { return SMEM_ROWS ? *p : __ldcg(p); };
+    if (!nrm.have_offset) {
+      // max over the states of alpha + beta - lp: the exponent offset of this warp's frames
+      float m = NEG;
+      for (int s = lane * 4; s < S; s += 128) {
+        const float4 av = row4(a_row + (s >> 2)), bv = row4(b_row + (s >> 2));
+        const int2 pk = *reinterpret_cast<const int2*>(packed + (s >> 1));
+        m = fmaxf(m, av.x + bv.x - lp_row[blank]);
+        if (s + 1 < S) m = fmaxf(m, av.y + bv.y - lp_row[pk.x & 255]);
+        if (s + 2 < S) m = fmaxf(m, av.z + bv.z - lp_row[blank]);
+        if (s + 3 < S) m = fmaxf(m, av.w + bv.w - lp_row[pk.y & 255]);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      nrm.offset2 = -m;
+      nrm.have_offset = true;
+      nrm.feasible = m > -1e29f;  // no alignment at all: zero gradient (the walk reports an infinite loss)
+    }
+    const float offset2 = nrm.offset2;
+    const float off_blank = offset2 - lp_row[blank];
+    float blank_acc = 0.f;
+    for (int base = 0; base < S; base += 128 * NP) {
+      // up to NP passes of 128 states issued together (2 NP x 16-byte loads in flight per lane)
+      float4 av[NP], bv[NP];
+#pragma unroll
+      for (int j = 0; j < NP; ++j) {
+        const int s = base + j * 128 + lane * 4;
+        if (s < S) {
+          av[j] = row4(a_row + (s >> 2));
+          bv[j] = row4(b_row + (s >> 2));
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < NP; ++j) {
+        const int s = base + j * 128 + lane * 4;
+        if (s < S) {
+          // s is a multiple of 4: states s, s+2 are blanks, s+1, s+3 carry labels s/2, s/2+1
+          // (one 8-byte read for both labels; past the last label it reads unused padding)
           const int2 pk = *reinterpret_cast<const int2*>(packed + (s >> 1));
-          m = fmaxf(m, av.x + bv.x - lp_row[blank]);
-          if (s + 1 < S) m = fmaxf(m, av.y + bv.y - lp_row[pk.x & 255]);
-          if (s + 2 < S) m = fmaxf(m, av.z + bv.z - lp_row[blank]);
-          if (s + 3 < S) m = fmaxf(m, av.w + bv.w - lp_row[pk.y & 255]);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        offset2 = -m;
-        have_offset = true;
-        feasible = m > -1e29f;  // no alignment at all: zero gradient (the walk reports an infinite loss)
-      }
-      const float off_blank = offset2 - lp_row[blank];
-      float blank_acc = 0.f;
-      for (int base = 0; base < S; base += 128 * NP) {
-        // up to NP passes of 128 states issued together (2 NP x 16-byte loads in flight per lane)
-        float4 av[NP], bv[NP];
-#pragma unroll
-        for (int j = 0; j < NP; ++j) {
-          const int s = base + j * 128 + lane * 4;
-          if (s < S) {
-            av[j] = __ldcg(a_row + (s >> 2));
-            bv[j] = __ldcg(b_row + (s >> 2));
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < NP; ++j) {
-          const int s = base + j * 128 + lane * 4;
-          if (s < S) {
-            // s is a multiple of 4: states s, s+2 are blanks, s+1, s+3 carry labels s/2, s/2+1
-            // (one 8-byte read for both labels; past the last label it reads unused padding)
-            const int2 pk = *reinterpret_cast<const int2*>(packed + (s >> 1));
-            blank_acc += ex2_approx(av[j].x + bv[j].x + off_blank);
-            if (s + 1 < S) xs[pk.x >> 8] = ex2_approx(av[j].y + bv[j].y - lp_row[pk.x & 255] + offset2);
-            if (s + 2 < S) blank_acc += ex2_approx(av[j].z + bv[j].z + off_blank);
-            if (s + 3 < S) xs[pk.y >> 8] = ex2_approx(av[j].w + bv[j].w - lp_row[pk.y & 255] + offset2);
-          }
+          blank_acc += ex2_approx(av[j].x + bv[j].x + off_blank);
+          if (s + 1 < S) xs[pk.x >> 8] = ex2_approx(av[j].y + bv[j].y - lp_row[pk.x & 255] + offset2);
+          if (s + 2 < S) blank_acc += ex2_approx(av[j].z + bv[j].z + off_blank);
+          if (s + 3 < S) xs[pk.y >> 8] = ex2_approx(av[j].w + bv[j].w - lp_row[pk.y & 255] + offset2);
         }
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) blank_acc += __shfl_xor_sync(0xffffffffu, blank_acc, o);
-      __syncwarp();
-      float occ[2] = {0.f, 0.f};
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int v = lane + 32 * h;
-        if (v < V) {
-          occ[h] = blank_acc;
-          if (v != blank) {
-            const int k0 = seg[v], k1 = seg[v + 1];
-            float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
-            int k = k0;
-            for (; k + 4 <= k1; k += 4) {
-              acc0 += xs[k];
-              acc1 += xs[k + 1];
-              acc2 += xs[k + 2];
-              acc3 += xs[k + 3];
-            }
-            for (; k < k1; ++k) acc0 += xs[k];
-            occ[h] = (acc0 + acc1) + (acc2 + acc3);
-          }
-        }
-      }
-      if (self_normalised) {
-        float total = occ[0] + occ[1];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
-        const float inv = feasible && total > 0.f ? 1.0f / total : 0.f;
-        occ[0] *= inv;
-        occ[1] *= inv;
-      }
-      float dLdp[2] = {0.f, 0.f};
-      float dot = 0.f;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int v = lane + 32 * h;
-        if (v < V) {
-          const float g = expf(lp_mine[h]) - occ[h];
-          dLdp[h] = g / (pv[h] + 1e-8f);
-          dot += pv[h] * dLdp[h];
-        }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-#pragma unroll
-      for (int h = 0; h < 2; ++h) dz[h] = feasible ? pv[h] * (dLdp[h] - dot) * grad_scale : 0.f;
-      __syncwarp();
     }
-    if (dz_f32 != nullptr) {
 #pragma unroll
-      for (int h = 0; h < 2; ++h)
-        if (lane + 32 * h < V) dz_f32[ro * V + lane + 32 * h] = dz[h];
-    }
-    if (dz_packed != nullptr) {
-      __nv_bfloat16* row = dz_packed + ro * row_elems;
+    for (int o = 16; o > 0; o >>= 1) blank_acc += __shfl_xor_sync(0xffffffffu, blank_acc, o);
+    __syncwarp();
+    float occ[2] = {0.f, 0.f};
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        if (fp16) {  // (uniform)
-          reinterpret_cast<uint16_t*>(row)[lane + 32 * h] = pack_16(dz[h], 1);
-          continue;
+    for (int h = 0; h < 2; ++h) {
+      const int v = lane + 32 * h;
+      if (v < V) {
+        occ[h] = blank_acc;
+        if (v != blank) {
+          const int k0 = c.seg[v], k1 = c.seg[v + 1];
+          float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+          int k = k0;
+          for (; k + 4 <= k1; k += 4) {
+            acc0 += xs[k];
+            acc1 += xs[k + 1];
+            acc2 += xs[k + 2];
+            acc3 += xs[k + 3];
+          }
+          for (; k < k1; ++k) acc0 += xs[k];
+          occ[h] = (acc0 + acc1) + (acc2 + acc3);
         }
-        const __nv_bfloat16 hi = __float2bfloat16_rn(dz[h]);
-        row[lane + 32 * h] = hi;
-        if (planes == 2) row[64 + lane + 32 * h] = __float2bfloat16_rn(dz[h] - __bfloat162float(hi));
       }
+    }
+    if (nrm.self_normalised) {
+      float total = occ[0] + occ[1];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+      const float inv = nrm.feasible && total > 0.f ? 1.0f / total : 0.f;
+      occ[0] *= inv;
+      occ[1] *= inv;
+    }
+    float dLdp[2] = {0.f, 0.f};
+    float dot = 0.f;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int v = lane + 32 * h;
+      if (v < V) {
+        const float g = expf(lp_mine[h]) - occ[h];
+        dLdp[h] = g / (pv[h] + 1e-8f);
+        dot += pv[h] * dLdp[h];
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) dz[h] = nrm.feasible ? pv[h] * (dLdp[h] - dot) * c.grad_scale : 0.f;
+    __syncwarp();
+  }
+  if (c.dz_f32 != nullptr) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+      if (lane + 32 * h < V) c.dz_f32[ro * V + lane + 32 * h] = dz[h];
+  }
+  if (c.dz_packed != nullptr) {
+    __nv_bfloat16* row = c.dz_packed + ro * (c.planes * 64);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (c.fp16) {  // (uniform)
+        reinterpret_cast<uint16_t*>(row)[lane + 32 * h] = pack_16(dz[h], 1);
+        continue;
+      }
+      const __nv_bfloat16 hi = __float2bfloat16_rn(dz[h]);
+      row[lane + 32 * h] = hi;
+      if (c.planes == 2) row[64 + lane + 32 * h] = __float2bfloat16_rn(dz[h] - __bfloat162float(hi));
     }
   }
 }
 
+// shared-memory carve-up of a gradient CTA: sorted labels, then per warp [lp_row VP | xs L_pad], then (staged
+// rows only) per warp two [alpha row | beta row] buffers
+struct GradSmem {
+  int* packed;
+  int* seg;
+  float* per_warp;
+  float* stage;
+  int warp_stride;
+};
+__device__ __forceinline__ GradSmem grad_smem(uint8_t* smem_raw, int L_max, int nwarps) {
+  const int L_pad = (L_max + 31) & ~31;
+  GradSmem g;
+  g.packed = reinterpret_cast<int*>(smem_raw);
+  g.seg = g.packed + L_pad;
+  g.per_warp = reinterpret_cast<float*>(g.seg + SORT_EXTRA);
+  g.warp_stride = VP + L_pad;
+  g.stage = g.per_warp + static_cast<size_t>(nwarps) * g.warp_stride;
+  return g;
+}
+__device__ __forceinline__ void load_sorted_labels(const GradSmem& g, const int* __restrict__ sort_ws, int b, int L,
+                                                   int L_max) {
+  const int L_pad = (L_max + 31) & ~31;
+  const int* src = sort_ws + static_cast<size_t>(b) * (L_pad + SORT_EXTRA);
+  for (int i = threadIdx.x; i < L; i += blockDim.x) g.packed[i] = __ldcg(src + i);
+  for (int i = threadIdx.x; i <= VP; i += blockDim.x) g.seg[i] = __ldcg(src + L_pad + i);
+  __syncthreads();
+}
+
+// Two-launch path: one block per (utterance, chunk of frames), one warp per frame, after the lattice kernel.
 __global__ void ctc_grad_sorted_kernel(const float* __restrict__ logp, const float* __restrict__ probs,
                                        const int32_t* __restrict__ labels,
                                        const int32_t* __restrict__ input_len,
@@ -1060,11 +1105,27 @@ __global__ void ctc_grad_sorted_kernel(const float* __restrict__ logp, const flo
                                        int planes, int fp16, int frames_per_block) {
   extern __shared__ uint8_t smem_raw[];
   ptx::pdl_launch_dependents();
+  const int b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int t_begin = blockIdx.x * frames_per_block;
   const int t_end = min(t_begin + frames_per_block, T);
+  const int L = label_len[b];
+  const int P = min(input_len[b], T);
+  const int S = 2 * L + 1;
   ptx::pdl_wait();  // alpha / beta / loss / the sorted labels come from the lattice kernel right before
-  grad_item<4>(smem_raw, blockIdx.y, t_begin, t_end, true, logp, probs, input_len, label_len, loss, alpha, beta, sort_ws,
-            dz_packed, dz_f32, grad_scale, T, V, L_max, blank, S_stride, planes, fp16);
+  const GradSmem g = grad_smem(smem_raw, L_max, nwarps);
+  if (t_begin < P) load_sorted_labels(g, sort_ws, b, L, L_max);  // (block-uniform)
+  const GradCtx c{logp, probs, dz_packed, dz_f32, grad_scale, T, V, blank, planes, fp16, g.packed, g.seg};
+  const float loss_b = loss[b];
+  GradNorm nrm{false, true, isfinite(loss_b), loss_b * LOG2E};
+  float* lp_row = g.per_warp + warp * g.warp_stride;
+  for (int t = t_begin + warp; t < t_end; t += nwarps) {
+    const size_t ro = static_cast<size_t>(b) * T + t;
+    FrameRows fr = {};
+    if (t < P) fr = load_frame_rows(c, b, t, lane);
+    grad_frame<4, false>(c, b, t, S, t < P, fr, reinterpret_cast<const float4*>(alpha + ro * S_stride),
+                         reinterpret_cast<const float4*>(beta + ro * S_stride), lp_row, lp_row + VP, nrm, lane);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1072,12 +1133,167 @@ __global__ void ctc_grad_sorted_kernel(const float* __restrict__ logp, const flo
 // remaining CTAs are persistent GRADIENT CTAs.  The gradient of frame t needs alpha_t (ready once the
 // alpha walk has passed t) and beta_t (ready once the beta walk, coming from the other end, has passed
 // t): the frames in the middle of an utterance become available when both walks are half way, the
-// outermost ones when they finish.  The gradient CTAs therefore process (utterance, frame chunk) items
-// from the middle outwards, waiting on the walkers' progress flags (ld.acquire.gpu), and the whole
-// bandwidth-bound gradient phase runs underneath the second half of the latency-bound walks — on the
-// SMs' idle issue slots and against lattice rows that are still in L2 — instead of as a second launch
-// after them.  Walkers never wait for gradient CTAs, and every CTA of the grid is co-resident (the
-// launcher sizes the grid with the occupancy API), so the waits cannot deadlock; they are bounded anyway.
+// outermost ones when they finish.  So the bandwidth-bound gradient phase runs underneath the second
+// half of the latency-bound walks — on the SMs' idle issue slots and against lattice rows that are still
+// in L2 — instead of as a second launch after them.
+//
+// Gradient CTA g serves utterance g % B together with the other CTAs of that residue: their warps deal
+// the utterance's frames round-robin IN ORDER OF AVAILABILITY (the middle frame first, then alternately
+// one further down / up).  Every warp is its own pipeline — no block barrier after the label load: lane 0
+// polls the two progress flags of the utterance (ld.acquire.gpu), the frame's rows are copied to shared
+// memory with cp.async (L2 path), and while they are in flight the warp works on the frame it fetched
+// before (two row buffers per warp).  Walkers never wait for gradient CTAs, and every CTA of the grid is
+// co-resident (the launcher sizes the grid with the occupancy API), so the waits cannot deadlock; they
+// are bounded anyway.
+template <bool STAGED>
+__device__ __noinline__ void grad_stream(uint8_t* smem_raw, int g_index, int G, const float* __restrict__ logp,
+                                         const float* __restrict__ probs, const int32_t* __restrict__ input_len,
+                                         const int32_t* __restrict__ label_len, const float* __restrict__ alpha,
+                                         const float* __restrict__ beta, const int* __restrict__ sort_ws,
+                                         const int* __restrict__ progress, __nv_bfloat16* __restrict__ dz_packed,
+                                         float* __restrict__ dz_f32, float grad_scale, int B, int T, int V,
+                                         int L_max, int blank, int S_stride, int planes, int fp16, int dbg) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int b = g_index % B;
+  if (b >= B || g_index >= G) return;
+  const int q = g_index / B;                 // this CTA's index among the CTAs serving utterance b
+  const int Q = (G - 1 - b) / B + 1;         // ... and their number
+  const int L = label_len[b];
+  const int P = min(input_len[b], T);
+  const int S = 2 * L + 1;
+  const int* flag_a = progress + 2 * b * FLAG_STRIDE;
+  const int* flag_b = flag_a + FLAG_STRIDE;
+  // lane 0 only.  The flags only grow: the values seen last are kept (per warp, and per CTA in shared memory:
+  // a warp first looks at what its neighbours have already seen), and memory is asked again only when they do
+  // not cover the frame yet — a ld.acquire.gpu is an L2 round trip of ~1 us, and thousands of warps hammering
+  // the same flag line delay the walkers' updates of it.  `lag`: steps the slower walk is still short of.
+  const GradSmem gs = grad_smem(smem_raw, L_max, nwarps);
+  volatile int* seen_cta = reinterpret_cast<volatile int*>(gs.seg + VP + 2);  // [2] (inside SORT_EXTRA's padding)
+  int seen_a = 0, seen_b = 0, lag = 0;
+  auto available = [&](int t) {
+    const int need_a = t + 1, need_b = P - t;
+    if (seen_a < need_a) seen_a = max(seen_a, seen_cta[0]);
+    if (seen_b < need_b) seen_b = max(seen_b, seen_cta[1]);
+    if (seen_a < need_a) {
+      seen_a = ld_acquire_gpu(flag_a);
+      seen_cta[0] = seen_a;  // (racy maximum: a stale smaller value only costs a neighbour one more poll)
+    }
+    if (seen_a >= need_a && seen_b < need_b) {
+      seen_b = ld_acquire_gpu(flag_b);
+      seen_cta[1] = seen_b;
+    }
+    lag = max(need_a - seen_a, need_b - seen_b);
+    return lag <= 0;
+  };
+  auto wait_available = [&](int t) {  // whole warp; returns once frame t's rows are visible to every lane
+    if (dbg == 3) return;  // (measurement aid: no waiting — results are garbage)
+    if (lane == 0) {
+      unsigned spins = 0;
+      while (!available(t)) {
+        // a lattice step takes ~0.1 us: sleep about half of what is still missing, at most 4 us
+        __nanosleep(min(4000, max(100, lag * 50)));
+        if (++spins > (1u << 22)) {
+          printf("speechless_b200: CTC gradient warp timed out waiting for the lattice walk (utterance %d)\n", b);
+          __trap();
+        }
+      }
+    }
+    __syncwarp();
+  };
+  // the sorted labels are published together with the first alpha progress
+  if (threadIdx.x == 0) {
+    seen_cta[0] = 0;
+    seen_cta[1] = 0;
+  }
+  if (P > 0) {
+    if (threadIdx.x == 0 && dbg != 3) {
+      unsigned spins = 0;
+      while (ld_acquire_gpu(flag_a) < 1) {
+        __nanosleep(500);
+        if (++spins > (1u << 22)) __trap();
+      }
+    }
+    __syncthreads();
+  }
+  if (P > 0) load_sorted_labels(gs, sort_ws, b, L, L_max);
+  __syncthreads();
+  if (dbg == 2) return;
+  const GradCtx c{logp, probs, dz_packed, dz_f32, grad_scale, T, V, blank, planes, fp16, gs.packed, gs.seg};
+  GradNorm nrm{true, false, true, 0.f};
+  float* lp_row = gs.per_warp + warp * gs.warp_stride;
+  float* xs = lp_row + VP;
+  float* stage = gs.stage + static_cast<size_t>(warp) * 4 * S_stride;
+
+  // i-th frame of the utterance in order of availability: the middle one, then alternately one further
+  // down / up, then what is left of the longer (upper) side; frames >= P (zero rows) keep their index
+  const int mid = P / 2;
+  auto frame_of = [&](int i) {
+    if (i >= P) return i;
+    if (i < 2 * mid) return (i & 1) ? mid - ((i + 1) >> 1) : mid + (i >> 1);
+    return i;  // i == 2 * mid == P - 1 (odd P): the last frame
+  };
+  auto prefetch_rows = [&](int t, int buf) {
+    const float* a = alpha + (static_cast<size_t>(b) * T + t) * S_stride;
+    const float* bb = beta + (static_cast<size_t>(b) * T + t) * S_stride;
+    float* dst = stage + buf * 2 * S_stride;
+    for (int i = lane * 4; i < S; i += 128) {
+      cp_async16_cg(dst + i, a + i);
+      cp_async16_cg(dst + S_stride + i, bb + i);
+    }
+    cp_async_commit();
+  };
+  const int stride = Q * nwarps;
+  int buf = 0;
+  int i = q * nwarps + warp;
+  FrameRows fr = {}, fr_next = {};  // the frame's log-prob / prob rows travel one frame ahead in registers
+  if (i < P) {
+    wait_available(frame_of(i));
+    if (STAGED) prefetch_rows(frame_of(i), 0);
+    fr = load_frame_rows(c, b, frame_of(i), lane);
+  }
+  for (; i < T; i += stride) {
+    const int t = frame_of(i);
+    const int i_next = i + stride;
+    bool next_issued = false;
+    if (i < P) {
+      if (i_next < P) {
+        // fetch the next frame's rows now if the walks are already past it
+        const int t_next = frame_of(i_next);
+        int ok = 0;
+        if (lane == 0) ok = (dbg == 3 || available(t_next)) ? 1 : 0;
+        ok = __shfl_sync(0xffffffffu, ok, 0);
+        if (ok) {
+          if (STAGED) prefetch_rows(t_next, buf ^ 1);
+          fr_next = load_frame_rows(c, b, t_next, lane);
+          next_issued = true;
+        }
+      }
+      if (STAGED) {
+        if (next_issued)
+          cp_async_wait<1>();
+        else
+          cp_async_wait<0>();
+        __syncwarp();
+      }
+    }
+    const size_t ro = static_cast<size_t>(b) * T + t;
+    const float* a_row = STAGED ? stage + buf * 2 * S_stride : alpha + ro * S_stride;
+    const float* b_row = STAGED ? stage + buf * 2 * S_stride + S_stride : beta + ro * S_stride;
+    grad_frame<1, STAGED>(c, b, t, S, i < P, fr, reinterpret_cast<const float4*>(a_row),
+                          reinterpret_cast<const float4*>(b_row), lp_row, xs, nrm, lane);
+    if (i_next < P) {
+      __syncwarp();  // every lane is done with the buffers
+      if (!next_issued) {
+        wait_available(frame_of(i_next));
+        if (STAGED) prefetch_rows(frame_of(i_next), buf ^ 1);
+        fr_next = load_frame_rows(c, b, frame_of(i_next), lane);
+      }
+      fr = fr_next;
+      buf ^= 1;
+    }
+  }
+}
+
 template <int SPT, int K, bool CL>
 __global__ void __launch_bounds__(1024)
     ctc_fused_kernel(const float* __restrict__ logp, const float* __restrict__ probs,
@@ -1086,57 +1302,68 @@ __global__ void __launch_bounds__(1024)
                      float* __restrict__ beta_loss, float* __restrict__ alpha, float* __restrict__ beta,
                      int* __restrict__ sort_ws, int* __restrict__ progress, __nv_bfloat16* __restrict__ dz_packed,
                      float* __restrict__ dz_f32, float grad_scale, int B, int T, int V, int L_max, int blank,
-                     int S_stride, int col_stride, int planes, int fp16, int n_walk, int frames_per_item) {
+                     int S_stride, int col_stride, int planes, int fp16, int n_walk, int walkers_per_sm,
+                     int staged, int dbg) {
   extern __shared__ uint8_t smem_raw[];
   ptx::pdl_launch_dependents();
-  if (static_cast<int>(blockIdx.x) < n_walk) {
-    const int csize = CL ? static_cast<int>(ptx::cluster_nctarank()) : 1;
-    lattice_cta_body<SPT, K, CL>(smem_raw, static_cast<int>(blockIdx.x) / csize, logp, labels, input_len, label_len,
-                                 loss, beta_loss, alpha, beta, sort_ws, T, L_max, blank, S_stride, col_stride,
-                                 progress);
+  // Roles.  The walks are latency bound: two walkers on one SM share its four schedulers and both slow down
+  // (measured: the same walkers inside a 592-CTA grid took 82 us instead of 65 when roles went by block index,
+  // because the block scheduler does not spread consecutive CTAs one per SM once several fit).  So a CTA
+  // becomes a walker if it is among the first `walkers_per_sm` CTAs to arrive on ITS SM (%smid) and walk
+  // units are left; everything else computes gradients.  Every unit is claimed whatever the placement: a CTA
+  // must claim once the unclaimed units are as many as the CTAs still to arrive (itself included).  The
+  // counters sit behind the progress flags and are zeroed with them.  Clusters keep roles by block index.
+  int walk_unit = -1, g = 0;
+  if constexpr (CL) {
+    if (static_cast<int>(blockIdx.x) < n_walk)
+      walk_unit = static_cast<int>(blockIdx.x) / static_cast<int>(ptx::cluster_nctarank());
+    else
+      g = static_cast<int>(blockIdx.x) - n_walk;
+  } else {
+    __shared__ int role_s[2];
+    if (threadIdx.x == 0) {
+      int* counters = progress + 2 * B * FLAG_STRIDE;  // [0,1]: arrived | claimed << 32, [2]: gradient CTAs, [32..]: per SM
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      const int slot = atomicAdd(counters + 32 + static_cast<int>(smid & 255u), 1);
+      const bool prefer = slot < walkers_per_sm;
+      unsigned long long* packed_counter = reinterpret_cast<unsigned long long*>(counters);
+      unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(packed_counter);
+      int unit = -1;
+      for (;;) {
+        const int arrived = static_cast<int>(old & 0xffffffffull), claimed = static_cast<int>(old >> 32);
+        const int unclaimed = n_walk - claimed, remaining = static_cast<int>(gridDim.x) - arrived;
+        const bool claim = unclaimed > 0 && (prefer || unclaimed >= remaining);
+        const unsigned long long want = static_cast<unsigned long long>(arrived + 1) |
+                                        (static_cast<unsigned long long>(claimed + (claim ? 1 : 0)) << 32);
+        const unsigned long long seen = atomicCAS(packed_counter, old, want);
+        if (seen == old) {
+          unit = claim ? claimed : -1;
+          break;
+        }
+        old = seen;
+      }
+      role_s[0] = unit;
+      role_s[1] = unit < 0 ? atomicAdd(counters + 2, 1) : 0;
+    }
+    __syncthreads();
+    walk_unit = role_s[0];
+    g = role_s[1];
+  }
+  if (walk_unit >= 0) {
+    lattice_cta_body<SPT, K, CL>(smem_raw, walk_unit, logp, labels, input_len, label_len, loss, beta_loss, alpha, beta,
+                                 sort_ws, T, L_max, blank, S_stride, col_stride, dbg == 4 ? nullptr : progress, dbg);
     return;
   }
+  if (dbg == 1 || dbg >= 4) return;  // measurement aids (SL_CTC_DBG): walkers (+ publication) only
   ptx::pdl_wait();  // logp / probs come from the output_conv kernel right before
-  const int g = static_cast<int>(blockIdx.x) - n_walk, G = static_cast<int>(gridDim.x) - n_walk;
-  const int n_chunks = (T + frames_per_item - 1) / frames_per_item;
-  const int items = B * n_chunks;
-  int loaded_b = -1;
-  for (int item = g; item < items; item += G) {
-    const int b = item % B, j = item / B;
-    const int P = min(input_len[b], T);
-    // j-th chunk of the utterance in order of availability: the middle one, then alternately one
-    // further down / up, then what is left of the longer side
-    const int c_mid = min((P / 2) / frames_per_item, n_chunks - 1);
-    const int down = c_mid, up = n_chunks - 1 - c_mid;
-    const int both = min(down, up);
-    int c;
-    if (j == 0) {
-      c = c_mid;
-    } else if (j <= 2 * both) {
-      const int q = (j + 1) >> 1;
-      c = (j & 1) ? c_mid - q : c_mid + q;
-    } else {
-      const int r = j - 2 * both;
-      c = down > up ? c_mid - both - r : c_mid + both + r;
-    }
-    const int t_begin = c * frames_per_item;
-    const int t_end = min(t_begin + frames_per_item, T);
-    if (threadIdx.x == 0 && t_begin < P) {
-      const int need_a = min(t_end, P), need_b = P - t_begin;
-      unsigned spins = 0;
-      while (ld_acquire_gpu(progress + 2 * b) < need_a || ld_acquire_gpu(progress + 2 * b + 1) < need_b) {
-        __nanosleep(200);
-        if (++spins > (1u << 24)) {
-          printf("speechless_b200: CTC gradient CTA timed out waiting for the lattice walk (utterance %d)\n", b);
-          __trap();
-        }
-      }
-    }
-    __syncthreads();  // flags seen (the acquire orders every thread's loads behind it); smem of the last item is free
-    grad_item<2>(smem_raw, b, t_begin, t_end, b != loaded_b, logp, probs, input_len, label_len, nullptr, alpha, beta,
-              sort_ws, dz_packed, dz_f32, grad_scale, T, V, L_max, blank, S_stride, planes, fp16);
-    if (t_begin < P) loaded_b = b;
-  }
+  const int G = static_cast<int>(gridDim.x) - n_walk;
+  if (staged)
+    grad_stream<true>(smem_raw, g, G, logp, probs, input_len, label_len, alpha, beta, sort_ws, progress, dz_packed,
+                      dz_f32, grad_scale, B, T, V, L_max, blank, S_stride, planes, fp16, dbg);
+  else
+    grad_stream<false>(smem_raw, g, G, logp, probs, input_len, label_len, alpha, beta, sort_ws, progress, dz_packed,
+                       dz_f32, grad_scale, B, T, V, L_max, blank, S_stride, planes, fp16, dbg);
 }
 
 // Greedy decode: one warp per utterance, 32 frames per iteration.  argmax (lowest index
@@ -1191,8 +1418,60 @@ size_t ctc_workspace_bytes(int B, int T, int L_max) {
   const size_t bl = (static_cast<size_t>(B) * sizeof(float) + 255) & ~static_cast<size_t>(255);
   const size_t sort = static_cast<size_t>(B) * (((L_max + 31) & ~31) + SORT_EXTRA) * sizeof(int);
   // ... | progress flags of the fused launch: steps completed per (utterance, direction)
-  const size_t flags = (static_cast<size_t>(2 * B) * sizeof(int) + 255) & ~static_cast<size_t>(255);
+  const size_t flags = (static_cast<size_t>(2 * B) * FLAG_STRIDE + ROLE_COUNTERS) * sizeof(int);
   return 2 * lat + bl + sort + flags + 512;
+}
+
+// co-resident CTAs of a fused-launch configuration on the current device, cached (benign race: idempotent)
+static cudaError_t fused_capacity(const void* kern, int threads, size_t smem, int cluster, int sms, int* capacity) {
+  struct Entry {
+    const void* kern;
+    int threads, cluster, dev, capacity;
+    size_t smem;
+  };
+  static Entry cache[64];
+  static int used = 0;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  for (int i = 0; i < used; ++i)
+    if (cache[i].kern == kern && cache[i].threads == threads && cache[i].smem == smem && cache[i].cluster == cluster &&
+        cache[i].dev == dev) {
+      *capacity = cache[i].capacity;
+      return cudaSuccess;
+    }
+  if (smem > 40 * 1024) {  // (the kernel also has a few bytes of static shared memory: opt in below the 48 KB line)
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+  }
+  int cap = 0;
+  if (cluster > 1) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(sms / cluster * cluster);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = static_cast<unsigned>(cluster);
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&clusters, kern, &cfg) != cudaSuccess) {
+      cudaGetLastError();
+      clusters = 0;
+    }
+    cap = clusters * cluster;
+  } else {
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
+    if (e != cudaSuccess) return e;
+    cap = per_sm * sms;
+  }
+  if (used < 64) cache[used++] = Entry{kern, threads, cluster, dev, cap, smem};
+  *capacity = cap;
+  return cudaSuccess;
 }
 
 int ctc_loss_launch(const float* logp, const float* probs, const int32_t* labels,
@@ -1263,55 +1542,45 @@ int ctc_loss_launch(const float* logp, const float* probs, const int32_t* labels
       const int threads = (nw + 1) * 32;
       const int nwarps = nw + 1;
       const int L_pad = (L_max + 31) & ~31;
-      const size_t gsmem = (L_pad + SORT_EXTRA) * sizeof(int) + static_cast<size_t>(nwarps) * (VP + L_pad) * sizeof(float);
+      size_t gsmem = (L_pad + SORT_EXTRA) * sizeof(int) + static_cast<size_t>(nwarps) * (VP + L_pad) * sizeof(float);
+      // row staging (two alpha + beta row pairs per warp) while a gradient CTA stays within a quarter of the
+      // SM's shared memory, i.e. while it does not lower the number of co-resident CTAs
+      const size_t stage_bytes = static_cast<size_t>(nwarps) * 4 * S_stride * sizeof(float);
+      int staged = gsmem + stage_bytes <= 56 * 1024 ? 1 : 0;
+      if (const char* e = std::getenv("SL_CTC_GRAD_STAGED")) staged = std::atoi(e) != 0 && gsmem + stage_bytes <= 200 * 1024;
+      if (staged) gsmem += stage_bytes;
       const size_t fsmem = smem > gsmem ? smem : gsmem;
       const int n_walk = 2 * B * cluster;
-      int frames_per_item = 2 * nwarps;
-      if (const char* e = std::getenv("SL_CTC_GRAD_FPI")) frames_per_item = std::max(1, std::atoi(e));  // tuning aid
-      const int items = B * ((T + frames_per_item - 1) / frames_per_item);
+      // no more gradient warps than frames; at least one gradient CTA per utterance (else: two launches)
+      const int max_useful = B * ((T + nwarps - 1) / nwarps);
       int dev = 0, sms = 148;
       SL_CUDA(cudaGetDevice(&dev));
       SL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-      int want_ctas = 2 * sms;
+      const char* dbg_env = std::getenv("SL_CTC_DBG");  // measurement aids, see ctc_fused_kernel
+      const int dbg = dbg_env ? std::atoi(dbg_env) : 0;
+      int want_ctas = 1 << 20;  // as many as can be co-resident: the gradient phase is latency bound
       if (const char* e = std::getenv("SL_CTC_GRAD_CTAS")) want_ctas = std::max(1, std::atoi(e));
 #define SL_LAUNCH_FUSED(SPT, KK)                                                                    \
   if (!launched && spt == SPT && kk == KK) {                                                        \
     auto kern = cluster > 1 ? ctc_fused_kernel<SPT, KK, true> : ctc_fused_kernel<SPT, KK, false>;   \
-    if (fsmem > 48 * 1024)                                                                          \
-      SL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(fsmem))); \
-    /* every CTA of the grid must be co-resident: the gradient CTAs wait for the walkers */        \
+    /* every CTA of the grid must be co-resident: the gradient CTAs wait for the walkers.  The occupancy  \
+       query (and the opt-in shared-memory size) are cached per (kernel, block, smem): they cost more host \
+       time than the kernel runs */                                                                  \
     int capacity = 0;                                                                               \
-    if (cluster > 1) {                                                                              \
-      cudaLaunchConfig_t cfg = {};                                                                  \
-      cfg.gridDim = dim3(sms / cluster * cluster);                                                  \
-      cfg.blockDim = dim3(threads);                                                                 \
-      cfg.dynamicSmemBytes = fsmem;                                                                 \
-      cudaLaunchAttribute attr[1];                                                                  \
-      attr[0].id = cudaLaunchAttributeClusterDimension;                                             \
-      attr[0].val.clusterDim.x = static_cast<unsigned>(cluster);                                    \
-      attr[0].val.clusterDim.y = 1;                                                                 \
-      attr[0].val.clusterDim.z = 1;                                                                 \
-      cfg.attrs = attr;                                                                             \
-      cfg.numAttrs = 1;                                                                             \
-      int clusters = 0;                                                                             \
-      if (cudaOccupancyMaxActiveClusters(&clusters, kern, &cfg) != cudaSuccess) {                   \
-        cudaGetLastError();                                                                         \
-        clusters = 0;                                                                               \
-      }                                                                                             \
-      capacity = clusters * cluster;                                                                \
-    } else {                                                                                        \
-      int per_sm = 0;                                                                               \
-      SL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, fsmem));        \
-      capacity = per_sm * sms;                                                                      \
-    }                                                                                               \
-    int n_grad = std::min(std::min(want_ctas, items), capacity - n_walk);                          \
+    SL_CUDA(fused_capacity(reinterpret_cast<const void*>(kern), threads, fsmem, cluster, sms, &capacity)); \
+    int n_grad = std::min(std::min(want_ctas, max_useful), capacity - n_walk);                     \
     n_grad = n_grad / cluster * cluster;                                                            \
-    if (n_grad >= cluster && n_grad >= 8) {                                                         \
-      SL_CUDA(cudaMemsetAsync(progress, 0, static_cast<size_t>(2 * B) * sizeof(int), stream));      \
+    if (std::getenv("SL_CTC_VERBOSE"))                                                              \
+      fprintf(stderr, "ctc fused: threads %d smem %zu capacity %d n_walk %d n_grad %d staged %d\n", threads, fsmem, \
+              capacity, n_walk, n_grad, staged);                                                    \
+    if (n_grad >= B) {                                                                              \
+      SL_CUDA(cudaMemsetAsync(progress, 0, (static_cast<size_t>(2 * B) * FLAG_STRIDE + ROLE_COUNTERS) * sizeof(int), \
+                              stream));                                                             \
       SL_CUDA(launch_pdl_cluster(PDL_CTC, ClusterX{cluster}, kern, dim3(n_walk + n_grad), dim3(threads), fsmem, stream, \
                                  logp, probs, labels, input_len, label_len, loss, beta_loss, alpha, beta, sort_ws,  \
                                  progress, reinterpret_cast<__nv_bfloat16*>(dlogits_packed), dlogits_f32, grad_scale, \
-                                 B, T, V, L_max, blank, S_stride, col_stride, planes, fp16, n_walk, frames_per_item)); \
+                                 B, T, V, L_max, blank, S_stride, col_stride, planes, fp16, n_walk,  \
+                                 (n_walk + sms - 1) / sms, staged, dbg));                           \
       launched = true;                                                                              \
       grad_done = true;                                                                             \
     }                                                                                               \

@@ -106,25 +106,57 @@ def ctc_required_frames(label: Sequence[int]) -> int:
     return len(label) + sum(1 for a, b in zip(label[:-1], label[1:]) if a == b)
 
 
+class _Arena:
+    """Named flat buffers of one tower that only grow.  Real corpora give almost every batch its own
+    longest utterance, i.e. its own (B, T): the per-shape workspaces below are therefore only VIEWS of these
+    buffers (sized by the largest shape seen so far), so a new shape costs a few Python objects instead of a
+    gigabyte of cudaMalloc + cudaHostAlloc per training step.  `generation` changes whenever a buffer had to
+    be replaced by a larger one; views taken before that are stale and get rebuilt."""
+
+    def __init__(self, device: torch.device):
+        self.device = device
+        self.buffers: Dict[str, torch.Tensor] = {}
+        self.generation = 0
+
+    def take(self, name: str, shape: Sequence[int], dtype: torch.dtype, pinned: bool = False) -> torch.Tensor:
+        count = 1
+        for extent in shape:
+            count *= int(extent)
+        nbytes = max(count * torch.empty((), dtype=dtype).element_size(), 16)
+        buffer = self.buffers.get(name)
+        if buffer is None or buffer.numel() < nbytes:
+            size = nbytes + nbytes // 8  # headroom: the next slightly longer batch does not reallocate again
+            buffer = torch.empty(size, dtype=torch.uint8, pin_memory=True) if pinned else \
+                torch.empty(size, dtype=torch.uint8, device=self.device)
+            self.buffers[name] = buffer
+            self.generation += 1
+        return buffer[:count * torch.empty((), dtype=dtype).element_size()].view(dtype).view(*shape)
+
+
 class _Workspace:
-    """Device buffers for one (B, T) batch shape; reused across steps."""
+    """Views of the tower's arena for one (B, T) batch shape (the small per-utterance vectors are its own).
+    Only one shape is in use on the compute stream at a time; the two input slots are separate buffers, so
+    the host->device copy of the NEXT batch (any shape) overlaps the step of the current one."""
 
     def __init__(self, tower: "ConvTower", B: int, T: int):
         dev, planes = tower.device, tower.planes
+        self._views: List[Tuple[str, torch.Tensor]] = []
+        self._arena = tower.arena
+        arena = self  # (take() below records which arena buffers this workspace looks at)
         first = tower.layers[0]
         self.B, self.T = B, T
         # T0: rows per utterance of the packed first-layer operand (frames, or receptive-field rows
         # of a windowed raw-wave layer)
         self.T0 = same_padding(T, first.kernel, first.stride)[0] if first.windowed else T
         self.T_alloc = round_up(self.T0, first.gemm_stride)
-        self.x_f32 = torch.empty((B, T, first.cin), dtype=torch.float32, device=dev)
-        self.x_host = torch.empty((B, T, first.cin), dtype=torch.float32, pin_memory=True)
-        # second slot for the pipelined training loop (copy of batch i+1 overlaps step i)
-        self.x_slots = [self.x_f32, None]
-        self.host_slots = [self.x_host, None]
-        self.slot_copied = [None, None]   # event on the copy stream: slot holds the new batch
-        self.slot_consumed = [None, None]  # event on the compute stream: pack kernel has read the slot
-        self.x_packed = torch.zeros((B, self.T_alloc, planes * first.cin_pad), dtype=tower.storage_dtype, device=dev)
+        # two input slots for the pipelined training loop (copy of batch i+1 overlaps step i); slot 0 doubles
+        # as the plain upload() target
+        self.x_slots = [arena.take("x_slot{}".format(i), (B, T, first.cin), torch.float32) for i in range(2)]
+        self.host_slots = [arena.take("host_slot{}".format(i), (B, T, first.cin), torch.float32, pinned=True)
+                           for i in range(2)]
+        self.x_f32, self.x_host = self.x_slots[0], self.host_slots[0]
+        # (the pack kernel writes every row of x_packed, allocation padding included)
+        self.x_packed = arena.take("x_packed", (B, self.T_alloc, planes * first.cin_pad), tower.storage_dtype)
         self.t_out: List[int] = []
         self.acts: List[torch.Tensor] = []
         t = T
@@ -139,16 +171,16 @@ class _Workspace:
         for index, (layer, t_out) in enumerate(zip(tower.layers[:-1], self.t_out[:-1])):
             alloc = round_up(t_out, tower.layers[index + 1].gemm_stride)
             self.t_alloc_out.append(alloc)
-            self.acts.append(torch.zeros((B, alloc, planes * layer.cout_pad), dtype=tower.storage_dtype, device=dev))
-            self.masks.append(torch.empty((B, t_out, layer.cout_pad // 8), dtype=torch.uint8, device=dev))
+            self.acts.append(arena.take("act{}".format(index), (B, alloc, planes * layer.cout_pad), tower.storage_dtype))
+            self.masks.append(arena.take("mask{}".format(index), (B, t_out, layer.cout_pad // 8), torch.uint8))
         V = tower.layers[-1].cout
-        self.probs = torch.empty((B, self.Tp, V), dtype=torch.float32, device=dev)
-        self.logits = torch.empty((B, self.Tp, V), dtype=torch.float32, device=dev)
-        self.logp = torch.empty((B, self.Tp, 64), dtype=torch.float32, device=dev)
+        self.probs = arena.take("probs", (B, self.Tp, V), torch.float32)
+        self.logits = arena.take("logits", (B, self.Tp, V), torch.float32)
+        self.logp = arena.take("logp", (B, self.Tp, 64), torch.float32)
         self.loss = torch.empty((B,), dtype=torch.float32, device=dev)
         self.input_len = torch.empty((B,), dtype=torch.int32, device=dev)
         self.label_len = torch.empty((B,), dtype=torch.int32, device=dev)
-        self.decoded = torch.empty((B, self.Tp), dtype=torch.int32, device=dev)
+        self.decoded = arena.take("decoded", (B, self.Tp), torch.int32)
         self.decoded_len = torch.empty((B,), dtype=torch.int32, device=dev)
         self.labels: Optional[torch.Tensor] = None
         self.ctc_ws: Optional[torch.Tensor] = None
@@ -164,14 +196,32 @@ class _Workspace:
         self.input_dropped = False  # raw-wave input: dropout was applied while packing
         self.loss_scale = 1.0  # power of two the packed gradients of the last ctc() call carry (fp16 mode)
 
+    def take(self, name: str, shape: Sequence[int], dtype: torch.dtype, pinned: bool = False) -> torch.Tensor:
+        view = self._arena.take(name, shape, dtype, pinned)
+        self._views.append((name, view))
+        return view
+
+    def stale(self) -> bool:
+        """True once the arena has replaced (grown) one of the buffers this workspace holds views of."""
+        buffers = self._arena.buffers
+        return any(buffers[name].data_ptr() != view.data_ptr() for name, view in self._views)
+
+    def zero_allocation_rows(self) -> None:
+        """The extra row of an activation whose consumer strides by 2 over an odd frame count must be zero, and
+        no kernel writes it: zero it when this shape takes over buffers another shape has used."""
+        for act, t_out, alloc in zip(self.acts, self.t_out, self.t_alloc_out):
+            if alloc > t_out:
+                act[:, t_out:].zero_()
+
     def ensure_backward(self, tower: "ConvTower"):
         if self.dz_packed is None:
-            dev, planes = tower.device, tower.planes
-            self.dz_packed = torch.empty((self.B, self.Tp, planes * 64), dtype=tower.storage_dtype, device=dev)
+            planes = tower.planes
+            self.dz_packed = self.take("dz_packed", (self.B, self.Tp, planes * 64), tower.storage_dtype)
             widest = max(layer.cout_pad for layer in tower.layers[:-1])
             rows = max(self.t_out)
             for i in range(2):
-                self.dact[i] = torch.empty((self.B, rows, planes * widest), dtype=tower.storage_dtype, device=dev)
+                self.dact[i] = self.take("dact{}".format(i), (self.B, rows, planes * widest), tower.storage_dtype)
+
 
 
 class ConvTower:
@@ -225,7 +275,11 @@ class ConvTower:
             self.adam_v: Optional[torch.Tensor] = None
             self.w_fwd = [torch.zeros((l.gemm_kernel, l.cout_pad, self.planes * l.cin_pad), dtype=self.storage_dtype,
                                       device=device) for l in layers]
+        self.arena = _Arena(device)
         self._workspaces: Dict[Tuple[int, int], _Workspace] = {}
+        self._bound: Optional[_Workspace] = None  # the workspace whose shape the arena buffers currently carry
+        self._slot_copied = [None, None]    # event on the copy stream: input slot holds the new batch
+        self._slot_consumed = [None, None]  # event on the compute stream: the pack kernel has read the slot
         self._current: Optional[_Workspace] = None
         self.launches = 0  # kernels launched through the C-ABI (bench.py reports it)
         # optional per-kernel timing: list of (kind, layer name, start event, stop event) on the
@@ -332,17 +386,24 @@ class ConvTower:
     def workspace(self, B: int, T: int) -> _Workspace:
         key = (B, T)
         ws = self._workspaces.get(key)
-        if ws is None:
-            if len(self._workspaces) >= 4:  # bound HBM held by stale batch shapes
+        if ws is None or ws.stale():
+            if len(self._workspaces) >= 64:  # (views only: the memory belongs to the arena)
                 self._workspaces.pop(next(iter(self._workspaces)))
             with torch.cuda.device(self.device):
                 ws = _Workspace(self, B, T)
             self._workspaces[key] = ws
         return ws
 
+    def _bind(self, ws: _Workspace) -> None:
+        """`ws` takes over the arena buffers on the compute stream (called where a step starts: packing)."""
+        if self._bound is not ws:
+            ws.zero_allocation_rows()
+            self._bound = ws
+
     def _pack_input(self, ws: _Workspace, x: torch.Tensor, training: bool) -> None:
         """fp32 (B,T,F) on the device -> packed bf16 operand of the first layer."""
         first = self.layers[0]
+        self._bind(ws)
         if first.windowed:
             drop = training and self.dropout is not None and 0 in self.dropout_layers
             # forward(training=True) advances dropout_step before it derives the other layers' seeds
@@ -401,34 +462,30 @@ class ConvTower:
             if F != self.layers[0].cin:
                 raise ValueError("expected {} features per time step, got {}".format(self.layers[0].cin, F))
             ws = self.workspace(B, T)
-            if ws.x_slots[slot] is None:
-                ws.x_slots[slot] = torch.empty_like(ws.x_f32)
             pinned = isinstance(input_batch, torch.Tensor) and input_batch.is_pinned() and \
                 input_batch.dtype == torch.float32 and input_batch.is_contiguous()
             if not pinned:
-                if ws.host_slots[slot] is None:
-                    ws.host_slots[slot] = torch.empty_like(ws.x_host).pin_memory()
-                if ws.slot_copied[slot] is not None:
-                    ws.slot_copied[slot].synchronize()  # the previous DMA out of this staging buffer is done
+                if self._slot_copied[slot] is not None:
+                    self._slot_copied[slot].synchronize()  # the previous DMA out of this staging buffer is done
                 source = input_batch if isinstance(input_batch, torch.Tensor) else torch.from_numpy(
                     np.ascontiguousarray(input_batch, dtype=np.float32))
                 ws.host_slots[slot].copy_(source)
                 input_batch = ws.host_slots[slot]
             copy = self._copy_stream
-            if ws.slot_consumed[slot] is not None:
-                copy.wait_event(ws.slot_consumed[slot])
+            if self._slot_consumed[slot] is not None:
+                copy.wait_event(self._slot_consumed[slot])
             with torch.cuda.stream(copy):
                 ws.x_slots[slot].copy_(input_batch, non_blocking=True)
-                ws.slot_copied[slot] = copy.record_event()
+                self._slot_copied[slot] = copy.record_event()
             return ws
 
     def consume_slot(self, ws: _Workspace, slot: int, training: bool = False) -> _Workspace:
         """Compute stream: wait for the slot's copy, pack it to bf16 and release the slot."""
         with torch.cuda.device(self.device):
             main = torch.cuda.current_stream(self.device)
-            main.wait_event(ws.slot_copied[slot])
+            main.wait_event(self._slot_copied[slot])
             self._pack_input(ws, ws.x_slots[slot], training)
-            ws.slot_consumed[slot] = main.record_event()
+            self._slot_consumed[slot] = main.record_event()
             self._current = ws
             return ws
 
@@ -452,9 +509,10 @@ class ConvTower:
                     raise RuntimeError("raw-wave input dropout is applied while packing: upload(training=True)")
                 if drop and index in self.dropout_layers and not layer.windowed:
                     if index not in ws.xdrop:
-                        ws.xdrop[index] = torch.zeros_like(x)  # zero: keeps the T_alloc padding rows zero
-                        ws.bwd_mask[index] = torch.empty((ws.B, t_in, layer.cin_pad // 8), dtype=torch.uint8,
-                                                         device=self.device)
+                        # (the dropout kernel writes the T_alloc padding rows as zeros itself)
+                        ws.xdrop[index] = ws.take("xdrop{}".format(index), tuple(x.shape), x.dtype)
+                        ws.bwd_mask[index] = ws.take("bwd_mask{}".format(index), (ws.B, t_in, layer.cin_pad // 8),
+                                                     torch.uint8)
                     relu_below = ws.masks[index - 1] if index > 0 and self.layers[index - 1].activation == "relu" \
                         else None
                     seed = self._dropout_seed(index)
@@ -513,7 +571,7 @@ class ConvTower:
             ws.label_len.copy_(torch.from_numpy(ll.astype(np.int32)))
             need_bytes = self.lib.sl_ctc_workspace_bytes(ws.B, ws.Tp, ws.labels.shape[1])
             if ws.ctc_ws is None or ws.ctc_ws.numel() < need_bytes:
-                ws.ctc_ws = torch.empty(need_bytes, dtype=torch.uint8, device=self.device)
+                ws.ctc_ws = ws.take("ctc_ws", (need_bytes,), torch.uint8)
 
     def set_prediction_lengths(self, ws: _Workspace, prediction_lengths: Sequence[int]) -> None:
         pl = np.asarray(prediction_lengths, dtype=np.int32).reshape(-1)
@@ -531,7 +589,7 @@ class ConvTower:
             if want_grad:
                 ws.ensure_backward(self)
                 if want_f32_grad and ws.dz_f32 is None:
-                    ws.dz_f32 = torch.empty((ws.B, ws.Tp, V), dtype=torch.float32, device=self.device)
+                    ws.dz_f32 = ws.take("dz_f32", (ws.B, ws.Tp, V), torch.float32)
             self._timed("ctc", "ctc_loss", lambda: self.lib.sl_ctc_loss(
                 ptr(ws.logp), ptr(ws.probs), ptr(ws.labels), ptr(ws.input_len), ptr(ws.label_len), ptr(ws.loss),
                 ptr(ws.dz_packed) if want_grad else None,
@@ -559,7 +617,7 @@ class ConvTower:
         with torch.cuda.device(self.device):
             need = self.lib.sl_ctc_beam_search_workspace_bytes(ws.B, ws.Tp, beam_width)
             if getattr(ws, "beam_ws", None) is None or ws.beam_ws.numel() < need:
-                ws.beam_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+                ws.beam_ws = ws.take("beam_ws", (need,), torch.uint8)
             decoded = torch.empty((ws.B, top_paths, ws.Tp), dtype=torch.int32, device=self.device)
             lengths = torch.empty((ws.B, top_paths), dtype=torch.int32, device=self.device)
             log_probabilities = torch.empty((ws.B, top_paths), dtype=torch.float32, device=self.device)
@@ -666,7 +724,7 @@ class ConvTower:
                     need = 0 if layer.gemm_stride != 1 else self.lib.sl_conv1d_dgrad_workspace_bytes(
                         ws.B, t_in, layer.gemm_cin, layer.cout, layer.gemm_kernel)
                     if need and (ws.dgrad_ws is None or ws.dgrad_ws.numel() < need):
-                        ws.dgrad_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+                        ws.dgrad_ws = ws.take("dgrad_ws", (need,), torch.uint8)
                     scratch = ws.dgrad_ws if need else None
                     self._lift_sm_limit()
                     self._timed("dgrad", layer.name, lambda: self.lib.sl_conv1d_dgrad(

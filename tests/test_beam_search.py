@@ -144,19 +144,26 @@ def _random_case(rng, B, T, V, peaky):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("tf_exact", [True, False])
 @pytest.mark.parametrize("B,T,V,beam_width,top_paths,merge,peaky", [
     (1, 5, 2, 1, 1, True, 1.0),
     (3, 40, 5, 1, 1, False, 2.0),
     (4, 60, 6, 4, 3, False, 2.0),      # narrow beam: prefixes drop out and come back
     (4, 60, 6, 4, 3, True, 3.0),
+    (6, 80, 5, 2, 2, False, 1.5),      # beam of two, flat distributions: TF's "deactivate child" rule matters
+    (6, 80, 5, 3, 3, False, 1.0),
     (3, 120, 29, 16, 4, False, 3.0),
     (2, 200, 29, 100, 8, False, 4.0),  # TF's default width, the English alphabet
     (2, 90, 33, 100, 2, False, 4.0),   # German alphabet
 ])
-def test_cuda_beam_search_matches_the_oracle(B, T, V, beam_width, top_paths, merge, peaky):
+def test_cuda_beam_search_matches_the_oracle(monkeypatch, B, T, V, beam_width, top_paths, merge, peaky, tf_exact):
+    """tf_exact (the default): TensorFlow's sequential child loop with its order-dependent "deactivate child"
+    side effect, against the oracle's literal restatement of ctc_beam_search.h; otherwise
+    (SL_BEAM_ORDER_INDEPENDENT=1) the parallel "W best of the union" rule against the oracle's same rule."""
     import torch
     from speechless_b200 import _lib
     lib = _lib.load()
+    monkeypatch.setenv("SL_BEAM_ORDER_INDEPENDENT", "0" if tf_exact else "1")
     rng = np.random.default_rng(B * 1000 + T + V + beam_width)
     probabilities, lengths = _random_case(rng, B, T, V, peaky)
     if T == 5:  # the reference's own vector
@@ -176,9 +183,8 @@ def test_cuda_beam_search_matches_the_oracle(B, T, V, beam_width, top_paths, mer
     out, out_len, out_logp = out.cpu().numpy(), out_len.cpu().numpy(), out_logp.cpu().numpy()
     for b in range(B):
         scores = np.log(probabilities[b, :lengths[b]].astype(np.float64) + 1e-8)  # net.py:430
-        # (the kernel implements the order-independent selection rule: see `tf_deactivation` in the oracle)
         want = bso.beam_search_decode(scores, beam_width=beam_width, top_paths=top_paths, merge_repeated=merge,
-                                      tf_deactivation=False)
+                                      tf_deactivation=tf_exact)
         for path, (labels, log_probability) in enumerate(want):
             got = out[b, path, :out_len[b, path]].tolist()
             # fp32 on the device vs fp64 in the oracle: hypotheses closer than 1e-3 nats may swap ranks
