@@ -218,7 +218,7 @@ __global__ void ctc_alpha_beta_kernel(const float* __restrict__ logp,
 // kernel (see ctc_grad_sorted_kernel) while the compute warps walk the lattice.
 constexpr float NEG = -1e30f;
 constexpr int FLAG_STRIDE = 32;  // ints: every progress flag has a 128-byte line of its own
-constexpr int ROLE_COUNTERS = 32 + 256;  // ints behind the flags: role counters of the fused launch (+ one per SM)
+constexpr int ROLE_COUNTERS = 96 + 256;  // ints behind the flags: role counters of the fused launch (+ one per SM)
 
 // progress flags between the lattice walkers and the gradient CTAs of one launch
 __device__ __forceinline__ void st_release_cta_shared(int* p, int v) {
@@ -298,7 +298,7 @@ __device__ __forceinline__ void halo_walk(const float* lp_s, float* col, int col
                                           int ls0, int lane, int tid, int nthreads, const float (&skipb)[SPT],
                                           const float (&onb)[SPT], const float* const (&em_ptr)[SPT], float* out,
                                           ptrdiff_t out_step, unsigned st_mask, int push_rank, int own_per_cta,
-                                          int* smem_progress, int dbg = 0) {
+                                          int* smem_progress) {
   constexpr int HALO = 2 * K;
   const bool owner = lane * SPT >= HALO;
   const bool pusher = CL && push_rank >= 0 && lane * SPT >= 32 * SPT - HALO;
@@ -372,12 +372,7 @@ __device__ __forceinline__ void halo_walk(const float* lp_s, float* col, int col
     if ((t0 & (CHUNK - 1)) == 0) cp_async_wait<0>();  // the chunk issued one chunk ago has long landed
     barrier();  // owned states of block kb-1 published; chunk visible; ring slot free
     // every lattice row of the steps < t0 has been stored by its thread: tell the publisher warp
-    if (!CL && smem_progress != nullptr && tid == 0 && t0 > 0) {
-      if (dbg == 6)
-        *reinterpret_cast<volatile int*>(smem_progress) = t0;
-      else
-        st_release_cta_shared(smem_progress, t0);
-    }
+    if (!CL && smem_progress != nullptr && tid == 0 && t0 > 0) st_release_cta_shared(smem_progress, t0);
     if ((t0 & (CHUNK - 1)) == 0 && t0 > 0) issue_chunk(t0 / CHUNK + 1);
     const float* pc = col + ((kb + 1) & 1) * col_stride + HALO + ls0;
 #pragma unroll
@@ -481,7 +476,6 @@ __device__ __forceinline__ void lattice_cta_body(uint8_t* smem_raw, int unit, co
     }
     // ... and publisher of the walk's progress (the sorted labels above are covered by the first fence)
     auto publish = [&](int done) {
-      if (dbg == 5) return;  // measurement aid: poll only
       __threadfence();
       if (lane == 0) st_relaxed_gpu(progress + unit * FLAG_STRIDE, done);
     };
@@ -543,11 +537,11 @@ __device__ __forceinline__ void lattice_cta_body(uint8_t* smem_raw, int unit, co
   const int push_rank = (CL && crank + 1 < csize && warp == (nthreads >> 5) - 1) ? crank + 1 : -1;
   if (dir == 0)
     halo_walk<SPT, K, 0, CL>(lp_s, col, col_stride, lp_b, P, ls0, lane, tid, nthreads, skipb, onb, em_ptr, lat + s0,
-                             static_cast<ptrdiff_t>(S_stride), st_mask, push_rank, own_per_cta, smem_progress, dbg);
+                             static_cast<ptrdiff_t>(S_stride), st_mask, push_rank, own_per_cta, smem_progress);
   else
     halo_walk<SPT, K, 1, CL>(lp_s, col, col_stride, lp_b, P, ls0, lane, tid, nthreads, skipb, onb, em_ptr,
                              lat + static_cast<size_t>(P > 0 ? P - 1 : 0) * S_stride + (S - 1 - s0),
-                             -static_cast<ptrdiff_t>(S_stride), st_mask, push_rank, own_per_cta, smem_progress, dbg);
+                             -static_cast<ptrdiff_t>(S_stride), st_mask, push_rank, own_per_cta, smem_progress);
 
   // the CTA owning the last state reports the loss (state S-2 is its own or sits in its halo)
   if (tid == 0 && (S - 1) / own_per_cta == crank) {
@@ -1310,9 +1304,9 @@ __global__ void __launch_bounds__(1024)
   // (measured: the same walkers inside a 592-CTA grid took 82 us instead of 65 when roles went by block index,
   // because the block scheduler does not spread consecutive CTAs one per SM once several fit).  So a CTA
   // becomes a walker if it is among the first `walkers_per_sm` CTAs to arrive on ITS SM (%smid) and walk
-  // units are left; everything else computes gradients.  Every unit is claimed whatever the placement: a CTA
-  // must claim once the unclaimed units are as many as the CTAs still to arrive (itself included).  The
-  // counters sit behind the progress flags and are zeroed with them.  Clusters keep roles by block index.
+  // units are left; everything else computes gradients.  Every unit is claimed whatever the placement: the last
+  // n_walk CTAs to arrive also try to claim.  The counters sit behind the progress flags and are zeroed with
+  // them.  Clusters keep roles by block index.
   int walk_unit = -1, g = 0;
   if constexpr (CL) {
     if (static_cast<int>(blockIdx.x) < n_walk)
@@ -1322,29 +1316,25 @@ __global__ void __launch_bounds__(1024)
   } else {
     __shared__ int role_s[2];
     if (threadIdx.x == 0) {
-      int* counters = progress + 2 * B * FLAG_STRIDE;  // [0,1]: arrived | claimed << 32, [2]: gradient CTAs, [32..]: per SM
+      // counters behind the flags, one 128-byte line each (atomics on one line serialise in its L2 slice):
+      // [0] walk units claimed, [32] gradient CTAs, [64] CTAs arrived, [96 + smid] CTAs arrived on that SM
+      // (plain fetch-and-adds: a compare-and-swap loop of 600 CTAs on one word took longer than the walk)
+      int* counters = progress + 2 * B * FLAG_STRIDE;
       unsigned smid;
       asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-      const int slot = atomicAdd(counters + 32 + static_cast<int>(smid & 255u), 1);
-      const bool prefer = slot < walkers_per_sm;
-      unsigned long long* packed_counter = reinterpret_cast<unsigned long long*>(counters);
-      unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(packed_counter);
+      const int slot = atomicAdd(counters + 96 + static_cast<int>(smid & 255u), 1);
+      const int ticket = atomicAdd(counters + 64, 1);
+      // claim a walk unit if this CTA is among the first on its SM — or among the last n_walk CTAs to ARRIVE,
+      // which mop up whatever an unexpected placement has left unclaimed (each of them tries exactly once, so
+      // every unit finds a walker whatever the hardware does; going by block index instead of arrival made
+      // the high-index CTAs, which start at the same time as everybody else, double up on SMs)
       int unit = -1;
-      for (;;) {
-        const int arrived = static_cast<int>(old & 0xffffffffull), claimed = static_cast<int>(old >> 32);
-        const int unclaimed = n_walk - claimed, remaining = static_cast<int>(gridDim.x) - arrived;
-        const bool claim = unclaimed > 0 && (prefer || unclaimed >= remaining);
-        const unsigned long long want = static_cast<unsigned long long>(arrived + 1) |
-                                        (static_cast<unsigned long long>(claimed + (claim ? 1 : 0)) << 32);
-        const unsigned long long seen = atomicCAS(packed_counter, old, want);
-        if (seen == old) {
-          unit = claim ? claimed : -1;
-          break;
-        }
-        old = seen;
+      if (slot < walkers_per_sm || ticket >= static_cast<int>(gridDim.x) - n_walk) {
+        const int u = atomicAdd(counters, 1);
+        if (u < n_walk) unit = u;
       }
       role_s[0] = unit;
-      role_s[1] = unit < 0 ? atomicAdd(counters + 2, 1) : 0;
+      role_s[1] = unit < 0 ? atomicAdd(counters + 32, 1) : 0;
     }
     __syncthreads();
     walk_unit = role_s[0];
@@ -1533,12 +1523,17 @@ int ctc_loss_launch(const float* logp, const float* probs, const int32_t* labels
     }
     SL_REQUIRE(nw <= 31, "SL_CTC_SPT too small for this label length");
     const int col_stride = ((nw * own + 2 * kk) + 3) & ~3;
-    const size_t smem = (2 * CHUNK * VP + 2 * col_stride + VP + 8) * sizeof(float);
+    size_t smem = (2 * CHUNK * VP + 2 * col_stride + VP + 8) * sizeof(float);
+    if (const char* e = std::getenv("SL_CTC_EXTRA_SMEM")) smem += static_cast<size_t>(std::atoi(e));  // measurement aid
     bool launched = false;
-    // Fused launch (default when a gradient is wanted): gradient CTAs ride along with the walkers
-    // (ctc_fused_kernel).  SL_CTC_FUSED=0 selects the two-launch path; SL_CTC_GRAD_CTAS bounds their number.
+    // Fused launch (opt-in, SL_CTC_FUSED=1): gradient CTAs ride along with the walkers (ctc_fused_kernel);
+    // SL_CTC_GRAD_CTAS bounds their number.  Measured on B200 at the bench shape (B = 64, 626 frames, S = 301):
+    // the gradient phase does hide under the second half of the walks (8 us left over instead of 42), but the
+    // same walkers run 15-20 % slower inside the big co-resident grid (65 -> 79 us with every gradient CTA
+    // exiting at once), so the launch pair and the fused launch both come to 0.107 ms; with clusters (long-form
+    // shapes) the fused launch is slower (0.93 vs 0.65 ms).  Hence two launches by default.
     const char* fused_env = std::getenv("SL_CTC_FUSED");
-    if (want_grad && !(fused_env && std::atoi(fused_env) == 0)) {
+    if (want_grad && fused_env && std::atoi(fused_env) != 0) {
       const int threads = (nw + 1) * 32;
       const int nwarps = nw + 1;
       const int L_pad = (L_max + 31) & ~31;

@@ -203,8 +203,9 @@ def test_ctc_tensorflow_known_answers_on_gpu(env):
 
 @pytest.mark.parametrize("fused", [1, 0])
 def test_ctc_loss_and_gradient_parity_ragged(env, monkeypatch, fused):
-    """fused = 1: gradient CTAs ride along with the lattice walkers in one launch (progress flags, every frame
-    normalised by its own likelihood); fused = 0: lattice launch, then gradient launch normalised by the loss."""
+    """fused = 1 (opt-in): gradient CTAs ride along with the lattice walkers in one launch (progress flags, every
+    frame normalised by its own likelihood); fused = 0 (default): lattice launch, then gradient launch
+    normalised by the loss."""
     monkeypatch.setenv("SL_CTC_FUSED", str(fused))
     rng = np.random.default_rng(17)
     B, T, V = 7, 313, 29
