@@ -408,8 +408,10 @@ def dp_equivalence(dp, device):
                                label_length=20) for s in range(2)]
     kwargs = dict(main_filter_count=128, out_filter_count=256, seed=3, device=device, compute_dtype="bf16x2")
     single = Wav2Letter(128, alphabet, **kwargs)
+    single.tower.retain_gradients = True  # (the step otherwise clears each gradient bucket after its update)
     single_losses = [single.train_on_batch(single._inputs_for_loss_net(b)[0]) for b in batches]
     net = Wav2Letter(128, alphabet, **kwargs)
+    net.tower.retain_gradients = True
     losses = []
     for b in batches:
         longest = max(e.z_normalized_transposed_spectrogram().shape[0] for e in b)

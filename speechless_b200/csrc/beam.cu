@@ -112,71 +112,68 @@ __device__ __forceinline__ int block_sum(BeamSmem& sm, int c, int& it) {
 // sm.selected in the format of the parallel selection.  All threads call it (barriers inside).
 __device__ __noinline__ int tf_exact_child_loop(BeamSmem& sm, const BeamGen& g, int n, int V, int blank, int W) {
   const int tid = threadIdx.x, lane = tid & 31;
+  uint32_t* leaf_key = reinterpret_cast<uint32_t*>(sm.leaf_score);  // order-preserving integer image of the score
   if (tid < n) {
-    sm.leaf_score[tid] = sm.totn[tid];
+    leaf_key[tid] = float_to_ordered(sm.totn[tid]);
     sm.leaf_idx[tid] = tid * V + blank;
   }
   __syncthreads();
   if (tid < 32) {
     int count = n;  // (continued prefixes of probability zero stay, as in TF, and are dropped at the end)
-    float bottom = INFINITY;
+    // bottom of the leaves: lane l caches the minimum of its own slots l, l + 32, ...; an insertion only
+    // touches the owner lane's cache, the warp minimum is one redux + ballot
+    uint32_t my_min = 0xffffffffu;
+    int my_pos = -1;
+    auto rescan = [&]() {
+      my_min = 0xffffffffu;
+      my_pos = -1;
+      for (int k = lane; k < count; k += 32) {
+        const uint32_t v = leaf_key[k];
+        if (v <= my_min) {
+          my_min = v;
+          my_pos = k;
+        }
+      }
+    };
+    uint32_t bottom = 0u;
     int bottom_pos = -1;
     auto find_bottom = [&]() {
-      float m = INFINITY;
-      int pos = -1;
-      for (int k = lane; k < count; k += 32) {
-        const float v = sm.leaf_score[k];
-        if (v < m || pos < 0) {
-          m = v;
-          pos = k;
-        }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float om = __shfl_xor_sync(0xffffffffu, m, o);
-        const int op = __shfl_xor_sync(0xffffffffu, pos, o);
-        if (op >= 0 && (pos < 0 || om < m || (om == m && op > pos))) {
-          m = om;
-          pos = op;
-        }
-      }
-      bottom = m;
-      bottom_pos = pos;
+      bottom = __reduce_min_sync(0xffffffffu, my_min);
+      const unsigned who = __ballot_sync(0xffffffffu, my_min == bottom && my_pos >= 0);
+      const int owner = 31 - __clz(who);
+      bottom_pos = __shfl_sync(0xffffffffu, my_pos, owner);
     };
+    rescan();
     find_bottom();
     for (int i = 0; i < n; ++i) {
       const float old_total = g.tot[i];
       // is_candidate(b.old): not wiped, finite, and (beam not full or better than the bottom)
-      if (sm.wiped[i] || !(old_total > -INFINITY) || !(count < W || old_total > bottom)) continue;
+      if (sm.wiped[i] || !(old_total > -INFINITY) || !(count < W || float_to_ordered(old_total) > bottom)) continue;
       const int lab_i = g.label[i];
       const unsigned long long in_beam = sm.child_active[i];
       // per lane: labels lane and lane + 32
-      float sc[2];
-      unsigned visit[2];
+      uint32_t sc[2];
+      unsigned beam_children[2], todo[2];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int c = lane + 32 * h;
-        sc[h] = -INFINITY;
-        bool v = false;
-        if (c < V && c != blank) {
-          sc[h] = sm.lp[c] + (c == lab_i ? g.pb[i] : g.tot[i]);
-          const bool beam_child = (in_beam >> c) & 1ull;
-          // worth a visit: a new candidate that may beat the bottom, or a beam entry that may have been displaced
-          v = beam_child || (sc[h] > -INFINITY && (count < W || sc[h] > bottom));
-        }
-        visit[h] = __ballot_sync(0xffffffffu, v);
+        sc[h] = 0u;
+        if (c < V && c != blank) sc[h] = float_to_ordered(sm.lp[c] + (c == lab_i ? g.pb[i] : g.tot[i]));
+        beam_children[h] = static_cast<unsigned>(in_beam >> (32 * h));
+        // worth a visit: a candidate that beats the bottom (which only rises), or a beam entry — it may have
+        // been displaced by now
+        todo[h] = __ballot_sync(0xffffffffu, sc[h] > ORD_NEG_INF && (count < W || sc[h] > bottom)) | beam_children[h];
       }
       for (int h = 0; h < 2; ++h) {
-        unsigned todo = visit[h];
-        while (todo) {
-          const int l = __ffs(todo) - 1;
-          todo &= todo - 1;
+        while (todo[h]) {
+          const int l = __ffs(todo[h]) - 1;
+          todo[h] &= todo[h] - 1;
           const int c = l + 32 * h;
-          const float score = __shfl_sync(0xffffffffu, sc[h], l);
-          const bool beam_child = (in_beam >> c) & 1ull;
+          const uint32_t score = __shfl_sync(0xffffffffu, sc[h], l);
+          const bool beam_child = (beam_children[h] >> l) & 1u;
           const int j = beam_child ? sm.child_slot[i][c] : -1;
           if (beam_child && !sm.displaced[j]) continue;  // active: already among the leaves
-          const bool candidate = score > -INFINITY && (count < W || score > bottom);
+          const bool candidate = score > ORD_NEG_INF && (count < W || score > bottom);
           if (!candidate) {
             if (beam_child && lane == 0) sm.wiped[j] = 1;  // "deactivate child"
             __syncwarp();
@@ -193,12 +190,19 @@ __device__ __noinline__ int tf_exact_child_loop(BeamSmem& sm, const BeamGen& g, 
           }
           __syncwarp();
           if (lane == 0) {
-            sm.leaf_score[pos] = score;
+            leaf_key[pos] = score;
             sm.leaf_idx[pos] = i * V + c;
             if (beam_child) sm.displaced[j] = 0;  // it is back among the leaves (as a fresh entry)
           }
           __syncwarp();
+          if ((pos & 31) == lane) rescan();
           find_bottom();
+          if (count == W) {
+            // the bottom has risen: drop the candidates of this entry that can no longer beat it
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh)
+              todo[hh] &= __ballot_sync(0xffffffffu, sc[hh] > bottom) | beam_children[hh];
+          }
         }
       }
     }
@@ -206,11 +210,11 @@ __device__ __noinline__ int tf_exact_child_loop(BeamSmem& sm, const BeamGen& g, 
     int kept = 0;
     for (int k0 = 0; k0 < count; k0 += 32) {
       const int k = k0 + lane;
-      const bool ok = k < count && sm.leaf_score[k] > -INFINITY;
+      const bool ok = k < count && leaf_key[k] > ORD_NEG_INF;
       const unsigned m = __ballot_sync(0xffffffffu, ok);
       if (ok) {
         const int at = kept + __popc(m & ((1u << lane) - 1));
-        sm.selected[at] = (static_cast<unsigned long long>(float_to_ordered(sm.leaf_score[k])) << 32) |
+        sm.selected[at] = (static_cast<unsigned long long>(leaf_key[k]) << 32) |
                           static_cast<unsigned long long>(0xffffffffu - static_cast<uint32_t>(sm.leaf_idx[k]));
       }
       kept += __popc(m);

@@ -291,6 +291,11 @@ class ConvTower:
         self._side_stream = None
         self._update_stream = None
         self._sm_limit_until = 0  # launch count at which sl_set_sm_limit is lifted again
+        # The weight-gradient kernels accumulate into `grads` (TMA reduce-add), so the buffer must be zero when
+        # backward starts.  `backward_and_update` zeroes each bucket on the update stream right after its Adam
+        # step — off the critical path — unless `retain_gradients` asks for the gradients to stay readable.
+        self.retain_gradients = False
+        self._grads_clean = False
         # bucketed all-reduce + Adam on an update stream, overlapped with backward (backward_and_update)
         self.pipeline_update = os.environ.get("SL_PIPELINE_UPDATE", "1") != "0"
         self.sm_count = torch.cuda.get_device_properties(device).multi_processor_count
@@ -679,7 +684,9 @@ class ConvTower:
                 if self._side_stream is None:
                     self._side_stream = torch.cuda.Stream(device=self.device)
                 side = self._side_stream
-            self.grads.zero_()
+            if not self._grads_clean:
+                self.grads.zero_()
+            self._grads_clean = False
             dy = ws.dz_packed
             flip = 0
             wgrad_done = None  # event: the wgrad that still reads the buffer the next dgrad overwrites
@@ -805,6 +812,7 @@ class ConvTower:
                     dp.allreduce_scalar(loss_sum)
                 for _, begin, end in self.grad_buckets():
                     self.adam_step_range(begin, end, *hyper)
+                self._clear_gradients(main)
                 return loss_sum
             if self._update_stream is None:
                 self._update_stream = torch.cuda.Stream(device=self.device)
@@ -823,6 +831,7 @@ class ConvTower:
             def consumed(begin, end):
                 update.wait_event(main.record_event())
                 self.adam_step_range(begin, end, *hyper, stream=update.cuda_stream)
+                self._clear_gradients(update, begin, end)
 
             try:
                 self.backward(ws, on_bucket_ready=ready, on_bucket_consumed=consumed)
@@ -831,7 +840,17 @@ class ConvTower:
             if dp:
                 dp.allreduce_scalar(loss_sum, stream=update, after=main)
             main.wait_stream(update)
+            self._grads_clean = not self.retain_gradients and self.first_trainable() == 0
         return loss_sum
+
+    def _clear_gradients(self, stream, begin: int = 0, end: Optional[int] = None) -> None:
+        """Zero grads[begin:end] on `stream` once the optimizer has consumed them (see `retain_gradients`)."""
+        if self.retain_gradients:
+            return
+        with torch.cuda.stream(stream):
+            self.grads[begin:end].zero_()
+        if end is None:
+            self._grads_clean = self.first_trainable() == 0
 
     def _lift_sm_limit(self, force: bool = False) -> None:
         """Back to full-width persistent grids once the launches that overlap an all-reduce are out."""

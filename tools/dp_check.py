@@ -48,6 +48,7 @@ def main():
 
     # --- single GPU on the full batches (every rank computes it; compare on each)
     single = Wav2Letter(128, alphabet, **kwargs)
+    single.tower.retain_gradients = True
     single_losses = [single.train_on_batch(single._inputs_for_loss_net(batch)[0]) for batch in batches]
     grads_single = single.tower.grads.clone()
     params_single = single.tower.params.clone()
@@ -57,6 +58,7 @@ def main():
     ok = True
     for arm in ("hook", "pipelined"):
         net = Wav2Letter(128, alphabet, **kwargs)
+        net.tower.retain_gradients = True  # (the pipelined step otherwise clears each bucket after its update)
         losses = []
         for batch in batches:
             inputs = shard_inputs(net, batch)

@@ -7,9 +7,9 @@ B="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-twins --no-config
 timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 1500 \
   --csv --log-file gpurun_out/r02_launches.csv $B > gpurun_out/r02_launches.log 2>&1
 # one --set full capture of the top kernels (fp16 step): big_conv_1 forward / input gradient / weight gradient
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'wgrad_kernel' -s 44 -c 1 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'wgrad_kernel' -s 57 -c 1 \
   -o gpurun_out/r02_wgrad_big1 $B > gpurun_out/r02_ncu_wgrad.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'conv_gemm_kernel' -s 120 -c 12 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'conv_gemm_kernel' -s 105 -c 21 \
   -o gpurun_out/r02_conv_gemm $B > gpurun_out/r02_ncu_conv.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'ctc_' -c 3 -o gpurun_out/r02_ctc_bench \
   tools/selftest ctc_bench > gpurun_out/r02_ncu_ctc.log 2>&1
