@@ -75,8 +75,8 @@ struct BeamSmem {
   int n_selected;
   int n_active;
   // TF-exact mode (sequential child loop of TensorFlow's CTCBeamSearchDecoder::Step, run by warp 0)
-  float leaf_score[BS_MAX_W];            // the `leaves_` TopN of the frame being built
-  int leaf_idx[BS_MAX_W];                // candidate index slot * V + symbol (symbol == blank: prefix `slot` continued)
+  int leaf_idx[BS_MAX_W];                // `leaves_` of the frame being built: candidate index slot * V + symbol
+                                         // (symbol == blank: prefix `slot` continued); the scores sit in registers
   unsigned char child_slot[BS_MAX_W][BS_VP];  // slot of the beam entry that is child (slot, symbol), valid where child_active
   unsigned char displaced[BS_MAX_W];     // beam entry popped from `leaves_` during this frame's child loop
   unsigned char wiped[BS_MAX_W];         // ... and then "deactivated" through its parent: it proposes no children
@@ -112,43 +112,40 @@ __device__ __forceinline__ int block_sum(BeamSmem& sm, int c, int& it) {
 // sm.selected in the format of the parallel selection.  All threads call it (barriers inside).
 __device__ __noinline__ int tf_exact_child_loop(BeamSmem& sm, const BeamGen& g, int n, int V, int blank, int W) {
   const int tid = threadIdx.x, lane = tid & 31;
-  uint32_t* leaf_key = reinterpret_cast<uint32_t*>(sm.leaf_score);  // order-preserving integer image of the score
-  if (tid < n) {
-    leaf_key[tid] = float_to_ordered(sm.totn[tid]);
-    sm.leaf_idx[tid] = tid * V + blank;
-  }
+  if (tid < n) sm.leaf_idx[tid] = tid * V + blank;
   __syncthreads();
   if (tid < 32) {
+    // The leaves: slot k = lane + 32 r lives in register key[r] of its lane as the order-preserving integer
+    // image of the score (an empty slot holds the largest key, so it is never the bottom); the candidate
+    // index of a slot sits in shared memory.  Bottom = one min per lane, one redux, one ballot.
+    constexpr int R = BS_MAX_W / 32;
+    uint32_t key[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) key[r] = lane + 32 * r < n ? float_to_ordered(sm.totn[lane + 32 * r]) : 0xffffffffu;
     int count = n;  // (continued prefixes of probability zero stay, as in TF, and are dropped at the end)
-    // bottom of the leaves: lane l caches the minimum of its own slots l, l + 32, ...; an insertion only
-    // touches the owner lane's cache, the warp minimum is one redux + ballot
-    uint32_t my_min = 0xffffffffu;
-    int my_pos = -1;
-    auto rescan = [&]() {
-      my_min = 0xffffffffu;
-      my_pos = -1;
-      for (int k = lane; k < count; k += 32) {
-        const uint32_t v = leaf_key[k];
-        if (v <= my_min) {
-          my_min = v;
-          my_pos = k;
-        }
-      }
-    };
     uint32_t bottom = 0u;
     int bottom_pos = -1;
     auto find_bottom = [&]() {
+      uint32_t my_min = key[0];
+      int my_pos = lane;
+#pragma unroll
+      for (int r = 1; r < R; ++r)
+        if (key[r] <= my_min && lane + 32 * r < count) {
+          my_min = key[r];
+          my_pos = lane + 32 * r;
+        }
       bottom = __reduce_min_sync(0xffffffffu, my_min);
-      const unsigned who = __ballot_sync(0xffffffffu, my_min == bottom && my_pos >= 0);
-      const int owner = 31 - __clz(who);
-      bottom_pos = __shfl_sync(0xffffffffu, my_pos, owner);
+      const unsigned who = __ballot_sync(0xffffffffu, my_min == bottom);
+      bottom_pos = __shfl_sync(0xffffffffu, my_pos, 31 - __clz(who));
     };
-    rescan();
     find_bottom();
     for (int i = 0; i < n; ++i) {
       const float old_total = g.tot[i];
-      // is_candidate(b.old): not wiped, finite, and (beam not full or better than the bottom)
-      if (sm.wiped[i] || !(old_total > -INFINITY) || !(count < W || float_to_ordered(old_total) > bottom)) continue;
+      // is_candidate(b.old): not wiped, finite, and (beam not full or better than the bottom).  The entries come
+      // in order of decreasing previous total and the bottom only rises: once a full beam's bottom has caught up
+      // with an entry's previous total, no later entry can propose anything either.
+      if (count == W && !(float_to_ordered(old_total) > bottom)) break;
+      if (sm.wiped[i] || !(old_total > -INFINITY)) continue;
       const int lab_i = g.label[i];
       const unsigned long long in_beam = sm.child_active[i];
       // per lane: labels lane and lane + 32
@@ -189,13 +186,14 @@ __device__ __noinline__ int tf_exact_child_loop(BeamSmem& sm, const BeamGen& g, 
             ++count;
           }
           __syncwarp();
-          if (lane == 0) {
-            leaf_key[pos] = score;
+          if (lane == (pos & 31)) {
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+              if (r == (pos >> 5)) key[r] = score;
             sm.leaf_idx[pos] = i * V + c;
-            if (beam_child) sm.displaced[j] = 0;  // it is back among the leaves (as a fresh entry)
           }
+          if (beam_child && lane == 0) sm.displaced[j] = 0;  // it is back among the leaves (as a fresh entry)
           __syncwarp();
-          if ((pos & 31) == lane) rescan();
           find_bottom();
           if (count == W) {
             // the bottom has risen: drop the candidates of this entry that can no longer beat it
@@ -208,13 +206,14 @@ __device__ __noinline__ int tf_exact_child_loop(BeamSmem& sm, const BeamGen& g, 
     }
     // keys of the surviving finite leaves, in the format of the parallel selection
     int kept = 0;
-    for (int k0 = 0; k0 < count; k0 += 32) {
-      const int k = k0 + lane;
-      const bool ok = k < count && leaf_key[k] > ORD_NEG_INF;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int k = lane + 32 * r;
+      const bool ok = k < count && key[r] > ORD_NEG_INF;
       const unsigned m = __ballot_sync(0xffffffffu, ok);
       if (ok) {
         const int at = kept + __popc(m & ((1u << lane) - 1));
-        sm.selected[at] = (static_cast<unsigned long long>(leaf_key[k]) << 32) |
+        sm.selected[at] = (static_cast<unsigned long long>(key[r]) << 32) |
                           static_cast<unsigned long long>(0xffffffffu - static_cast<uint32_t>(sm.leaf_idx[k]));
       }
       kept += __popc(m);
