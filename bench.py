@@ -339,6 +339,40 @@ def ctc_algorithmic_bytes(frames, examples, V=29):
                for f, e in zip(frames, examples))
 
 
+def varying_shapes_run(arm, steps, distinct=4):
+    """Real corpora give every batch its own longest utterance: the public pipelined training call
+    (`Wav2Letter.fit_batches`, host inputs) over `distinct` ragged batches of different padded lengths in turn —
+    each step re-binds the per-shape workspace views of the tower's arena (no allocation after the first round)."""
+    import torch
+    from speechless_b200.synthetic import synthetic_batch
+    net, dp = arm.net, arm.dp
+    batches = []
+    for k in range(distinct):
+        frames = workload_frames(arm.workload, arm.batch, 1000 * (k + 1) + dp.rank)
+        examples = synthetic_batch(arm.batch, frames, arm.alphabet, seed=77 + k + 10 * dp.rank)
+        inputs, _ = net._inputs_for_loss_net(examples)
+        inputs[arm.names.input_batch] = torch.from_numpy(inputs[arm.names.input_batch]).pin_memory()
+        batches.append((inputs, sum(frames), max(frames)))
+
+    def run(n):
+        return net.fit_batches((batches[i % distinct][0] for i in range(n)), global_batch_size=arm.global_batch,
+                               data_parallel=dp if dp.active else None)
+    run(2 * distinct)  # first round allocates
+    torch.cuda.synchronize()
+    dp.barrier()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    start.record()
+    run(steps)
+    stop.record()
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) * 1e3
+    ms = dp.max_over_ranks(max(start.elapsed_time(stop), wall)) / steps
+    valid = sum(batches[i % distinct][1] for i in range(steps)) / steps * dp.world_size
+    return {"ms_per_step": round(ms, 4), "value": valid / (ms * 1e-3), "unit": "frames/s (valid frames, end to end)",
+            "distinct_shapes": distinct, "padded_lengths": [b[2] for b in batches], "steps": steps}
+
+
 def precision_record(dtype, device):
     """Measured error of `dtype` against the fp64 oracle on a small reference-width case (250/2000 filters,
     2 ragged utterances): logits, CTC loss, and the gradient of every kernel/bias — raw, and given the ReLU
@@ -554,7 +588,9 @@ def run_ours(args):
             _, conv = sub.conv_summary(sub_kernels, peaks)
             ctc_ms = per_kernel_ctc(sub_kernels)
             ctc_bytes = ctc_algorithmic_bytes(sub.frames, sub.examples)
+            varying = varying_shapes_run(sub, sub_steps) if name == "ragged" else None
             configs.append({"config": config_record(name, sub_batch, world, sub.frames, len(sub.examples[0].label)),
+                            "varying_shapes": varying,
                             "dtype": sub.dtype, "ms_per_step": round(sub_ms, 4),
                             "value": sub.frames_per_step / (sub_ms * 1e-3),
                             "value_padded_frames": sub.padded_frames_per_step / (sub_ms * 1e-3), "unit": "frames/s",

@@ -10,7 +10,7 @@ Two layers:
   * `torch.distributed` is the plumbing: rendezvous, barriers, scalar max over ranks, and the
     side channel that hands rank 0's communicator id to the other ranks.
   * The data plane is the library's own communicator (`sl_comm_init_rank` / `sl_allreduce_sum`,
-    include/speechless_b200.h): NCCL created with a bounded CTA count (`max_ctas`, default 8), because
+    include/speechless_b200.h): NCCL created with a bounded CTA count (`max_ctas`, default 16), because
     the collective runs next to persistent one-CTA-per-SM tensor-core kernels.  Without CUDA (the
     world-size-2 gloo tests) the all-reduce goes through `torch.distributed` instead.
 """
@@ -42,7 +42,7 @@ class DataParallel:
         self.bucket_bytes = bucket_bytes
         # CTAs the all-reduce kernels may occupy, and how many of the backward launches following the
         # start of a bucket's all-reduce run on 148 - max_ctas CTAs (ConvTower.backward_and_update)
-        self.max_ctas = int(os.environ.get("SL_COMM_MAX_CTAS", "8")) if max_ctas is None else max_ctas
+        self.max_ctas = int(os.environ.get("SL_COMM_MAX_CTAS", "16")) if max_ctas is None else max_ctas
         self.limited_launches = int(os.environ.get("SL_COMM_LIMITED_LAUNCHES", "2")) \
             if limited_launches is None else limited_launches
         self._pending = []
