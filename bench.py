@@ -275,8 +275,12 @@ class Arm:
         self.padded_frames_per_step = self.global_batch * max(self.frames)
 
     def device_step(self):
-        tower, net, ws = self.tower, self.net, self.ws
-        tower.upload(ws.x_f32)  # re-pack from the HBM-resident fp32 batch
+        tower, net = self.tower, self.net
+        ws = tower.upload(self.ws.x_f32)  # re-pack from the HBM-resident fp32 batch
+        if ws is not self.ws:  # (the tower's arena grew under another shape: fresh views of the same buffers)
+            tower.set_labels(ws, self.inputs[self.names.label_batch], self.inputs[self.names.prediction_lengths],
+                             self.inputs[self.names.label_lengths])
+            self.ws = ws
         tower.forward(ws)
         loss = tower.ctc(ws, want_grad=True, grad_scale=1.0 / self.global_batch)
         net.optimizer.iterations += 1

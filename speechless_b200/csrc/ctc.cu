@@ -1088,6 +1088,10 @@ __device__ __forceinline__ void load_sorted_labels(const GradSmem& g, const int*
 }
 
 // Two-launch path: one block per (utterance, chunk of frames), one warp per frame, after the lattice kernel.
+// STAGED: the warp's next frame's alpha / beta rows travel to shared memory with cp.async (two row buffers per
+// warp) while it works on the current frame — the kernel is bound by the latency of those rows, not by DRAM
+// bandwidth (29 % of peak with direct loads), and registers cap it at three blocks per SM.
+template <bool STAGED>
 __global__ void ctc_grad_sorted_kernel(const float* __restrict__ logp, const float* __restrict__ probs,
                                        const int32_t* __restrict__ labels,
                                        const int32_t* __restrict__ input_len,
@@ -1113,12 +1117,54 @@ __global__ void ctc_grad_sorted_kernel(const float* __restrict__ logp, const flo
   const float loss_b = loss[b];
   GradNorm nrm{false, true, isfinite(loss_b), loss_b * LOG2E};
   float* lp_row = g.per_warp + warp * g.warp_stride;
-  for (int t = t_begin + warp; t < t_end; t += nwarps) {
-    const size_t ro = static_cast<size_t>(b) * T + t;
-    FrameRows fr = {};
-    if (t < P) fr = load_frame_rows(c, b, t, lane);
-    grad_frame<4, false>(c, b, t, S, t < P, fr, reinterpret_cast<const float4*>(alpha + ro * S_stride),
-                         reinterpret_cast<const float4*>(beta + ro * S_stride), lp_row, lp_row + VP, nrm, lane);
+  if constexpr (!STAGED) {
+    for (int t = t_begin + warp; t < t_end; t += nwarps) {
+      const size_t ro = static_cast<size_t>(b) * T + t;
+      FrameRows fr = {};
+      if (t < P) fr = load_frame_rows(c, b, t, lane);
+      grad_frame<4, false>(c, b, t, S, t < P, fr, reinterpret_cast<const float4*>(alpha + ro * S_stride),
+                           reinterpret_cast<const float4*>(beta + ro * S_stride), lp_row, lp_row + VP, nrm, lane);
+    }
+  } else {
+    float* stage = g.stage + static_cast<size_t>(warp) * 4 * S_stride;
+    auto prefetch_rows = [&](int t, int buf) {
+      const float* a = alpha + (static_cast<size_t>(b) * T + t) * S_stride;
+      const float* bb = beta + (static_cast<size_t>(b) * T + t) * S_stride;
+      float* dst = stage + buf * 2 * S_stride;
+      for (int i = lane * 4; i < S; i += 128) {
+        cp_async16_cg(dst + i, a + i);
+        cp_async16_cg(dst + S_stride + i, bb + i);
+      }
+      cp_async_commit();
+    };
+    const int t_last = min(t_end, P);  // frames beyond P only get zero rows
+    int buf = 0;
+    FrameRows fr = {}, fr_next = {};
+    if (t_begin + warp < t_last && nrm.feasible) {
+      prefetch_rows(t_begin + warp, 0);
+      fr = load_frame_rows(c, b, t_begin + warp, lane);
+    }
+    for (int t = t_begin + warp; t < t_end; t += nwarps) {
+      const bool live = t < t_last && nrm.feasible;
+      if (live) {
+        if (t + nwarps < t_last) {
+          prefetch_rows(t + nwarps, buf ^ 1);
+          fr_next = load_frame_rows(c, b, t + nwarps, lane);
+          cp_async_wait<1>();
+        } else {
+          cp_async_wait<0>();
+        }
+        __syncwarp();
+      }
+      grad_frame<1, true>(c, b, t, S, t < P, fr, reinterpret_cast<const float4*>(stage + buf * 2 * S_stride),
+                          reinterpret_cast<const float4*>(stage + buf * 2 * S_stride + S_stride), lp_row, lp_row + VP, nrm,
+                          lane);
+      if (live) {
+        __syncwarp();  // every lane is done with this buffer before the prefetch two frames on refills it
+        fr = fr_next;
+        buf ^= 1;
+      }
+    }
   }
 }
 
@@ -1662,18 +1708,34 @@ int ctc_loss_launch(const float* logp, const float* probs, const int32_t* labels
   }
 
   if (want_grad && !grad_done) {
-    int frames_per_block = 32;  // 4 frames per warp (measured at the bench shape: 8 / 16 / 32 / 64 frames per block
-                                // -> 0.1022 / 0.0994 / 0.0976 / 0.0976 ms for loss + gradient)
-    if (const char* e = std::getenv("SL_CTC_GRAD_FPB")) frames_per_block = std::max(1, std::atoi(e));  // tuning aid
+    // frames per block (8 warps): measured at the bench shape, loss + gradient: direct loads 16 / 32 / 64 frames
+    // -> 0.1068 / 0.1079 / 0.1154 ms; rows staged with cp.async one frame ahead -> 0.1015 / 0.1006 / 0.0985 ms
+    int frames_per_block = 64;
+    bool fpb_given = false;
+    if (const char* e = std::getenv("SL_CTC_GRAD_FPB")) {  // tuning aid
+      frames_per_block = std::max(1, std::atoi(e));
+      fpb_given = true;
+    }
     const int warps = 8;
     dim3 grid((T + frames_per_block - 1) / frames_per_block, B);
     const int L_pad = (L_max + 31) & ~31;
     if (legacy == 0) {
-      const size_t gsmem = (L_pad + SORT_EXTRA) * sizeof(int) + static_cast<size_t>(warps) * (VP + L_pad) * sizeof(float);
-      if (gsmem > 48 * 1024)
-        SL_CUDA(cudaFuncSetAttribute(ctc_grad_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(gsmem)));
-      SL_CUDA(launch_pdl(PDL_CTC, ctc_grad_sorted_kernel, grid, dim3(warps * 32), gsmem, stream, logp, probs, labels,
+      size_t gsmem = (L_pad + SORT_EXTRA) * sizeof(int) + static_cast<size_t>(warps) * (VP + L_pad) * sizeof(float);
+      const size_t stage_bytes = static_cast<size_t>(warps) * 4 * S_stride * sizeof(float);
+      bool staged = gsmem + stage_bytes <= 64 * 1024 && frames_per_block > warps;  // (>= 2 frames per warp to overlap)
+      if (const char* e = std::getenv("SL_CTC_GRAD_STAGED")) staged = std::atoi(e) != 0 && gsmem + stage_bytes <= 200 * 1024;
+      if (staged) gsmem += stage_bytes;
+      if (!staged && !fpb_given) {  // direct loads like fewer frames per block
+        frames_per_block = 32;
+        grid = dim3((T + frames_per_block - 1) / frames_per_block, B);
+      }
+      auto grad_kernel = staged ? ctc_grad_sorted_kernel<true> : ctc_grad_sorted_kernel<false>;
+      static size_t opted_in[2] = {0, 0};  // largest dynamic shared memory size set so far, per variant
+      if (gsmem > 48 * 1024 && gsmem > opted_in[staged ? 1 : 0]) {
+        SL_CUDA(cudaFuncSetAttribute(grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(gsmem)));
+        opted_in[staged ? 1 : 0] = gsmem;
+      }
+      SL_CUDA(launch_pdl(PDL_CTC, grad_kernel, grid, dim3(warps * 32), gsmem, stream, logp, probs, labels,
                          input_len, label_len, static_cast<const float*>(loss), static_cast<const float*>(alpha),
                          static_cast<const float*>(beta), static_cast<const int*>(sort_ws),
                          reinterpret_cast<__nv_bfloat16*>(dlogits_packed), dlogits_f32, grad_scale, T, V, L_max, blank,

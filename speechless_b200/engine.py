@@ -285,6 +285,7 @@ class ConvTower:
         # optional per-kernel timing: list of (kind, layer name, start event, stop event) on the
         # launching stream; bench.py turns it on to measure roofline fractions live
         self.profile: Optional[list] = None
+        self.nvtx = os.environ.get("SL_NVTX", "0") == "1"
         self.overlap_backward = False
         self._adam_tables = None
         self._copy_stream = None
@@ -306,7 +307,15 @@ class ConvTower:
         return torch.cuda.current_stream(self.device).cuda_stream
 
     def _timed(self, kind: str, name: str, rc_fn) -> None:
-        """Run one C-ABI launch (rc_fn returns its code), bracketed by CUDA events when profiling."""
+        """Run one C-ABI launch (rc_fn returns its code), bracketed by CUDA events when profiling and by an
+        NVTX range (`kind:layer`) when SL_NVTX=1, so that a timeline shows the step's structure."""
+        if self.nvtx:
+            torch.cuda.nvtx.range_push("{}:{}".format(kind, name))
+            try:
+                check(rc_fn())
+            finally:
+                torch.cuda.nvtx.range_pop()
+            return
         if self.profile is None:
             check(rc_fn())
             return

@@ -141,3 +141,29 @@ def test_layer_table_with_raw_wave_input():
     assert same_padding(160001, 250, 160) == (1001, 124)
     plain = wav2letter_layers(128, 29)
     assert len(plain) == 11 and not any(l.windowed for l in plain)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the driver's reference arm) on a tiny sample: one JSON line on stdout with the
+    contract's keys, the same `config` record the GPU arm prints, and `e2e` / `cpu_baseline` describing this run."""
+    import json
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    out = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--workload", "small",
+                          "--batch-per-gpu", "2", "--steps", "1", "--warmup", "0"], capture_output=True, text=True,
+                         timeout=600, cwd=str(root))
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["unit"] == "frames/s" and line["higher_is_better"] is True
+    for key in ("metric", "value", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "vs_baseline", "dtype", "data",
+                "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["steps"] == 1 and line["warmup"] == 0 and line["vs_baseline"] is None
+    assert line["config"]["global_batch"] == 2 and line["config"]["frames_per_utterance"] == 1251
+    assert line["e2e"] == {"value": line["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["value"] > 0
