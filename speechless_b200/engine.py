@@ -403,8 +403,13 @@ class ConvTower:
         if ws is None or ws.stale():
             if len(self._workspaces) >= 64:  # (views only: the memory belongs to the arena)
                 self._workspaces.pop(next(iter(self._workspaces)))
+            generation = self.arena.generation
             with torch.cuda.device(self.device):
                 ws = _Workspace(self, B, T)
+            if self.arena.generation != generation:
+                # a buffer was replaced by a larger one: cached workspaces that still look at the old storage
+                # would keep it alive (a corpus whose batches keep getting longer must not pile up arenas)
+                self._workspaces = {k: w for k, w in self._workspaces.items() if not w.stale()}
             self._workspaces[key] = ws
         return ws
 

@@ -570,6 +570,38 @@ def test_fit_batches_pipeline_equals_stepwise(env):
     assert pipelined.fit_batches(iter([])) == []
 
 
+def test_changing_batch_shapes_share_one_arena(env):
+    """Real corpora give almost every batch its own (B, T): the per-shape workspaces are views of arena buffers
+    that only grow.  Training over shapes that grow, shrink and repeat must give the same losses whether the arena
+    grows step by step (views of replaced buffers are rebuilt) or was grown to the largest shape beforehand —
+    and the same as the oracle for the last batch."""
+    from speechless_b200.synthetic import synthetic_batch
+    kwargs = dict(main_filter_count=64, out_filter_count=128, seed=33, device="cuda:0")
+    shapes = [(3, 150), (2, 231), (3, 150), (4, 317), (2, 231), (3, 95)]
+    batches = [synthetic_batch(b, [t - 7 * i for i in range(b)], env.alphabet, seed=60 + n, label_length=6)
+               for n, (b, t) in enumerate(shapes)]
+    grown_step_by_step = env.Wav2Letter(128, env.alphabet, **kwargs)
+    grown_beforehand = env.Wav2Letter(128, env.alphabet, **kwargs)
+    largest = grown_beforehand._inputs_for_loss_net(batches[3])[0]
+    copy = env.Wav2Letter(128, env.alphabet, **kwargs)  # (throw-away weights: the warm-up step below moves them)
+    grown_beforehand.tower.arena = copy.tower.arena  # share an arena that has already seen the largest shape
+    copy.train_on_batch(largest)
+    generation = grown_beforehand.tower.arena.generation
+    a = [grown_step_by_step.train_on_batch(grown_step_by_step._inputs_for_loss_net(b)[0]) for b in batches]
+    b = [grown_beforehand.train_on_batch(grown_beforehand._inputs_for_loss_net(x)[0]) for x in batches]
+    assert grown_beforehand.tower.arena.generation == generation  # nothing had to grow
+    assert grown_step_by_step.tower.arena.generation > 3            # ... while this one re-allocated on the way
+    assert np.abs(np.array(a) / np.array(b) - 1).max() < 1e-5
+    assert len(grown_step_by_step.tower._workspaces) <= len(set(shapes))
+    for la, lb in zip(grown_step_by_step.predictive_net.layers, grown_beforehand.predictive_net.layers):
+        for u, v in zip(la.get_weights(), lb.get_weights()):
+            assert np.abs(u - v).max() < 7e-4  # 6 Adam steps of 1e-4 (noise-floor gradients may flip a step's sign)
+    # the pipelined loop over the same changing shapes (next batch staged while the current one computes)
+    pipelined = env.Wav2Letter(128, env.alphabet, **kwargs)
+    c = pipelined.fit_batches(pipelined._inputs_for_loss_net(x)[0] for x in batches)
+    assert np.abs(np.array(c) / np.array(a) - 1).max() < 1e-5
+
+
 def test_dropout_statistics_and_parity_given_masks(env):
     """Dropout (reference net.py:133,301-303): the masks come from a counter hash, so they cannot
     match TF's bit for bit; what must hold is (i) Bernoulli(1-p) keep statistics, (ii) inference
