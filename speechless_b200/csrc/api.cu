@@ -4,6 +4,10 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <algorithm>
+#include <cstdio>
+#include <vector>
 
 #include "conv_umma.h"
 #include "tmap.h"
@@ -53,6 +57,45 @@ static int dbg_mode() {
   return e ? std::atoi(e) : 0;
 }
 static int planes_of(int prec) { return prec_planes(prec); }
+
+// Measurement aid (env SL_TIMELINE=1, tools/selftest perf only): the conv GEMM kernels stamp clock64() at
+// their phase boundaries; after every launch the host synchronises and prints, over the CTAs, the median and
+// the maximum of each phase in SM cycles.  Never set in production (it serialises every launch).
+static long long* timeline_buffer() {
+  static long long* buf = nullptr;
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = std::getenv("SL_TIMELINE");
+    enabled = e != nullptr && std::atoi(e) != 0;
+  }
+  if (!enabled) return nullptr;
+  if (buf == nullptr && cudaMalloc(&buf, 1024 * 32 * sizeof(long long)) != cudaSuccess) return nullptr;
+  cudaMemset(buf, 0, 1024 * 32 * sizeof(long long));
+  return buf;
+}
+static void timeline_report(const char* what, const long long* dev) {
+  if (dev == nullptr) return;
+  static std::vector<long long> h(1024 * 32);
+  if (cudaDeviceSynchronize() != cudaSuccess) return;
+  cudaMemcpy(h.data(), dev, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+  struct Phase { const char* name; int from, to; };
+  const Phase phases[] = {{"entry->setup", 0, 1},      {"setup->pdl", 1, 2},         {"pdl->first operands", 2, 3},
+                          {"operands->tile0 issued", 3, 4}, {"tile0->tile1 issued", 4, 5}, {"tile1->tile2 issued", 5, 6},
+                          {"tile0 issued->complete", 4, 10}, {"tile0 epilogue", 10, 16},    {"tile1 epilogue", 11, 17},
+                          {"tile2 epilogue", 12, 18},   {"tile1 first operands after tile0 issue", 4, 26},
+                          {"last store drained->exit sync", 22, 23}, {"entry->exit", 0, 23}, {"dealloc", 23, 24}};
+  std::fprintf(stderr, "timeline %s (SM cycles: median / max over CTAs)\n", what);
+  for (const Phase& ph : phases) {
+    std::vector<long long> d;
+    for (int c = 0; c < 1024; ++c) {
+      const long long a = h[c * 32 + ph.from], b = h[c * 32 + ph.to];
+      if (a != 0 && b != 0) d.push_back(b - a);
+    }
+    if (d.empty()) continue;
+    std::sort(d.begin(), d.end());
+    std::fprintf(stderr, "  %-42s %8lld / %8lld  (%zu CTAs)\n", ph.name, d[d.size() / 2], d.back(), d.size());
+  }
+}
 static bool valid_prec(int prec) { return prec == SL_PREC_BF16 || prec == SL_PREC_BF16X2 || prec == SL_PREC_FP16; }
 
 static int g_sm_limit = 0;  // sl_set_sm_limit: CTAs the persistent conv grids may use (0 = all SMs)
@@ -104,21 +147,95 @@ static int make_weight_map(CUtensorMap* m, const void* base, int k_total, int ro
   return make_tmap(m, TMAP_BF16, 3, base, dims, strides, box, true);
 }
 
-// Tail splitting of the persistent conv grid (see ConvGemmParams::tail_split)
-static void plan_tail(int total_tiles, int bn, bool allow, int* full_tiles, int* split) {
+// Tail of the persistent conv grid (ConvGemmParams::tail_split / tail_ksplit).  Default: the tiles of the last,
+// partial wave are cut into up to 4 narrower tiles (SL_TAIL_SPLIT=0 disables; SL_TAIL_SPLIT_ALL=n splits EVERY
+// tile): an M = 128 MMA costs the same ~153 cycles for N = 64 as for N = 256, so this only shortens the
+// epilogue of the wave (inner_conv: 42 vs 44 us).  SL_TAIL_KSPLIT=n (opt-in) splits those tiles over the
+// contraction instead — the experiment of DESIGN.md §4.1: parity-green, measured slower.
+struct TailScratch {
+  float* data;
+  unsigned* tickets;
+  unsigned* done;
+};
+constexpr int kTailSlots = 148;  // tiles of a partial wave: fewer than the grid
+// one zero-filled scratch buffer per (device, stream): launches on one stream are ordered, launches on
+// different streams may overlap and must not share partial sums
+static int tail_scratch(cudaStream_t stream, int bn, TailScratch* out) {
+  struct Entry {
+    int dev;
+    cudaStream_t stream;
+    TailScratch s;
+  };
+  static Entry table[32];
+  static int used = 0;
+  static std::mutex mu;
+  int dev = 0;
+  SL_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  for (int i = 0; i < used; ++i)
+    if (table[i].dev == dev && table[i].stream == stream) {
+      *out = table[i].s;
+      return 0;
+    }
+  if (used == 32) {
+    out->data = nullptr;  // caller falls back to whole tiles
+    return 0;
+  }
+  (void)bn;
+  const size_t data_bytes = static_cast<size_t>(kTailSlots) * 128 * 256 * sizeof(float);
+  uint8_t* base = nullptr;
+  SL_CUDA(cudaMalloc(&base, data_bytes + 2 * kTailSlots * sizeof(unsigned)));
+  SL_CUDA(cudaMemset(base, 0, data_bytes + 2 * kTailSlots * sizeof(unsigned)));
+  SL_CUDA(cudaDeviceSynchronize());
+  Entry& e = table[used++];
+  e.dev = dev;
+  e.stream = stream;
+  e.s.data = reinterpret_cast<float*>(base);
+  e.s.tickets = reinterpret_cast<unsigned*>(base + data_bytes);
+  e.s.done = e.s.tickets + kTailSlots;
+  *out = e.s;
+  return 0;
+}
+static void plan_tail(int total_tiles, int bn, int chunks, bool allow, int* full_tiles, int* split, int* ksplit,
+                      int* per_split) {
   const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
   const int rest = total_tiles % grid;
   *full_tiles = total_tiles;
   *split = 1;
-  const char* e = std::getenv("SL_TAIL_SPLIT");      // max split factor (0/1 = off)
+  *ksplit = 1;
+  *per_split = chunks;
+  const char* e = std::getenv("SL_TAIL_SPLIT");      // max narrow-tile split factor (0/1 = off)
   const char* all = std::getenv("SL_TAIL_SPLIT_ALL");  // measurement aid: split EVERY tile by this factor
   if (allow && all && std::atoi(all) > 1 && bn / std::atoi(all) >= 64) {
     *full_tiles = 0;
     *split = std::atoi(all);
     return;
   }
+  if (!allow || rest == 0) return;
+  const char* ke = std::getenv("SL_TAIL_KSPLIT");  // max tail K split (default off: measured slower)
+  const int max_ksplit = ke ? std::atoi(ke) : 0;
+  if (max_ksplit >= 2 && chunks >= 2 && rest <= kTailSlots && bn == 256) {
+    // cost of the partial wave in tile times: rounds x the share of the contraction per item, plus the
+    // reduce / fold epilogue of a split tile
+    double best = 1.0;
+    for (int s = 2; s <= max_ksplit && s <= chunks; ++s) {
+      const int per = (chunks + s - 1) / s;
+      const int items = (chunks + per - 1) / per;  // non-empty splits
+      const int rounds = (rest * items + grid - 1) / grid;
+      const double cost = rounds * (static_cast<double>(per) / chunks + 0.2);
+      if (cost < best - 0.05) {
+        best = cost;
+        *ksplit = items;
+        *per_split = per;
+      }
+    }
+    if (*ksplit > 1) {
+      *full_tiles = total_tiles - rest;
+      return;
+    }
+  }
   const int max_split = e ? std::atoi(e) : 4;
-  if (!allow || rest == 0 || max_split < 2) return;
+  if (max_split < 2) return;
   double best = 1.0;  // cost of the partial wave in units of one full-width tile
   for (int s = 2; s <= max_split && bn / s >= 64; s *= 2) {
     const double cost = static_cast<double>((rest * s + grid - 1) / grid) / s;
@@ -128,6 +245,25 @@ static void plan_tail(int total_tiles, int bn, bool allow, int* full_tiles, int*
     }
   }
   if (*split > 1) *full_tiles = total_tiles - rest;
+}
+// fills the scratch fields of a plan that chose the tail K split (or reverts it when no scratch is to be had)
+static int bind_tail_scratch(ConvGemmParams* p, int bn, cudaStream_t stream) {
+  if (p->tail_ksplit <= 1) return 0;
+  TailScratch s;
+  int rc = tail_scratch(stream, bn, &s);
+  if (rc) return rc;
+  if (s.data == nullptr) {
+    p->tail_ksplit = 1;
+    p->full_tiles = p->m_units * p->n_tiles;
+    return 0;
+  }
+  p->tail_scratch = s.data;
+  p->tail_tickets = s.tickets;
+  p->tail_done = s.done;
+  const uint64_t dims[3] = {static_cast<uint64_t>(bn), 128, static_cast<uint64_t>(kTailSlots)};
+  const uint64_t strides[2] = {static_cast<uint64_t>(bn) * 4, static_cast<uint64_t>(bn) * 4 * 128};
+  const uint32_t box[3] = {32, 32, 1};
+  return make_tmap(&p->tmScratch, TMAP_F32, 3, s.data, dims, strides, box, true);
 }
 
 // halo mode plan (ConvGemmParams::halo): SL_HALO=0 disables, SL_HALO_BASE selects the descriptor
@@ -330,7 +466,10 @@ int sl_conv1d_fwd(const void* x_packed, const void* w_fwd, const float* bias, vo
     p.full_tiles = p.m_units * p.n_tiles;
     p.tail_split = 1;
   } else {
-    plan_tail(B * p.m_tiles_per_utt * p.n_tiles, bn, act != SL_ACT_SOFTMAX, &p.full_tiles, &p.tail_split);
+    plan_tail(B * p.m_tiles_per_utt * p.n_tiles, bn, cin_pad / 64, act != SL_ACT_SOFTMAX, &p.full_tiles, &p.tail_split,
+              &p.tail_ksplit, &p.tail_per);
+    rc = bind_tail_scratch(&p, bn, static_cast<cudaStream_t>(stream));
+    if (rc) return rc;
   }
   if (p.tail_split > 1) {
     rc = make_weight_map(&p.tmBtail, w_fwd, planes * cin_pad, cout_pad, k, bn / p.tail_split);
@@ -372,7 +511,10 @@ int sl_conv1d_fwd(const void* x_packed, const void* w_fwd, const float* bias, vo
     rc = make_act_map3(&p.tmY, y_packed, planes * cout_pad, T_out, B, 32, T_out_alloc);
     if (rc) return rc;
   }
-  return conv_gemm_launch(p, bn, epi, false, num_sms(), static_cast<cudaStream_t>(stream));
+  p.timeline = timeline_buffer();
+  rc = conv_gemm_launch(p, bn, epi, false, num_sms(), static_cast<cudaStream_t>(stream));
+  timeline_report("conv forward", p.timeline);
+  return rc;
 }
 
 // split-K plan of the input-gradient GEMM: worthwhile when the tile count leaves the last
@@ -441,7 +583,10 @@ static int dgrad_launch_rows(const void* dy_packed, const void* w_fwd, const voi
     p.full_tiles = p.m_units * p.n_tiles;
     p.tail_split = 1;
   } else {
-    plan_tail(B * p.m_tiles_per_utt * p.n_tiles, bn, p.b_grouped != 0, &p.full_tiles, &p.tail_split);
+    plan_tail(B * p.m_tiles_per_utt * p.n_tiles, bn, cout_pad / 64, p.b_grouped != 0, &p.full_tiles, &p.tail_split,
+              &p.tail_ksplit, &p.tail_per);
+    rc = bind_tail_scratch(&p, bn, s);
+    if (rc) return rc;
   }
   if (p.tail_split > 1) {
     rc = make_weight_group_map(&p.tmBtail, w_fwd, planes * cin_pad, cout_pad, k, 64, bn / p.tail_split / 64);
@@ -484,13 +629,17 @@ static int dgrad_launch_rows(const void* dy_packed, const void* w_fwd, const voi
     p.ksplit = ksplit;
     p.full_tiles = p.m_units * p.n_tiles;
     p.tail_split = 1;
+    p.tail_ksplit = 1;
     p.mask_bits_in = nullptr;
     rc = conv_gemm_launch(p, bn, EPI_F32, true, num_sms(), s);
     if (rc) return rc;
     return dgrad_finalize_launch(static_cast<const float*>(workspace), relu_mask, dx_packed,
                                  static_cast<size_t>(B) * T, cin_pad, prec, out_scale, s);
   }
-  return conv_gemm_launch(p, bn, EPI_PACKED, true, num_sms(), s);
+  p.timeline = timeline_buffer();
+  rc = conv_gemm_launch(p, bn, EPI_PACKED, true, num_sms(), s);
+  timeline_report("conv input gradient", p.timeline);
+  return rc;
 }
 
 int sl_conv1d_dgrad(const void* dy_packed, const void* w_fwd, const void* relu_mask, void* dx_packed,

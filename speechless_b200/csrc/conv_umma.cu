@@ -69,13 +69,14 @@ struct Cfg {
 // tile of the last partial wave.
 struct WorkItem {
   int b, t0, n0, width, chunk_begin, chunk_end;  // [chunk_begin, chunk_end): 64-channel chunks of the contraction
+  int tail;  // tail K split: index of the tile within the partial wave (its scratch slot), else -1
 };
 // `rank`: this CTA's rank in its pair (0 without pairs); a pair works on the frame tiles
 // 2 * unit and 2 * unit + 1 of one filter tile.  The odd tile out (if any) gets b = p.B: its loads
 // are zero-filled and its stores clipped by the tensor maps.
 template <int BN, int CTAS>
 __device__ __forceinline__ WorkItem decode_item(const ConvGemmParams& p, int item, int rank) {
-  int tile = item, sub = 0, width = BN;
+  int tile = item, sub = 0, width = BN, tail = -1;
   int chunk_begin = 0, chunk_end = p.chunks;
   if (p.ksplit > 1) {
     // Split K over CHANNEL chunks (all taps each), not over tap ranges: a tap-range item still needs
@@ -89,6 +90,12 @@ __device__ __forceinline__ WorkItem decode_item(const ConvGemmParams& p, int ite
     const int per = (p.chunks + p.ksplit - 1) / p.ksplit;
     chunk_begin = split * per < p.chunks ? split * per : p.chunks;
     chunk_end = chunk_begin + per < p.chunks ? chunk_begin + per : p.chunks;
+  } else if (item >= p.full_tiles && p.tail_ksplit > 1) {
+    const int r = item - p.full_tiles;
+    tail = r / p.tail_ksplit;
+    tile = p.full_tiles + tail;
+    chunk_begin = (r - tail * p.tail_ksplit) * p.tail_per;
+    chunk_end = chunk_begin + p.tail_per < p.chunks ? chunk_begin + p.tail_per : p.chunks;
   } else if (item >= p.full_tiles) {
     const int r = item - p.full_tiles;
     tile = p.full_tiles + r / p.tail_split;
@@ -111,6 +118,7 @@ __device__ __forceinline__ WorkItem decode_item(const ConvGemmParams& p, int ite
   w.width = width;
   w.chunk_begin = chunk_begin;
   w.chunk_end = chunk_end;
+  w.tail = tail;
   return w;
 }
 
@@ -148,7 +156,20 @@ __device__ __forceinline__ void arrive_leader(uint64_t* bar) {
     mbar_arrive(bar);
 }
 
-template <int BN, int EPI, bool BMN, int CTAS>
+// tail K split: counters shared by the work items of one tile
+__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add_u32(unsigned* p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// TAILK: built with the tail-K-split epilogue paths (ConvGemmParams::tail_ksplit); a separate instantiation so
+// that the default kernel does not carry their registers
+template <int BN, int EPI, bool BMN, int CTAS, bool TAILK>
 __global__ void __launch_bounds__(Threads<EPI>::kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   using C = Cfg<BN, CTAS>;
@@ -172,10 +193,15 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   uint64_t* tmem_full = bars + 20;
   uint64_t* tmem_empty = bars + 22;
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 24);
+  volatile uint32_t* tail_role_s = reinterpret_cast<volatile uint32_t*>(bars + 26);  // [2], by accumulator stage
   static_assert(C::kStages <= 8 && C::kStagesB <= 8 && C::kStagesB >= 2, "barrier block layout");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  auto stamp = [&](int slot) {  // measurement aid (SL_TIMELINE=1, api.cu)
+    if (p.timeline != nullptr && slot < 32) p.timeline[blockIdx.x * 32 + slot] = clock64();
+  };
+  if (threadIdx.x == 0) stamp(0);
 
   pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
@@ -183,6 +209,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     prefetch_tmap(&p.tmB);
     if (p.halo) prefetch_tmap(&p.tmAhalo);
     if (p.tail_split > 1) prefetch_tmap(&p.tmBtail);
+    if (TAILK && p.tail_ksplit > 1) prefetch_tmap(&p.tmScratch);
     if (EPI != EPI_SOFTMAX) prefetch_tmap(&p.tmY);
   }
   if (warp == 1 && lane == 0) {
@@ -214,11 +241,14 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
+  if (threadIdx.x == 0) stamp(1);
   pdl_wait();  // setup above overlapped the previous kernel's tail; its outputs are visible from here
+  if (threadIdx.x == 0) stamp(2);
 
   const int total_tiles = p.m_units * p.n_tiles;
   const int num_tiles = p.ksplit > 1 ? total_tiles * p.ksplit
-                                     : p.full_tiles + (total_tiles - p.full_tiles) * p.tail_split;  // work items
+                                     : p.full_tiles + (total_tiles - p.full_tiles) *
+                                                          (p.tail_ksplit > 1 ? p.tail_ksplit : p.tail_split);  // work items
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -410,6 +440,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       for (int ks = 0; ks < ksteps; ++ks) {
         mbar_wait(&full_bar[stage], phase);
         tcgen05_fence_after();
+        if (lane == 0 && ks == 0) stamp(it == 0 ? 3 : 25 + it);
         if (lane == 0) {
           const uint32_t a_addr = smem_u32(smem + stage * C::STAGE_BYTES);
           const uint32_t b_addr = a_addr + A_BYTES;
@@ -426,7 +457,10 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
               umma_bf16(tmem_d, da, db, idesc, (ks | k) != 0 ? 1u : 0u);
           }
           commit<CTAS>(&empty_bar[stage]);  // frees the smem slot (of both CTAs) when these MMAs retire
-          if (ks == ksteps - 1) commit<CTAS>(&tmem_full[as]);
+          if (ks == ksteps - 1) {
+            commit<CTAS>(&tmem_full[as]);
+            if (it < 6) stamp(4 + it);
+          }
         }
         __syncwarp();
         if (++stage == C::kStages) {
@@ -479,8 +513,31 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           if (c < n_chunks && (c % kEpiSets) == set) mask_in[c] = __ldg(mp + c);
       }
 
+      // tail K split: 1 = this item adds its partial sums to the tile's scratch slot; 2 = it drew the last
+      // ticket: it waits for the others' sums, folds them into its accumulator and runs the epilogue
+      int tail_role = 0;
+      if constexpr (TAILK) {
+        if (w.tail >= 0) {
+          if (et == 0) {
+            const unsigned splits = static_cast<unsigned>(p.tail_ksplit);
+            const unsigned ticket = atomicInc(p.tail_tickets + w.tail, splits - 1);  // wraps to 0 after the last
+            if (ticket == splits - 1) {
+              while (ld_acquire_gpu_u32(p.tail_done + w.tail) != splits - 1) __nanosleep(64);
+              p.tail_done[w.tail] = 0;  // nobody else touches it before the next launch
+              fence_proxy_async_all();  // the sums were written through the async proxy
+              tail_role_s[as] = 2;
+            } else {
+              tail_role_s[as] = 1;
+            }
+          }
+          named_bar_sync(2, kEpiThreads);
+          tail_role = static_cast<int>(tail_role_s[as]);
+        }
+      }
+
       mbar_wait(&tmem_full[as], aphase);
       tcgen05_fence_after();
+      if (warp == 4 && lane == 0 && it < 6) stamp(10 + it);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) +
                              static_cast<uint32_t>(as * BN);
 
@@ -510,6 +567,41 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) arrive_leader<CTAS>(&tmem_empty[as]);
+      } else if (TAILK && tail_role == 1) {
+        // fp32 accumulator -> per-warp swizzled slab -> TMA reduce-add into the tile's scratch slot
+#pragma unroll 1
+        for (int c = set; c < BN / 32; c += kEpiSets) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c * 32, r);
+          tmem_ld_wait();
+          if (lane == 0) tma_wait_group_read<0>();
+          __syncwarp();
+          uint8_t* rowp = sbuf + lane * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int phys = j ^ (lane & 7);
+            *reinterpret_cast<uint4*>(rowp + phys * 16) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_reduce_add_3d(&p.tmScratch, sbuf, c * 32, ew * 32, w.tail);
+            tma_commit_group();
+          }
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          arrive_leader<CTAS>(&tmem_empty[as]);
+          tma_wait_group<0>();  // the sums have landed, not just left the slab
+          fence_proxy_async_all();
+          __threadfence();
+        }
+        named_bar_sync(2, kEpiThreads);
+        if (et == 0) {
+          __threadfence();
+          red_release_gpu_add_u32(p.tail_done + w.tail, 1u);
+        }
       } else if (EPI == EPI_PACKED) {
         if (set >= n_chunks) {  // narrow tail tile: nothing for this warp, but the MMA warp counts every arrival
           tcgen05_fence_before();
@@ -533,6 +625,39 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           for (int i = 0; i < 32; ++i) {
             v[i] = __uint_as_float(r0[i]);
             v[32 + i] = __uint_as_float(r1[i]);
+          }
+          if (TAILK && tail_role == 2) {
+            // the other items' partial sums: read coalesced (and replaced by zeros, so that the slot is clean
+            // for the next launch), transposed through the warp's slab so that every lane gets its own row
+            const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              float* base = p.tail_scratch + (static_cast<size_t>(w.tail) * BLOCK_M + ew * 32) * BN + c * 64 + h * 32;
+              if (lane == 0) tma_wait_group_read<0>();  // the store that last read sbuf is done
+              __syncwarp();
+              float4 q[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float4* g = reinterpret_cast<float4*>(base + (j * 4 + (lane >> 3)) * BN) + (lane & 7);
+                q[j] = __ldcg(g);
+                __stcg(g, zero4);
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const int rr = j * 4 + (lane >> 3);
+                *reinterpret_cast<float4*>(sbuf + rr * 128 + (((lane & 7) ^ (rr & 7)) << 4)) = q[j];
+              }
+              __syncwarp();
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 t = *reinterpret_cast<const float4*>(sbuf + lane * 128 + ((j ^ (lane & 7)) << 4));
+                v[h * 32 + 4 * j] += t.x;
+                v[h * 32 + 4 * j + 1] += t.y;
+                v[h * 32 + 4 * j + 2] += t.z;
+                v[h * 32 + 4 * j + 3] += t.w;
+              }
+              __syncwarp();
+            }
           }
           if (p.bias != nullptr) {  // (uniform) the input-gradient GEMMs have none
             const float4* bs = reinterpret_cast<const float4*>(bias_s + c * 64);
@@ -670,8 +795,10 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           }
         }
       }
+      if (warp == 4 && lane == 0 && it < 6) stamp(16 + it);
     }
     if (EPI != EPI_SOFTMAX && lane == 0) tma_wait_group<0>();
+    if (warp == 4 && lane == 0) stamp(22);
   }
 
   tcgen05_fence_before();
@@ -679,16 +806,18 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     cluster_sync_all();  // neither CTA may exit while the other can still signal its barriers
   else
     __syncthreads();
+  if (threadIdx.x == 0) stamp(23);
   if (warp == 2) {
     tcgen05_fence_after();
     if constexpr (CTAS == 2)
       tmem_dealloc_pair(tmem_base, C::TMEM_COLS);
     else
       tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if (lane == 0) stamp(24);
   }
 }
 
-template <int BN, int EPI, bool BMN, int CTAS>
+template <int BN, int EPI, bool BMN, int CTAS, bool TAILK = false>
 int launch(const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
   using C = Cfg<BN, CTAS>;
   // the opt-in shared-memory size is a per-device function attribute
@@ -697,13 +826,13 @@ int launch(const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
   int dev = 0;
   SL_CUDA(cudaGetDevice(&dev));
   if (!((configured >> (dev & 63)) & 1ull)) {
-    SL_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, EPI, BMN, CTAS>,
+    SL_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, EPI, BMN, CTAS, TAILK>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     configured |= 1ull << (dev & 63);
   }
   const int num_tiles = p.m_units * p.n_tiles * (p.ksplit > 1 ? p.ksplit : 1);
   if (CTAS == 2) {
-    if (p.tail_split != 1 || p.full_tiles != p.m_units * p.n_tiles || p.dbg_mode != 0) {
+    if (p.tail_split != 1 || p.tail_ksplit > 1 || p.full_tiles != p.m_units * p.n_tiles || p.dbg_mode != 0) {
       set_error("conv_gemm: the CTA-pair kernel takes whole tiles only");
       return 1;
     }
@@ -722,7 +851,7 @@ int launch(const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
     if (mc == 0) {
       cfg.gridDim = dim3(num_sms & ~1);
       int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, conv_gemm_kernel<BN, EPI, BMN, CTAS>, &cfg) != cudaSuccess || n <= 0) {
+      if (cudaOccupancyMaxActiveClusters(&n, conv_gemm_kernel<BN, EPI, BMN, CTAS, TAILK>, &cfg) != cudaSuccess || n <= 0) {
         cudaGetLastError();
         n = num_sms / 2;
       }
@@ -730,15 +859,16 @@ int launch(const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
     }
     const int pairs = num_tiles < mc ? num_tiles : mc;
     cfg.gridDim = dim3(2 * pairs);
-    SL_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BN, EPI, BMN, CTAS>, p));
+    SL_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BN, EPI, BMN, CTAS, TAILK>, p));
     return 0;
   }
   const int grid = num_tiles < num_sms ? num_tiles : num_sms;
-  if (p.ksplit <= 1 && (p.full_tiles + (num_tiles - p.full_tiles) * p.tail_split < grid || p.tail_split < 1)) {
+  if (p.ksplit <= 1 && (p.full_tiles + (num_tiles - p.full_tiles) * (p.tail_ksplit > 1 ? p.tail_ksplit : p.tail_split) < grid ||
+                        p.tail_split < 1 || (p.tail_ksplit > 1) != TAILK || (TAILK && p.tail_split != 1))) {
     set_error("conv_gemm: inconsistent tail split");
     return 1;
   }
-  SL_CUDA(launch_pdl(PDL_CONV, conv_gemm_kernel<BN, EPI, BMN, CTAS>, dim3(grid), dim3(Threads<EPI>::kThreads), C::SMEM_BYTES, stream,
+  SL_CUDA(launch_pdl(PDL_CONV, conv_gemm_kernel<BN, EPI, BMN, CTAS, TAILK>, dim3(grid), dim3(Threads<EPI>::kThreads), C::SMEM_BYTES, stream,
                      p));
   return 0;
 }
@@ -775,6 +905,9 @@ int conv_gemm_launch(const ConvGemmParams& p, int block_n, int epi, bool b_mn_ma
       return b_mn_major ? launch<128, EPI_PACKED, true, 1>(p, num_sms, stream)
                         : launch<128, EPI_PACKED, false, 1>(p, num_sms, stream);
     case 256:
+      if (p.tail_ksplit > 1)
+        return b_mn_major ? launch<256, EPI_PACKED, true, 1, true>(p, num_sms, stream)
+                          : launch<256, EPI_PACKED, false, 1, true>(p, num_sms, stream);
       return b_mn_major ? launch<256, EPI_PACKED, true, 1>(p, num_sms, stream)
                         : launch<256, EPI_PACKED, false, 1>(p, num_sms, stream);
     default:

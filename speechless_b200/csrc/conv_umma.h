@@ -28,6 +28,19 @@ struct ConvGemmParams {
   // tail_split (1, 2 or 4) narrower tiles so that the wave costs 1/tail_split of a tile time
   int full_tiles;  // tiles [0, full_tiles) are whole; the rest are split
   int tail_split;
+  // tail K split (EPI_PACKED, single CTAs): a tcgen05.mma of M = 128 takes the same ~153 cycles for N = 64 as
+  // for N = 256 (measured), so narrow tiles do not shorten the partial wave — splitting the contraction does.
+  // Each tile of the partial wave becomes tail_ksplit work items over tail_per 64-channel chunks (all taps)
+  // each.  The items that finish first add their fp32 partial sums into the tile's slot of a zero-filled
+  // scratch buffer (TMA reduce-add); the item that draws the last ticket waits for them, adds the slot to
+  // its own accumulator, writes zeros back (the buffer is all zeros again when the kernel ends) and runs
+  // the normal epilogue.  tail_tickets / tail_done: one self-resetting counter pair per tile of the wave.
+  int tail_ksplit;  // 1 = off
+  int tail_per;
+  CUtensorMap tmScratch;  // fp32 {BN, 128, tiles of the wave}, box {32, 32, 1}
+  float* tail_scratch;
+  unsigned* tail_tickets;
+  unsigned* tail_done;
   // split K (EPI_F32 only): every tile is computed by ksplit work items, each over a contiguous
   // range of 64-channel chunks of the contraction (all taps), whose fp32 partial sums meet in HBM
   // through TMA reduce-add
@@ -68,6 +81,9 @@ struct ConvGemmParams {
   int out_t_scale;
   int out_t_off;
   int dbg_mode;   // bring-up only (env SL_DBG_MODE): 1 = stop issuing TMA loads after the first ring fill
+  // measurement aid (env SL_TIMELINE=1): 32 clock64() stamps per CTA — entry, setup done, first operands
+  // landed, last MMA issued / accumulator complete / epilogue done of the CTA's first tiles, exit
+  long long* timeline;
   int b_grouped;  // MN-major B: tmB is rank 4 {64, cout, cin_total/64, taps}, one box {64,64,BN/64,1} per stage
   float* probs;   // EPI_SOFTMAX outputs
   float* logits;

@@ -10,6 +10,8 @@ finishes in seconds, and once on a shape where the planner picks it by itself ("
     wgrad<256>     : K-split TMA reduce-add into dW                                (big_conv_1 / big_conv_2)
     wgrad tap pair : two taps share one N = 256 accumulator                        (striding_conv, 128 mel bins)
     tail split     : narrow tiles in the last partial wave of the persistent grid  (forward / dgrad)
+    tail K split   : (opt-in, SL_TAIL_KSPLIT) those tiles split over the contraction instead; partial sums
+                     meet in a zero-filled scratch slot and the item with the last ticket folds them in
 
 Tolerances: rel = max|got - want| / max|want| against the fp64 oracle; 1e-4 in the split-bf16 mode
 (bf16x2), 2e-2 in bf16 and 3e-3 in fp16 (one rounding of each operand to 8 / 11 mantissa bits).
@@ -171,14 +173,23 @@ def test_weight_gradient_bench_shapes(env, monkeypatch, mode, name, B, T, cin, c
     assert rel_err(dw.cpu().numpy()[:, :cout, :cin].transpose(0, 2, 1), 2 * dw_want * scale) < TOL[mode], name
 
 
-# ------------------------------------------------------------------ tail-split forward tiles
+# ------------------------------------------------------------------ tail of the persistent grid: forward tiles
+TAIL_VARIANTS = {"narrow": {}, "k-split": {"SL_TAIL_KSPLIT": "8"}, "whole": {"SL_TAIL_SPLIT": "0"}}
+
+
+@pytest.mark.parametrize("variant", list(TAIL_VARIANTS))
 @pytest.mark.parametrize("mode", ["bf16", "bf16x2", "fp16"])
 @pytest.mark.parametrize("B,T,cin,cout,k", [
-    (20, 1000, 250, 250, 7),   # inner_conv: 160 tiles = 148 + 12 -> the 12 are cut into 4 narrow tiles each
-    (3, 900, 250, 2000, 32),   # big_conv_1: 24 x 8 = 192 tiles = 148 + 44 -> split in 2
+    (20, 1000, 250, 250, 7),   # inner_conv: 160 tiles = 148 + 12 -> the 12 are split over their 4 channel chunks
+    (3, 900, 250, 2000, 32),   # big_conv_1 (A-halo loop): 24 x 8 = 192 tiles = 148 + 44 -> split in 2
+    (3, 900, 2000, 2000, 1),   # big_conv_2: 192 tiles, 32 channel chunks -> split in 3 (11 + 11 + 10 chunks)
 ])
-def test_forward_tail_split_tiles(env, mode, B, T, cin, cout, k):
+def test_forward_tail_split_tiles(env, monkeypatch, variant, mode, B, T, cin, cout, k):
     torch, lib, check, ptr = env.torch, env.lib, env._lib.check, env._lib.ptr
+    if variant == "whole" and (mode != "fp16" or cin == 2000):
+        pytest.skip("the unsplit variant runs once per shape, in the benchmark's mode")
+    for key, value in TAIL_VARIANTS[variant].items():
+        monkeypatch.setenv(key, value)
     prec = PRECS[mode]
     tiles = B * -(-T // 128) * (pad64(cout) // min(pad64(cout), 256))
     assert tiles > 148 and tiles % 148 != 0, "shape must leave a partial last wave"
@@ -189,15 +200,58 @@ def test_forward_tail_split_tiles(env, mode, B, T, cin, cout, k):
     xp, wf = pack(env, x, prec), pack_w(env, w, prec)
     bd = torch.from_numpy(bias).to("cuda:0")
     cop = pad64(cout)
-    yp = torch.zeros((B, T, planes(prec) * cop), dtype=storage(torch, prec), device="cuda:0")
-    mask = torch.zeros((B, T, cop // 8), dtype=torch.uint8, device="cuda:0")
-    check(lib.sl_conv1d_fwd(ptr(xp), ptr(wf), ptr(bd), ptr(yp), ptr(mask), None, None, None, B, T, T, T, cin, cout, k,
-                            1, 1, prec, None))
-    got = unpack(env, yp, B, T, cout, prec)
     want = np.maximum(env.oracle.conv1d_same(x.astype(np.float64), w.astype(np.float64), bias.astype(np.float64), 1), 0)
-    assert rel_err(got, want) < TOL[mode]
-    bits = np.unpackbits(mask.cpu().numpy(), axis=2, bitorder="little")[..., :cout].astype(bool)
-    assert (bits == (got > 0))[np.abs(want) > 1e-3].all()
+    first = None
+    for launch in range(3):  # the scratch slots must be all zeros again after every launch
+        yp = torch.zeros((B, T, planes(prec) * cop), dtype=storage(torch, prec), device="cuda:0")
+        mask = torch.zeros((B, T, cop // 8), dtype=torch.uint8, device="cuda:0")
+        check(lib.sl_conv1d_fwd(ptr(xp), ptr(wf), ptr(bd), ptr(yp), ptr(mask), None, None, None, B, T, T, T, cin, cout, k,
+                                1, 1, prec, None))
+        got = unpack(env, yp, B, T, cout, prec)
+        assert rel_err(got, want) < TOL[mode]
+        bits = np.unpackbits(mask.cpu().numpy(), axis=2, bitorder="little")[..., :cout].astype(bool)
+        assert (bits == (got > 0))[np.abs(want) > 1e-3].all()
+        if first is None:
+            first = got
+        else:
+            # the order in which partial sums arrive may change the fp32 rounding of a split tile, i.e. at most
+            # the last bit of a packed output value
+            assert rel_err(got, first) < 0.5 * TOL[mode]
+
+
+@pytest.mark.parametrize("mode", ["bf16", "bf16x2", "fp16"])
+@pytest.mark.parametrize("B,T,cin,cout,k", [
+    (20, 1000, 250, 250, 7),   # inner_conv input gradient: 160 tiles
+    (3, 900, 2000, 2000, 1),   # big_conv_2 input gradient: 192 tiles
+])
+def test_input_gradient_tail_k_split(env, monkeypatch, mode, B, T, cin, cout, k):
+    torch, lib, check, ptr = env.torch, env.lib, env._lib.check, env._lib.ptr
+    prec = PRECS[mode]
+    rng = np.random.default_rng(T + k + 1)
+    dy = (rng.standard_normal((B, T, cout)) * (rng.random((B, T, cout)) < 0.5)).astype(np.float32)
+    w = (rng.standard_normal((k, cin, cout)) / np.sqrt(k * cout)).astype(np.float32)
+    below = rng.random((B, T, cin)) < 0.6
+    cip = pad64(cin)
+    bits = np.zeros((B, T, cip), dtype=np.uint8)
+    bits[..., :cin] = below
+    mask = torch.from_numpy(np.packbits(bits, axis=2, bitorder="little")).to("cuda:0")
+    dyp, wf = pack(env, dy, prec), pack_w(env, w, prec)
+    want = env.oracle.conv1d_same_backward_input(w.astype(np.float64), dy.astype(np.float64), T, 1) * below
+    results = {}
+    for variant in ("k-split", "narrow"):
+        if variant == "k-split":
+            monkeypatch.setenv("SL_TAIL_KSPLIT", "8")
+        else:
+            monkeypatch.delenv("SL_TAIL_KSPLIT")
+        for launch in range(2):
+            dxp = torch.full((B, T, planes(prec) * cip), 3.0, dtype=storage(torch, prec), device="cuda:0")
+            check(lib.sl_conv1d_dgrad(ptr(dyp), ptr(wf), ptr(mask), ptr(dxp), B, T, cin, cout, k, 1, prec, 1.0, None, 0,
+                                      None))
+            got = unpack(env, dxp, B, T, cin, prec)
+            assert rel_err(got, want) < max(TOL[mode], 3e-4), (variant, launch)
+            assert float(dxp.view(B, T, planes(prec), cip)[..., cin:].float().abs().max()) == 0.0
+        results[variant] = got
+    assert rel_err(results["k-split"], results["narrow"]) < max(TOL[mode], 3e-4)
 
 
 # ------------------------------------------------------------------ full-width tower: logits and gradients per mode
