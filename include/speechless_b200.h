@@ -182,13 +182,50 @@ int sl_ctc_greedy_decode(const float* probs, const int32_t* input_len,
  * out_logp[b, p] (log P(prefix | x)), best first.  merge_repeated follows TF: it only drops, from the
  * OUTPUT, a label equal to its predecessor ("A A _ A A" -> [0] with, [0, 0] without; reference
  * test_ctc_decoders.py:38-39) — the reference calls it with merge_repeated = 0 (net.py:441-447).
- * The KenLM scorer of the patched TensorFlow fork (net.py:420-422) is not part of this entry point. */
+ * Stock scorer; the language-model scorer is sl_ctc_beam_search_decode_lm below. */
 size_t sl_ctc_beam_search_workspace_bytes(int B, int T, int beam_width);
 int sl_ctc_beam_search_decode(const float* scores, const int32_t* input_len, int32_t* out,
                               int32_t* out_len, float* out_logp, int B, int T, int V, int blank,
                               int beam_width, int top_paths, int merge_repeated,
                               int inputs_are_probs, void* workspace, size_t workspace_bytes,
                               void* stream);
+
+/* ---- beam-search decode with a word n-gram model inside the search (the reference's KenLM branch:
+ * tf.nn.ctc_beam_search_decoder(kenlm_directory_path, kenlm_weight = .8, word_count_weight = 0,
+ * valid_word_count_weight = 2.3) of a patched TensorFlow, net.py:420-422,444-451) ---- */
+/* The scorer hooks of TF's decoder (ExpandState / GetStateExpansionScore / ExpandStateEnd) run on the
+ * device: the letters of the unfinished word walk a vocabulary trie, the space label scores the finished
+ * word with an ARPA back-off model, an unfinished word carries the lowest unigram score below its trie node
+ * as a look-ahead.  A finished hypothesis collects
+ *   weight * log10 P_lm(words </s>) + word_count_weight * #words + valid_word_count_weight * #known words
+ * on top of its CTC log-probability (weight = kenlm_weight * ln 10); out_logp holds that sum.  All table
+ * pointers are DEVICE pointers owned by the caller (speechless_b200/language_model.py builds them from an
+ * ARPA file); the struct itself is passed from host memory.  Semantics: oracle/beam_search_oracle.py
+ * (WordLanguageModelScorer; parity with the fork is unpinned — its source is not in the reference tree). */
+typedef struct SlWordLm {
+  const int32_t* trie_children;  /* (n_trie_nodes, n_labels): child node per symbol, -1 = none; node 0 = root */
+  const int32_t* trie_word;      /* (n_trie_nodes): id of the word that ends at the node, -1 = none */
+  const float* trie_min_unigram; /* (n_trie_nodes): lowest unigram log10 probability of the words below */
+  const int32_t* ngrams;         /* (ngram_mask + 1, 8): open-addressing table {n, id0..id4 (-1 padded),
+                                    log10 p, log10 back-off as float bits}; n = 0 marks an empty slot; slot =
+                                    FNV-1a over the n ids (32 bit), linear probing */
+  uint32_t ngram_mask;           /* table size - 1 (a power of two) */
+  int32_t n_labels;              /* = V of the decode call */
+  int32_t space_label;           /* the symbol that ends a word */
+  int32_t order;                 /* n-gram order, 1..5 */
+  int32_t bos_id, eos_id, unk_id; /* word ids of <s>, </s>, <unk>; unk_id is any unused id when has_unk = 0 */
+  int32_t has_unk;
+  float unknown_log10;           /* unigram score of <unk> (or -100 when the model has none): what a word
+                                    outside the model, or a prefix outside the trie, costs */
+  float weight;                  /* kenlm_weight * ln 10 */
+  float word_count_weight;
+  float valid_word_count_weight;
+} SlWordLm;
+int sl_ctc_beam_search_decode_lm(const float* scores, const int32_t* input_len, int32_t* out,
+                                 int32_t* out_len, float* out_logp, int B, int T, int V, int blank,
+                                 int beam_width, int top_paths, int merge_repeated,
+                                 int inputs_are_probs, const SlWordLm* lm, void* workspace,
+                                 size_t workspace_bytes, void* stream);
 
 /* ---- audio front end (replaces the librosa pipeline of labeled_example.py:99-140) ---- */
 /* audio (B, audio_stride) fp32 raw samples (sample_counts[b] valid each) ->

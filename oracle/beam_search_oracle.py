@@ -19,6 +19,21 @@ third-party dependency, absent from /root/reference), so its published behaviour
   it), which is why "A A _ A A" gives [0] with merging and [0, 0] without
   (reference speechless/test/test_ctc_decoders.py:5-9,38-39).
 
+Word language model inside the search (`WordLanguageModelScorer`, PARITY UNPINNED): the reference passes
+`kenlm_directory_path, kenlm_weight=.8, word_count_weight=0, valid_word_count_weight=2.3` to a patched
+TensorFlow (net.py:444-451; fork github.com/timediv/tensorflow-with-kenlm, README.md:17 — absent from the
+tree, not installable here).  TF's decoder exposes exactly four scorer hooks (`InitializeState`, `ExpandState`,
+`GetStateExpansionScore`, `ExpandStateEnd` / `GetStateEndExpansionScore`, ctc_beam_search.h /
+ctc_beam_scorer.h) and `beam_search_decode(scorer=...)` calls them where TF does.  The scorer behind them
+is restated from the published design of the KenLM beam scorers of that time (three weights with these
+names; Mozilla DeepSpeech 0.1 `beam_search.h`): a vocabulary trie follows the letters of the incomplete
+word, a word is scored by the n-gram model when the space label arrives, and an unfinished word carries
+the most pessimistic unigram score below its trie node (or the <unk> score once it has left the
+vocabulary) as a look-ahead that is taken back when the word ends.  The total a finished hypothesis gets is
+    kenlm_weight * ln P_lm(words </s>) + word_count_weight * #words + valid_word_count_weight * #known words,
+the formula of `speechless_b200.language_model.NBestRescorer`; units (ln) and where the bonuses enter are
+this restatement's choice — the fork's source is not available to check against.
+
 Pinning: the two beam-search rows of the reference's own test (test_ctc_decoders.py:38-39,
 beam_width=1) are checked in tests/test_beam_search.py; with a beam wide enough to hold every
 prefix the search is exact and is checked against brute-force enumeration of all V^T paths.
@@ -41,7 +56,7 @@ def _lse(a: float, b: float) -> float:
 
 
 class _Entry:
-    __slots__ = ("parent", "label", "children", "old", "new")
+    __slots__ = ("parent", "label", "children", "old", "new", "state")
 
     def __init__(self, parent: Optional["_Entry"], label: int):
         self.parent = parent
@@ -49,6 +64,7 @@ class _Entry:
         self.children: Dict[int, "_Entry"] = {}
         self.old = [LOG_ZERO, LOG_ZERO, LOG_ZERO]  # total, blank, label
         self.new = [LOG_ZERO, LOG_ZERO, LOG_ZERO]
+        self.state = None  # scorer state (TF: BeamEntry::state)
 
     def active(self) -> bool:
         return self.new[0] != LOG_ZERO
@@ -68,8 +84,28 @@ def log_softmax(rows: np.ndarray) -> np.ndarray:
     return rows - m - np.log(np.exp(rows - m).sum(axis=-1, keepdims=True))
 
 
+class StockScorer:
+    """TF's BaseBeamScorer: every expansion score is the incoming probability."""
+
+    def initialize_state(self):
+        return None
+
+    def expand_state(self, from_state, from_label: int, to_label: int):
+        return None
+
+    def expansion_score(self, state, previous: float) -> float:
+        return previous
+
+    def expand_state_end(self, state):
+        return state
+
+    def end_expansion_score(self, state) -> float:
+        return 0.0
+
+
 def beam_search_decode(inputs: np.ndarray, beam_width: int = 100, top_paths: int = 1, merge_repeated: bool = True,
-                       blank: Optional[int] = None, tf_deactivation: bool = True) -> List[Tuple[List[int], float]]:
+                       blank: Optional[int] = None, tf_deactivation: bool = True,
+                       scorer=None) -> List[Tuple[List[int], float]]:
     """inputs: (T, V) unnormalised log-scores of ONE utterance (the reference feeds log(p + 1e-8)); they
     are log-softmax-normalised per frame like TF's `Step`.  Returns up to `top_paths` (labels, log
     probability) pairs, best first.
@@ -85,8 +121,10 @@ def beam_search_decode(inputs: np.ndarray, beam_width: int = 100, top_paths: int
     T, V = inputs.shape
     blank = V - 1 if blank is None else blank
     lp = log_softmax(np.asarray(inputs, dtype=np.float64))
+    scorer = scorer or StockScorer()
     root = _Entry(None, -1)
     root.new = [0.0, 0.0, LOG_ZERO]
+    root.state = scorer.initialize_state()
     leaves: List[_Entry] = [root]
     for t in range(T):
         branches = sorted(leaves, key=lambda e: -e.new[0])
@@ -98,7 +136,7 @@ def beam_search_decode(inputs: np.ndarray, beam_width: int = 100, top_paths: int
             if b.parent is not None:
                 if b.parent.active():
                     previous = b.parent.old[1] if b.label == b.parent.label else b.parent.old[0]
-                    b.new[2] = _lse(b.new[2], previous)
+                    b.new[2] = _lse(b.new[2], scorer.expansion_score(b.state, previous))
                 b.new[2] += lp[t, b.label]
             b.new[1] = b.old[0] + lp[t, blank]
             b.new[0] = _lse(b.new[1], b.new[2])
@@ -121,7 +159,8 @@ def beam_search_decode(inputs: np.ndarray, beam_width: int = 100, top_paths: int
                     c = b.children[label] = _Entry(b, label)
                 if c.active() or (not tf_deactivation and c in in_beam_before):
                     continue
-                previous = b.old[1] if label == b.label else b.old[0]
+                c.state = scorer.expand_state(b.state, b.label, label)
+                previous = scorer.expansion_score(c.state, b.old[1] if label == b.label else b.old[0])
                 c.new = [lp[t, label] + previous, LOG_ZERO, lp[t, label] + previous]
                 if is_candidate(c.new[0]):
                     if len(leaves) == beam_width:
@@ -132,8 +171,14 @@ def beam_search_decode(inputs: np.ndarray, beam_width: int = 100, top_paths: int
                 else:
                     c.old = [LOG_ZERO, LOG_ZERO, LOG_ZERO]
                     c.new = [LOG_ZERO, LOG_ZERO, LOG_ZERO]
-    best = sorted(leaves, key=lambda e: -e.new[0])[:top_paths]
-    return [(e.sequence(merge_repeated), float(e.new[0])) for e in best]
+    # TF TopPaths: every leaf's state is closed (end of sentence) before the leaves are ranked
+    finished = []
+    for e in leaves:
+        if e.new[0] == LOG_ZERO:
+            continue
+        finished.append((e.new[0] + scorer.end_expansion_score(scorer.expand_state_end(e.state)), e))
+    finished.sort(key=lambda pair: -pair[0])
+    return [(e.sequence(merge_repeated), float(total)) for total, e in finished[:top_paths]]
 
 
 def collapse(path: Sequence[int], blank: int) -> Tuple[int, ...]:
@@ -157,3 +202,118 @@ def brute_force_labelings(inputs: np.ndarray, blank: Optional[int] = None) -> Di
         key = collapse(path, blank)
         totals[key] = _lse(totals.get(key, LOG_ZERO), score)
     return totals
+
+
+# ---------------------------------------------------------------------------------------------------------
+# word n-gram model inside the search (see the header: parity unpinned)
+# ---------------------------------------------------------------------------------------------------------
+LN10 = float(np.log(10.0))
+
+
+class BackOffModel:
+    """ARPA back-off n-gram model: {word tuple: (log10 probability, log10 back-off)}."""
+
+    def __init__(self, ngrams: Dict[Tuple[str, ...], Tuple[float, float]]):
+        self.ngrams = dict(ngrams)
+        self.order = max(len(k) for k in self.ngrams)
+        self.unknown = self.ngrams.get(("<unk>",), (-100.0, 0.0))[0]
+
+    def knows(self, word: str) -> bool:
+        return (word,) in self.ngrams
+
+    def log10_probability(self, word: str, history: Sequence[str]) -> float:
+        if not self.knows(word):
+            word = "<unk>"
+            if not self.knows(word):
+                return self.unknown
+        history = tuple(history[-(self.order - 1):]) if self.order > 1 else ()
+        penalty = 0.0
+        while True:
+            entry = self.ngrams.get(history + (word,))
+            if entry is not None:
+                return penalty + entry[0]
+            if not history:
+                return penalty + self.unknown
+            context = self.ngrams.get(history)
+            if context is not None:
+                penalty += context[1]
+            history = history[1:]
+
+
+class WordLanguageModelScorer:
+    """The scorer hooks of TF's CTC beam search with a word n-gram model behind them.
+
+    State = (incomplete word, history of finished words, weighted LM total of the finished words,
+    score = that total + look-ahead of the incomplete word, delta = score - score of the state it was
+    expanded from).  `alphabet[label]` is the character of a label; `" "` ends a word."""
+
+    def __init__(self, model: BackOffModel, alphabet: Sequence[str], kenlm_weight: float = .8,
+                 word_count_weight: float = 0., valid_word_count_weight: float = 2.3):
+        self.model, self.alphabet = model, list(alphabet)
+        self.weight = kenlm_weight * LN10
+        self.word_count_weight, self.valid_word_count_weight = word_count_weight, valid_word_count_weight
+        typeable = set(self.alphabet) - {" "}
+        self.vocabulary = [w for (w,) in (k for k in model.ngrams if len(k) == 1)
+                           if w not in ("<s>", "</s>", "<unk>") and w and set(w) <= typeable]
+        self.min_unigram: Dict[str, float] = {}  # prefix -> lowest unigram log10 probability of a word below it
+        for w in self.vocabulary:
+            p = model.ngrams[(w,)][0]
+            for n in range(len(w) + 1):
+                prefix = w[:n]
+                self.min_unigram[prefix] = min(self.min_unigram.get(prefix, 0.0), p)
+
+    def _look_ahead(self, incomplete: str) -> float:
+        if not incomplete:
+            return 0.0
+        return self.weight * self.min_unigram.get(incomplete, self.model.unknown)
+
+    def _word(self, word: str, history: Tuple[str, ...]) -> Tuple[float, Tuple[str, ...]]:
+        known = word in self.vocabulary_set
+        total = self.weight * self.model.log10_probability(word if known else "<unk>", history)
+        total += self.word_count_weight + (self.valid_word_count_weight if known else 0.0)
+        return total, (history + (word if known else "<unk>",))[-max(self.model.order - 1, 1):]
+
+    @property
+    def vocabulary_set(self):
+        if not hasattr(self, "_vocabulary_set"):
+            self._vocabulary_set = set(self.vocabulary)
+        return self._vocabulary_set
+
+    def initialize_state(self):
+        return ("", ("<s>",), 0.0, 0.0, 0.0)
+
+    def expand_state(self, from_state, from_label: int, to_label: int):
+        incomplete, history, total, score, _ = from_state
+        if self.alphabet[to_label] != " ":
+            incomplete = incomplete + self.alphabet[to_label]
+            new_score = total + self._look_ahead(incomplete)
+            return (incomplete, history, total, new_score, new_score - score)
+        gained, history = self._word(incomplete, history)
+        total += gained
+        return ("", history, total, total, total - score)
+
+    def expansion_score(self, state, previous: float) -> float:
+        return previous + state[4]
+
+    def expand_state_end(self, state):
+        incomplete, history, total, score, _ = state
+        if incomplete:
+            gained, history = self._word(incomplete, history)
+            total += gained
+        total += self.weight * self.model.log10_probability("</s>", history)
+        return ("", history, total, total, total - score)
+
+    def end_expansion_score(self, state) -> float:
+        return state[4]
+
+    def sentence_score(self, text: str) -> float:
+        """What a finished hypothesis collects in total (== NBestRescorer.score minus the CTC term)."""
+        history: Tuple[str, ...] = ("<s>",)
+        total = 0.0
+        words = text.split(" ") if text else []
+        if words and words[-1] == "":  # a trailing space has already finished the last word
+            words = words[:-1]
+        for word in words:
+            gained, history = self._word(word, history)
+            total += gained
+        return total + self.weight * self.model.log10_probability("</s>", history)

@@ -47,6 +47,9 @@ SIGNATURES = {
     "sl_ctc_beam_search_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "sl_ctc_beam_search_decode": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                           c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "sl_ctc_beam_search_decode_lm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                             c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t,
+                                             c_void_p]),
     "sl_spectrogram": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                c_void_p]),
     "sl_z_normalize": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),

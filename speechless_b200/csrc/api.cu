@@ -49,7 +49,7 @@ int ctc_greedy_launch(const float*, const int32_t*, int32_t*, int32_t*, int, int
                       cudaStream_t);
 size_t beam_search_workspace_bytes(int B, int T, int beam_width);
 int beam_search_launch(const float*, const int32_t*, int32_t*, int32_t*, float*, int, int, int, int, int, int, int,
-                       int, void*, size_t, cudaStream_t);
+                       int, const SlWordLm*, void*, size_t, cudaStream_t);
 
 static int round64(int c) { return (c + 63) & ~63; }
 static int dbg_mode() {
@@ -496,6 +496,10 @@ int sl_conv1d_fwd(const void* x_packed, const void* w_fwd, const float* bias, vo
     SL_REQUIRE(probs != nullptr, "softmax epilogue needs the probs output");
     SL_REQUIRE(cout_pad == 64, "softmax epilogue supports up to 64 symbols");
     epi = EPI_SOFTMAX;
+    {
+      const char* e = std::getenv("SL_REVERSE_OUTPUT");  // 0: first-to-last tile order (A/B runs)
+      p.reverse_order = e ? std::atoi(e) : 1;
+    }
     p.probs = probs;
     p.logits = logits;
     p.logp = logp;
@@ -810,7 +814,18 @@ int sl_ctc_beam_search_decode(const float* scores, const int32_t* input_len, int
   SL_REQUIRE(scores && input_len && out && out_len && out_logp && workspace, "null pointer");
   SL_REQUIRE(B > 0 && T > 0 && V > 0, "bad shape");
   return beam_search_launch(scores, input_len, out, out_len, out_logp, B, T, V, blank, beam_width, top_paths,
-                            merge_repeated, inputs_are_probs, workspace, workspace_bytes,
+                            merge_repeated, inputs_are_probs, nullptr, workspace, workspace_bytes,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int sl_ctc_beam_search_decode_lm(const float* scores, const int32_t* input_len, int32_t* out, int32_t* out_len,
+                                 float* out_logp, int B, int T, int V, int blank, int beam_width, int top_paths,
+                                 int merge_repeated, int inputs_are_probs, const SlWordLm* lm, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+  SL_REQUIRE(scores && input_len && out && out_len && out_logp && workspace && lm, "null pointer");
+  SL_REQUIRE(B > 0 && T > 0 && V > 0, "bad shape");
+  return beam_search_launch(scores, input_len, out, out_len, out_logp, B, T, V, blank, beam_width, top_paths,
+                            merge_repeated, inputs_are_probs, lm, workspace, workspace_bytes,
                             static_cast<cudaStream_t>(stream));
 }
 

@@ -29,8 +29,20 @@
 // BeamEntry object in its tree, and its surviving children still point at it — so (parent node, label)
 // -> node is kept in an open-addressing hash table in global memory, and parent slots are re-derived
 // from node ids every frame.
+//
+// Word language model inside the search (sl_ctc_beam_search_decode_lm; the reference's KenLM branch,
+// net.py:444-451): the four scorer hooks of TF's decoder are implemented on the device.  Every beam slot
+// carries the scorer state of its prefix (trie node of the unfinished word, the last order - 1 finished
+// words, the weighted LM total, the score including the look-ahead of the unfinished word, and the delta to
+// the state it was expanded from); a state is a function of the prefix alone, so a prefix that re-enters the
+// beam gets it re-derived from its parent and nothing is stored per tree node.  Per frame the deltas of all
+// beam_width x V possible children are computed in parallel (letters: two reads of the vocabulary trie; the
+// space label: a back-off walk through the n-gram hash table), then the selection runs as before on
+// lp + previous mass + delta.  Restated from oracle/beam_search_oracle.py (WordLanguageModelScorer; parity
+// with the patched TensorFlow fork is unpinned, see there).
 #include <cstdlib>
 
+#include "../../include/speechless_b200.h"
 #include "common.cuh"
 
 namespace sl {
@@ -55,6 +67,85 @@ __device__ __forceinline__ float logaddexp(float a, float b) {
   return m + log1pf(expf(fminf(a, b) - m));
 }
 
+constexpr int LM_CTX = 4;  // finished words a state remembers: n-gram order <= 5
+struct LmState {
+  int trie;          // node of the unfinished word in the vocabulary trie: 0 = no letters yet, -1 = not a prefix of any word
+  int ctx[LM_CTX];   // ids of the last finished words, newest last, -1 = none
+  float total;       // weighted LM total of the finished words (incl. word bonuses)
+  float score;       // total + look-ahead of the unfinished word
+  float delta;       // score - score of the state this one was expanded from (TF: GetStateExpansionScore - previous)
+};
+
+// ---- n-gram table: open addressing, 8 ints per slot {n, id0..id4 (-1 padded), log10 p, log10 back-off};
+//      slot = FNV-1a over the n ids, linear probing (speechless_b200/language_model.py builds it)
+__device__ __forceinline__ bool lm_find(const SlWordLm& lm, const int* ids, int n, float* logp, float* backoff) {
+  uint32_t h = 2166136261u;
+  for (int k = 0; k < n; ++k) h = (h ^ static_cast<uint32_t>(ids[k])) * 16777619u;
+  for (uint32_t slot = h & lm.ngram_mask;; slot = (slot + 1) & lm.ngram_mask) {
+    const int4 a = __ldg(reinterpret_cast<const int4*>(lm.ngrams) + 2 * slot);
+    if (a.x == 0) return false;
+    if (a.x != n) continue;
+    const int4 b = __ldg(reinterpret_cast<const int4*>(lm.ngrams) + 2 * slot + 1);
+    const int key[5] = {a.y, a.z, a.w, b.x, b.y};
+    bool same = true;
+    for (int k = 0; k < n; ++k) same = same && key[k] == ids[k];
+    if (!same) continue;
+    *logp = __int_as_float(b.z);
+    *backoff = __int_as_float(b.w);
+    return true;
+  }
+}
+// log10 P(word | ctx) with ARPA back-off semantics
+__device__ float lm_word_log10(const SlWordLm& lm, const int* ctx, int word) {
+  if (word == lm.unk_id && !lm.has_unk) return lm.unknown_log10;
+  int ids[LM_CTX + 1];
+  int m = 0;
+  for (int k = 0; k < LM_CTX; ++k)
+    if (ctx[k] >= 0 && LM_CTX - k <= lm.order - 1) ids[m++] = ctx[k];
+  ids[m] = word;
+  float penalty = 0.f;
+  for (int s0 = 0;; ++s0) {
+    float logp, backoff;
+    if (lm_find(lm, ids + s0, m - s0 + 1, &logp, &backoff)) return penalty + logp;
+    if (s0 == m) return penalty + lm.unknown_log10;
+    if (lm_find(lm, ids + s0, m - s0, &logp, &backoff)) penalty += backoff;
+  }
+}
+// a finished word: what it adds to the total, and the new context
+__device__ float lm_finish_word(const SlWordLm& lm, int trie, int* ctx) {
+  const int word = trie > 0 ? __ldg(lm.trie_word + trie) : -1;
+  const bool known = word >= 0;
+  const int id = known ? word : lm.unk_id;
+  const float gained = lm.weight * lm_word_log10(lm, ctx, id) + lm.word_count_weight +
+                       (known ? lm.valid_word_count_weight : 0.f);
+  for (int k = 0; k + 1 < LM_CTX; ++k) ctx[k] = ctx[k + 1];
+  ctx[LM_CTX - 1] = id;
+  return gained;
+}
+// TF ExpandState: the state of prefix + label
+__device__ LmState lm_expand(const SlWordLm& lm, const LmState& from, int label, int V) {
+  LmState to = from;
+  if (label != lm.space_label) {
+    to.trie = from.trie >= 0 ? __ldg(lm.trie_children + static_cast<size_t>(from.trie) * V + label) : -1;
+    to.score = from.total + lm.weight * (to.trie >= 0 ? __ldg(lm.trie_min_unigram + to.trie) : lm.unknown_log10);
+  } else {
+    to.total = from.total + lm_finish_word(lm, from.trie, to.ctx);
+    to.score = to.total;
+    to.trie = 0;
+  }
+  to.delta = to.score - from.score;
+  return to;
+}
+// TF ExpandStateEnd + GetStateEndExpansionScore: the unfinished word and the end of the sentence
+__device__ float lm_end_delta(const SlWordLm& lm, const LmState& s) {
+  int ctx[LM_CTX];
+  for (int k = 0; k < LM_CTX; ++k) ctx[k] = s.ctx[k];
+  float total = s.total;
+  if (s.trie != 0) total += lm_finish_word(lm, s.trie, ctx);
+  total += lm.weight * lm_word_log10(lm, ctx, lm.eos_id);
+  return total - s.score;
+}
+
 struct BeamGen {  // one generation of the beam (slots sorted best first)
   int node[BS_MAX_W];
   int label[BS_MAX_W];
@@ -62,6 +153,7 @@ struct BeamGen {  // one generation of the beam (slots sorted best first)
   float pb[BS_MAX_W];
   float pl[BS_MAX_W];
   float tot[BS_MAX_W];
+  LmState st[BS_MAX_W];  // scorer state of the slot's prefix (language-model decode only)
 };
 
 struct BeamSmem {
@@ -80,6 +172,7 @@ struct BeamSmem {
   unsigned char child_slot[BS_MAX_W][BS_VP];  // slot of the beam entry that is child (slot, symbol), valid where child_active
   unsigned char displaced[BS_MAX_W];     // beam entry popped from `leaves_` during this frame's child loop
   unsigned char wiped[BS_MAX_W];         // ... and then "deactivated" through its parent: it proposes no children
+  float cand_delta[BS_MAX_W][BS_VP];     // language model: delta of the state of child (slot, symbol)
 };
 
 constexpr int BS_CPT = BS_MAX_CAND / BS_THREADS;  // candidates per thread, kept in registers
@@ -110,7 +203,8 @@ __device__ __forceinline__ int block_sum(BeamSmem& sm, int c, int& it) {
 // cheap: one warp, `leaves_` in shared memory, per beam entry one ballot of the labels whose score beats the
 // bottom (it only rises) and a visit of those few.  Returns the number of leaves; their keys go to
 // sm.selected in the format of the parallel selection.  All threads call it (barriers inside).
-__device__ __noinline__ int tf_exact_child_loop(BeamSmem& sm, const BeamGen& g, int n, int V, int blank, int W) {
+__device__ __noinline__ int tf_exact_child_loop(BeamSmem& sm, const BeamGen& g, int n, int V, int blank, int W,
+                                                bool with_lm) {
   const int tid = threadIdx.x, lane = tid & 31;
   if (tid < n) sm.leaf_idx[tid] = tid * V + blank;
   __syncthreads();
@@ -155,7 +249,8 @@ __device__ __noinline__ int tf_exact_child_loop(BeamSmem& sm, const BeamGen& g, 
       for (int h = 0; h < 2; ++h) {
         const int c = lane + 32 * h;
         sc[h] = 0u;
-        if (c < V && c != blank) sc[h] = float_to_ordered(sm.lp[c] + (c == lab_i ? g.pb[i] : g.tot[i]));
+        if (c < V && c != blank)
+          sc[h] = float_to_ordered(sm.lp[c] + (c == lab_i ? g.pb[i] : g.tot[i]) + (with_lm ? sm.cand_delta[i][c] : 0.f));
         beam_children[h] = static_cast<unsigned>(in_beam >> (32 * h));
         // worth a visit: a candidate that beats the bottom (which only rises), or a beam entry — it may have
         // been displaced by now
@@ -224,12 +319,13 @@ __device__ __noinline__ int tf_exact_child_loop(BeamSmem& sm, const BeamGen& g, 
   return sm.n_selected;
 }
 
+template <bool LM>
 __global__ void __launch_bounds__(BS_THREADS)
     ctc_beam_search_kernel(const float* __restrict__ scores, const int32_t* __restrict__ input_len,
                            int32_t* __restrict__ out, int32_t* __restrict__ out_len, float* __restrict__ out_logp,
                            int2* __restrict__ nodes_all, unsigned long long* __restrict__ hash_all, int hash_cap,
                            int T, int V, int blank, int W, int top_paths, int merge_repeated, int inputs_are_probs,
-                           int tf_exact) {
+                           int tf_exact, const SlWordLm lm) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   BeamSmem& sm = *reinterpret_cast<BeamSmem*>(smem_raw);
   const int b = blockIdx.x;
@@ -248,6 +344,11 @@ __global__ void __launch_bounds__(BS_THREADS)
     g.pb[0] = 0.f;
     g.pl[0] = -INFINITY;
     g.tot[0] = 0.f;
+    if constexpr (LM) {  // TF InitializeState: nothing typed, history = <s>
+      g.st[0].trie = 0;
+      for (int k = 0; k < LM_CTX; ++k) g.st[0].ctx[k] = k == LM_CTX - 1 ? lm.bos_id : -1;
+      g.st[0].total = g.st[0].score = g.st[0].delta = 0.f;
+    }
     sm.n_active = 1;
   }
   // the frame's scores are fetched one frame ahead (warp 0, two symbols per lane)
@@ -300,7 +401,8 @@ __global__ void __launch_bounds__(BS_THREADS)
       float pl = -INFINITY;
       if (lab >= 0) {
         const int ps = g.pslot[tid];
-        const float previous = ps >= 0 ? (lab == g.label[ps] ? g.pb[ps] : g.tot[ps]) : -INFINITY;
+        float previous = ps >= 0 ? (lab == g.label[ps] ? g.pb[ps] : g.tot[ps]) : -INFINITY;
+        if constexpr (LM) previous += g.st[tid].delta;  // TF GetStateExpansionScore(b->state, previous)
         pl = logaddexp(g.pl[tid], previous) + sm.lp[lab];
         if (ps >= 0) {
           atomicOr(&sm.child_active[ps], 1ull << lab);
@@ -312,10 +414,18 @@ __global__ void __launch_bounds__(BS_THREADS)
       sm.pln[tid] = pl;
       sm.totn[tid] = logaddexp(pb, pl);
     }
+    if constexpr (LM) {
+      // the scorer deltas of every possible child (TF calls ExpandState inside its child loop; a state is a
+      // function of the prefix alone, so computing them up front changes nothing)
+      for (int idx = tid; idx < n * V; idx += BS_THREADS) {
+        const int i = idx / V, c = idx - i * V;
+        if (c != blank) sm.cand_delta[i][c] = lm_expand(lm, g.st[i], c, V).delta;
+      }
+    }
     __syncthreads();
     int n_next;
     if (tf_exact) {
-      n_next = tf_exact_child_loop(sm, g, n, V, blank, W);  // fills sm.selected[0 .. n_next)
+      n_next = tf_exact_child_loop(sm, g, n, V, blank, W, LM);  // fills sm.selected[0 .. n_next)
     } else {
       // 3. candidates (slot i, symbol c), BS_CPT per thread in registers; c == blank stands for
       //    "prefix i continued".  Order-preserving integer image of the score; 0 = no candidate.
@@ -331,7 +441,7 @@ __global__ void __launch_bounds__(BS_THREADS)
             if (c == blank)
               key = sm.totn[i];
             else if (!((sm.child_active[i] >> c) & 1ull))
-              key = sm.lp[c] + (c == g.label[i] ? g.pb[i] : g.tot[i]);
+              key = sm.lp[c] + (c == g.label[i] ? g.pb[i] : g.tot[i]) + (LM ? sm.cand_delta[i][c] : 0.f);
             kv[q] = float_to_ordered(key);
           }
         }
@@ -398,6 +508,7 @@ __global__ void __launch_bounds__(BS_THREADS)
         nx.pb[slot] = sm.pbn[i];
         nx.pl[slot] = sm.pln[i];
         nx.tot[slot] = sm.totn[i];
+        if constexpr (LM) nx.st[slot] = g.st[i];
         sm.parent_node[slot] = nodes[node].x;
       } else {
         // the prefix (node of i) + c: reuse its node if it has been in the beam before
@@ -422,6 +533,7 @@ __global__ void __launch_bounds__(BS_THREADS)
         nx.pb[slot] = -INFINITY;
         nx.pl[slot] = f;
         nx.tot[slot] = f;
+        if constexpr (LM) nx.st[slot] = lm_expand(lm, g.st[i], c, V);
         sm.parent_node[slot] = pn;
       }
     }
@@ -442,19 +554,32 @@ __global__ void __launch_bounds__(BS_THREADS)
   // to the label of the node visited just before it, i.e. its successor, is dropped)
   const BeamGen& g = sm.gen[cur];
   const int n = sm.n_active;
+  if constexpr (LM) {
+    // TF TopPaths: every leaf's state is closed (unfinished word, end of sentence) before the leaves are ranked
+    if (tid < n) sm.totn[tid] = g.tot[tid] + lm_end_delta(lm, g.st[tid]);
+    __syncthreads();
+    if (tid < n) {
+      int rank = 0;
+      for (int s2 = 0; s2 < n; ++s2)
+        rank += (sm.totn[s2] > sm.totn[tid] || (sm.totn[s2] == sm.totn[tid] && s2 < tid)) ? 1 : 0;
+      sm.leaf_idx[rank] = tid;
+    }
+    __syncthreads();
+  }
   if (tid < top_paths) {
     int32_t* o = out + (static_cast<size_t>(b) * top_paths + tid) * T;
     int len = 0;
+    const int src = (LM && tid < n) ? sm.leaf_idx[tid] : tid;  // slot of the tid-th best finished hypothesis
     if (tid < n) {
       int prev = -1;
-      for (int node = g.node[tid]; node > 0; node = nodes[node].x) {
+      for (int node = g.node[src]; node > 0; node = nodes[node].x) {
         const int lab = nodes[node].y;
         if (!merge_repeated || lab != prev) ++len;
         prev = lab;
       }
       int pos = len;
       prev = -1;
-      for (int node = g.node[tid]; node > 0; node = nodes[node].x) {
+      for (int node = g.node[src]; node > 0; node = nodes[node].x) {
         const int lab = nodes[node].y;
         if (!merge_repeated || lab != prev) o[--pos] = lab;
         prev = lab;
@@ -462,7 +587,7 @@ __global__ void __launch_bounds__(BS_THREADS)
     }
     for (int i = len; i < T; ++i) o[i] = -1;
     out_len[b * top_paths + tid] = tid < n ? len : 0;
-    out_logp[b * top_paths + tid] = tid < n ? g.tot[tid] : -INFINITY;
+    out_logp[b * top_paths + tid] = tid < n ? (LM ? sm.totn[src] : g.tot[src]) : -INFINITY;
   }
 }
 
@@ -484,7 +609,8 @@ size_t beam_search_workspace_bytes(int B, int T, int beam_width) {
 
 int beam_search_launch(const float* scores, const int32_t* input_len, int32_t* out, int32_t* out_len, float* out_logp,
                        int B, int T, int V, int blank, int beam_width, int top_paths, int merge_repeated,
-                       int inputs_are_probs, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+                       int inputs_are_probs, const SlWordLm* lm, void* workspace, size_t workspace_bytes,
+                       cudaStream_t stream) {
   SL_REQUIRE(V >= 2 && V <= BS_VP, "beam search supports 2..64 symbols (incl. blank)");
   SL_REQUIRE(blank >= 0 && blank < V, "blank out of range");
   SL_REQUIRE(beam_width >= 1 && beam_width <= BS_MAX_W, "beam_width must be 1..128");
@@ -493,18 +619,36 @@ int beam_search_launch(const float* scores, const int32_t* input_len, int32_t* o
   SL_REQUIRE(workspace_bytes >= beam_search_workspace_bytes(B, T, beam_width), "beam search workspace too small");
   SL_REQUIRE(static_cast<size_t>(T) * beam_width < (1u << 24), "too many frames x beam entries");
   const size_t smem = sizeof(BeamSmem);
-  SL_CUDA(cudaFuncSetAttribute(ctc_beam_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               static_cast<int>(smem)));
+  if (lm != nullptr) {
+    SL_REQUIRE(lm->trie_children && lm->trie_word && lm->trie_min_unigram && lm->ngrams, "language model: null table");
+    SL_REQUIRE(lm->order >= 1 && lm->order <= LM_CTX + 1, "language model: n-gram order must be 1..5");
+    SL_REQUIRE(lm->n_labels == V, "language model: the trie must have one column per symbol");
+    SL_REQUIRE(lm->space_label >= 0 && lm->space_label < V && lm->space_label != blank, "language model: bad space label");
+    SL_REQUIRE((lm->ngram_mask & (lm->ngram_mask + 1)) == 0, "language model: the table size must be a power of two");
+    SL_CUDA(cudaFuncSetAttribute(ctc_beam_search_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(smem)));
+  } else {
+    SL_CUDA(cudaFuncSetAttribute(ctc_beam_search_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(smem)));
+  }
   const int hash_cap = beam_hash_capacity(T, beam_width);
   unsigned long long* hash = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(workspace) +
                                                                    beam_nodes_bytes(B, T, beam_width));
   SL_CUDA(cudaMemsetAsync(hash, 0, static_cast<size_t>(B) * hash_cap * sizeof(unsigned long long), stream));
   const char* oi = std::getenv("SL_BEAM_ORDER_INDEPENDENT");  // 1: parallel selection rule (A/B, see the header comment)
-  const int tf_exact = (oi && std::atoi(oi) != 0) ? 0 : 1;
-  ctc_beam_search_kernel<<<B, BS_THREADS, smem, stream>>>(scores, input_len, out, out_len, out_logp,
-                                                          reinterpret_cast<int2*>(workspace), hash, hash_cap, T, V,
-                                                          blank, beam_width, top_paths, merge_repeated,
-                                                          inputs_are_probs, tf_exact);
+  // (with a language model always TF's loop: a word bonus can lift a child above its parent, and then "the W
+  // best of the union" also takes children of parents that TF's is_candidate(parent) test never expands)
+  const int tf_exact = (oi && std::atoi(oi) != 0 && lm == nullptr) ? 0 : 1;
+  if (lm != nullptr)
+    ctc_beam_search_kernel<true><<<B, BS_THREADS, smem, stream>>>(scores, input_len, out, out_len, out_logp,
+                                                                  reinterpret_cast<int2*>(workspace), hash, hash_cap,
+                                                                  T, V, blank, beam_width, top_paths, merge_repeated,
+                                                                  inputs_are_probs, tf_exact, *lm);
+  else
+    ctc_beam_search_kernel<false><<<B, BS_THREADS, smem, stream>>>(scores, input_len, out, out_len, out_logp,
+                                                                   reinterpret_cast<int2*>(workspace), hash, hash_cap,
+                                                                   T, V, blank, beam_width, top_paths, merge_repeated,
+                                                                   inputs_are_probs, tf_exact, SlWordLm{});
   SL_CUDA(cudaGetLastError());
   return 0;
 }

@@ -102,6 +102,7 @@ __device__ __forceinline__ WorkItem decode_item(const ConvGemmParams& p, int ite
     sub = r - (r / p.tail_split) * p.tail_split;
     width = BN / p.tail_split;
   }
+  if (p.reverse_order) tile = p.m_units * p.n_tiles - 1 - tile;  // (whole tiles only, see conv_gemm_launch)
   // filter tile fastest: the n_tiles CTAs that share an activation tile run together, so the
   // A operand comes from HBM once and from L2 afterwards (the weights are L2 resident anyway;
   // with the filter tile slowest, big_conv_2 re-read its 164 MB input 8 times from HBM)
@@ -888,6 +889,9 @@ int conv_gemm_launch(const ConvGemmParams& p, int block_n, int epi, bool b_mn_ma
                       : launch<256, EPI_PACKED, false, 2>(p, num_sms, stream);
   }
   SL_REQUIRE(p.ctas == 1, "ctas must be 1 or 2");
+  SL_REQUIRE(!p.reverse_order || (p.ksplit <= 1 && p.tail_split == 1 && p.tail_ksplit <= 1 &&
+                                  p.full_tiles == p.m_units * p.n_tiles),
+             "reverse tile order is for whole tiles");
   if (epi == EPI_SOFTMAX) {
     SL_REQUIRE(block_n == 64 && !b_mn_major, "softmax epilogue needs a 64-wide K-major tile");
     return launch<64, EPI_SOFTMAX, false, 1>(p, num_sms, stream);

@@ -80,6 +80,10 @@ struct ConvGemmParams {
   int mask_T;
   int out_t_scale;
   int out_t_off;
+  // 1: walk the tiles from the last frame tile to the first.  A layer whose input is larger than L2 and was
+  // written by the launch just before it (output_conv reading the 164 MB of big_conv_2) then starts on the
+  // tiles that are still L2 resident instead of evicting them with the oldest ones
+  int reverse_order;
   int dbg_mode;   // bring-up only (env SL_DBG_MODE): 1 = stop issuing TMA loads after the first ring fill
   // measurement aid (env SL_TIMELINE=1): 32 clock64() stamps per CTA — entry, setup done, first operands
   // landed, last MMA issued / accumulator complete / epilogue done of the CTA's first tiles, exit

@@ -628,9 +628,11 @@ class ConvTower:
         return ws.decoded, ws.decoded_len
 
     def beam_search_decode(self, ws: _Workspace, beam_width: int = 100, top_paths: int = 1,
-                           merge_repeated: bool = False) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-        """Prefix beam search over the softmax output of `forward` (tf.nn.ctc_beam_search_decoder with the
-        stock scorer, reference net.py:444-451).  Returns (decoded (B, top_paths, T') int32 padded with -1,
+                           merge_repeated: bool = False, language_model=None
+                           ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """Prefix beam search over the softmax output of `forward` (tf.nn.ctc_beam_search_decoder, reference
+        net.py:444-451): with the stock scorer, or — `language_model`: a `DeviceLanguageModel` — with the word
+        n-gram scorer inside the search.  Returns (decoded (B, top_paths, T') int32 padded with -1,
         lengths (B, top_paths), log-probabilities (B, top_paths)), best path first."""
         V = self.layers[-1].cout
         with torch.cuda.device(self.device):
@@ -640,10 +642,17 @@ class ConvTower:
             decoded = torch.empty((ws.B, top_paths, ws.Tp), dtype=torch.int32, device=self.device)
             lengths = torch.empty((ws.B, top_paths), dtype=torch.int32, device=self.device)
             log_probabilities = torch.empty((ws.B, top_paths), dtype=torch.float32, device=self.device)
-            check(self.lib.sl_ctc_beam_search_decode(ptr(ws.probs), ptr(ws.input_len), ptr(decoded), ptr(lengths),
-                                                     ptr(log_probabilities), ws.B, ws.Tp, V, V - 1, beam_width,
-                                                     top_paths, 1 if merge_repeated else 0, 1, ptr(ws.beam_ws),
-                                                     ws.beam_ws.numel(), self.stream))
+            if language_model is not None:
+                import ctypes
+                check(self.lib.sl_ctc_beam_search_decode_lm(
+                    ptr(ws.probs), ptr(ws.input_len), ptr(decoded), ptr(lengths), ptr(log_probabilities), ws.B, ws.Tp,
+                    V, V - 1, beam_width, top_paths, 1 if merge_repeated else 0, 1,
+                    ctypes.addressof(language_model.struct), ptr(ws.beam_ws), ws.beam_ws.numel(), self.stream))
+            else:
+                check(self.lib.sl_ctc_beam_search_decode(ptr(ws.probs), ptr(ws.input_len), ptr(decoded), ptr(lengths),
+                                                         ptr(log_probabilities), ws.B, ws.Tp, V, V - 1, beam_width,
+                                                         top_paths, 1 if merge_repeated else 0, 1, ptr(ws.beam_ws),
+                                                         ws.beam_ws.numel(), self.stream))
             self.launches += 1
         return decoded, lengths, log_probabilities
 

@@ -240,6 +240,7 @@ class Wav2Letter:
                  seed: Optional[int] = None,
                  decoder_beam_width: int = 100,
                  decoder_top_paths: int = 32,
+                 language_model_mode: str = "in-search",
                  data_parallel=None):
         if frozen_layer_count > 0 and load_model_from_directory is None:
             raise ValueError("Layers cannot be frozen if model is trained from scratch.")
@@ -248,6 +249,10 @@ class Wav2Letter:
 
         self.kenlm_directory = kenlm_directory
         self.rescorer = None
+        self.device_language_model = None
+        if language_model_mode not in ("in-search", "rescoring"):
+            raise ValueError("language_model_mode must be 'in-search' or 'rescoring'")
+        self.language_model_mode = language_model_mode
         self.decoder_beam_width = decoder_beam_width
         self.decoder_top_paths = min(decoder_top_paths, decoder_beam_width)
         self.grapheme_encoding = AsgGraphemeEncoding(allowed_characters=allowed_characters) \
@@ -284,17 +289,24 @@ class Wav2Letter:
                 raise ValueError("Allowed characters {} differ from those expected by kenlm decoder: {}".
                                  format(allowed_characters, expected_characters))
             # The reference hands the directory to a patched TensorFlow whose beam search scores words with
-            # KenLM (net.py:420-422,444-451).  Here: device beam search (stock scorer) + n-best re-scoring
-            # with a word n-gram model in ARPA text format, same three weights (language_model.py).
-            from speechless_b200.language_model import ArpaLanguageModel, NBestRescorer, find_arpa_file
+            # KenLM (net.py:420-422,444-451).  Here: a word n-gram model in ARPA text format with the same three
+            # weights, scored INSIDE the device beam search (`language_model_mode="in-search"`, default) or used
+            # to re-rank the finished hypotheses of the plain search ("rescoring") — language_model.py.
+            from speechless_b200.language_model import (ArpaLanguageModel, DeviceLanguageModel, NBestRescorer,
+                                                        find_arpa_file)
             arpa_file = find_arpa_file(self.kenlm_directory)
             if arpa_file is None:
                 raise NotImplementedError(
                     "No *.arpa file in {}: KenLM's binary format needs the KenLM library of the reference's patched "
                     "TensorFlow (net.py:420-422), which is not available; export the model as ARPA text.".format(
                         self.kenlm_directory))
-            self.rescorer = NBestRescorer(ArpaLanguageModel.read(arpa_file), kenlm_weight=.8, word_count_weight=0,
+            arpa_model = ArpaLanguageModel.read(arpa_file)
+            self.rescorer = NBestRescorer(arpa_model, kenlm_weight=.8, word_count_weight=0,
                                           valid_word_count_weight=2.3)
+            if language_model_mode == "in-search":
+                self.device_language_model = DeviceLanguageModel(
+                    arpa_model, alphabet=allowed_characters, symbol_count=self.grapheme_encoding.grapheme_set_size,
+                    device=self.tower.device, kenlm_weight=.8, word_count_weight=0, valid_word_count_weight=2.3)
 
         if load_model_from_directory is not None:
             self.load_weights(
@@ -461,12 +473,13 @@ class Wav2Letter:
         return decoded[:, :width], loss.cpu().numpy().reshape(-1, 1)
 
     def beam_search_batch(self, ws, beam_width: Optional[int] = None, top_paths: int = 1,
-                          merge_repeated: bool = False) -> List[List[Tuple[List[int], float]]]:
+                          merge_repeated: bool = False, language_model=None) -> List[List[Tuple[List[int], float]]]:
         """Device prefix beam search over a forwarded workspace: per utterance the `top_paths` best
         (grapheme indices, log-probability) pairs, best first (tf.nn.ctc_beam_search_decoder semantics; the
         reference calls it with merge_repeated=False, net.py:441-447)."""
         decoded, lengths, log_probabilities = self.tower.beam_search_decode(
-            ws, beam_width=beam_width or self.decoder_beam_width, top_paths=top_paths, merge_repeated=merge_repeated)
+            ws, beam_width=beam_width or self.decoder_beam_width, top_paths=top_paths, merge_repeated=merge_repeated,
+            language_model=language_model)
         decoded, lengths, log_probabilities = decoded.cpu().numpy(), lengths.cpu().numpy(), log_probabilities.cpu().numpy()
         return [[(decoded[b, p, :lengths[b, p]].tolist(), float(log_probabilities[b, p]))
                  for p in range(decoded.shape[1]) if numpy.isfinite(log_probabilities[b, p])]
@@ -486,11 +499,17 @@ class Wav2Letter:
                 for hypotheses in self.beam_search_batch(ws, beam_width=beam_width, top_paths=top_paths)]
 
     def _beam_search_with_language_model(self, ws) -> ndarray:
-        """Dense (B, max length) grapheme matrix, -1 padded like the greedy path: the hypothesis of the
-        device beam search that the language model re-scores best."""
-        n_best = self.beam_search_batch(ws, top_paths=self.decoder_top_paths, merge_repeated=False)
+        """Dense (B, max length) grapheme matrix, -1 padded like the greedy path: the best hypothesis of the
+        device beam search with the language model inside the search, or (`language_model_mode="rescoring"`)
+        the hypothesis of the plain search that the language model re-scores best."""
+        in_search = self.device_language_model is not None
+        n_best = self.beam_search_batch(ws, top_paths=1 if in_search else self.decoder_top_paths, merge_repeated=False,
+                                        language_model=self.device_language_model)
         winners = []
         for hypotheses in n_best:
+            if in_search:
+                winners.append(hypotheses[0][0] if hypotheses else [])
+                continue
             if not hypotheses:  # no finite hypothesis (e.g. NaN probabilities): empty transcription, not a crash
                 winners.append([])
                 continue
