@@ -15,10 +15,11 @@ Differences that are deliberate and documented in DESIGN.md:
 * `use_raw_wave_input=True` adds `wave_conv` (k250 s160, net.py:310-312) in front; its receptive
   fields are laid out as rows on the device so it runs on the same tensor-core kernels;
 * `kenlm_directory` keeps the vocabulary check of net.py:171-177 and decodes with the device prefix
-  beam search (`sl_ctc_beam_search_decode`), re-scoring its n-best list with a word n-gram model read
-  from a `*.arpa` file of that directory (language_model.py); the in-search KenLM scorer of the
-  reference's patched TensorFlow (net.py:420-422) is not reproducible, a KenLM binary alone raises
-  `NotImplementedError`; `use_asg=True` raises at loss time exactly like the reference;
+  beam search with a word n-gram model inside the search (`sl_ctc_beam_search_decode_lm`; the model is read
+  from a `*.arpa` file of that directory, language_model.py; `language_model_mode="rescoring"` re-ranks the
+  n-best list of the plain search instead).  The scorer of the reference's patched TensorFlow (net.py:420-422)
+  is not in the tree, so parity with it is unpinned; a KenLM binary alone raises `NotImplementedError`;
+  `use_asg=True` raises at loss time exactly like the reference;
 * `dropout` masks come from a counter-based hash, so they cannot equal TF's bit for bit; the
   arithmetic given the masks is what the parity tests check.
 """

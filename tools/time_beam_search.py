@@ -1,4 +1,6 @@
-"""Times sl_ctc_beam_search_decode at the bench shape (64 x 626 frames, V = 29) for a few beam widths."""
+"""Times sl_ctc_beam_search_decode at the bench shape (64 x 626 frames, V = 29) for a few beam widths, and
+sl_ctc_beam_search_decode_lm (word n-gram model inside the search) with a synthetic 20 000-word trigram model."""
+import ctypes
 import sys
 from pathlib import Path
 
@@ -52,4 +54,45 @@ for name in ("flat", "trained-like"):
         e1.record()
         torch.cuda.synchronize()
         print("%-12s beam_width %3d: %.3f ms per batch of %d x %d frames (mean decoded length %.1f)" % (
+            name, width, e0.elapsed_time(e1) / 3, B, T, out_len.float().mean().item()))
+
+
+# ---- the same search with a word n-gram model inside: 20 000 random words, 100 000 bigrams, 100 000 trigrams
+from speechless_b200 import english_frequent_characters  # noqa: E402
+from speechless_b200.language_model import ArpaLanguageModel, DeviceLanguageModel  # noqa: E402
+
+alphabet = list(english_frequent_characters)
+letters = [c for c in alphabet if c != " "]
+words = sorted({"".join(rng.choice(letters, size=rng.integers(2, 9))) for _ in range(20000)})
+ngrams = {("<s>",): (-99.0, -0.4), ("</s>",): (-1.3, 0.0), ("<unk>",): (-3.0, -0.1)}
+for w in words:
+    ngrams[(w,)] = (float(-rng.random() * 3 - 1), float(-rng.random() * 0.5))
+for n, count in ((2, 100000), (3, 100000)):
+    picks = rng.integers(0, len(words), size=(count, n))
+    for row in picks:
+        ngrams[tuple(words[i] for i in row)] = (float(-rng.random() * 2 - 0.1), float(-rng.random() * 0.4) if n == 2 else 0.0)
+lm = DeviceLanguageModel(ArpaLanguageModel(ngrams, 3), alphabet, V, torch.device("cuda"))
+print("language model: %d n-grams, table of %d slots, trie of %d nodes" % (
+    len(ngrams), lm.tables.ngrams.shape[0], lm.tables.trie_children.shape[0]))
+for name in ("flat", "trained-like"):
+    probs = scenario(name)
+    for width in (16, 100):
+        out = torch.empty((B, 1, T), dtype=torch.int32, device="cuda")
+        out_len = torch.empty((B, 1), dtype=torch.int32, device="cuda")
+        out_logp = torch.empty((B, 1), dtype=torch.float32, device="cuda")
+        ws = torch.empty(lib.sl_ctc_beam_search_workspace_bytes(B, T, width), dtype=torch.uint8, device="cuda")
+
+        def run_lm():
+            _lib.check(lib.sl_ctc_beam_search_decode_lm(_lib.ptr(probs), _lib.ptr(lengths), _lib.ptr(out),
+                                                        _lib.ptr(out_len), _lib.ptr(out_logp), B, T, V, V - 1, width, 1,
+                                                        0, 1, ctypes.addressof(lm.struct), _lib.ptr(ws), ws.numel(), None))
+        run_lm()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            run_lm()
+        e1.record()
+        torch.cuda.synchronize()
+        print("%-12s with language model, beam_width %3d: %.3f ms per batch of %d x %d frames (mean decoded length %.1f)" % (
             name, width, e0.elapsed_time(e1) / 3, B, T, out_len.float().mean().item()))
