@@ -11,7 +11,8 @@ Differences that are deliberate and documented in DESIGN.md:
   default-argument instance between all models, net.py:132);
 * batches of size 1 work (the reference needs the duplication workaround of net.py:492-495,
   which is kept so results are identical either way);
-* weights are saved as `.npz` keyed by the Keras layer names when `h5py` is unavailable;
+* weights are saved as `.npz` keyed by the Keras layer names and, for `.h5` paths, in Keras' HDF5 layout
+  (h5py when installed, else the pure-Python `hdf5_lite`); `.h5` files written by Keras load the same way;
 * `use_raw_wave_input=True` adds `wave_conv` (k250 s160, net.py:310-312) in front; its receptive
   fields are laid out as rows on the device so it runs on the same tensor-core kernels;
 * `kenlm_directory` keeps the vocabulary check of net.py:171-177 and decodes with the device prefix
@@ -119,48 +120,67 @@ class PredictiveNet:
         return path if path.suffix == ".npz" else path.with_suffix(".npz")
 
     def save_weights(self, path) -> None:
+        """`.npz` keyed by the Keras layer names, or — a path ending in `.h5` / `.hdf5` — the HDF5 layout of
+        Keras' `save_weights` (root attribute `layer_names`, one group per layer with `weight_names` and the
+        datasets `<layer>/kernel:0`, `<layer>/bias:0`, reference net.py:572), written by h5py when it is
+        installed and by `speechless_b200.hdf5_lite` otherwise; next to an `.h5` the `.npz` is always written too
+        (hdf5_lite's writer could not be checked against libhdf5 in this image)."""
         arrays = {}
         for layer in self.conv_layers:
             kernel, bias = layer.get_weights()
             arrays["{}/kernel".format(layer.name)] = kernel
             arrays["{}/bias".format(layer.name)] = bias
+        numpy.savez(str(self._npz_path(path)), **arrays)
+        if Path(str(path)).suffix not in (".h5", ".hdf5"):
+            return
+        layer_names = [layer.name.encode("utf8") for layer in self.conv_layers]
+        weight_names = {layer.name: ["{}/kernel:0".format(layer.name), "{}/bias:0".format(layer.name)]
+                        for layer in self.conv_layers}
         try:
-            import h5py  # optional: Keras-compatible container when available
+            import h5py  # optional
         except ImportError:
-            numpy.savez(str(self._npz_path(path)), **arrays)
+            from speechless_b200 import hdf5_lite
+            tree = {layer.name: {weight_names[layer.name][0]: arrays["{}/kernel".format(layer.name)],
+                                 weight_names[layer.name][1]: arrays["{}/bias".format(layer.name)]}
+                    for layer in self.conv_layers}
+            attrs = {"/": {"layer_names": layer_names, "backend": b"tensorflow", "keras_version": b"2.0.4"}}
+            for name, names in weight_names.items():
+                attrs[name] = {"weight_names": [n.encode("utf8") for n in names]}
+            hdf5_lite.write(path, tree, attrs)
             return
         with h5py.File(str(path), "w") as f:
-            f.attrs["layer_names"] = [layer.name.encode("utf8") for layer in self.conv_layers]
+            f.attrs["layer_names"] = layer_names
             for layer in self.conv_layers:
                 group = f.create_group(layer.name)
-                names = ["{}/kernel:0".format(layer.name), "{}/bias:0".format(layer.name)]
+                names = weight_names[layer.name]
                 group.attrs["weight_names"] = [n.encode("utf8") for n in names]
                 group.create_dataset(names[0], data=arrays["{}/kernel".format(layer.name)])
                 group.create_dataset(names[1], data=arrays["{}/bias".format(layer.name)])
 
     def load_weights(self, path) -> None:
-        """The exact file given wins; `weights-epochN.npz` next to it is the fallback when the `.h5` does not
-        exist or cannot be read for lack of h5py (this image has none, so the `.h5` branch is unreachable
-        here: DESIGN.md §7)."""
+        """The exact file given wins: an `.h5` written by Keras (h5py's default file format) is read with h5py
+        when it is installed, else with `speechless_b200.hdf5_lite` (pure Python; validated on a genuine
+        libhdf5-written file, tests/test_hdf5_lite.py); `weights-epochN.npz` next to it is the fallback when
+        the `.h5` does not exist."""
         npz = self._npz_path(path)
-        try:
-            import h5py
-        except ImportError:
-            h5py = None
         exact = Path(str(path))
-        use_npz = npz.exists() and (exact == npz or not exact.exists() or h5py is None)
-        if use_npz:
+        if npz.exists() and (exact == npz or not exact.exists()):
             with numpy.load(str(npz)) as arrays:
                 for layer in self.conv_layers:
                     layer.set_weights([arrays["{}/kernel".format(layer.name)], arrays["{}/bias".format(layer.name)]])
             return
-        if h5py is None:
-            raise IOError("{} not found and h5py is unavailable to read {}".format(npz, path))
-        with h5py.File(str(path), "r") as f:
+        try:
+            import h5py
+            opened = h5py.File(str(path), "r")
+        except ImportError:
+            from speechless_b200 import hdf5_lite
+            opened = hdf5_lite.File(path)
+        with opened as f:
             root = f["model_weights"] if "model_weights" in f else f
             for layer in self.conv_layers:
                 group = root[layer.name]
                 names = [n.decode("utf8") if isinstance(n, bytes) else n for n in group.attrs["weight_names"]]
+                # Keras stores (kernel, bias) in `weight_names` order; a Conv1D kernel is (k, C_in, C_out)
                 layer.set_weights([numpy.asarray(group[names[0]]), numpy.asarray(group[names[1]])])
 
 

@@ -499,6 +499,14 @@ def test_save_load_and_transfer_learning(env, tmp_path):
     kernel, _ = last.get_weights()
     last.set_weights([kernel, rng.standard_normal(29).astype(np.float32)])
     english.predictive_net.save_weights(str(tmp_path / env.Wav2Letter.model_file_name(7)))
+    # the .h5 has Keras' layout (reference net.py:572 / Keras save_weights): layer_names, weight_names, <layer>/kernel:0
+    from speechless_b200 import hdf5_lite
+    with hdf5_lite.File(tmp_path / "weights-epoch7.h5") as f:
+        names = [n.decode() for n in f.attrs["layer_names"]]
+        assert names == [l.name for l in english.predictive_net.layers] and names[-1] == "output_conv"
+        assert [n.decode() for n in f["big_conv_1"].attrs["weight_names"]] == ["big_conv_1/kernel:0", "big_conv_1/bias:0"]
+        assert f["output_conv/output_conv/kernel:0"].shape == (1, 64, 29)
+    (tmp_path / "weights-epoch7.npz").unlink()  # what follows loads from the .h5 alone
     same = env.Wav2Letter(128, env.alphabet, main_filter_count=64, out_filter_count=64, seed=99, device="cuda:0",
                           load_model_from_directory=tmp_path, load_epoch=7)
     for a, b in zip(english.predictive_net.layers, same.predictive_net.layers):
@@ -538,7 +546,8 @@ def test_train_loop_epoch_and_checkpoint_semantics(env, tmp_path):
               net_directory=tmp_path / "nets", batches_per_epoch=2, epochs=2)
     # epoch 0 is not saved, epoch 1 is (reference net.py:569-572)
     saved = sorted(p.name for p in (tmp_path / "nets").iterdir())
-    assert saved == ["weights-epoch1.npz"] or saved == ["weights-epoch1.h5"]
+    assert saved == ["weights-epoch1.h5", "weights-epoch1.npz"]  # Keras' HDF5 layout + the .npz twin
+    (tmp_path / "nets" / "weights-epoch1.npz").unlink()  # resuming reads the .h5 (hdf5_lite without h5py)
     lines = [json.loads(l) for l in (tmp_path / "tb" / "scalars.jsonl").read_text().splitlines()]
     assert [l["epoch"] for l in lines] == [0, 1] and all(np.isfinite(l["loss"]) for l in lines)
     assert net.optimizer.iterations == 4
