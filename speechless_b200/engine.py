@@ -666,11 +666,16 @@ class ConvTower:
 
     def grad_buckets(self) -> List[Tuple[int, int, int]]:
         """(first layer index, begin, end) float ranges of the flat gradient buffer, in the order
-        backward completes them: [output_conv + big_conv_2], [big_conv_1], [everything below]
-        (16 / 64 / 18 MB at reference widths)."""
+        backward completes them: [output_conv + big_conv_2], [big_conv_1], [the inner layers], [the first
+        trainable layer] (16 / 64 / 12 / 6 MB at reference widths).  The last bucket is the only
+        one whose all-reduce and Adam update nothing is left to hide behind, so it is kept to the one layer whose
+        weight gradient finishes last (SL_BUCKET_SPLIT_FIRST=0: one 18 MB bucket for everything below big_conv_1)."""
         n = len(self.layers)
         first = self.first_trainable()
-        cuts = sorted({max(first, n - 2), max(first, n - 3), first})
+        cuts = {max(first, n - 2), max(first, n - 3), first}
+        if os.environ.get("SL_BUCKET_SPLIT_FIRST", "1") != "0" and first + 1 < n - 3:
+            cuts.add(first + 1)
+        cuts = sorted(cuts)
         cuts = [c for c in cuts if c < n]
         buckets = []
         end_layer = n
