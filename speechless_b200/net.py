@@ -734,7 +734,10 @@ class Wav2Letter:
                          callback_step: int = 1, save_step: int = 1, save: bool = True) -> List[Callable]:
         """Epoch-end hooks with the reference's semantics (net.py:562-576): run `callback` every
         `callback_step` epochs, save `weights-epoch{N}` every `save_step` epochs for N > 0.  The
-        TensorBoard callback becomes a JSON-lines scalar log in `tensor_board_log_directory`."""
+        TensorBoard callback (net.py:574) writes the epoch's scalars as a TensorBoard event file when the
+        `tensorboard` package is importable (no TensorFlow needed), and always as a JSON-lines log
+        (`scalars.jsonl`) in `tensor_board_log_directory`."""
+        event_writer = []  # created on first use, one per training run
 
         def custom_callback(epoch: int, logs=()):
             if epoch % callback_step == 0:
@@ -749,6 +752,17 @@ class Wav2Letter:
             mkdir(tensor_board_log_directory)
             with (Path(tensor_board_log_directory) / "scalars.jsonl").open("a") as f:
                 f.write(json.dumps(dict(epoch=epoch, **dict(logs))) + "\n")
+            try:
+                from tensorboard.compat.proto.event_pb2 import Event
+                from tensorboard.compat.proto.summary_pb2 import Summary
+                from tensorboard.summary.writer.event_file_writer import EventFileWriter
+            except ImportError:
+                return
+            if not event_writer:
+                event_writer.append(EventFileWriter(str(tensor_board_log_directory)))
+            values = [Summary.Value(tag=str(name), simple_value=float(value)) for name, value in dict(logs).items()]
+            event_writer[0].add_event(Event(wall_time=time.time(), step=epoch, summary=Summary(value=values)))
+            event_writer[0].flush()
 
         return [scalar_log, custom_callback]
 

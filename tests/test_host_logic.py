@@ -1,5 +1,6 @@
 """Host-side pieces that need no GPU: result types, tools, the C-ABI library's symbol table."""
 import ctypes
+import json
 import math
 import re
 from pathlib import Path
@@ -167,3 +168,25 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["e2e"] == {"value": line["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["value"] > 0
+
+
+def test_epoch_callback_writes_tensorboard_events_and_a_json_log(tmp_path):
+    """The reference's TensorBoard callback (net.py:574): scalars per epoch, readable by TensorBoard itself."""
+    from speechless_b200.net import Wav2Letter
+    calls = []
+    scalar_log, custom = Wav2Letter.create_callbacks(object(), lambda: calls.append(1), tmp_path / "tb", tmp_path / "nets",
+                                                     callback_step=2, save=False)
+    for epoch, loss in enumerate([3.5, 2.25, 1.125]):
+        scalar_log(epoch, {"loss": loss})
+        custom(epoch)
+    assert len(calls) == 2  # epochs 0 and 2
+    lines = [json.loads(line) for line in (tmp_path / "tb" / "scalars.jsonl").read_text().splitlines()]
+    assert [(l["epoch"], l["loss"]) for l in lines] == [(0, 3.5), (1, 2.25), (2, 1.125)]
+    pytest.importorskip("tensorboard")
+    from tensorboard.backend.event_processing.event_file_loader import RawEventFileLoader
+    from tensorboard.compat.proto.event_pb2 import Event
+    event_files = sorted((tmp_path / "tb").glob("events.out.tfevents.*"))
+    assert len(event_files) == 1
+    events = [Event.FromString(raw) for raw in RawEventFileLoader(str(event_files[0])).Load()]
+    scalars = [(e.step, v.tag, v.simple_value) for e in events for v in e.summary.value]
+    assert scalars == [(0, "loss", 3.5), (1, "loss", 2.25), (2, "loss", 1.125)]
