@@ -262,7 +262,8 @@ class Wav2Letter:
                  decoder_beam_width: int = 100,
                  decoder_top_paths: int = 32,
                  language_model_mode: str = "in-search",
-                 data_parallel=None):
+                 data_parallel=None,
+                 devices=None):
         if frozen_layer_count > 0 and load_model_from_directory is None:
             raise ValueError("Layers cannot be frozen if model is trained from scratch.")
         if compute_dtype not in PRECISIONS:
@@ -297,6 +298,22 @@ class Wav2Letter:
         # `train` shard every batch by utterance and `test_and_predict_batches` shard by batch; the device
         # defaults to the rank's own GPU and rank 0's initial weights are broadcast to every replica.
         self.data_parallel = data_parallel if (data_parallel is not None and data_parallel.active) else None
+        # `devices`: the GPUs of the job.  One entry = `device`; several entries name the GPUs of a
+        # data-parallel job, one process per GPU — this process takes the entry of its local rank.
+        if devices is not None:
+            devices = list(devices)
+            if device is not None or not devices:
+                raise ValueError("pass either device or a non-empty devices list")
+            if len(devices) == 1:
+                device = devices[0]
+            elif self.data_parallel is None or self.data_parallel.world_size != len(devices):
+                raise ValueError("{} devices need one process per GPU: launch with torchrun --nproc-per-node {} and "
+                                 "pass data_parallel=speechless_b200.distributed.DataParallel()".format(
+                                     len(devices), len(devices)))
+            else:
+                device = devices[self.data_parallel.local_rank]
+            if isinstance(device, int):
+                device = "cuda:{}".format(device)
         if device is None and self.data_parallel is not None:
             device = "cuda:{}".format(self.data_parallel.local_rank)
         self._device = device

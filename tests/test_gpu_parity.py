@@ -489,6 +489,13 @@ def test_error_behaviour(env):
         asg.test_and_predict_batch([ok, ok])
     assert net.input_to_prediction_length_ratio == 2
     assert net.predictive_net.input_shape == (None, None, 128)
+    # `devices`: one entry is the device; several need one process per GPU (torchrun + data_parallel)
+    one = env.Wav2Letter(128, env.alphabet, main_filter_count=64, out_filter_count=64, seed=1, devices=[0])
+    assert str(one.tower.device) == "cuda:0"
+    with pytest.raises(ValueError, match="one process per GPU"):
+        env.Wav2Letter(128, env.alphabet, main_filter_count=64, out_filter_count=64, devices=[0, 1])
+    with pytest.raises(ValueError, match="either device or"):
+        env.Wav2Letter(128, env.alphabet, main_filter_count=64, out_filter_count=64, device="cuda:0", devices=[0])
 
 
 def test_save_load_and_transfer_learning(env, tmp_path):
