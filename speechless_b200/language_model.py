@@ -168,7 +168,7 @@ class LanguageModelTables:
         self.has_unk = "<unk>" in self.word_id
         self.unk_id = self.word_id.get("<unk>", len(words))
         self.bos_id = self.word_id.get("<s>", len(words) + 1)
-        self.eos_id = self.word_id.get("</s>", len(words) + 2)
+        self.eos_id = self.word_id.get("</s>", self.unk_id)  # (a model without </s> scores the end as an unknown word)
         self.unknown_log10 = model.unknown
         # ---- trie of the words that can be typed with the alphabet
         label_of = {c: i for i, c in enumerate(alphabet) if c != " "}
