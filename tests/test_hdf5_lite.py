@@ -110,3 +110,32 @@ def test_rejects_what_is_not_hdf5(tmp_path):
     path.write_bytes(b"PK\x03\x04" + b"\x00" * 2000)
     with pytest.raises(hdf5_lite.Hdf5FormatError):
         hdf5_lite.File(path)
+
+
+def test_reads_object_headers_with_continuation_blocks(tmp_path):
+    """libhdf5 moves messages into continuation blocks when attributes are added after an object was created —
+    which is how Keras writes `layer_names` / `weight_names`.  The writer never needs them, so the file is
+    assembled here: every object header keeps its first message and a continuation message, the rest of the
+    messages live in a block elsewhere in the file."""
+    class Splitting(hdf5_lite._Writer):
+        def _object_header(self, messages):
+            if len(messages) < 3:
+                return super()._object_header(messages)
+            rest = b"".join(messages[1:])
+            block = self._append(rest)
+            continuation = hdf5_lite._message(0x10, struct.pack("<QQ", block, len(rest)))
+            first = messages[0] + continuation
+            return self._append(struct.pack("<BBHII", 1, 0, len(messages) + 1, 1, len(first)) + b"\x00" * 4 + first)
+
+    writer = Splitting()
+    kernel = np.arange(24, dtype=np.float32).reshape(2, 3, 4)
+    dataset = writer.dataset(kernel, {"note": b"kept in the continuation block"})
+    group = writer.group({"kernel:0": dataset}, {"weight_names": [b"conv/kernel:0"], "extra": np.int32(7)})
+    root = writer.group({"conv": group}, {"layer_names": [b"conv"], "backend": b"tensorflow"})
+    path = tmp_path / "continued.h5"
+    path.write_bytes(writer.finish(root))
+    with hdf5_lite.File(path) as f:
+        assert f.attrs["layer_names"].tolist() == [b"conv"] and f.attrs["backend"] == b"tensorflow"
+        assert f["conv"].attrs["weight_names"].tolist() == [b"conv/kernel:0"] and f["conv"].attrs["extra"] == 7
+        np.testing.assert_array_equal(np.asarray(f["conv/kernel:0"]), kernel)
+        assert f["conv/kernel:0"].attrs["note"] == b"kept in the continuation block"
