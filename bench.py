@@ -287,6 +287,20 @@ class Arm:
         tower.backward_and_update(ws, loss, net.optimizer, data_parallel=self.dp)
         return loss
 
+    def ctc_lattices_only_ms(self, repetitions=20):
+        """The alpha / beta lattice kernel alone (`sl_ctc_loss` without the gradient output) on the probabilities of
+        the last step, CUDA-event timed back to back: what is left of the `ctc` time is the gradient kernel."""
+        torch = self.torch
+        for _ in range(3):
+            self.tower.ctc(self.ws, want_grad=False)
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        for _ in range(repetitions):
+            self.tower.ctc(self.ws, want_grad=False)
+        stop.record()
+        torch.cuda.synchronize()
+        return start.elapsed_time(stop) / repetitions
+
     def timed(self, steps, warmup):
         """ms/step, device-timed with CUDA events, max over ranks."""
         torch, dp = self.torch, self.dp
@@ -652,6 +666,23 @@ def run_ours(args):
                            "frac": round(ctc_bytes / (ctc_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
                            "algorithmic_bytes": ctc_bytes, "ms": round(ctc_ms, 4),
                            "traffic": ncu_traffic("ctc:ctc_loss", args.workload, dtype)}
+        # the two kernels behind that number: the lattice walk is a chain of T' dependent steps (latency), the
+        # gradient kernel streams the alpha / beta rows (bandwidth) — DESIGN.md §4.3
+        lattice_ms = arm.ctc_lattices_only_ms()
+        if 0 < lattice_ms < ctc_ms:
+            V = len(arm.alphabet) + 1
+            gradient_bytes = sum((f // 2) * (2 * (2 * len(e.label) + 1) * 4 + 2 * V * 4)
+                                 for f, e in zip(arm.frames, arm.examples))
+            gradient_ms = ctc_ms - lattice_ms
+            roofline["ctc"]["lattice_kernel"] = {
+                "ms": round(lattice_ms, 4), "dependent_steps": max(arm.frames) // 2,
+                "ns_per_step": round(lattice_ms * 1e6 / (max(arm.frames) // 2), 1), "bound": "latency",
+                "timing": "sl_ctc_loss without the gradient output, 20 back-to-back calls after the timed region"}
+            roofline["ctc"]["gradient_kernel"] = {
+                "ms": round(gradient_ms, 4), "bound": "hbm", "algorithmic_bytes": gradient_bytes,
+                "achieved": round(gradient_bytes / (gradient_ms * 1e-3) / 1e9, 1), "unit": "GB/s",
+                "frac": round(gradient_bytes / (gradient_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
+                "timing": "ctc ms of the instrumented steps minus the lattice kernel's"}
 
     precision = None if args.no_precision_check else precision_record(dtype, device)
     cpu = None
