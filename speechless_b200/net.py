@@ -524,9 +524,13 @@ class Wav2Letter:
                 for b in range(decoded.shape[0])]
 
     def predict_batch_with_beam_search(self, spectrograms: List[ndarray], beam_width: Optional[int] = None,
-                                       top_paths: int = 1) -> List[List[Tuple[str, float]]]:
+                                       top_paths: int = 1, use_language_model: bool = False
+                                       ) -> List[List[Tuple[str, float]]]:
         """Beam-search counterpart of `predict_batch_greedily`: per utterance the `top_paths` best
-        (text, log-probability) hypotheses of the device prefix beam search (no language model)."""
+        (text, log-probability) hypotheses of the device prefix beam search; `use_language_model` scores the
+        words of `kenlm_directory`'s model inside the search (the scores then include the language-model terms)."""
+        if use_language_model and self.device_language_model is None:
+            raise ValueError("use_language_model needs kenlm_directory (and language_model_mode='in-search')")
         input_batch, prediction_lengths = self._input_batch_and_prediction_lengths(spectrograms)
         tower = self.tower
         ws = tower.upload(input_batch)
@@ -534,7 +538,9 @@ class Wav2Letter:
         tower.set_prediction_lengths(ws, prediction_lengths)
         return [[(self.grapheme_encoding.decode_graphemes(graphemes, merge_repeated=False), log_probability)
                  for graphemes, log_probability in hypotheses]
-                for hypotheses in self.beam_search_batch(ws, beam_width=beam_width, top_paths=top_paths)]
+                for hypotheses in self.beam_search_batch(
+                    ws, beam_width=beam_width, top_paths=top_paths,
+                    language_model=self.device_language_model if use_language_model else None)]
 
     def _beam_search_with_language_model(self, ws) -> ndarray:
         """Dense (B, max length) grapheme matrix, -1 padded like the greedy path: the best hypothesis of the

@@ -423,6 +423,12 @@ def test_wav2letter_decodes_with_beam_search_and_language_model(tmp_path):
         texts = ["".join(english_frequent_characters[c] for c in labels) for labels, _ in want]
         assert result.predicted == texts[0] or (result.predicted == texts[1] and abs(want[0][1] - want[1][1]) < 2e-3)
     assert [r.loss for r in searched.results] == pytest.approx([r.loss for r in without.results], rel=1e-5)
+    spectrograms_ = [e.z_normalized_transposed_spectrogram() for e in batch]
+    ranked_lm = in_search.predict_batch_with_beam_search(spectrograms_, beam_width=16, top_paths=3, use_language_model=True)
+    assert [h[0][0] for h in ranked_lm] == [r.predicted for r in searched.results]
+    assert all([s for _, s in h] == sorted([s for _, s in h], reverse=True) for h in ranked_lm)
+    with pytest.raises(ValueError, match="kenlm_directory"):
+        greedy.predict_batch_with_beam_search(spectrograms_, use_language_model=True)
     # the public beam-search call: best hypothesis first, log-probabilities descending; with width 1 on
     # these near-uniform outputs it still returns exactly one hypothesis per utterance
     spectrograms = [e.z_normalized_transposed_spectrogram() for e in batch]
