@@ -228,13 +228,67 @@ class LanguageModelTables:
         self.ngrams = table
 
 
-class DeviceLanguageModel:
-    """`LanguageModelTables` in device memory plus the `SlWordLm` struct that points at them."""
+    # ---- cache: parsing a large ARPA file and hashing its n-grams in Python takes minutes, loading arrays seconds
+    _SCALARS = ("order", "symbol_count", "space_label", "has_unk", "unk_id", "bos_id", "eos_id", "unknown_log10")
 
-    def __init__(self, model: ArpaLanguageModel, alphabet: Sequence[str], symbol_count: int, device,
+    def save(self, path, fingerprint: str) -> None:
+        import numpy
+        numpy.savez(str(path), trie_children=self.trie_children, trie_word=self.trie_word,
+                    trie_min_unigram=self.trie_min_unigram, ngrams=self.ngrams, fingerprint=numpy.array(fingerprint),
+                    scalars=numpy.array([float(getattr(self, name)) for name in self._SCALARS], dtype=numpy.float64))
+
+    @classmethod
+    def load(cls, path, fingerprint: str) -> Optional["LanguageModelTables"]:
+        """The tables saved under `path` if they were built from the same model file and alphabet, else None."""
+        import numpy
+        try:
+            with numpy.load(str(path)) as z:
+                if str(z["fingerprint"]) != fingerprint:
+                    return None
+                tables = cls.__new__(cls)
+                tables.trie_children, tables.trie_word = z["trie_children"], z["trie_word"]
+                tables.trie_min_unigram, tables.ngrams = z["trie_min_unigram"], z["ngrams"]
+                for name, value in zip(cls._SCALARS, z["scalars"]):
+                    setattr(tables, name, float(value) if name == "unknown_log10" else int(value))
+                tables.has_unk = bool(tables.has_unk)
+                tables.word_id = None  # (only needed while building)
+                return tables
+        except (OSError, KeyError, ValueError):
+            return None
+
+    @classmethod
+    def from_arpa_file(cls, arpa_file: Path, alphabet: Sequence[str], symbol_count: int,
+                       cache: bool = True) -> "LanguageModelTables":
+        """Tables of the model in `arpa_file`; cached next to it as `<name>.sl_tables.npz`, keyed by the file's size
+        and modification time and by the alphabet (a stale or unwritable cache is simply rebuilt / skipped)."""
+        arpa_file = Path(arpa_file)
+        stat = arpa_file.stat()
+        fingerprint = "{}:{}:{}:{}:{}".format(arpa_file.name, stat.st_size, int(stat.st_mtime), symbol_count,
+                                              "".join(alphabet))
+        cache_path = arpa_file.with_name(arpa_file.name + ".sl_tables.npz")
+        if cache and cache_path.exists():
+            tables = cls.load(cache_path, fingerprint)
+            if tables is not None:
+                return tables
+        tables = cls(ArpaLanguageModel.read(arpa_file), alphabet, symbol_count)
+        if cache:
+            try:
+                tables.save(cache_path, fingerprint)
+            except OSError:
+                pass
+        return tables
+
+
+class DeviceLanguageModel:
+    """`LanguageModelTables` in device memory plus the `SlWordLm` struct that points at them.  `model`: an
+    `ArpaLanguageModel`, or ready-made `LanguageModelTables` (e.g. `LanguageModelTables.from_arpa_file`)."""
+
+    def __init__(self, model, alphabet: Sequence[str], symbol_count: int, device,
                  kenlm_weight: float = .8, word_count_weight: float = 0., valid_word_count_weight: float = 2.3):
         import torch
-        tables = LanguageModelTables(model, alphabet, symbol_count)
+        tables = model if isinstance(model, LanguageModelTables) else LanguageModelTables(model, alphabet, symbol_count)
+        if tables.symbol_count != symbol_count or tables.space_label != list(alphabet).index(" "):
+            raise ValueError("the language-model tables were built for another alphabet")
         self.tables = tables
         self._tensors = [torch.from_numpy(a).to(device).contiguous() for a in
                          (tables.trie_children, tables.trie_word, tables.trie_min_unigram, tables.ngrams)]

@@ -338,13 +338,17 @@ class Wav2Letter:
                     "No *.arpa file in {}: KenLM's binary format needs the KenLM library of the reference's patched "
                     "TensorFlow (net.py:420-422), which is not available; export the model as ARPA text.".format(
                         self.kenlm_directory))
-            arpa_model = ArpaLanguageModel.read(arpa_file)
-            self.rescorer = NBestRescorer(arpa_model, kenlm_weight=.8, word_count_weight=0,
-                                          valid_word_count_weight=2.3)
             if language_model_mode == "in-search":
+                # (device tables are cached next to the ARPA file: a large model is parsed once)
+                from speechless_b200.language_model import LanguageModelTables
+                symbol_count = self.grapheme_encoding.grapheme_set_size
                 self.device_language_model = DeviceLanguageModel(
-                    arpa_model, alphabet=allowed_characters, symbol_count=self.grapheme_encoding.grapheme_set_size,
-                    device=self.tower.device, kenlm_weight=.8, word_count_weight=0, valid_word_count_weight=2.3)
+                    LanguageModelTables.from_arpa_file(arpa_file, allowed_characters, symbol_count),
+                    alphabet=allowed_characters, symbol_count=symbol_count, device=self.tower.device,
+                    kenlm_weight=.8, word_count_weight=0, valid_word_count_weight=2.3)
+            else:
+                self.rescorer = NBestRescorer(ArpaLanguageModel.read(arpa_file), kenlm_weight=.8, word_count_weight=0,
+                                              valid_word_count_weight=2.3)
 
         if load_model_from_directory is not None:
             self.load_weights(

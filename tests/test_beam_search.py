@@ -260,6 +260,29 @@ def test_language_model_tables_hold_every_ngram_and_the_vocabulary_trie():
     assert tables.trie_word.max() < len(tables.word_id) and (tables.trie_word >= 0).sum() == 40  # (4 letters: 84 possible)
 
 
+def test_language_model_tables_are_cached_next_to_the_arpa_file(tmp_path, monkeypatch):
+    from speechless_b200 import language_model
+    from speechless_b200.language_model import ArpaLanguageModel, LanguageModelTables
+    arpa = tmp_path / "tiny.arpa"
+    arpa.write_text(ARPA.replace("-1.5\tthe cat is not a word\t0.0\n", "-1.5\tdog\t0.0\n"), encoding="utf8")
+    alphabet = list("abcdefghijklmnopqrstuvwxyz '")
+    built = LanguageModelTables.from_arpa_file(arpa, alphabet, len(alphabet) + 1)
+    assert (tmp_path / "tiny.arpa.sl_tables.npz").exists()
+
+    def no_parsing(path):
+        raise AssertionError("the ARPA file was parsed again")
+    monkeypatch.setattr(ArpaLanguageModel, "read", staticmethod(no_parsing))
+    cached = LanguageModelTables.from_arpa_file(arpa, alphabet, len(alphabet) + 1)
+    for name in ("trie_children", "trie_word", "trie_min_unigram", "ngrams"):
+        np.testing.assert_array_equal(getattr(cached, name), getattr(built, name))
+    for name in LanguageModelTables._SCALARS:
+        assert getattr(cached, name) == getattr(built, name), name
+    assert language_model.find_arpa_file(tmp_path) == arpa  # the cache is not mistaken for a model
+    # another alphabet (or a changed file) invalidates the cache
+    with pytest.raises(AssertionError, match="parsed again"):
+        LanguageModelTables.from_arpa_file(arpa, alphabet[:-1] + ["-"], len(alphabet) + 1)
+
+
 def test_oracle_language_model_search_is_exact_with_a_wide_beam():
     """The scorer's deltas telescope: a finished hypothesis holds its CTC probability plus the rescoring formula,
     so a beam wide enough for every prefix returns the arg max of that sum over ALL labelings."""
