@@ -401,16 +401,17 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           for (int ti = 0; ti < ntaps; ++ti) {
             mbar_wait(&full_bar[stage], phase);
             tcgen05_fence_after();
-            if (lane == 0) {
+            if (elect_one()) {  // (a single-taker branch ptxas can see: operands stay in uniform registers)
               // tap j reads halo rows [j, j + 128): start address advanced by j rows of 128 B
               const uint32_t a_addr = halo_addr + static_cast<uint32_t>(ti) * 128u;
               const uint32_t b_addr = b_ring + stage * C::B_BYTES;
+              const uint64_t db0 = BMN ? make_smem_desc_sw128(b_addr, BLOCK_K * 128, 1024)
+                                       : make_smem_desc_sw128(b_addr, 16, 1024);
 #pragma unroll
               for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
                 const uint32_t aa = a_addr + k * UMMA_K * 2;
                 const uint64_t da = make_smem_desc_sw128_off(aa, 16, 1024, p.halo_base_mode ? (aa >> 7) & 7u : 0u);
-                const uint64_t db = BMN ? make_smem_desc_sw128(b_addr + k * 2048, BLOCK_K * 128, 1024)
-                                        : make_smem_desc_sw128(b_addr + k * UMMA_K * 2, 16, 1024);
+                const uint64_t db = db0 + static_cast<uint64_t>(k * (BMN ? (2048 >> 4) : ((UMMA_K * 2) >> 4)));
                 if constexpr (CTAS == 2)
                   umma_bf16_pair(tmem_d, da, db, idesc, first ? 0u : 1u);
                 else
@@ -422,6 +423,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
               if (ti == ntaps - 1 && ct == n_ct - 1) commit<CTAS>(&tmem_full[as]);
             }
             __syncwarp();
+            first = 0;
             if (++stage == C::kStagesB) {
               stage = 0;
               phase ^= 1;
@@ -438,10 +440,44 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         }
         continue;
       }
+      if constexpr (CTAS == 1) {
+        // The issue loop is bound by this one thread's instruction stream, not by the tensor pipe (§7.1 of
+        // four extra clock reads per MMA cost +85 cycles each, and only two MMAs are ever in
+        // flight), so it is kept as short as it gets: the leader is chosen with elect.sync — a branch ptxas
+        // knows to have a single taker, so the operands can live in uniform registers — and the four
+        // descriptors of a stage differ only in their 14-bit address field (one add each).
+        const uint32_t ring = smem_u32(smem);
+        for (int ks = 0; ks < ksteps; ++ks) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          if (lane == 0 && ks == 0) stamp(it == 0 ? 3 : 25 + it);
+          if (elect_one()) {
+            const uint32_t a_addr = ring + stage * C::STAGE_BYTES;
+            const uint64_t da0 = make_smem_desc_sw128(a_addr, 16, 1024);
+            const uint64_t db0 = BMN ? make_smem_desc_sw128(a_addr + A_BYTES, BLOCK_K * 128, 1024)
+                                     : make_smem_desc_sw128(a_addr + A_BYTES, 16, 1024);
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              // K-major: 16 contraction elements = 32 B further along the swizzled row; MN-major B: two 8-row
+              // swizzle atoms (2048 B) per 16 contraction rows
+              const uint64_t da = da0 + static_cast<uint64_t>(k * ((UMMA_K * 2) >> 4));
+              const uint64_t db = db0 + static_cast<uint64_t>(k * (BMN ? (2048 >> 4) : ((UMMA_K * 2) >> 4)));
+              umma_bf16(tmem_d, da, db, idesc, (ks | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+            if (ks == ksteps - 1) umma_commit(&tmem_full[as]);
+          }
+          __syncwarp();
+          if (lane == 0 && ks == ksteps - 1 && it < 6) stamp(4 + it);
+          if (++stage == C::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      } else {
       for (int ks = 0; ks < ksteps; ++ks) {
         mbar_wait(&full_bar[stage], phase);
         tcgen05_fence_after();
-        if (lane == 0 && ks == 0) stamp(it == 0 ? 3 : 25 + it);
         if (lane == 0) {
           const uint32_t a_addr = smem_u32(smem + stage * C::STAGE_BYTES);
           const uint32_t b_addr = a_addr + A_BYTES;
@@ -452,22 +488,17 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             // groups are BLOCK_K * 128 B apart (leading byte offset)
             const uint64_t db = BMN ? make_smem_desc_sw128(b_addr + k * 2048, BLOCK_K * 128, 1024)
                                     : make_smem_desc_sw128(b_addr + k * UMMA_K * 2, 16, 1024);
-            if constexpr (CTAS == 2)
-              umma_bf16_pair(tmem_d, da, db, idesc, (ks | k) != 0 ? 1u : 0u);
-            else
-              umma_bf16(tmem_d, da, db, idesc, (ks | k) != 0 ? 1u : 0u);
+            umma_bf16_pair(tmem_d, da, db, idesc, (ks | k) != 0 ? 1u : 0u);
           }
           commit<CTAS>(&empty_bar[stage]);  // frees the smem slot (of both CTAs) when these MMAs retire
-          if (ks == ksteps - 1) {
-            commit<CTAS>(&tmem_full[as]);
-            if (it < 6) stamp(4 + it);
-          }
+          if (ks == ksteps - 1) commit<CTAS>(&tmem_full[as]);
         }
         __syncwarp();
         if (++stage == C::kStages) {
           stage = 0;
           phase ^= 1;
         }
+      }
       }
       if (ksteps == 0 && lane == 0) {  // empty tap range (never planned)
         mbar_arrive(&tmem_full[as]);

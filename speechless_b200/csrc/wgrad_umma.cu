@@ -218,14 +218,18 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
       for (int ks = 0; ks < ksteps; ++ks) {
         mbar_wait(&full_bar[stage], phase);
         tcgen05_fence_after();
-        if (lane == 0) {
+        // The issue loop is bound by this one thread's instruction stream, so the leader is
+        // chosen with elect.sync — a single-taker branch ptxas can see, which keeps the operands in uniform
+        // registers — and the descriptors of a stage differ only in their address field (one add each).
+        if (elect_one()) {
           const uint32_t a_addr = smem_u32(smem + stage * C::STAGE_BYTES);
-          const uint32_t b_addr = a_addr + A_BYTES;
+          const uint64_t da0 = make_smem_desc_sw128(a_addr, LBO, SBO);
+          const uint64_t db0 = make_smem_desc_sw128(a_addr + A_BYTES, LBO, SBO);
 #pragma unroll
           for (int k = 0; k < KT / UMMA_K; ++k) {
             // 16 frames = two 8-row swizzle atoms = 2048 B further along K
-            const uint64_t da = make_smem_desc_sw128(a_addr + k * 2048, LBO, SBO);
-            const uint64_t db = make_smem_desc_sw128(b_addr + k * 2048, LBO, SBO);
+            const uint64_t da = da0 + static_cast<uint64_t>(k * (2048 >> 4));
+            const uint64_t db = db0 + static_cast<uint64_t>(k * (2048 >> 4));
             umma_bf16(tmem_d, da, db, idesc, (ks | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);
