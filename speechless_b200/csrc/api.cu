@@ -271,14 +271,16 @@ static int bind_tail_scratch(ConvGemmParams* p, int bn, cudaStream_t stream) {
 static int make_act_load_map(CUtensorMap* m, const void* base, int c_total, int stride, int T_alloc, int B,
                              int box_rows);
 static int plan_halo(ConvGemmParams* p, const void* act, int c_total, int T_alloc, int B, int taps, int stride) {
-  // default: on for long filters (big_conv_1, k = 32: -4 % bf16, -15 % split-bf16 on its input
-  // gradient); for k = 7 the extra halo buffers cost more than the saved loads (measured).
+  // default: on for stride-1 filters of 5 taps and more.  (While the MMA issue loop was bound by its own
+  // instruction stream — DESIGN.md §7.1 — the halo only paid for long filters: big_conv_1, k = 32, -4 % bf16,
+  // -15 % split-bf16 on its input gradient, and k = 7 lost a little.  With the loop at the tensor pipe's pace
+  // the saved operand traffic shows: inner_conv, k = 7, forward 0.040 -> 0.037 ms, input gradient 0.040 -> 0.036.)
   // SL_HALO=0 disables, SL_HALO=1 forces it for every stride-1 layer with more than one tap.
   const char* e = std::getenv("SL_HALO");
   const int mode = e ? std::atoi(e) : -1;
   p->halo = 0;
   if (mode == 0 || stride != 1 || taps < 2 || 128 + taps - 1 > 256) return 0;
-  if (mode < 0 && taps < 16) return 0;
+  if (mode < 0 && taps < 5) return 0;
   if (mode < 0 && p->ctas == 2) return 0;  // a CTA pair is faster without it (0.905 vs 0.95 ms, big_conv_1 forward)
   p->halo = 1;
   p->halo_rows = 128 + taps - 1;
