@@ -478,16 +478,17 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       for (int ks = 0; ks < ksteps; ++ks) {
         mbar_wait(&full_bar[stage], phase);
         tcgen05_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {  // (as in the single-CTA loop: single-taker branch, descriptors one add apart)
           const uint32_t a_addr = smem_u32(smem + stage * C::STAGE_BYTES);
-          const uint32_t b_addr = a_addr + A_BYTES;
+          const uint64_t da0 = make_smem_desc_sw128(a_addr, 16, 1024);
+          // MN-major B: 16 contraction rows = two 8-row swizzle atoms (2048 B); 64-channel
+          // groups are BLOCK_K * 128 B apart (leading byte offset)
+          const uint64_t db0 = BMN ? make_smem_desc_sw128(a_addr + A_BYTES, BLOCK_K * 128, 1024)
+                                   : make_smem_desc_sw128(a_addr + A_BYTES, 16, 1024);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t da = make_smem_desc_sw128(a_addr + k * UMMA_K * 2, 16, 1024);
-            // MN-major B: 16 contraction rows = two 8-row swizzle atoms (2048 B); 64-channel
-            // groups are BLOCK_K * 128 B apart (leading byte offset)
-            const uint64_t db = BMN ? make_smem_desc_sw128(b_addr + k * 2048, BLOCK_K * 128, 1024)
-                                    : make_smem_desc_sw128(b_addr + k * UMMA_K * 2, 16, 1024);
+            const uint64_t da = da0 + static_cast<uint64_t>(k * ((UMMA_K * 2) >> 4));
+            const uint64_t db = db0 + static_cast<uint64_t>(k * (BMN ? (2048 >> 4) : ((UMMA_K * 2) >> 4)));
             umma_bf16_pair(tmem_d, da, db, idesc, (ks | k) != 0 ? 1u : 0u);
           }
           commit<CTAS>(&empty_bar[stage]);  // frees the smem slot (of both CTAs) when these MMAs retire
