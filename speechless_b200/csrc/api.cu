@@ -149,7 +149,7 @@ static int make_weight_map(CUtensorMap* m, const void* base, int k_total, int ro
 
 // Tail of the persistent conv grid (ConvGemmParams::tail_split / tail_ksplit).  Default: the tiles of the last,
 // partial wave are cut into up to 4 narrower tiles (SL_TAIL_SPLIT=0 disables; SL_TAIL_SPLIT_ALL=n splits EVERY
-// tile): an M = 128 MMA costs the same ~153 cycles for N = 64 as for N = 256, so this only shortens the
+// tile): an M = 128 MMA costs the same ~147 cycles for N = 64 as for N = 256, so this only shortens the
 // epilogue of the wave (inner_conv: 42 vs 44 us).  SL_TAIL_KSPLIT=n (opt-in) splits those tiles over the
 // contraction instead — the experiment of DESIGN.md §4.1: parity-green, measured slower.
 struct TailScratch {

@@ -28,7 +28,7 @@ struct ConvGemmParams {
   // tail_split (1, 2 or 4) narrower tiles so that the wave costs 1/tail_split of a tile time
   int full_tiles;  // tiles [0, full_tiles) are whole; the rest are split
   int tail_split;
-  // tail K split (EPI_PACKED, single CTAs): a tcgen05.mma of M = 128 takes the same ~153 cycles for N = 64 as
+  // tail K split (EPI_PACKED, single CTAs): a tcgen05.mma of M = 128 takes the same ~147 cycles for N = 64 as
   // for N = 256 (measured), so narrow tiles do not shorten the partial wave — splitting the contraction does.
   // Each tile of the partial wave becomes tail_ksplit work items over tail_per 64-channel chunks (all taps)
   // each.  The items that finish first add their fp32 partial sums into the tile's slot of a zero-filled
