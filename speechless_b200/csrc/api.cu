@@ -295,7 +295,9 @@ static int plan_halo(ConvGemmParams* p, const void* act, int c_total, int T_allo
 // CTA pairs (ConvGemmParams::ctas, cta_group::2).  Measured on B200 (profiles/README.md): correct, but not
 // faster than single CTAs with A-halo reuse — big_conv_1 forward 0.905 ms either way without the halo for
 // the pair, 0.95 ms with it; the short inner / striding layers lose 10-15 % — so the pair kernel is
-// opt-in: SL_CTA2=1 uses it for every 256-filter tile, SL_CTA2=2 only for layers with >= 2 filter tiles.
+// opt-in: SL_CTA2=1 uses it for every 256-filter tile, SL_CTA2=2 only for layers with >= 2 filter tiles,
+// SL_CTA2=3 only for 1-tap layers with >= 2 filter tiles (big_conv_2: the one place it measured faster after
+// the issue-loop fix, profiles/r02_cta_pairs_after_fix.log; not validated as a default yet).
 static int cta_pairs() {
   const char* e = std::getenv("SL_CTA2");
   return e ? std::atoi(e) : 0;
@@ -452,7 +454,8 @@ int sl_conv1d_fwd(const void* x_packed, const void* w_fwd, const float* bias, vo
   int bn = cout_pad >= 256 ? 256 : cout_pad;
   SL_REQUIRE(cout_pad % bn == 0 && (bn == 64 || bn == 128 || bn == 256), "unsupported filter count");
   p.ctas = (bn == 256 && act != SL_ACT_SOFTMAX && dbg_mode() == 0 &&
-            (cta_pairs() == 1 || (cta_pairs() == 2 && cout_pad / bn >= 2))) ? 2 : 1;
+            (cta_pairs() == 1 || (cta_pairs() == 2 && cout_pad / bn >= 2) ||
+             (cta_pairs() == 3 && cout_pad / bn >= 2 && k == 1))) ? 2 : 1;
   int rc = make_act_load_map(&p.tmA, x_packed, planes * cin_pad, stride, T_in_alloc, B, 128);
   if (rc) return rc;
   rc = make_weight_map(&p.tmB, w_fwd, planes * cin_pad, cout_pad, k, bn / p.ctas);
@@ -571,7 +574,8 @@ static int dgrad_launch_rows(const void* dy_packed, const void* w_fwd, const voi
   // boxes of 64 co rows x 64 ci, consumed MN-major
   p.b_grouped = grouped_tma();
   p.ctas = (bn == 256 && p.b_grouped && dbg_mode() == 0 &&
-            (cta_pairs() == 1 || (cta_pairs() == 2 && cin_pad / bn >= 2 && cout_pad >= 512))) ? 2 : 1;
+            (cta_pairs() == 1 || (cta_pairs() == 2 && cin_pad / bn >= 2 && cout_pad >= 512) ||
+             (cta_pairs() == 3 && cin_pad / bn >= 2 && cout_pad >= 512 && n_taps == 1))) ? 2 : 1;
   rc = p.b_grouped ? make_weight_group_map(&p.tmB, w_fwd, planes * cin_pad, cout_pad, k, 64, bn / 64 / p.ctas)
                    : make_weight_map(&p.tmB, w_fwd, planes * cin_pad, cout_pad, k, 64);
   if (rc) return rc;
