@@ -254,6 +254,41 @@ def test_input_gradient_tail_k_split(env, monkeypatch, mode, B, T, cin, cout, k)
     assert rel_err(results["k-split"], results["narrow"]) < max(TOL[mode], 3e-4)
 
 
+# ------------------------------------------------------------------ narrowed persistent grids (data-parallel window)
+@pytest.mark.parametrize("B,T,cin,cout,k", [
+    (20, 1000, 250, 250, 7),   # inner_conv (A-halo loop): 160 tiles
+    (3, 900, 2000, 2000, 1),   # big_conv_2: 192 tiles
+])
+def test_forward_on_a_narrowed_grid_is_bitwise_the_same(env, B, T, cin, cout, k):
+    """`sl_set_sm_limit` (the window in which a gradient bucket's all-reduce shares the GPU) only
+    changes which CTA computes which tile — and which tiles of the last wave are cut narrower — never a value."""
+    torch, lib, check, ptr = env.torch, env.lib, env._lib.check, env._lib.ptr
+    prec = PRECS["fp16"]
+    rng = np.random.default_rng(T + k + 5)
+    x = rng.standard_normal((B, T, cin)).astype(np.float32)
+    w = (rng.standard_normal((k, cin, cout)) / np.sqrt(k * cin)).astype(np.float32)
+    bias = rng.standard_normal(cout).astype(np.float32)
+    xp, wf = pack(env, x, prec), pack_w(env, w, prec)
+    bd = torch.from_numpy(bias).to("cuda:0")
+    cop = pad64(cout)
+    outputs = []
+    try:
+        for limit in (0, 132, 100, 37):
+            check(lib.sl_set_sm_limit(limit))
+            yp = torch.zeros((B, T, cop), dtype=storage(torch, prec), device="cuda:0")
+            mask = torch.zeros((B, T, cop // 8), dtype=torch.uint8, device="cuda:0")
+            check(lib.sl_conv1d_fwd(ptr(xp), ptr(wf), ptr(bd), ptr(yp), ptr(mask), None, None, None, B, T, T, T, cin, cout,
+                                    k, 1, 1, prec, None))
+            check(lib.sl_sync_check())
+            outputs.append((yp.clone(), mask.clone()))
+    finally:
+        check(lib.sl_set_sm_limit(0))
+    for yp, mask in outputs[1:]:
+        assert torch.equal(yp, outputs[0][0]) and torch.equal(mask, outputs[0][1])
+    want = np.maximum(env.oracle.conv1d_same(x.astype(np.float64), w.astype(np.float64), bias.astype(np.float64), 1), 0)
+    assert rel_err(unpack(env, outputs[0][0], B, T, cout, prec), want) < TOL["fp16"]
+
+
 # ------------------------------------------------------------------ full-width tower: logits and gradients per mode
 def _tower_case(env, mode, seed=1):
     from tests.test_gpu_parity import make_pair
