@@ -626,3 +626,27 @@ def write(path, tree: Dict[str, object], attrs: Optional[Dict[str, Dict[str, obj
     root = emit(expand(tree), "")
     with open(str(path), "wb") as handle:
         handle.write(writer.finish(root))
+
+
+def describe(path) -> List[str]:
+    """One line per object of the file: `python -m speechless_b200.hdf5_lite weights-epoch12.h5`."""
+    lines: List[str] = []
+
+    def walk(group: Group, indent: int) -> None:
+        for name, value in sorted(group.attrs.items()):
+            lines.append("{}@{} = {!r}".format("  " * indent, name, value.tolist() if hasattr(value, "tolist") else value))
+        for key in group.keys():
+            node = group[key]
+            if isinstance(node, Group):
+                lines.append("{}{}/".format("  " * indent, key))
+                walk(node, indent + 1)
+            else:
+                lines.append("{}{}  {} {}".format("  " * indent, key, node.dtype, node.shape))
+    with File(path) as f:
+        walk(f, 0)
+    return lines
+
+
+if __name__ == "__main__":
+    import sys
+    print("\n".join(describe(sys.argv[1])))

@@ -139,3 +139,12 @@ def test_reads_object_headers_with_continuation_blocks(tmp_path):
         assert f["conv"].attrs["weight_names"].tolist() == [b"conv/kernel:0"] and f["conv"].attrs["extra"] == 7
         np.testing.assert_array_equal(np.asarray(f["conv/kernel:0"]), kernel)
         assert f["conv/kernel:0"].attrs["note"] == b"kept in the continuation block"
+
+
+def test_describe_lists_groups_datasets_and_attributes(tmp_path):
+    path = tmp_path / "w.h5"
+    hdf5_lite.write(path, {"conv": {"conv/kernel:0": np.zeros((7, 3, 5), np.float32)}},
+                    {"/": {"layer_names": [b"conv"]}, "conv": {"weight_names": [b"conv/kernel:0"]}})
+    lines = hdf5_lite.describe(path)
+    assert lines[0] == "@layer_names = [b'conv']" and "conv/" in lines
+    assert any(line.strip() == "kernel:0  float32 (7, 3, 5)" for line in lines)
